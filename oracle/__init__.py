@@ -1,0 +1,333 @@
+"""ctypes binding of the CPU oracle (oracle/dgsem_oracle.cc).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(warpii_b200) must never import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_REF_PATH = os.path.join(_HERE, "_ref", "libwarpii_ref.so")
+
+BC_WALL, BC_OUTFLOW, BC_INFLOW = 0, 1, 2
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_up = C.POINTER(C.c_uint)
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when /root/reference exists)."""
+    if force or not os.path.exists(_LIB_PATH) or (
+            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "dgsem_oracle.cc"))):
+        subprocess.check_call(["make", "-C", _HERE, "_build/liboracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_ln_avg.restype = C.c_double
+        L.orc_ln_avg.argtypes = [C.c_double, C.c_double]
+        L.orc_pressure.restype = C.c_double
+        L.orc_pressure.argtypes = [_dp, C.c_double]
+        L.orc_euler_flux.argtypes = [C.c_int, _dp, C.c_double, _dp]
+        L.orc_lf_flux.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, _dp]
+        L.orc_ec_flux.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp]
+        L.orc_es_flux.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, _dp]
+        L.orc_entropy_variables.argtypes = [_dp, C.c_double, _dp]
+        L.orc_mathematical_entropy.restype = C.c_double
+        L.orc_mathematical_entropy.argtypes = [_dp, C.c_double]
+        L.orc_entropy_flux.argtypes = [C.c_int, _dp, C.c_double, _dp]
+        L.orc_primitive_to_conserved.argtypes = [_dp, C.c_double, _dp]
+        for name in ("orc_pencil_stride",):
+            getattr(L, name).restype = C.c_uint
+            getattr(L, name).argtypes = [C.c_uint, C.c_uint]
+        L.orc_pencil_base.restype = C.c_uint
+        L.orc_pencil_base.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint]
+        L.orc_quadrature_point_neighbor.restype = C.c_uint
+        L.orc_quadrature_point_neighbor.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+        L.orc_quad_point_1d_index.restype = C.c_uint
+        L.orc_quad_point_1d_index.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint]
+        L.orc_pencil_starts.restype = C.c_int
+        L.orc_pencil_starts.argtypes = [C.c_int, C.c_uint, C.c_uint, _up]
+        L.orc_gll.argtypes = [C.c_int, _dp, _dp]
+        L.orc_gauss.argtypes = [C.c_int, _dp, _dp]
+        L.orc_diff_matrix.argtypes = [C.c_int, _dp]
+        L.orc_legendre_analysis_1d.argtypes = [C.c_int, _dp]
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _ip, _dp, _dp, _ip, _ip]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.orc_n_elems.restype = C.c_int64
+        L.orc_n_elems.argtypes = [C.c_void_p]
+        L.orc_n_dofs.restype = C.c_int64
+        L.orc_n_dofs.argtypes = [C.c_void_p]
+        L.orc_n_components.argtypes = [C.c_void_p]
+        L.orc_nodes_per_elem.argtypes = [C.c_void_p]
+        L.orc_n_boundaries.argtypes = [C.c_void_p]
+        L.orc_node_coords.argtypes = [C.c_void_p, _dp]
+        L.orc_set_inflow.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+        L.orc_rhs.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp]
+        L.orc_alpha.argtypes = [C.c_void_p, _dp, _dp]
+        L.orc_cell_residual.argtypes = [C.c_void_p, _dp, C.c_double, _dp]
+        L.orc_shock_indicator.restype = C.c_double
+        L.orc_shock_indicator.argtypes = [C.c_void_p, _dp]
+        L.orc_forward_euler_step.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_double, C.c_double,
+                                             C.c_double, _dp, _dp]
+        L.orc_max_transport_speed.restype = C.c_double
+        L.orc_max_transport_speed.argtypes = [C.c_void_p, _dp]
+        L.orc_recommend_dt.restype = C.c_double
+        L.orc_recommend_dt.argtypes = [C.c_void_p, _dp]
+        L.orc_ssprk2_step.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_double, _dp, _dp]
+        L.orc_solve.restype = C.c_int64
+        L.orc_solve.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int64, C.c_double]
+        L.orc_global_integral.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
+        _lib = L
+    return _lib
+
+
+STEP_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_double, C.c_void_p)
+DT_FN = C.CFUNCTYPE(C.c_double, C.c_void_p)
+CB_FN = C.CFUNCTYPE(None, C.c_double, C.c_int, C.c_void_p)
+
+
+def advance(step, t_end, recommend_dt, callbacks):
+    """callbacks: list of (interval, fn(t), perform_zeroth, perform_final). Mirrors timestepper.cc:6-56."""
+    L = lib()
+    L.orc_advance.argtypes = [STEP_FN, C.c_double, DT_FN, C.c_int, _dp, _ip, _ip, CB_FN, C.c_void_p]
+    n = len(callbacks)
+    iv = (C.c_double * max(n, 1))(*[c[0] for c in callbacks])
+    pz = (C.c_int * max(n, 1))(*[int(c[2]) for c in callbacks])
+    pf = (C.c_int * max(n, 1))(*[int(c[3]) for c in callbacks])
+    s = STEP_FN(lambda t, dt, _u: 1 if step(t, dt) else 0)
+    d = DT_FN(lambda _u: recommend_dt())
+    cb = CB_FN(lambda t, i, _u: callbacks[i][1](t))
+    L.orc_advance(s, t_end, d, n, iv, pz, pf, cb, None)
+
+
+# ---- point physics helpers -------------------------------------------------
+def ln_avg(a, b):
+    return lib().orc_ln_avg(a, b)
+
+
+def pressure(q, gamma):
+    return lib().orc_pressure(_ptr(_f64(q)), gamma)
+
+
+def euler_flux(dim, q, gamma):
+    F = np.zeros((5, dim))
+    lib().orc_euler_flux(dim, _ptr(_f64(q)), gamma, _ptr(F))
+    return F
+
+
+def ec_flux(dim, qj, ql, gamma):
+    F = np.zeros((5, dim))
+    lib().orc_ec_flux(dim, _ptr(_f64(qj)), _ptr(_f64(ql)), gamma, _ptr(F))
+    return F
+
+
+def es_flux(dim, qj, ql, n, gamma):
+    out = np.zeros(5)
+    lib().orc_es_flux(dim, _ptr(_f64(qj)), _ptr(_f64(ql)), _ptr(_f64(n)), gamma, _ptr(out))
+    return out
+
+
+def lf_flux(dim, qin, qout, n, gamma):
+    out = np.zeros(5)
+    lib().orc_lf_flux(dim, _ptr(_f64(qin)), _ptr(_f64(qout)), _ptr(_f64(n)), gamma, _ptr(out))
+    return out
+
+
+def entropy_variables(q, gamma):
+    w = np.zeros(5)
+    lib().orc_entropy_variables(_ptr(_f64(q)), gamma, _ptr(w))
+    return w
+
+
+def mathematical_entropy(q, gamma):
+    return lib().orc_mathematical_entropy(_ptr(_f64(q)), gamma)
+
+
+def entropy_flux(dim, q, gamma):
+    out = np.zeros(dim)
+    lib().orc_entropy_flux(dim, _ptr(_f64(q)), gamma, _ptr(out))
+    return out
+
+
+def primitive_to_conserved(prim, gamma):
+    """prim[..., 5] = [rho, ux, uy, uz, p] -> conserved [..., 5] (species_func.cc:15-28), elementwise."""
+    prim = _f64(prim)
+    out = np.empty_like(prim)
+    flat_in = prim.reshape(-1, 5)
+    flat_out = out.reshape(-1, 5)
+    L = lib()
+    if flat_in.shape[0] > 4096:
+        # vectorised restatement with the same operation order
+        rho = flat_in[:, 0]
+        flat_out[:, 0] = rho
+        ke = np.zeros_like(rho)
+        for d in range(3):
+            flat_out[:, d + 1] = rho * flat_in[:, d + 1]
+            ke = ke + 0.5 * rho * flat_in[:, d + 1] * flat_in[:, d + 1]
+        flat_out[:, 4] = ke + flat_in[:, 4] / (gamma - 1)
+        return out
+    for i in range(flat_in.shape[0]):
+        L.orc_primitive_to_conserved(_ptr(flat_in[i]), gamma, _ptr(flat_out[i]))
+    return out
+
+
+def gll(Np):
+    x = np.zeros(Np)
+    w = np.zeros(Np)
+    lib().orc_gll(Np, _ptr(x), _ptr(w))
+    return x, w
+
+
+def gauss(n):
+    x = np.zeros(n)
+    w = np.zeros(n)
+    lib().orc_gauss(n, _ptr(x), _ptr(w))
+    return x, w
+
+
+def diff_matrix(Np):
+    D = np.zeros((Np, Np))
+    lib().orc_diff_matrix(Np, _ptr(D))
+    return D
+
+
+def legendre_analysis_1d(Np):
+    V = np.zeros((Np, Np))
+    lib().orc_legendre_analysis_1d(Np, _ptr(V))
+    return V
+
+
+class Oracle:
+    """Discretised ES-DGSEM operator on a Cartesian box, CPU restatement of the reference."""
+
+    def __init__(self, dim, fe_degree, nx, left, right, periodic=None, gamma=1.6666666666667,
+                 n_species=1, fields_enabled=False, bc_kinds=None, threads=1):
+        L = lib()
+        self.dim, self.p, self.gamma, self.nsp = dim, fe_degree, gamma, n_species
+        periodic = [1] * dim if periodic is None else [int(bool(x)) for x in periodic]
+        nx_a = (C.c_int * dim)(*[int(v) for v in nx])
+        l_a = (C.c_double * dim)(*[float(v) for v in left])
+        r_a = (C.c_double * dim)(*[float(v) for v in right])
+        p_a = (C.c_int * dim)(*periodic)
+        bc_a = None
+        if bc_kinds is not None:
+            flat = np.asarray(bc_kinds, dtype=np.int32).reshape(-1)
+            assert flat.size == n_species * 2 * dim
+            bc_a = (C.c_int * flat.size)(*[int(v) for v in flat])
+        self.h = L.orc_create(dim, fe_degree, n_species, int(fields_enabled), gamma, nx_a, l_a, r_a, p_a, bc_a)
+        if not self.h:
+            raise ValueError("orc_create failed")
+        self.n_elems = L.orc_n_elems(self.h)
+        self.nc = L.orc_n_components(self.h)
+        self.NN = L.orc_nodes_per_elem(self.h)
+        self.n_dofs = L.orc_n_dofs(self.h)
+        self.n_boundaries = L.orc_n_boundaries(self.h)
+        self.shape = (self.n_elems, self.nc, self.NN)
+        if threads != 1:
+            L.orc_set_threads(self.h, threads)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def set_threads(self, n):
+        lib().orc_set_threads(self.h, n)
+
+    def node_coords(self):
+        xyz = np.zeros((self.n_elems, self.NN, self.dim))
+        lib().orc_node_coords(self.h, _ptr(xyz))
+        return xyz
+
+    def set_inflow(self, species, boundary_id, q):
+        lib().orc_set_inflow(self.h, species, boundary_id, _ptr(_f64(q)))
+
+    def project(self, prim_fn, species=0, u=None, conserved=False):
+        """Nodal interpolation of an IC given as fn(xyz[...,dim]) -> [...,5] (dg_solution_helper.cc:24-48)."""
+        if u is None:
+            u = np.zeros(self.shape)
+        xyz = self.node_coords()
+        vals = _f64(prim_fn(xyz))
+        cons = vals if conserved else primitive_to_conserved(vals, self.gamma)
+        u[:, 5 * species:5 * species + 5, :] = np.transpose(cons, (0, 2, 1))
+        return u
+
+    def rhs(self, u, t=0.0):
+        u = _f64(u)
+        dudt = np.zeros(self.shape)
+        bif = np.zeros(5 * self.n_boundaries)
+        lib().orc_rhs(self.h, _ptr(u), t, _ptr(dudt), _ptr(bif))
+        return dudt, bif
+
+    def alpha(self, u):
+        u = _f64(u)
+        a = np.zeros((self.n_elems, self.nsp))
+        lib().orc_alpha(self.h, _ptr(u), _ptr(a))
+        return a
+
+    def cell_residual(self, ue, alpha):
+        ue = _f64(ue)
+        R = np.zeros((5, self.NN))
+        lib().orc_cell_residual(self.h, _ptr(ue), alpha, _ptr(R))
+        return R
+
+    def shock_indicator(self, v):
+        return lib().orc_shock_indicator(self.h, _ptr(_f64(v)))
+
+    def forward_euler_step(self, dst, u, dt, t, a=1.0, beta=0.0, bif_dst=None, bif_u=None):
+        assert dst.flags.c_contiguous and dst.dtype == np.float64
+        u = _f64(u)
+        lib().orc_forward_euler_step(self.h, _ptr(dst), _ptr(u), dt, t, a, beta,
+                                     _ptr(bif_dst) if bif_dst is not None else None,
+                                     _ptr(bif_u) if bif_u is not None else None)
+        return dst
+
+    def max_transport_speed(self, u):
+        return lib().orc_max_transport_speed(self.h, _ptr(_f64(u)))
+
+    def recommend_dt(self, u):
+        return lib().orc_recommend_dt(self.h, _ptr(_f64(u)))
+
+    def ssprk2_step(self, u, dt, t, bif=None):
+        assert u.flags.c_contiguous and u.dtype == np.float64
+        f1 = np.zeros_like(u)
+        bif_f1 = np.zeros(5 * self.n_boundaries) if bif is not None else None
+        lib().orc_ssprk2_step(self.h, _ptr(u), _ptr(f1), dt, t,
+                              _ptr(bif) if bif is not None else None,
+                              _ptr(bif_f1) if bif is not None else None)
+        return u
+
+    def solve(self, u, t_end, bif=None, max_steps=0, fixed_dt=0.0):
+        assert u.flags.c_contiguous and u.dtype == np.float64
+        return lib().orc_solve(self.h, _ptr(u), t_end, _ptr(bif) if bif is not None else None, max_steps, fixed_dt)
+
+    def global_integral(self, u, species=0):
+        out = np.zeros(5)
+        lib().orc_global_integral(self.h, _ptr(_f64(u)), species, _ptr(out))
+        return out
