@@ -1,0 +1,161 @@
+/* ============================================================================
+ * warpii_gpu.h -- C ABI of the B200-native ES-DGSEM operator (libwarpii_b200.so)
+ *
+ * This is the drop-in boundary for WarpII's hot path: everything below
+ * `FluidFluxESDGSEMOperator<dim>::perform_forward_euler_step` and
+ * `::recommend_dt` (reference src/five_moment/fluid_flux_es_dgsem_operator.h:62-71)
+ * runs on the GPU behind these entry points.  Plain pointers and sizes only; no
+ * C++ or torch types cross the boundary.  INTEGRATION.md shows the adapter a
+ * WarpII maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     available from warpii_gpu_last_error() (thread-local).  No exceptions
+ *     cross the ABI (the reference throws dealii::ExcMessage; the adapter
+ *     re-throws from the status code).
+ *   - one context per rank/GPU, all calls from one host thread (the reference
+ *     is single-threaded per rank: nodal_dg_discretization.cc:25-26).
+ *   - state vectors live in HBM between calls and are named by small integer
+ *     ids; the host only sees them through upload/download.
+ *   - device state layout: u[elem][comp][node], comp = 5*species + {rho, mx,
+ *     my, mz, E}, then 8 field comps if fields_enabled; nodes lexicographic
+ *     (x fastest) at the Gauss-Lobatto points.  This is deal.II's FE_DGQ^nc
+ *     cell-local ordering; a DoF index table passed to
+ *     upload/download translates any other host numbering.
+ * ==========================================================================*/
+#ifndef WARPII_GPU_H
+#define WARPII_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct warpii_gpu_ctx warpii_gpu_ctx;
+
+/* Boundary-condition kinds, as Species::create_from_parameters maps them
+ * (reference src/five_moment/species.cc:44-58): "Wall", "Outflow" (supersonic), "Inflow". */
+enum { WARPII_BC_WALL = 0, WARPII_BC_OUTFLOW = 1, WARPII_BC_INFLOW = 2 };
+
+/* Flags for warpii_gpu_forward_euler_step_ex. */
+enum {
+    WARPII_FUSE_CFL = 1 /* also reduce the max transport speed of dst inside the stage kernel, so that the
+                           next warpii_gpu_recommend_dt(dst) needs no extra sweep over the state */
+};
+
+/* Flat mesh tables, built once on the host from the triangulation
+ * (replaces what dealii::MatrixFree::reinit derives in nodal_dg_discretization.cc:6-29).
+ * All pointers are host pointers, copied during create. */
+typedef struct warpii_gpu_mesh {
+    int32_t dim;              /* 1, 2 or 3 */
+    int32_t fe_degree;        /* 1..6 (five_moment.h:116) */
+    int32_t n_species;        /* >= 1 */
+    int32_t fields_enabled;   /* 0/1: 8 extra components [Ex,Ey,Ez,Bx,By,Bz,phi,psi] (five_moment.h:123-138) */
+    double gas_gamma;
+    int64_t n_elems;          /* elements owned by this rank */
+    int64_t n_ghost_faces;    /* face traces received from other ranks (0 on one GPU) */
+    int64_t n_boundary_faces; /* non-periodic domain-boundary faces of owned elements */
+    int32_t n_boundaries;     /* number of boundary ids (n_boundaries input key) */
+    double h[3];              /* Cartesian element size per dimension (HyperRectangle grid, grid_descriptions.cc:51-74) */
+    /* face-pair table, [n_elems][2*dim], face f = 2*d + side (deal.II face numbering of a hypercube):
+     *   0 <= v < n_elems            : owned neighbour element v (its face f^1 matches, same tangential order)
+     *   n_elems <= v                : ghost trace slot v - n_elems
+     *   v < 0                       : boundary face number -1 - v (index into the boundary tables below) */
+    const int32_t* face_neighbor;
+    const int32_t* boundary_face_elem;  /* [n_boundary_faces] owning element   */
+    const int32_t* boundary_face_side;  /* [n_boundary_faces] local face index */
+    const int32_t* boundary_face_id;    /* [n_boundary_faces] boundary id (< n_boundaries) */
+    const int32_t* bc_kind;             /* [n_species][n_boundaries], WARPII_BC_* (bc_helper.h) */
+    int32_t n_vectors;                  /* number of state vectors to allocate (>= 2: solution and f_1, rk.h:111-117) */
+} warpii_gpu_mesh;
+
+/* Halo description for an element-sharded run.  Faces are exchanged as nodal traces
+ * of all fluid components: [face][5*n_species][Np^(dim-1)] doubles.  send lists are grouped by peer. */
+typedef struct warpii_gpu_halo {
+    int32_t n_peers;
+    const int32_t* peer_rank;        /* [n_peers] */
+    const int64_t* send_offset;      /* [n_peers+1] into send_elem/send_side */
+    const int32_t* send_elem;        /* [n_send] owned element whose trace is sent */
+    const int32_t* send_side;        /* [n_send] its local face index */
+    const int64_t* recv_offset;      /* [n_peers+1] ghost slots [recv_offset[p], recv_offset[p+1]) come from peer p */
+    int64_t n_interface_elems;       /* elements [0, n_interface_elems) touch a ghost face; the rest are interior
+                                        and are advanced while the exchange is in flight */
+} warpii_gpu_halo;
+
+const char* warpii_gpu_last_error(void);
+int warpii_gpu_abi_version(void);
+
+/* -- lifetime -------------------------------------------------------------- */
+int warpii_gpu_create(const warpii_gpu_mesh* mesh, int device, warpii_gpu_ctx** out);
+int warpii_gpu_destroy(warpii_gpu_ctx* ctx);
+int64_t warpii_gpu_n_dofs(const warpii_gpu_ctx* ctx);            /* n_elems * n_components * Np^dim */
+int warpii_gpu_synchronize(warpii_gpu_ctx* ctx);
+
+/* -- state transfer (FiveMSolutionVec::mesh_sol <-> HBM; solution_vec.h:45-51) ----------------------
+ * dof_index == NULL: host array is already in device layout.  Otherwise host[dof_index[i]] <-> device[i]
+ * (build it once from cell->get_dof_indices()). */
+int warpii_gpu_upload_state(warpii_gpu_ctx* ctx, int vec, const double* host, const int64_t* dof_index);
+int warpii_gpu_download_state(warpii_gpu_ctx* ctx, int vec, double* host, const int64_t* dof_index);
+int warpii_gpu_zero_state(warpii_gpu_ctx* ctx, int vec);
+int warpii_gpu_copy_state(warpii_gpu_ctx* ctx, int dst, int src);
+/* raw device pointer of a state vector (for zero-copy producers/consumers such as a CUDA-aware writer) */
+int warpii_gpu_device_ptr(warpii_gpu_ctx* ctx, int vec, void** out);
+
+/* -- boundary data ----------------------------------------------------------------------------------
+ * Conserved inflow state of (species, boundary id): what EulerBCMap::get_inflow evaluates
+ * (fluid_flux_es_dgsem_operator.h:377-380).  Call again before a stage if the function depends on t
+ * (the reference calls set_time(t) at :140-144). */
+int warpii_gpu_set_inflow(warpii_gpu_ctx* ctx, int species, int boundary_id, const double q[5]);
+
+/* -- the operator ----------------------------------------------------------------------------------
+ * dst = beta*dst + alpha*(u + dt * M^-1 R(u)), and the same for the boundary-integrated fluxes
+ * (replaces perform_forward_euler_step, fluid_flux_es_dgsem_operator.h:127-214). dst != u. */
+int warpii_gpu_forward_euler_step(warpii_gpu_ctx* ctx, int dst, int u, double dt, double t, double alpha,
+                                  double beta);
+int warpii_gpu_forward_euler_step_ex(warpii_gpu_ctx* ctx, int dst, int u, double dt, double t, double alpha,
+                                     double beta, int flags);
+/* dt = 0.5 / (vmax * (p+1)^2), vmax reduced over nodes, elements, species and ranks
+ * (replaces recommend_dt + compute_cell_transport_speed, :442-514; MPI::max -> ncclAllReduce(max)). */
+int warpii_gpu_recommend_dt(warpii_gpu_ctx* ctx, int vec, double* dt_out);
+int warpii_gpu_max_transport_speed(warpii_gpu_ctx* ctx, int vec, double* vmax_out);
+/* One SSPRK2 step (replaces SSPRK2Integrator::evolve_one_time_step, rk.h:97-106): two stages, the second with
+ * the fused CFL reduction. */
+int warpii_gpu_ssprk2_step(warpii_gpu_ctx* ctx, int solution, int f1, double dt, double t);
+/* Time loop resident on the device side of the ABI: repeats {dt = min(recommend_dt, t_stop - t); ssprk2} until
+ * t >= t_stop - 1e-12 (the inner loop of advance(), timestepper.cc:34-42).  fixed_dt > 0 overrides recommend_dt.
+ * max_steps > 0 bounds the number of steps.  *t_inout is advanced; *steps_out receives the step count. */
+int warpii_gpu_advance_to(warpii_gpu_ctx* ctx, int solution, int f1, double* t_inout, double t_stop,
+                          double fixed_dt, int64_t max_steps, int64_t* steps_out);
+
+/* -- diagnostics ------------------------------------------------------------------------------------ */
+/* boundary_integrated_fluxes of a vector, 5*n_boundaries doubles (solution_vec.h:10-43) */
+int warpii_gpu_boundary_fluxes(warpii_gpu_ctx* ctx, int vec, double* out);
+int warpii_gpu_set_boundary_fluxes(warpii_gpu_ctx* ctx, int vec, const double* in);
+/* sum_q u_q JxW_q per component of one species (compute_global_integral, dg_solution_helper.cc:71-98);
+ * summed over ranks when a communicator is attached. */
+int warpii_gpu_global_integral(warpii_gpu_ctx* ctx, int vec, int species, double out[5]);
+/* blending factor per owned element and species, alpha[elem][species] (persson_peraire_shock_indicator.h:44-123) */
+int warpii_gpu_shock_indicator(warpii_gpu_ctx* ctx, int vec, double* alpha_out);
+/* bare M^-1 R(u) into vector dst (dst != u), for parity checks of one RHS evaluation */
+int warpii_gpu_rhs(warpii_gpu_ctx* ctx, int dst, int u, double t);
+
+/* -- multi-GPU (one process per GPU; NCCL over NVLink) ----------------------------------------------- */
+#define WARPII_GPU_NCCL_ID_BYTES 128
+int warpii_gpu_nccl_unique_id(char id[WARPII_GPU_NCCL_ID_BYTES]);
+int warpii_gpu_attach_comm(warpii_gpu_ctx* ctx, const char id[WARPII_GPU_NCCL_ID_BYTES], int rank, int n_ranks,
+                           const warpii_gpu_halo* halo);
+
+/* -- measurement hooks -------------------------------------------------------------------------------- */
+/* kernels launched by this context so far */
+int64_t warpii_gpu_launch_count(const warpii_gpu_ctx* ctx);
+/* device time in ms of the stage kernels launched since the last reset (CUDA events on the launching stream),
+ * and how many there were; used by bench.py for the roofline line. */
+int warpii_gpu_stage_timing(warpii_gpu_ctx* ctx, int enable, double* ms_total, int64_t* n_launches);
+/* the CUDA stream (cudaStream_t) all work of this context is issued on */
+int warpii_gpu_stream(warpii_gpu_ctx* ctx, void** stream_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WARPII_GPU_H */

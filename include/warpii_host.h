@@ -1,0 +1,86 @@
+/* ============================================================================
+ * warpii_host.h -- C entry points of the C++ host layer (box grids)
+ *
+ * The host layer (warpii_b200/host/) mirrors the reference's C++ classes above the
+ * operator: FiveMomentDGSolver (src/five_moment/dg_solver.{h,cc}), SSPRK2Integrator
+ * (src/rk.h:79-117), advance() (src/timestepper.cc:6-56) and the HyperRectangle grid
+ * (src/grid_descriptions.cc:51-74).  These wrappers exist so that non-C++ callers
+ * (the Python tests, bench.py) can drive that layer; a C++ caller includes the
+ * headers in warpii_b200/host/ directly.  Status/err conventions as warpii_gpu.h.
+ * ==========================================================================*/
+#ifndef WARPII_HOST_H
+#define WARPII_HOST_H
+
+#include <stdint.h>
+
+#include "warpii_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct warpii_box_solver warpii_box_solver;
+
+/* message of the last failing warpii_box_solver_* / warpii_host_* call on this thread (C++ exceptions of the host
+ * layer, including the ones that carry a warpii_gpu_last_error() text, end up here) */
+const char* warpii_host_last_error(void);
+
+/* Box grid description + discretisation parameters (the input-file keys of five_moment.h:99-147 and
+ * grid_descriptions.cc:27-49 that reach the hot path). bc_kinds[n_species][n_boundaries] may be NULL when
+ * n_boundaries == 0.  rank/n_ranks shard the elements in slabs along the last dimension. */
+int warpii_box_solver_create(int dim, int fe_degree, int n_species, int fields_enabled, double gas_gamma,
+                             const int32_t* nx, const double* left, const double* right,
+                             const int32_t* periodic, int n_boundaries, const int32_t* bc_kinds, int rank,
+                             int n_ranks, int device, warpii_box_solver** out);
+int warpii_box_solver_destroy(warpii_box_solver* s);
+/* the operator context underneath, for direct use of the warpii_gpu_* ABI (vector 0 = solution, 1 = f_1) */
+warpii_gpu_ctx* warpii_box_solver_ctx(warpii_box_solver* s);
+
+int64_t warpii_box_solver_n_local_elems(const warpii_box_solver* s);
+int64_t warpii_box_solver_n_interface_elems(const warpii_box_solver* s);
+int64_t warpii_box_solver_n_ghost_faces(const warpii_box_solver* s);
+int warpii_box_solver_n_components(const warpii_box_solver* s);
+int warpii_box_solver_nodes_per_elem(const warpii_box_solver* s);
+/* global (lexicographic, x fastest) index of every owned element, in device order */
+int warpii_box_solver_local_to_global(const warpii_box_solver* s, int64_t* out);
+/* xyz[elem][node][dim] of the owned elements, in device order */
+int warpii_box_solver_node_coords(const warpii_box_solver* s, double* xyz);
+
+/* state <-> host, in device order [local elem][comp][node] */
+int warpii_box_solver_set_state(warpii_box_solver* s, const double* host);
+int warpii_box_solver_get_state(warpii_box_solver* s, double* host);
+int warpii_box_solver_set_inflow(warpii_box_solver* s, int species, int boundary_id, const double q[5]);
+
+/* attach the NCCL communicator (id from warpii_gpu_nccl_unique_id on rank 0, broadcast by the caller) */
+int warpii_box_solver_attach_comm(warpii_box_solver* s, const char id[WARPII_GPU_NCCL_ID_BYTES]);
+
+/* FiveMomentDGSolver::solve: advance() with SSPRK2 steps and recommend_dt every step, one callback of the given
+ * interval (NULL = none).  fixed_dt > 0 replaces recommend_dt (for parity runs).  Returns steps in *steps_out. */
+typedef void (*warpii_callback_fn)(double t, void* user);
+int warpii_box_solver_solve(warpii_box_solver* s, double t_end, double fixed_dt, double callback_interval,
+                            warpii_callback_fn cb, void* user, int64_t* steps_out);
+/* SSPRK2Integrator::evolve_one_time_step / operator.recommend_dt on the solver's own solution vector */
+int warpii_box_solver_step(warpii_box_solver* s, double dt, double t);
+int warpii_box_solver_recommend_dt(warpii_box_solver* s, double* dt_out);
+
+/* the time loop alone (timestepper.cc:6-56) with C callbacks, for the reference's TimestepperTest cases */
+typedef int (*warpii_step_fn)(double t, double dt, void* user);
+typedef double (*warpii_dt_fn)(void* user);
+typedef void (*warpii_cb_index_fn)(double t, int index, void* user);
+int warpii_host_advance(warpii_step_fn step, double t_end, warpii_dt_fn recommend_dt, int n_callbacks,
+                        const double* intervals, const int32_t* perform_zeroth, const int32_t* perform_final,
+                        warpii_cb_index_fn cb, void* user);
+
+/* mesh-table builder alone (no GPU): fills caller-provided arrays for tests of the partitioning logic.
+ * Pass NULL output pointers to query sizes through the counts array:
+ * counts = {n_local, n_interface, n_ghost_faces, n_boundary_faces, n_peers, n_send}. */
+int warpii_host_box_tables(int dim, const int32_t* nx, const int32_t* periodic, int rank, int n_ranks,
+                           int64_t counts[6], int64_t* local_to_global, int32_t* face_neighbor,
+                           int32_t* bf_elem, int32_t* bf_side, int32_t* bf_id, int32_t* peer_rank,
+                           int64_t* send_offset, int64_t* recv_offset, int32_t* send_elem, int32_t* send_side,
+                           int64_t* ghost_global_elem, int32_t* ghost_side);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WARPII_HOST_H */

@@ -1,0 +1,112 @@
+"""Initial conditions and case builders shared by the parity tests and bench.py.
+
+All ICs return PRIMITIVE variables [rho, ux, uy, uz, p] at the given points (the reference's default
+VariablesType, species_func.cc:33); conversion to conserved variables follows species_func.cc:15-28.
+"""
+import math
+
+import numpy as np
+
+PI = math.pi
+
+
+def primitive_to_conserved(prim, gamma):
+    """species_func.cc:15-28, vectorised with the same operation order."""
+    prim = np.asarray(prim, dtype=np.float64)
+    out = np.empty_like(prim)
+    rho = prim[..., 0]
+    out[..., 0] = rho
+    ke = np.zeros_like(rho)
+    for d in range(3):
+        out[..., d + 1] = rho * prim[..., d + 1]
+        ke = ke + 0.5 * rho * prim[..., d + 1] * prim[..., d + 1]
+    out[..., 4] = ke + prim[..., 4] / (gamma - 1)
+    return out
+
+
+def to_state(prim_nodes, gamma, nc=5, species=0, u=None):
+    """prim_nodes[elem][node][5] -> state[elem][comp][node]."""
+    cons = primitive_to_conserved(prim_nodes, gamma)
+    if u is None:
+        u = np.zeros((cons.shape[0], nc, cons.shape[1]))
+    u[:, 5 * species:5 * species + 5, :] = np.transpose(cons, (0, 2, 1))
+    return u
+
+
+def sine_wave(rho0=1.0, amp=0.6, vel=(1.0, 0.0, 0.0), p=1.0, wave=(1, 0, 0)):
+    """test/input_test.cc:32-34, test/conservation_test.cc:22-24"""
+    def fn(xyz):
+        s = sum(xyz[..., d] * wave[d] for d in range(xyz.shape[-1]))
+        out = np.zeros(xyz.shape[:-1] + (5,))
+        out[..., 0] = rho0 + amp * np.sin(2 * PI * s)
+        out[..., 1], out[..., 2], out[..., 3] = vel
+        out[..., 4] = p
+        return out
+    return fn
+
+
+def isentropic_vortex(gamma=1.4, beta=5.0, center=(5.0, 0.0), background=(1.0, 0.0)):
+    """Isentropic vortex of src/tutorial-67.cc:111-141 at t = 0 (BASELINE configs 2 and 4; extruded in z for 3D)."""
+    def fn(xyz):
+        x, y = xyz[..., 0], xyz[..., 1]
+        r2 = (x - center[0]) ** 2 + (y - center[1]) ** 2
+        factor = beta / (2 * PI) * np.exp(1.0 - r2)
+        density_log = np.log2(np.abs(1.0 - (gamma - 1.0) / gamma * 0.25 * factor * factor))
+        rho = np.exp2(density_log * (1.0 / (gamma - 1.0)))
+        out = np.zeros(xyz.shape[:-1] + (5,))
+        out[..., 0] = rho
+        out[..., 1] = background[0] - factor * (y - center[1])
+        out[..., 2] = background[1] + factor * (x - center[0])
+        out[..., 4] = np.exp2(density_log * (gamma / (gamma - 1.0)))
+        return out
+    return fn
+
+
+def sod(x_split=0.5):
+    """test/input_test.cc:90-92"""
+    def fn(xyz):
+        x = xyz[..., 0]
+        out = np.zeros(x.shape + (5,))
+        out[..., 0] = np.where(x < x_split, 1.0, 0.10)
+        out[..., 4] = np.where(x < x_split, 1.0, 0.125)
+        return out
+    return fn
+
+
+def kelvin_helmholtz(k=1.2 * PI):
+    """codes/cartesian_euler/kelvin_helmholtz.cc:45-88 (rho tanh 1.0 -> 0.3, shear u_y, perturbed interface)."""
+    def fn(xyz):
+        x, y = xyz[..., 0], xyz[..., 1]
+        bx = 0.003 * np.sin(k * y)
+        jump = 1.0 - 0.3
+        out = np.zeros(x.shape + (5,))
+        out[..., 0] = 0.5 * jump + 0.3 + 0.5 * jump * np.tanh(-(x - bx) * 20.0)
+        out[..., 2] = 0.1 * np.tanh(-x * 20.0)
+        out[..., 4] = 1.0
+        return out
+    return fn
+
+
+def smooth_blob_3d(amp=0.2):
+    """A smooth, fully 3-D periodic state with all three velocity components active."""
+    def fn(xyz):
+        x = [xyz[..., d] for d in range(xyz.shape[-1])] + [0.0, 0.0]
+        s = np.sin(2 * PI * x[0]) * np.cos(2 * PI * x[1]) + 0.5 * np.sin(2 * PI * (x[2] + x[0]))
+        out = np.zeros(xyz.shape[:-1] + (5,))
+        out[..., 0] = 1.0 + amp * s
+        out[..., 1] = 0.3 + amp * np.cos(2 * PI * x[1])
+        out[..., 2] = -0.2 + amp * np.sin(2 * PI * x[2])
+        out[..., 3] = 0.1 + amp * np.sin(2 * PI * x[0])
+        out[..., 4] = 1.0 + 0.5 * amp * np.cos(2 * PI * (x[0] + x[1] + x[2]))
+        return out
+    return fn
+
+
+def rel_l2_per_component(a, b):
+    """Relative L2 difference per component of states [elem][comp][node]."""
+    out = []
+    for c in range(a.shape[1]):
+        den = np.linalg.norm(b[:, c, :])
+        num = np.linalg.norm(a[:, c, :] - b[:, c, :])
+        out.append(num / den if den > 0 else num)
+    return np.array(out)

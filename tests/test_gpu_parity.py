@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle (run on the B200 box, -m gpu).
+
+Tolerances are the ones BASELINE.json's north_star states: one RHS evaluation relative L2 <= 1e-12 per
+component, <= 1e-10 after 100 steps, conservation to round-off.  Integer-like outputs (nothing here) would
+be bit-exact; everything on this path is FP64.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import Oracle
+from tests import cases
+from warpii_b200 import BC_INFLOW, BC_OUTFLOW, BC_WALL, BoxSolver
+
+pytestmark = pytest.mark.gpu
+
+RHS_TOL = 1e-12       # north_star: one RHS evaluation, relative L2 per component
+STEPS_TOL = 1e-10     # north_star: after 100 steps
+DT_TOL = 1e-13        # recommend_dt (parity unpinned in the reference; oracle restatement)
+
+
+def make_pair(dim, p, nx, left, right, periodic=None, gamma=1.4, n_species=1, fields=False, bc=None, threads=4):
+    o = Oracle(dim, p, nx, left, right, periodic=periodic, gamma=gamma, n_species=n_species, fields_enabled=fields,
+               bc_kinds=bc, threads=threads)
+    nb = None
+    if periodic is not None and not all(periodic):
+        nb = 2 * dim
+    g = BoxSolver(dim, p, nx, left, right, periodic=periodic, gamma=gamma, n_species=n_species, fields_enabled=fields,
+                  n_boundaries=nb, bc_kinds=bc)
+    assert g.shape == o.shape
+    # single rank: device order == global lexicographic order
+    assert np.array_equal(g.local_to_global(), np.arange(o.n_elems))
+    assert np.allclose(g.node_coords(), o.node_coords(), rtol=0, atol=1e-15)
+    return o, g
+
+
+def check_rhs(o, g, u, tol=RHS_TOL):
+    g.upload(0, u)
+    g.rhs(1, 0)
+    got = g.download(1)
+    want, _ = o.rhs(u)
+    err = cases.rel_l2_per_component(got, want)
+    assert np.isfinite(got).all()
+    assert (err <= tol).all(), f"relative L2 per component {err}"
+    return err
+
+
+RHS_CASES = [
+    # dim, p, nx, left, right, ic, gamma
+    (1, 2, [20], [0.0], [1.0], cases.sine_wave(), 5.0 / 3.0),
+    (1, 4, [7], [0.0], [1.0], cases.sine_wave(vel=(0.7, 0.2, -0.1)), 5.0 / 3.0),
+    (1, 1, [16], [0.0], [1.0], cases.sine_wave(amp=0.3), 1.4),
+    (2, 3, [16, 16], [0.0, -5.0], [10.0, 5.0], cases.isentropic_vortex(), 1.4),
+    (2, 2, [9, 5], [0.0, 0.0], [1.0, 0.5], cases.sine_wave(vel=(1.0, 1.0, 0.0), wave=(1, 2, 0)), 5.0 / 3.0),
+    (2, 5, [4, 6], [0.0, 0.0], [1.0, 1.0], cases.smooth_blob_3d(), 5.0 / 3.0),
+    (3, 3, [5, 4, 6], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], cases.smooth_blob_3d(), 5.0 / 3.0),
+    (3, 4, [4, 4, 4], [0.0, -5.0, -5.0], [10.0, 5.0, 5.0], cases.isentropic_vortex(), 1.4),
+    (3, 2, [6, 6, 3], [0.0, 0.0, 0.0], [1.0, 2.0, 1.0], cases.smooth_blob_3d(0.1), 1.4),
+    (3, 6, [2, 2, 2], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], cases.smooth_blob_3d(0.1), 5.0 / 3.0),
+]
+
+
+@pytest.mark.parametrize("dim,p,nx,left,right,ic,gamma", RHS_CASES)
+def test_one_rhs_periodic(dim, p, nx, left, right, ic, gamma):
+    o, g = make_pair(dim, p, nx, left, right, gamma=gamma)
+    u = o.project(ic)
+    check_rhs(o, g, u)
+    # blending factors agree (all zero for these smooth states, but compare the tables anyway)
+    assert np.allclose(g.shock_indicator(0), o.alpha(u), rtol=0, atol=1e-12)
+    g.close()
+
+
+def test_sod_rhs_with_shock_capturing_and_outflow():
+    """BASELINE config 1: 1D Sod, p=2, 200 cells, Outflow at both ends; alpha > 0 at the discontinuity."""
+    gamma = 5.0 / 3.0
+    bc = [[BC_OUTFLOW, BC_OUTFLOW]]
+    o, g = make_pair(1, 2, [200], [0.0], [1.0], periodic=[0], gamma=gamma, bc=bc)
+    u = o.project(cases.sod())
+    a_ref = o.alpha(u)
+    assert a_ref.max() > 0
+    g.upload(0, u)
+    a_gpu = g.shock_indicator(0)
+    assert np.allclose(a_gpu, a_ref, rtol=1e-10, atol=1e-12)
+    check_rhs(o, g, u)
+    # after some steps the profile has a rarefaction, contact and shock: compare again there
+    o.solve(u, 0.02)
+    check_rhs(o, g, u)
+    g.close()
+
+
+def test_sod_full_run_config1():
+    gamma = 5.0 / 3.0
+    bc = [[BC_OUTFLOW, BC_OUTFLOW]]
+    o, g = make_pair(1, 2, [200], [0.0], [1.0], periodic=[0], gamma=gamma, bc=bc)
+    u = o.project(cases.sod())
+    g.set_state(u)
+    steps_g = g.solve(0.1)
+    steps_o = o.solve(u, 0.1)
+    got = g.get_state()
+    assert steps_g == steps_o
+    # A shock run is chaotic in the last bits (alpha switches); the profiles must still agree closely.
+    err = cases.rel_l2_per_component(got, u)
+    assert err[0] < 1e-8 and err[1] < 1e-8 and err[4] < 1e-8, err
+    g.close()
+
+
+def test_inflow_outflow_bif_and_balance():
+    """test/conservation_test.cc:85-137 through the GPU path, and parity of the boundary-integrated fluxes."""
+    gamma = 1.6666666666667
+    bc = [[BC_INFLOW, BC_OUTFLOW]]
+    o, g = make_pair(1, 4, [1], [0.0], [1.0], periodic=[0], gamma=gamma, bc=bc)
+    q_in = oracle.primitive_to_conserved([3.857, 2.629, 0.0, 0.0, 10.333], gamma)
+    o.set_inflow(0, 0, q_in)
+    g.set_inflow(0, 0, q_in)
+    u = o.project(cases.sine_wave())
+    ic = o.global_integral(u)
+    g.set_state(u)
+    assert np.allclose(g.global_integral(0), ic, rtol=0, atol=1e-15)
+    steps = g.solve(0.04)
+    assert steps > 0
+    bif = g.boundary_fluxes(0)
+    now = g.global_integral(0)
+    balance = now + bif[0:5] + bif[5:10]
+    for c in range(3):
+        assert abs(balance[c] - ic[c]) < 1e-14
+    bif_o = np.zeros(10)
+    steps_o = o.solve(u, 0.04, bif=bif_o)
+    assert steps_o == steps
+    assert np.allclose(bif, bif_o, rtol=1e-11, atol=1e-13)
+    assert (cases.rel_l2_per_component(g.get_state(), u)[[0, 1, 4]] < STEPS_TOL).all()
+    g.close()
+
+
+def test_walls_2d_kelvin_helmholtz_rhs():
+    """Walls in x, periodic in y (the reference KH set-up): Gauss(p+2) boundary-face path in 2D."""
+    gamma = 5.0 / 3.0
+    k = 1.2 * np.pi
+    bc = [[BC_WALL, BC_WALL, BC_WALL, BC_WALL]]
+    o, g = make_pair(2, 3, [12, 10], [-0.5, 0.0], [0.5, 2 * np.pi / k], periodic=[0, 1], gamma=gamma, bc=bc)
+    u = o.project(cases.kelvin_helmholtz(k))
+    check_rhs(o, g, u)
+    a_ref = o.alpha(u)
+    assert np.allclose(g.shock_indicator(0), a_ref, rtol=1e-9, atol=1e-12)
+    g.close()
+
+
+def test_mixed_bcs_3d_rhs():
+    gamma = 1.4
+    bc = [[BC_INFLOW, BC_OUTFLOW, BC_WALL, BC_WALL, BC_OUTFLOW, BC_WALL]]
+    o, g = make_pair(3, 2, [4, 3, 3], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], periodic=[0, 0, 0], gamma=gamma, bc=bc)
+    q_in = oracle.primitive_to_conserved([1.1, 0.4, 0.1, -0.05, 1.2], gamma)
+    o.set_inflow(0, 0, q_in)
+    g.set_inflow(0, 0, q_in)
+    u = o.project(cases.smooth_blob_3d(0.1))
+    check_rhs(o, g, u)
+    g.close()
+
+
+def test_two_species_with_fields_rhs_and_step():
+    """nc = 18: two fluids + 8 field components that the operator carries through unchanged."""
+    gamma = 5.0 / 3.0
+    o, g = make_pair(2, 3, [6, 5], [0.0, 0.0], [1.0, 1.0], gamma=gamma, n_species=2, fields=True)
+    u = o.project(cases.sine_wave(vel=(0.5, 0.3, 0.1), wave=(1, 1, 0)), species=0)
+    u = o.project(cases.smooth_blob_3d(0.15), species=1, u=u)
+    rng = np.random.default_rng(12345)
+    u[:, 10:18, :] = rng.standard_normal(u[:, 10:18, :].shape)
+    check_rhs(o, g, u)
+    dt = 0.3 * o.recommend_dt(u)
+    g.upload(0, u)
+    g.ssprk2_step(dt, 0.0)
+    got = g.download(0)
+    want = u.copy()
+    o.ssprk2_step(want, dt, 0.0)
+    assert (cases.rel_l2_per_component(got, want) < 1e-13).all()
+    assert np.array_equal(got[:, 10:18, :], u[:, 10:18, :])   # fields: 0.5*u + 0.5*(u + dt*0) exactly
+    g.close()
+
+
+@pytest.mark.parametrize("dim,p,nx,left,right,ic,gamma", [RHS_CASES[0], RHS_CASES[3], RHS_CASES[6]])
+def test_recommend_dt_parity(dim, p, nx, left, right, ic, gamma):
+    o, g = make_pair(dim, p, nx, left, right, gamma=gamma)
+    u = o.project(ic)
+    g.upload(0, u)
+    want = o.recommend_dt(u)
+    got = g.recommend_dt(0)
+    assert abs(got - want) <= DT_TOL * want
+    # fused CFL of the second SSPRK2 stage == stand-alone sweep of the same vector
+    dt = 0.5 * want
+    g.ssprk2_step(dt, 0.0)
+    fused = g.recommend_dt(0)
+    unew = g.download(0)
+    g.upload(0, unew)          # invalidates the cached reduction
+    assert g.recommend_dt(0) == fused
+    o.ssprk2_step(u, dt, 0.0)
+    assert abs(fused - o.recommend_dt(u)) <= 1e-12 * fused
+    g.close()
+
+
+def test_hundred_steps_vortex_2d():
+    """north_star: <= 1e-10 after 100 steps, mass/momentum/energy conserved to round-off."""
+    gamma = 1.4
+    o, g = make_pair(2, 3, [16, 16], [0.0, -5.0], [10.0, 5.0], gamma=gamma, threads=8)
+    u = o.project(cases.isentropic_vortex(gamma))
+    ic = o.global_integral(u)
+    g.set_state(u)
+    t, steps = g.advance_to(0.0, 1e9, max_steps=100)
+    assert steps == 100
+    so = o.solve(u, t, max_steps=100)
+    assert so == 100
+    got = g.get_state()
+    err = cases.rel_l2_per_component(got, u)
+    assert (err[[0, 1, 2, 4]] <= STEPS_TOL).all(), err
+    now = g.global_integral(0)
+    for c in (0, 1, 2, 4):
+        assert abs(now[c] - ic[c]) <= 1e-12 * max(1.0, abs(ic[c])), (c, now[c], ic[c])
+    g.close()
+
+
+def test_hundred_steps_3d():
+    gamma = 5.0 / 3.0
+    o, g = make_pair(3, 3, [4, 4, 4], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], gamma=gamma, threads=8)
+    u = o.project(cases.smooth_blob_3d(0.1))
+    ic = o.global_integral(u)
+    g.set_state(u)
+    t, steps = g.advance_to(0.0, 1e9, max_steps=100)
+    o.solve(u, t, max_steps=100)
+    err = cases.rel_l2_per_component(g.get_state(), u)
+    assert (err <= STEPS_TOL).all(), err
+    now = g.global_integral(0)
+    for c in range(5):
+        assert abs(now[c] - ic[c]) <= 1e-12 * max(1.0, abs(ic[c]))
+    g.close()
+
+
+def test_reference_periodic_1d_conservation():
+    """test/conservation_test.cc:45-83 through the GPU path: one p=4 cell, periodic onto itself."""
+    o, g = make_pair(1, 4, [1], [0.0], [1.0], gamma=1.6666666666667)
+    u = o.project(cases.sine_wave())
+    g.set_state(u)
+    ic = g.global_integral(0)
+    assert g.solve(0.04) > 0
+    now = g.global_integral(0)
+    for c in range(3):
+        assert abs(now[c] - ic[c]) < 1e-13
+    g.close()
+
+
+def test_reference_freestream_1d_convergence():
+    """test/input_test.cc:18-66 through the GPU path."""
+    from tests.test_oracle_golden import _l2_error_density
+    errs = []
+    for nx in (20, 30):
+        o, g = make_pair(1, 2, [nx], [0.0], [1.0], gamma=1.6666666666667)
+        g.set_state(o.project(cases.sine_wave()))
+        g.solve(0.04)
+        errs.append(_l2_error_density(o, g.get_state(), lambda x: 1 + 0.6 * np.sin(2 * np.pi * (x - 0.04)), 2))
+        g.close()
+    assert abs(errs[1]) < 1e-4
+    assert abs(errs[0] / errs[1] - 1.5 ** 3) < 1.0
+
+
+def test_solver_callbacks_and_step_count():
+    """FiveMomentDGSolver::solve + advance(): the writeout callback fires at the frame times and at t_end."""
+    o, g = make_pair(1, 2, [10], [0.0], [1.0], gamma=1.6666666666667)
+    g.set_state(o.project(cases.sine_wave()))
+    times = []
+    steps = g.solve(0.05, callback=times.append, callback_interval=0.01)
+    assert steps >= 5
+    assert len(times) == 5 and abs(times[-1] - 0.05) < 1e-12 and abs(times[0] - 0.01) < 1e-12
+    g.close()
+
+
+def test_error_conventions():
+    from warpii_b200 import WarpiiGpuError
+    o, g = make_pair(1, 2, [4], [0.0], [1.0])
+    with pytest.raises(WarpiiGpuError):
+        g.forward_euler_step(0, 0, 0.1, 0.0)          # dst must differ from u
+    with pytest.raises(WarpiiGpuError):
+        g.forward_euler_step(0, 7, 0.1, 0.0)          # unknown vector
+    g.close()
+    with pytest.raises(WarpiiGpuError):                # non-periodic box without boundary conditions declared
+        BoxSolver(1, 2, [4], [0.0], [1.0], periodic=[0], n_boundaries=0)
+
+
+# ---- full-size checks on the bench workload (size-independent properties; the oracle would take minutes here) ----
+def test_full_size_c2_properties():
+    """BASELINE config 2 (512x512, p=3): conservation over steps, free-stream preservation, translation invariance."""
+    gamma = 1.4
+    n = 512
+    g = BoxSolver(2, 3, [n, n], [0.0, -5.0], [10.0, 5.0], gamma=gamma)
+    xyz = g.node_coords()
+    u0 = cases.to_state(cases.isentropic_vortex(gamma)(xyz), gamma)
+    g.set_state(u0)
+    ic = g.global_integral(0)
+    t, steps = g.advance_to(0.0, 1e9, max_steps=10)
+    assert steps == 10
+    now = g.global_integral(0)
+    for c in (0, 1, 2, 4):
+        assert abs(now[c] - ic[c]) <= 2e-12 * max(1.0, abs(ic[c])), (c, now[c] - ic[c])
+    u10 = g.get_state()
+    assert np.isfinite(u10).all()
+    # translation invariance: shifting the initial state by 64 elements in x and 32 in y shifts the answer, bit for bit
+    sx, sy = 64, 32
+    shifted = np.roll(np.roll(u0.reshape(n, n, 5, 16), sy, axis=0), sx, axis=1).reshape(u0.shape)
+    g.set_state(shifted)
+    g.advance_to(0.0, 1e9, max_steps=10)
+    u10s = g.get_state()
+    back = np.roll(np.roll(u10s.reshape(n, n, 5, 16), -sy, axis=0), -sx, axis=1).reshape(u0.shape)
+    assert np.array_equal(back, u10)
+    # free stream: a uniform state has zero residual up to round-off of the flux differences
+    uni = np.zeros_like(u0)
+    uni[:, :, :] = cases.primitive_to_conserved(np.array([1.3, 0.4, -0.7, 0.1, 0.9]), gamma)[None, :, None]
+    g.upload(0, uni)
+    g.rhs(1, 0)
+    r = g.download(1)
+    assert np.abs(r).max() < 1e-9   # |D| / h ~ 3e2, flux ~ 1, eps ~ 1e-16
+    g.close()

@@ -1,0 +1,316 @@
+"""ctypes binding of include/warpii_gpu.h and include/warpii_host.h (no compute happens in Python)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+BC_WALL, BC_OUTFLOW, BC_INFLOW = 0, 1, 2
+FUSE_CFL = 1
+NCCL_ID_BYTES = 128
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+
+class WarpiiGpuError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libwarpii_b200.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load libwarpii_b200.so; there is deliberately no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise WarpiiGpuError(
+            f"{path} is missing: build it with `make -C warpii_b200` (or __graft_entry__.build()). "
+            "warpii_b200 has no CPU or PyTorch fallback.")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.warpii_gpu_last_error.restype = C.c_char_p
+    L.warpii_host_last_error.restype = C.c_char_p
+    L.warpii_gpu_abi_version.restype = C.c_int
+    L.warpii_gpu_n_dofs.restype = C.c_int64
+    L.warpii_gpu_n_dofs.argtypes = [vp]
+    L.warpii_gpu_synchronize.argtypes = [vp]
+    L.warpii_gpu_upload_state.argtypes = [vp, C.c_int, _dp, _i64p]
+    L.warpii_gpu_download_state.argtypes = [vp, C.c_int, _dp, _i64p]
+    L.warpii_gpu_zero_state.argtypes = [vp, C.c_int]
+    L.warpii_gpu_copy_state.argtypes = [vp, C.c_int, C.c_int]
+    L.warpii_gpu_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.warpii_gpu_set_inflow.argtypes = [vp, C.c_int, C.c_int, _dp]
+    L.warpii_gpu_forward_euler_step.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.warpii_gpu_forward_euler_step_ex.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+    L.warpii_gpu_recommend_dt.argtypes = [vp, C.c_int, _dp]
+    L.warpii_gpu_max_transport_speed.argtypes = [vp, C.c_int, _dp]
+    L.warpii_gpu_ssprk2_step.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.warpii_gpu_advance_to.argtypes = [vp, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int64, _i64p]
+    L.warpii_gpu_boundary_fluxes.argtypes = [vp, C.c_int, _dp]
+    L.warpii_gpu_set_boundary_fluxes.argtypes = [vp, C.c_int, _dp]
+    L.warpii_gpu_global_integral.argtypes = [vp, C.c_int, C.c_int, _dp]
+    L.warpii_gpu_shock_indicator.argtypes = [vp, C.c_int, _dp]
+    L.warpii_gpu_rhs.argtypes = [vp, C.c_int, C.c_int, C.c_double]
+    L.warpii_gpu_nccl_unique_id.argtypes = [C.c_char_p]
+    L.warpii_gpu_launch_count.restype = C.c_int64
+    L.warpii_gpu_launch_count.argtypes = [vp]
+    L.warpii_gpu_stage_timing.argtypes = [vp, C.c_int, _dp, _i64p]
+    L.warpii_gpu_stream.argtypes = [vp, C.POINTER(vp)]
+    L.warpii_gpu_destroy.argtypes = [vp]
+    L.warpii_box_solver_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _i32p, _dp, _dp, _i32p, C.c_int,
+                                           _i32p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.warpii_box_solver_destroy.argtypes = [vp]
+    L.warpii_box_solver_ctx.restype = vp
+    L.warpii_box_solver_ctx.argtypes = [vp]
+    for name in ("n_local_elems", "n_interface_elems", "n_ghost_faces"):
+        f = getattr(L, "warpii_box_solver_" + name)
+        f.restype = C.c_int64
+        f.argtypes = [vp]
+    L.warpii_box_solver_n_components.argtypes = [vp]
+    L.warpii_box_solver_nodes_per_elem.argtypes = [vp]
+    L.warpii_box_solver_local_to_global.argtypes = [vp, _i64p]
+    L.warpii_box_solver_node_coords.argtypes = [vp, _dp]
+    L.warpii_box_solver_set_state.argtypes = [vp, _dp]
+    L.warpii_box_solver_get_state.argtypes = [vp, _dp]
+    L.warpii_box_solver_set_inflow.argtypes = [vp, C.c_int, C.c_int, _dp]
+    L.warpii_box_solver_attach_comm.argtypes = [vp, C.c_char_p]
+    L.warpii_box_solver_solve.argtypes = [vp, C.c_double, C.c_double, C.c_double, vp, vp, _i64p]
+    L.warpii_box_solver_step.argtypes = [vp, C.c_double, C.c_double]
+    L.warpii_box_solver_recommend_dt.argtypes = [vp, _dp]
+    _lib = L
+    return L
+
+
+def _check(status, host=False):
+    if status != 0:
+        L = lib()
+        msg = (L.warpii_host_last_error() if host else L.warpii_gpu_last_error()) or b""
+        if host and not msg:
+            msg = L.warpii_gpu_last_error() or b""
+        raise WarpiiGpuError(msg.decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _arr32(v):
+    return np.ascontiguousarray(v, dtype=np.int32)
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    _check(lib().warpii_gpu_nccl_unique_id(buf))
+    return buf.raw
+
+
+STEP_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_double, C.c_void_p)
+DT_FN = C.CFUNCTYPE(C.c_double, C.c_void_p)
+CBI_FN = C.CFUNCTYPE(None, C.c_double, C.c_int, C.c_void_p)
+CB_FN = C.CFUNCTYPE(None, C.c_double, C.c_void_p)
+
+
+def host_advance(step, t_end, recommend_dt, callbacks):
+    """The product's advance() (warpii_b200/host/gpu_operator.hpp); callbacks = [(interval, fn, zeroth, final)]."""
+    L = lib()
+    L.warpii_host_advance.argtypes = [STEP_FN, C.c_double, DT_FN, C.c_int, _dp, _i32p, _i32p, CBI_FN, C.c_void_p]
+    n = len(callbacks)
+    iv = np.array([c[0] for c in callbacks] or [0.0], dtype=np.float64)
+    pz = _arr32([int(c[2]) for c in callbacks] or [0])
+    pf = _arr32([int(c[3]) for c in callbacks] or [0])
+    s = STEP_FN(lambda t, dt, _u: 1 if step(t, dt) else 0)
+    d = DT_FN(lambda _u: recommend_dt())
+    cb = CBI_FN(lambda t, i, _u: callbacks[i][1](t))
+    _check(L.warpii_host_advance(s, t_end, d, n, _ptr(iv), pz.ctypes.data_as(_i32p), pf.ctypes.data_as(_i32p), cb, None), host=True)
+
+
+def box_tables(dim, nx, periodic, rank=0, n_ranks=1):
+    """Mesh tables of one rank (no GPU needed): dict of numpy arrays."""
+    L = lib()
+    L.warpii_host_box_tables.argtypes = [C.c_int, _i32p, _i32p, C.c_int, C.c_int, _i64p, _i64p, _i32p, _i32p, _i32p, _i32p,
+                                         _i32p, _i64p, _i64p, _i32p, _i32p, _i64p, _i32p]
+    nx_a, per_a = _arr32(nx), _arr32([int(bool(p)) for p in periodic])
+    counts = np.zeros(6, dtype=np.int64)
+    none32, none64 = C.cast(None, _i32p), C.cast(None, _i64p)
+    _check(L.warpii_host_box_tables(dim, nx_a.ctypes.data_as(_i32p), per_a.ctypes.data_as(_i32p), rank, n_ranks,
+                                    counts.ctypes.data_as(_i64p), none64, none32, none32, none32, none32, none32, none64,
+                                    none64, none32, none32, none64, none32), host=True)
+    n_local, n_iface, n_ghost, n_bf, n_peers, n_send = [int(v) for v in counts]
+    t = {
+        "n_local": n_local, "n_interface": n_iface, "n_ghost": n_ghost, "n_bfaces": n_bf,
+        "local_to_global": np.zeros(n_local, dtype=np.int64),
+        "face_neighbor": np.zeros((n_local, 2 * dim), dtype=np.int32),
+        "bf_elem": np.zeros(n_bf, dtype=np.int32), "bf_side": np.zeros(n_bf, dtype=np.int32),
+        "bf_id": np.zeros(n_bf, dtype=np.int32), "peer_rank": np.zeros(n_peers, dtype=np.int32),
+        "send_offset": np.zeros(n_peers + 1, dtype=np.int64), "recv_offset": np.zeros(n_peers + 1, dtype=np.int64),
+        "send_elem": np.zeros(n_send, dtype=np.int32), "send_side": np.zeros(n_send, dtype=np.int32),
+        "ghost_global_elem": np.zeros(n_ghost, dtype=np.int64), "ghost_side": np.zeros(n_ghost, dtype=np.int32),
+    }
+    p32 = lambda k: t[k].ctypes.data_as(_i32p)
+    p64 = lambda k: t[k].ctypes.data_as(_i64p)
+    _check(L.warpii_host_box_tables(dim, nx_a.ctypes.data_as(_i32p), per_a.ctypes.data_as(_i32p), rank, n_ranks,
+                                    counts.ctypes.data_as(_i64p), p64("local_to_global"), p32("face_neighbor"), p32("bf_elem"),
+                                    p32("bf_side"), p32("bf_id"), p32("peer_rank"), p64("send_offset"), p64("recv_offset"),
+                                    p32("send_elem"), p32("send_side"), p64("ghost_global_elem"), p32("ghost_side")), host=True)
+    return t
+
+
+class BoxSolver:
+    """FiveMomentGpuSolver on a box grid (warpii_b200/host/dg_solver.hpp) through the C ABI.
+
+    Vector 0 is the solution, vector 1 the SSPRK2 scratch f_1.  State arrays are [local elem][comp][node].
+    """
+
+    def __init__(self, dim, fe_degree, nx, left, right, periodic=None, gamma=1.6666666666667, n_species=1,
+                 fields_enabled=False, n_boundaries=None, bc_kinds=None, rank=0, n_ranks=1, device=0):
+        L = lib()
+        periodic = [1] * dim if periodic is None else [int(bool(p)) for p in periodic]
+        if n_boundaries is None:
+            n_boundaries = 0 if all(periodic) else 2 * dim
+        self.dim, self.p, self.gamma, self.nsp, self.n_boundaries = dim, fe_degree, gamma, n_species, n_boundaries
+        nx_a, per_a = _arr32(nx), _arr32(periodic)
+        l_a = np.ascontiguousarray(left, dtype=np.float64)
+        r_a = np.ascontiguousarray(right, dtype=np.float64)
+        bc_p = C.cast(None, _i32p)
+        if bc_kinds is not None and n_boundaries > 0:
+            self._bc = _arr32(np.asarray(bc_kinds).reshape(n_species, n_boundaries))
+            bc_p = self._bc.ctypes.data_as(_i32p)
+        h = C.c_void_p()
+        _check(L.warpii_box_solver_create(dim, fe_degree, n_species, int(fields_enabled), gamma, nx_a.ctypes.data_as(_i32p),
+                                          _ptr(l_a), _ptr(r_a), per_a.ctypes.data_as(_i32p), n_boundaries, bc_p, rank, n_ranks,
+                                          device, C.byref(h)), host=True)
+        self.h = h
+        self.ctx = C.c_void_p(L.warpii_box_solver_ctx(h))
+        self.n_elems = L.warpii_box_solver_n_local_elems(h)
+        self.nc = L.warpii_box_solver_n_components(h)
+        self.NN = L.warpii_box_solver_nodes_per_elem(h)
+        self.shape = (self.n_elems, self.nc, self.NN)
+        self.n_dofs = self.n_elems * self.nc * self.NN
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().warpii_box_solver_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    # ---- host layer ---------------------------------------------------------------------------------
+    def local_to_global(self):
+        out = np.zeros(self.n_elems, dtype=np.int64)
+        _check(lib().warpii_box_solver_local_to_global(self.h, out.ctypes.data_as(_i64p)), host=True)
+        return out
+
+    def node_coords(self):
+        xyz = np.zeros((self.n_elems, self.NN, self.dim))
+        _check(lib().warpii_box_solver_node_coords(self.h, _ptr(xyz)), host=True)
+        return xyz
+
+    def set_state(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.size == self.n_dofs
+        _check(lib().warpii_box_solver_set_state(self.h, _ptr(u)), host=True)
+
+    def get_state(self):
+        u = np.zeros(self.shape)
+        _check(lib().warpii_box_solver_get_state(self.h, _ptr(u)), host=True)
+        return u
+
+    def set_inflow(self, species, boundary_id, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        _check(lib().warpii_box_solver_set_inflow(self.h, species, boundary_id, _ptr(q)), host=True)
+
+    def attach_comm(self, nccl_id):
+        _check(lib().warpii_box_solver_attach_comm(self.h, nccl_id), host=True)
+
+    def solve(self, t_end, fixed_dt=0.0, callback=None, callback_interval=0.0):
+        steps = C.c_int64(0)
+        cb = CB_FN(lambda t, _u: callback(t)) if callback else None
+        _check(lib().warpii_box_solver_solve(self.h, t_end, fixed_dt, callback_interval, C.cast(cb, C.c_void_p) if cb else None,
+                                             None, C.byref(steps)), host=True)
+        return steps.value
+
+    # ---- operator ABI ---------------------------------------------------------------------------------
+    def upload(self, vec, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.size == self.n_dofs
+        _check(lib().warpii_gpu_upload_state(self.ctx, vec, _ptr(u), None))
+
+    def download(self, vec):
+        u = np.zeros(self.shape)
+        _check(lib().warpii_gpu_download_state(self.ctx, vec, _ptr(u), None))
+        return u
+
+    def zero(self, vec):
+        _check(lib().warpii_gpu_zero_state(self.ctx, vec))
+
+    def forward_euler_step(self, dst, u, dt, t, alpha=1.0, beta=0.0, flags=0):
+        _check(lib().warpii_gpu_forward_euler_step_ex(self.ctx, dst, u, dt, t, alpha, beta, flags))
+
+    def rhs(self, dst, u, t=0.0):
+        _check(lib().warpii_gpu_rhs(self.ctx, dst, u, t))
+
+    def ssprk2_step(self, dt, t, solution=0, f1=1):
+        _check(lib().warpii_gpu_ssprk2_step(self.ctx, solution, f1, dt, t))
+
+    def advance_to(self, t, t_stop, fixed_dt=0.0, max_steps=0, solution=0, f1=1):
+        tt = C.c_double(t)
+        steps = C.c_int64(0)
+        _check(lib().warpii_gpu_advance_to(self.ctx, solution, f1, C.byref(tt), t_stop, fixed_dt, max_steps, C.byref(steps)))
+        return tt.value, steps.value
+
+    def recommend_dt(self, vec=0):
+        dt = C.c_double(0)
+        _check(lib().warpii_gpu_recommend_dt(self.ctx, vec, C.byref(dt)))
+        return dt.value
+
+    def max_transport_speed(self, vec=0):
+        v = C.c_double(0)
+        _check(lib().warpii_gpu_max_transport_speed(self.ctx, vec, C.byref(v)))
+        return v.value
+
+    def boundary_fluxes(self, vec=0):
+        out = np.zeros(5 * max(self.n_boundaries, 1))
+        _check(lib().warpii_gpu_boundary_fluxes(self.ctx, vec, _ptr(out)))
+        return out[:5 * self.n_boundaries]
+
+    def global_integral(self, vec=0, species=0):
+        out = np.zeros(5)
+        _check(lib().warpii_gpu_global_integral(self.ctx, vec, species, _ptr(out)))
+        return out
+
+    def shock_indicator(self, vec=0):
+        a = np.zeros((self.n_elems, self.nsp))
+        _check(lib().warpii_gpu_shock_indicator(self.ctx, vec, _ptr(a)))
+        return a
+
+    def synchronize(self):
+        _check(lib().warpii_gpu_synchronize(self.ctx))
+
+    def launch_count(self):
+        return lib().warpii_gpu_launch_count(self.ctx)
+
+    def stage_timing(self, enable=True):
+        ms = C.c_double(0)
+        n = C.c_int64(0)
+        _check(lib().warpii_gpu_stage_timing(self.ctx, int(enable), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def device_ptr(self, vec):
+        p = C.c_void_p()
+        _check(lib().warpii_gpu_device_ptr(self.ctx, vec, C.byref(p)))
+        return p.value
+
+    def stream(self):
+        p = C.c_void_p()
+        _check(lib().warpii_gpu_stream(self.ctx, C.byref(p)))
+        return p.value

@@ -1,0 +1,75 @@
+// Kernel parameter blocks and launch prototypes of the ES-DGSEM stage (host <-> device contract inside the
+// library; nothing here is part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wgpu {
+
+constexpr int kMaxNp = 7;   // fe_degree <= 6 (five_moment.h:116)
+
+// 1-D reference-element tables (Gauss-Lobatto on [0,1]); filled by reference_element.hpp on the host.
+struct ElemTables {
+    double D[kMaxNp * kMaxNp];    // D[j*Np+l] = l_l'(x_j)
+    double w[kMaxNp];             // GLL weights
+    double V[kMaxNp * kMaxNp];    // Legendre analysis, V[k*Np+q] = (k+1/2) w_q sqrt2 P_k(2x_q-1)
+};
+
+struct StageParams {
+    const double* u;              // input state  [elem][comp][node]
+    double* dst;                  // output state (same layout); dst != u
+    const int32_t* nbr;           // [n_elems][2*dim] face-pair table (warpii_gpu.h)
+    const double* ghost;          // [n_ghost][5*nsp][nF] received face traces
+    const double* bres;           // [n_bfaces][nsp][5][nF] boundary-face rate contributions (boundary kernel)
+    double* alpha_out;            // optional [n_elems][nsp]
+    unsigned long long* vmax;     // optional: max transport speed of dst (bits of a non-negative double)
+    int64_t elem_begin, elem_end; // element range of this launch
+    int64_t n_elems;
+    int32_t nc, nsp;
+    int32_t mode;                 // 0: dst = beta*dst + a*(u + dt*rate); 1: dst = rate
+    double gamma, dt, a, beta;
+    double inv_h[3];              // 1/h_d
+    double inv_hw[3];             // 1/(h_d * w_0): face lifting factor (face JxW / cell JxW on a Cartesian cell)
+    double max_eig;               // sqrt(lambda_max(J^-T J^-1)), :487-502 of the reference operator
+    ElemTables T;
+};
+
+struct BoundaryParams {
+    const double* u;
+    double* bres;                 // [n_bfaces][nsp][5][nF]
+    double* bflux;                // [n_bfaces][nsp][5]  integrated numerical flux per face (for bif)
+    const int32_t* bf_elem;
+    const int32_t* bf_side;
+    const int32_t* bf_id;
+    const int32_t* bc_kind;       // [nsp][n_boundaries]
+    const double* inflow;         // [nsp][n_boundaries][5]
+    int64_t n_bfaces;
+    int32_t nc, nsp, n_boundaries;
+    double gamma;
+    double inv_h[3], h[3];
+    double w[kMaxNp];             // GLL weights
+    int32_t Ng;
+    double wg[kMaxNp + 1];        // Gauss(p+2) weights
+    double Ig[(kMaxNp + 1) * kMaxNp];   // Ig[q*Np+i] = l_i(xg_q)
+};
+
+void launch_stage(int dim, int Np, const StageParams& P, cudaStream_t s);
+void launch_boundary(int dim, int Np, const BoundaryParams& P, cudaStream_t s);
+// bif_rate[n_boundaries*5] = sum over faces/species of bflux (fixed order); then the stage update of the
+// boundary-integrated fluxes (fluid_flux_es_dgsem_operator.h:207-212)
+void launch_bif_update(const double* bflux, const int32_t* bf_id, int64_t n_bfaces, int nsp, int n_boundaries,
+                       double* bif_dst, const double* bif_u, double dt, double a, double beta, int mode,
+                       cudaStream_t s);
+void launch_cfl(int dim, int Np, const double* u, int64_t n_elems, int nc, int nsp, double gamma,
+                const double* inv_h, double max_eig, unsigned long long* vmax, cudaStream_t s);
+// deterministic two-pass reduction: out[5] = sum_e sum_j u * (Jdet * w_j); partial must hold 5*n_blocks doubles
+int integral_blocks(int64_t n_elems);
+void launch_integral(int dim, int Np, const double* u, int64_t n_elems, int nc, int species, double Jdet,
+                     const double* w, double* partial, double* out, cudaStream_t s);
+// halo: sendbuf[i][5*nsp][nF] = trace of (send_elem[i], send_side[i])
+void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, const int32_t* send_side,
+                 int64_t n_send, int nc, int nsp, double* sendbuf, cudaStream_t s);
+void launch_gather(const double* src, const int64_t* index, double* dst, int64_t n, cudaStream_t s);   // dst[i] = src[index[i]]
+void launch_scatter(const double* src, const int64_t* index, double* dst, int64_t n, cudaStream_t s);  // dst[index[i]] = src[i]
+
+}  // namespace wgpu

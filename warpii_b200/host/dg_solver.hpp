@@ -1,0 +1,140 @@
+// FiveMomentGpuSolver: host-side mirror of five_moment::FiveMomentDGSolver<dim> (dg_solver.h:34-74, dg_solver.cc:7-38)
+// for box grids: owns the mesh tables, the GPU context, the solution vector, the SSPRK2 integrator and the
+// operator; reinit / project_initial_condition / solve keep the reference's meaning.
+#pragma once
+#include <array>
+#include <functional>
+#include <memory>
+#include <vector>
+
+#include "box_mesh.hpp"
+#include "gpu_operator.hpp"
+#include "reference_element.hpp"
+
+namespace warpii_b200 {
+
+struct SpeciesBC {
+    std::vector<int32_t> kind;                     // per boundary id: WARPII_BC_*
+    std::vector<std::array<double, 5>> inflow;     // conserved inflow state per boundary id
+};
+
+class FiveMomentGpuSolver {
+   public:
+    using Integrator = SSPRK2Integrator<double, GpuSolutionVec, GpuFluidFluxESDGSEMOperator>;
+
+    FiveMomentGpuSolver(const BoxDescription& box, int fe_degree, int n_species, bool fields_enabled, double gas_gamma,
+                        double t_end, int n_boundaries, std::vector<SpeciesBC> bcs, int rank, int n_ranks, int device)
+        : t_end_(t_end), fe_degree_(fe_degree), n_species_(n_species), fields_enabled_(fields_enabled), gas_gamma_(gas_gamma),
+          n_boundaries_(n_boundaries), bcs_(std::move(bcs)), device_(device), tables_(box, rank, n_ranks), element_(fe_degree) {
+        nc_ = 5 * n_species + (fields_enabled ? 8 : 0);
+        nn_ = 1;
+        for (int d = 0; d < box.dim; d++) nn_ *= fe_degree + 1;
+        // a box with non-periodic sides has boundary ids up to 2*dim-1 whether or not the input declared them;
+        // the reference throws "Unknown boundary id" from the face loop in that case, the ABI does so at create.
+    }
+
+    // dg_solver.cc:7-12
+    void reinit() {
+        std::vector<int32_t> bc_kind((size_t)n_species_ * (n_boundaries_ > 0 ? n_boundaries_ : 0), WARPII_BC_WALL);
+        for (int s = 0; s < n_species_ && s < (int)bcs_.size(); s++)
+            for (int b = 0; b < n_boundaries_ && b < (int)bcs_[s].kind.size(); b++) bc_kind[(size_t)s * n_boundaries_ + b] = bcs_[s].kind[b];
+        warpii_gpu_mesh mesh;
+        tables_.fill(mesh, fe_degree_, n_species_, fields_enabled_, gas_gamma_, n_boundaries_, bc_kind, 2);
+        ctx_ = std::make_shared<GpuContext>(mesh, device_);
+        solution_ = std::make_unique<GpuSolutionVec>(ctx_);
+        op_ = std::make_unique<GpuFluidFluxESDGSEMOperator>(ctx_);
+        integrator_ = std::make_unique<Integrator>();
+        integrator_->reinit(*solution_, 3);
+        for (int s = 0; s < n_species_ && s < (int)bcs_.size(); s++)
+            for (int b = 0; b < n_boundaries_ && b < (int)bcs_[s].inflow.size(); b++)
+                if (bcs_[s].kind[b] == WARPII_BC_INFLOW) op_->set_inflow(s, b, bcs_[s].inflow[b].data());
+    }
+
+    // Node coordinates of the owned elements in device order, xyz[elem][node][dim].
+    std::vector<double> node_coords() const {
+        const BoxDescription& box = tables_.box();
+        const int Np = fe_degree_ + 1;
+        std::vector<double> xyz((size_t)tables_.n_local() * nn_ * box.dim);
+        for (int64_t l = 0; l < tables_.n_local(); l++) {
+            int idx[3];
+            tables_.elem_multi_index(tables_.local_to_global()[l], idx);
+            for (int j = 0; j < nn_; j++) {
+                int t = j;
+                for (int d = 0; d < box.dim; d++) {
+                    xyz[((size_t)l * nn_ + j) * box.dim + d] = box.left[d] + (idx[d] + element_.x[t % Np]) * tables_.h(d);
+                    t /= Np;
+                }
+            }
+        }
+        return xyz;
+    }
+
+    // Nodal interpolation of the initial condition (project_fluid_quantities, dg_solution_helper.cc:24-48), with the
+    // Primitive -> conserved conversion of SpeciesFunc::value (species_func.cc:9-30).  f(x, out5) fills
+    // [rho, ux, uy, uz, p] (primitive = true) or the conserved state.
+    void project_initial_condition(int species, const std::function<void(const double* x, double* out5)>& f, bool primitive = true) {
+        if (host_.empty()) host_.assign((size_t)ctx_->n_dofs(), 0.0);
+        const std::vector<double> xyz = node_coords();
+        const int dim = tables_.box().dim;
+        for (int64_t l = 0; l < tables_.n_local(); l++)
+            for (int j = 0; j < nn_; j++) {
+                double v[5], q[5];
+                f(&xyz[((size_t)l * nn_ + j) * dim], v);
+                if (primitive) {
+                    const double rho = v[0];
+                    q[0] = rho;
+                    double ke = 0.0;
+                    for (int d = 0; d < 3; d++) { q[d + 1] = rho * v[d + 1]; ke += 0.5 * rho * v[d + 1] * v[d + 1]; }
+                    q[4] = ke + v[4] / (gas_gamma_ - 1);
+                } else {
+                    for (int k = 0; k < 5; k++) q[k] = v[k];
+                }
+                for (int k = 0; k < 5; k++) host_[((size_t)l * nc_ + 5 * species + k) * nn_ + j] = q[k];
+            }
+        solution_->upload(host_.data());
+    }
+
+    // dg_solver.cc:23-38
+    void solve(TimestepCallback writeout_callback) {
+        steps_ = 0;
+        auto step = [&](double t, double dt) -> bool {
+            integrator_->evolve_one_time_step(*op_, *solution_, dt, t);
+            steps_++;
+            return true;
+        };
+        auto recommend_dt = [&]() -> double { return fixed_dt_ > 0 ? fixed_dt_ : op_->recommend_dt(*solution_); };
+        std::vector<TimestepCallback> callbacks = {writeout_callback};
+        advance(step, t_end_, recommend_dt, callbacks);
+    }
+
+    GpuSolutionVec& get_solution() { return *solution_; }
+    GpuFluidFluxESDGSEMOperator& get_fluid_flux_operator() { return *op_; }
+    const BoxMeshTables& tables() const { return tables_; }
+    std::shared_ptr<GpuContext> context() const { return ctx_; }
+    int64_t steps_taken() const { return steps_; }
+    void set_t_end(double t) { t_end_ = t; }
+    void set_fixed_dt(double dt) { fixed_dt_ = dt; }
+    int n_components() const { return nc_; }
+    int nodes_per_elem() const { return nn_; }
+
+   private:
+    double t_end_;
+    int fe_degree_, n_species_;
+    bool fields_enabled_;
+    double gas_gamma_;
+    int n_boundaries_;
+    std::vector<SpeciesBC> bcs_;
+    int device_;
+    BoxMeshTables tables_;
+    ReferenceElement element_;
+    int nc_ = 5, nn_ = 1;
+    std::shared_ptr<GpuContext> ctx_;
+    std::unique_ptr<GpuSolutionVec> solution_;
+    std::unique_ptr<GpuFluidFluxESDGSEMOperator> op_;
+    std::unique_ptr<Integrator> integrator_;
+    std::vector<double> host_;
+    int64_t steps_ = 0;
+    double fixed_dt_ = 0.0;
+};
+
+}  // namespace warpii_b200

@@ -1,0 +1,182 @@
+// Host-side mirror of the reference's operator / integrator / time-loop interface, over the C ABI.
+//
+//   GpuSolutionVec                      <-> five_moment::FiveMSolutionVec            (solution_vec.h:45-51)
+//   GpuFluidFluxESDGSEMOperator         <-> FluidFluxESDGSEMOperator<dim>             (fluid_flux_es_dgsem_operator.h:46-125)
+//   SSPRK2Integrator<Number,Vec,Op>     <-> SSPRK2Integrator                          (rk.h:79-117)
+//   TimestepCallback, advance()         <-> timestepper.h:9-28, timestepper.cc:6-56
+//
+// Same names, argument meaning and error behaviour (errors surface as C++ exceptions carrying the ABI's
+// message, as AssertThrow does in the reference), so a caller written against the reference compiles against
+// these with the type names swapped.  The state never leaves HBM between calls.
+#pragma once
+#include <cmath>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "warpii_gpu.h"
+
+namespace warpii_b200 {
+
+enum ZeroOutPolicy { DO_ZERO_DST_VECTOR, DO_NOT_ZERO_DST_VECTOR };   // dof_utils.h:44-47
+
+inline void check(int status) {
+    if (status != 0) throw std::runtime_error(warpii_gpu_last_error());
+}
+
+// Owns the context; shared by all vectors / operators built on it.
+class GpuContext {
+   public:
+    GpuContext(const warpii_gpu_mesh& mesh, int device) {
+        n_vectors_ = mesh.n_vectors < 2 ? 2 : mesh.n_vectors;
+        check(warpii_gpu_create(&mesh, device, &ctx_));
+        in_use_.assign(n_vectors_, false);
+        n_boundaries_ = mesh.n_boundaries;
+        fe_degree_ = mesh.fe_degree;
+    }
+    ~GpuContext() { warpii_gpu_destroy(ctx_); }
+    GpuContext(const GpuContext&) = delete;
+    GpuContext& operator=(const GpuContext&) = delete;
+    warpii_gpu_ctx* get() const { return ctx_; }
+    int64_t n_dofs() const { return warpii_gpu_n_dofs(ctx_); }
+    int n_boundaries() const { return n_boundaries_; }
+    int fe_degree() const { return fe_degree_; }
+    int acquire_vector() {
+        for (int i = 0; i < n_vectors_; i++)
+            if (!in_use_[i]) { in_use_[i] = true; return i; }
+        throw std::runtime_error("GpuContext: all device vectors are in use; raise warpii_gpu_mesh::n_vectors");
+    }
+    void release_vector(int id) { if (id >= 0 && id < n_vectors_) in_use_[id] = false; }
+
+   private:
+    warpii_gpu_ctx* ctx_ = nullptr;
+    int n_vectors_ = 2, n_boundaries_ = 0, fe_degree_ = 1;
+    std::vector<bool> in_use_;
+};
+
+// A state vector resident in HBM (mesh_sol) with its boundary-integrated fluxes.
+class GpuSolutionVec {
+   public:
+    GpuSolutionVec() = default;
+    explicit GpuSolutionVec(std::shared_ptr<GpuContext> ctx) { bind(ctx); }
+    ~GpuSolutionVec() { if (ctx_) ctx_->release_vector(id_); }
+    GpuSolutionVec(const GpuSolutionVec&) = delete;
+    GpuSolutionVec& operator=(const GpuSolutionVec&) = delete;
+
+    // FiveMSolutionVec::reinit(other): same size and partitioning, zero contents (solution_vec.cc:5-8)
+    void reinit(const GpuSolutionVec& other) {
+        if (!ctx_) bind(other.ctx_);
+        check(warpii_gpu_zero_state(ctx_->get(), id_));
+    }
+    void upload(const double* host, const int64_t* dof_index = nullptr) { check(warpii_gpu_upload_state(ctx_->get(), id_, host, dof_index)); }
+    void download(double* host, const int64_t* dof_index = nullptr) const { check(warpii_gpu_download_state(ctx_->get(), id_, host, dof_index)); }
+    std::vector<double> boundary_integrated_fluxes() const {
+        std::vector<double> out((size_t)5 * ctx_->n_boundaries(), 0.0);
+        if (!out.empty()) check(warpii_gpu_boundary_fluxes(ctx_->get(), id_, out.data()));
+        return out;
+    }
+    int id() const { return id_; }
+    bool bound() const { return (bool)ctx_; }
+    const std::shared_ptr<GpuContext>& context() const { return ctx_; }
+
+   private:
+    void bind(std::shared_ptr<GpuContext> ctx) {
+        ctx_ = std::move(ctx);
+        id_ = ctx_->acquire_vector();
+        check(warpii_gpu_zero_state(ctx_->get(), id_));
+    }
+    std::shared_ptr<GpuContext> ctx_;
+    int id_ = -1;
+};
+
+class GpuFluidFluxESDGSEMOperator {
+   public:
+    explicit GpuFluidFluxESDGSEMOperator(std::shared_ptr<GpuContext> ctx) : ctx_(std::move(ctx)) {}
+
+    // dst = beta*dst + alpha*(u + dt*M^-1 R(u)).  sol_registers is accepted for signature parity; the reference
+    // only uses them as zero-initialised scratch (fluid_flux_es_dgsem_operator.h:135-137), which the fused kernel
+    // does not need.  A ZeroOutPolicy other than the default has no effect for the same reason.
+    void perform_forward_euler_step(GpuSolutionVec& dst, const GpuSolutionVec& u, std::vector<GpuSolutionVec>& /*sol_registers*/,
+                                    const double dt, const double t, const double alpha = 1.0, const double beta = 0.0,
+                                    const ZeroOutPolicy /*zero_out_policy*/ = DO_NOT_ZERO_DST_VECTOR) {
+        // the second SSPRK2 stage is the one whose result recommend_dt is asked about next: fuse the CFL sweep there
+        const int flags = (beta != 0.0) ? WARPII_FUSE_CFL : 0;
+        check(warpii_gpu_forward_euler_step_ex(ctx_->get(), dst.id(), u.id(), dt, t, alpha, beta, flags));
+    }
+
+    // the reference also takes the MatrixFree object; its role is played by the context
+    double recommend_dt(const GpuSolutionVec& sol) {
+        double dt = 0.0;
+        check(warpii_gpu_recommend_dt(ctx_->get(), sol.id(), &dt));
+        return dt;
+    }
+
+    void set_inflow(int species, int boundary_id, const double q[5]) { check(warpii_gpu_set_inflow(ctx_->get(), species, boundary_id, q)); }
+
+   private:
+    std::shared_ptr<GpuContext> ctx_;
+};
+
+// rk.h:79-117
+template <typename Number, typename SolutionVec, typename Operator>
+class SSPRK2Integrator {
+   public:
+    SSPRK2Integrator() {}
+
+    void evolve_one_time_step(Operator& forward_euler_operator, SolutionVec& solution, const double dt, const double t) {
+        forward_euler_operator.perform_forward_euler_step(f_1, solution, sol_registers, dt, t);
+        forward_euler_operator.perform_forward_euler_step(solution, f_1, sol_registers, dt, t + dt, 0.5, 0.5);
+    }
+
+    // The GPU operator needs no scratch registers, so sol_register_count device vectors are NOT allocated:
+    // at C4 size each would cost 10.5 GB of HBM for nothing.
+    void reinit(const SolutionVec& sol, int /*sol_register_count*/) { f_1.reinit(sol); }
+
+   private:
+    SolutionVec f_1;
+    std::vector<SolutionVec> sol_registers;
+};
+
+// timestepper.h:9-21
+struct TimestepCallback {
+    TimestepCallback(double interval, std::function<void(double)> callback, bool perform_zeroth = true, bool perform_final = true)
+        : interval(interval), callback(std::move(callback)), perform_zeroth(perform_zeroth), perform_final(perform_final) {}
+    double interval;
+    std::function<void(double t)> callback;
+    bool perform_zeroth;   // fire at t = 0
+    bool perform_final;    // fire at t_end even if not scheduled
+};
+
+// timestepper.cc:6-56: adaptive dt clipped to the next callback / end time, 1e-12 of slack against stutter steps
+inline void advance(std::function<bool(double t, double dt)> step, double t_end, std::function<double()> recommend_dt,
+                    std::vector<TimestepCallback>& callbacks) {
+    const double slack = 1e-12;
+    double t = 0.0;
+    std::vector<double> due(callbacks.size());
+    for (size_t i = 0; i < callbacks.size(); i++) {
+        if (callbacks[i].perform_zeroth) callbacks[i].callback(0.0);
+        due[i] = t + callbacks[i].interval;
+    }
+    while (t < t_end - slack) {
+        size_t next = 0;
+        for (size_t i = 1; i < due.size(); i++)
+            if (due[i] < due[next]) next = i;
+        const double next_due = callbacks.empty() ? t_end : due[next];
+        const bool fire = next_due < t_end && std::fabs(next_due - t_end) > slack;
+        const double stop = std::fmin(next_due, t_end);
+        while (t < stop - slack) {
+            const double dt = std::fmin(recommend_dt(), stop - t);
+            if (step(t, dt)) t += dt;
+        }
+        if (fire) {
+            callbacks[next].callback(t);
+            due[next] = t + callbacks[next].interval;
+        }
+    }
+    for (size_t i = 0; i < callbacks.size(); i++)
+        if (std::fabs(t_end - due[i]) < slack || callbacks[i].perform_final) callbacks[i].callback(t_end);
+}
+
+}  // namespace warpii_b200

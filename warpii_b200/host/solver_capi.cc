@@ -1,0 +1,188 @@
+// C wrappers of the C++ host layer (include/warpii_host.h).
+#include "warpii_host.h"
+
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "dg_solver.hpp"
+
+using namespace warpii_b200;
+
+struct warpii_box_solver {
+    std::unique_ptr<FiveMomentGpuSolver> solver;
+    int rank = 0, n_ranks = 1;
+};
+
+namespace {
+thread_local std::string g_host_error;
+
+// Host-layer failures are reported through the same accessor as the GPU ABI: stash the text where
+// warpii_gpu_last_error() can see it by routing through a failing ABI call is not possible, so the host layer
+// keeps its own message and warpii_host_last_error() exposes it.
+int host_fail(const std::exception& e) {
+    g_host_error = e.what();
+    return 1;
+}
+}  // namespace
+
+extern "C" {
+
+const char* warpii_host_last_error(void) { return g_host_error.c_str(); }
+
+#define GUARD(body)                                   \
+    try {                                             \
+        body;                                         \
+        return 0;                                     \
+    } catch (const std::exception& e) {               \
+        return host_fail(e);                          \
+    }
+
+int warpii_box_solver_create(int dim, int fe_degree, int n_species, int fields_enabled, double gas_gamma, const int32_t* nx,
+                             const double* left, const double* right, const int32_t* periodic, int n_boundaries,
+                             const int32_t* bc_kinds, int rank, int n_ranks, int device, warpii_box_solver** out) {
+    GUARD({
+        if (!out || !nx || !left || !right) throw std::invalid_argument("warpii_box_solver_create: null argument");
+        if (dim < 1 || dim > 3) throw std::invalid_argument("n_dims must be 1, 2, or 3");
+        BoxDescription box;
+        box.dim = dim;
+        for (int d = 0; d < dim; d++) {
+            box.nx[d] = nx[d];
+            box.left[d] = left[d];
+            box.right[d] = right[d];
+            box.periodic[d] = periodic ? periodic[d] != 0 : true;
+        }
+        std::vector<SpeciesBC> bcs(n_species);
+        for (int s = 0; s < n_species; s++) {
+            bcs[s].kind.assign(n_boundaries, WARPII_BC_WALL);   // species.cc:17: default "Wall"
+            bcs[s].inflow.assign(n_boundaries, std::array<double, 5>{{0, 0, 0, 0, 0}});
+            if (bc_kinds)
+                for (int b = 0; b < n_boundaries; b++) bcs[s].kind[b] = bc_kinds[s * n_boundaries + b];
+        }
+        auto* s = new warpii_box_solver();
+        s->rank = rank;
+        s->n_ranks = n_ranks;
+        try {
+            s->solver = std::make_unique<FiveMomentGpuSolver>(box, fe_degree, n_species, fields_enabled != 0, gas_gamma, 0.0,
+                                                              n_boundaries, bcs, rank, n_ranks, device);
+            s->solver->reinit();
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        *out = s;
+    })
+}
+
+int warpii_box_solver_destroy(warpii_box_solver* s) {
+    delete s;
+    return 0;
+}
+
+warpii_gpu_ctx* warpii_box_solver_ctx(warpii_box_solver* s) { return s ? s->solver->context()->get() : nullptr; }
+int64_t warpii_box_solver_n_local_elems(const warpii_box_solver* s) { return s->solver->tables().n_local(); }
+int64_t warpii_box_solver_n_interface_elems(const warpii_box_solver* s) { return s->solver->tables().n_interface(); }
+int64_t warpii_box_solver_n_ghost_faces(const warpii_box_solver* s) { return s->solver->tables().n_ghost_faces(); }
+int warpii_box_solver_n_components(const warpii_box_solver* s) { return s->solver->n_components(); }
+int warpii_box_solver_nodes_per_elem(const warpii_box_solver* s) { return s->solver->nodes_per_elem(); }
+
+int warpii_box_solver_local_to_global(const warpii_box_solver* s, int64_t* out) {
+    GUARD({
+        const auto& v = s->solver->tables().local_to_global();
+        std::memcpy(out, v.data(), v.size() * sizeof(int64_t));
+    })
+}
+
+int warpii_box_solver_node_coords(const warpii_box_solver* s, double* xyz) {
+    GUARD({
+        const std::vector<double> v = s->solver->node_coords();
+        std::memcpy(xyz, v.data(), v.size() * sizeof(double));
+    })
+}
+
+int warpii_box_solver_set_state(warpii_box_solver* s, const double* host) { GUARD({ s->solver->get_solution().upload(host); }) }
+int warpii_box_solver_get_state(warpii_box_solver* s, double* host) { GUARD({ s->solver->get_solution().download(host); }) }
+int warpii_box_solver_set_inflow(warpii_box_solver* s, int species, int boundary_id, const double q[5]) {
+    GUARD({ s->solver->get_fluid_flux_operator().set_inflow(species, boundary_id, q); })
+}
+
+int warpii_box_solver_attach_comm(warpii_box_solver* s, const char id[WARPII_GPU_NCCL_ID_BYTES]) {
+    GUARD({
+        warpii_gpu_halo halo;
+        s->solver->tables().fill(halo);
+        check(warpii_gpu_attach_comm(s->solver->context()->get(), id, s->rank, s->n_ranks, &halo));
+    })
+}
+
+int warpii_box_solver_solve(warpii_box_solver* s, double t_end, double fixed_dt, double callback_interval, warpii_callback_fn cb,
+                            void* user, int64_t* steps_out) {
+    GUARD({
+        s->solver->set_t_end(t_end);
+        s->solver->set_fixed_dt(fixed_dt);
+        // FiveMomentApp::run (five_moment.h:233-243): the writeout callback skips t = 0
+        const double interval = (cb && callback_interval > 0) ? callback_interval : t_end;
+        TimestepCallback callback(interval, [&](double t) { if (cb) cb(t, user); }, false, true);
+        s->solver->solve(callback);
+        if (steps_out) *steps_out = s->solver->steps_taken();
+    })
+}
+
+int warpii_box_solver_step(warpii_box_solver* s, double dt, double t) {
+    GUARD({
+        // one evolve_one_time_step through the same integrator solve() uses
+        s->solver->set_t_end(0.0);
+        check(warpii_gpu_ssprk2_step(s->solver->context()->get(), 0, 1, dt, t));
+    })
+}
+
+int warpii_box_solver_recommend_dt(warpii_box_solver* s, double* dt_out) {
+    GUARD({ *dt_out = s->solver->get_fluid_flux_operator().recommend_dt(s->solver->get_solution()); })
+}
+
+int warpii_host_advance(warpii_step_fn step, double t_end, warpii_dt_fn recommend_dt, int n_callbacks, const double* intervals,
+                        const int32_t* perform_zeroth, const int32_t* perform_final, warpii_cb_index_fn cb, void* user) {
+    GUARD({
+        std::vector<TimestepCallback> cbs;
+        for (int i = 0; i < n_callbacks; i++)
+            cbs.emplace_back(intervals[i], [=](double t) { cb(t, i, user); }, perform_zeroth[i] != 0, perform_final[i] != 0);
+        advance([&](double t, double dt) { return step(t, dt, user) != 0; }, t_end, [&]() { return recommend_dt(user); }, cbs);
+    })
+}
+
+int warpii_host_box_tables(int dim, const int32_t* nx, const int32_t* periodic, int rank, int n_ranks, int64_t counts[6],
+                           int64_t* local_to_global, int32_t* face_neighbor, int32_t* bf_elem, int32_t* bf_side, int32_t* bf_id,
+                           int32_t* peer_rank, int64_t* send_offset, int64_t* recv_offset, int32_t* send_elem, int32_t* send_side,
+                           int64_t* ghost_global_elem, int32_t* ghost_side) {
+    GUARD({
+        BoxDescription box;
+        box.dim = dim;
+        for (int d = 0; d < dim; d++) {
+            box.nx[d] = nx[d];
+            box.left[d] = 0.0;
+            box.right[d] = 1.0;
+            box.periodic[d] = periodic ? periodic[d] != 0 : true;
+        }
+        BoxMeshTables t(box, rank, n_ranks);
+        counts[0] = t.n_local();
+        counts[1] = t.n_interface();
+        counts[2] = t.n_ghost_faces();
+        counts[3] = (int64_t)t.boundary_face_elem().size();
+        counts[4] = (int64_t)t.peer_rank().size();
+        counts[5] = (int64_t)t.send_elem().size();
+        auto cp = [](auto* dst, const auto& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+        cp(local_to_global, t.local_to_global());
+        cp(face_neighbor, t.face_neighbor());
+        cp(bf_elem, t.boundary_face_elem());
+        cp(bf_side, t.boundary_face_side());
+        cp(bf_id, t.boundary_face_id());
+        cp(peer_rank, t.peer_rank());
+        cp(send_offset, t.send_offset());
+        cp(recv_offset, t.recv_offset());
+        cp(send_elem, t.send_elem());
+        cp(send_side, t.send_side());
+        cp(ghost_global_elem, t.ghost_global_elem());
+        cp(ghost_side, t.ghost_side());
+    })
+}
+
+}  // extern "C"
