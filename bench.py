@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 DoF-updates/s of the ES-DGSEM RHS + SSPRK2 hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (libwarpii_b200.so on N GPUs, one rank per GPU)
+  python bench.py --impl reference --steps K --warmup W    reference arm: the CPU restatement of the reference
+                                                           algorithm (oracle/), all host threads, rank 0 only
+
+One "step" is one SSPRK2 time step of the workload = 2 RHS evaluations (+ the CFL reduction the time loop asks
+for every step, fluid_flux_es_dgsem_operator.h:442-448), so DoF-updates per step = 2 * n_dofs.
+Workload at N=1: BASELINE config 2 (2D Euler isentropic vortex, p=3, 512x512, periodic).  For N>1 the mesh is
+extended by 512 element rows per GPU (weak scaling) and sharded in slabs with an NCCL halo exchange per RHS.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import dgsem_cases as cases  # noqa: E402
+
+METRIC = "FP64 DoF-updates/sec (RHS evals x DoFs/s)"
+UNIT = "DoF-updates/s"
+BYTES_PER_DOF_UPDATE = 20.0   # stage 1 = 16 B, stage 2 = 24 B per DoF, SSPRK2 average 20 B
+
+WORKLOADS = {
+    # name: (dim, p, nx per GPU, left, right, gamma, ic, n_species, fields)
+    "C2": dict(dim=2, p=3, nx=[512, 512], left=[0.0, -5.0], right=[10.0, 5.0], gamma=1.4, ic="vortex",
+               label="C2: 2D Euler periodic isentropic vortex, degree 3, 512x512 elements"),
+    "C3p": dict(dim=2, p=3, nx=[1024, 1024], left=[0.0, -5.0], right=[10.0, 5.0], gamma=1.4, ic="vortex",
+                label="2D Euler periodic vortex, degree 3, 1024x1024 elements (C3 size, doubly periodic)"),
+    "V3D3": dict(dim=3, p=3, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[10.0, 5.0, 5.0], gamma=1.4, ic="vortex",
+                 label="3D Euler periodic vortex, degree 3, 64^3 elements"),
+    "C4s": dict(dim=3, p=4, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[10.0, 5.0, 5.0], gamma=1.4, ic="vortex",
+                label="3D Euler periodic vortex, degree 4, 64^3 elements per GPU (C4 shape)"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_ic(w, xyz):
+    if w["ic"] == "vortex":
+        return cases.to_state(cases.isentropic_vortex(w["gamma"])(xyz), w["gamma"])
+    raise ValueError(w["ic"])
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_run(w, steps, warmup, threads, budget_s, rows=None):
+    """Time SSPRK2 steps of the oracle on a bounded sample: the workload's mesh cut to `rows` element rows in the
+    last dimension (same h, same degree, same initial condition, periodic)."""
+    import oracle
+    from oracle import Oracle
+    oracle.build()
+    dim, nx = w["dim"], list(w["nx"])
+    full_last = nx[-1]
+    if rows is None:
+        # calibrate on a thin slab, then size the sample so that (steps + warmup) steps fit in the budget
+        probe = 4
+        nxp = nx[:-1] + [probe]
+        right = list(w["right"])
+        right[-1] = w["left"][-1] + (w["right"][-1] - w["left"][-1]) * probe / full_last
+        o = Oracle(dim, w["p"], nxp, w["left"], right, gamma=w["gamma"], threads=threads)
+        u = build_ic(w, o.node_coords())
+        dt = o.recommend_dt(u)
+        t0 = time.perf_counter()
+        o.ssprk2_step(u, dt, 0.0)
+        per_row = (time.perf_counter() - t0) / probe
+        rows = int(max(probe, min(full_last, budget_s / max(per_row * (steps + warmup), 1e-9))))
+    nxs = nx[:-1] + [rows]
+    right = list(w["right"])
+    right[-1] = w["left"][-1] + (w["right"][-1] - w["left"][-1]) * rows / full_last
+    o = Oracle(dim, w["p"], nxs, w["left"], right, gamma=w["gamma"], threads=threads)
+    u = build_ic(w, o.node_coords())
+    t = 0.0
+    for _ in range(warmup):
+        dt = o.recommend_dt(u)
+        o.ssprk2_step(u, dt, t)
+        t += dt
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dt = o.recommend_dt(u)
+        o.ssprk2_step(u, dt, t)
+        t += dt
+    el = time.perf_counter() - t0
+    n_dofs = o.n_dofs
+    return {"value": 2.0 * n_dofs * steps / el, "ms_per_step": 1e3 * el / steps, "n_dofs": int(n_dofs),
+            "sample": f"{steps} SSPRK2 steps on {'x'.join(str(v) for v in nxs)} of the {'x'.join(str(v) for v in nx)} elements "
+                      f"(same h, degree, IC; {n_dofs} DoFs)"}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    r = cpu_run(w, args.steps, args.warmup, threads, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "note": "CPU restatement (oracle/) of the reference algorithm; the reference itself "
+                   "needs deal.II 9.5.1 + MPI and cannot be built in this image"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from warpii_b200 import BoxSolver, nccl_unique_id
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    dim, p, gamma = w["dim"], w["p"], w["gamma"]
+    nx = list(w["nx"])
+    left, right = list(w["left"]), list(w["right"])
+    # weak scaling: one workload-sized slab per GPU along the last dimension
+    nx[-1] *= world
+    right[-1] = left[-1] + (right[-1] - left[-1]) * world
+    g = BoxSolver(dim, p, nx, left, right, gamma=gamma, rank=rank, n_ranks=world, device=local_rank)
+    if world > 1:
+        if rank == 0:
+            uid = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        else:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        g.attach_comm(bytes(uid.cpu().tolist()))
+    u0 = build_ic(w, g.node_coords())
+    n_dofs_local = g.n_dofs
+    n_dofs_total = n_dofs_local * world
+    host = torch.empty(n_dofs_local, dtype=torch.float64).pin_memory()
+    host_np = host.numpy()
+    host_np[:] = u0.reshape(-1)
+    del u0
+    g.upload(0, host_np)
+    stream = torch.cuda.ExternalStream(g.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        g.synchronize()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -----------------------------------------------------------------
+    t = 0.0
+    t, _ = g.advance_to(t, 1e30, max_steps=args.warmup)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    g.stage_timing(True)
+    launches0 = g.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t, steps = g.advance_to(t, 1e30, max_steps=args.steps)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = g.launch_count() - launches0
+    stage_ms, stage_n = g.stage_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    assert steps == args.steps
+    value = 2.0 * n_dofs_total * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------------------
+    # every step: pinned host state -> HBM, recommend_dt + one SSPRK2 step, HBM -> pinned host state
+    import ctypes as C
+    from warpii_b200 import lib as _lib
+    L = _lib()
+    hp = host_np.ctypes.data_as(C.POINTER(C.c_double))
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step(tt):
+        assert L.warpii_gpu_upload_state(g.ctx, 0, hp, None) == 0
+        tt, _ = g.advance_to(tt, 1e30, max_steps=1)
+        assert L.warpii_gpu_download_state(g.ctx, 0, hp, None) == 0
+        return tt
+
+    assert L.warpii_gpu_download_state(g.ctx, 0, hp, None) == 0
+    for _ in range(2):
+        t = e2e_step(t)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        t = e2e_step(t)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_wall = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_ms = max(e2e_ms, e2e_wall)   # the host-side copies are synchronous: count whichever clock saw more
+    e2e_value = 2.0 * n_dofs_total * e2e_steps / (e2e_ms * 1e-3)
+    assert np.isfinite(host_np).all()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        # dominant kernel = the fused stage kernel; algorithmic bytes per launch = 20 B (SSPRK2 average) x local DoFs
+        avg_stage_ms = stage_ms / max(stage_n, 1)
+        achieved = BYTES_PER_DOF_UPDATE * n_dofs_local / (avg_stage_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": w["label"] + (f" per GPU ({nx[-1]} rows in total, slab-sharded)" if world > 1 else ""),
+                       "n_dofs": int(n_dofs_total), "state_bytes": int(8 * n_dofs_local),
+                       "l2_policy": "state (2 x %.0f MB per GPU) exceeds the 126 MB L2; no flush" % (8e-6 * n_dofs_local),
+                       "parallelism": f"elements sharded over {world} GPU(s), NCCL send/recv halo + allreduce(max) dt"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_dofs_local),
+                    "d2h_bytes_per_step": int(8 * n_dofs_local), "steps": e2e_steps,
+                    "note": "per step: pinned host state -> HBM, recommend_dt + SSPRK2 step through the C ABI, HBM -> host"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": f"wgpu::stage_kernel<{dim},{p + 1}>", "peak_source": peak_src,
+                         "avg_launch_ms": avg_stage_ms, "launches_timed": int(stage_n),
+                         "algorithmic_bytes_per_launch": BYTES_PER_DOF_UPDATE * n_dofs_local},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            nthreads = os.cpu_count() or 1
+            cb = cpu_run(w, 1, 0, nthreads, budget_s=12.0)
+            cb1 = cpu_run(w, 1, 0, 1, budget_s=8.0)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": nthreads, "kind": "port", "sample": cb["sample"],
+                                    "single_core_value": cb1["value"], "single_core_sample": cb1["sample"]}
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -230,6 +230,7 @@ class Oracle:
                  n_species=1, fields_enabled=False, bc_kinds=None, threads=1):
         L = lib()
         self.dim, self.p, self.gamma, self.nsp = dim, fe_degree, gamma, n_species
+        self.nx, self.left, self.right = list(nx), list(left), list(right)
         periodic = [1] * dim if periodic is None else [int(bool(x)) for x in periodic]
         nx_a = (C.c_int * dim)(*[int(v) for v in nx])
         l_a = (C.c_double * dim)(*[float(v) for v in left])

@@ -110,3 +110,37 @@ def rel_l2_per_component(a, b):
         num = np.linalg.norm(a[:, c, :] - b[:, c, :])
         out.append(num / den if den > 0 else num)
     return np.array(out)
+
+
+def summand_scale(u, gamma, dim, h, D):
+    """L2 norm, per fluid component, of the magnitude of the terms that are DIFFERENCED to form the RHS:
+    (2 dim max|D| / min h) * max_d |f_{c,d}(u)| at every node.  A component whose exact RHS is (near) zero - e.g.
+    z-momentum of a flow extruded in z, or x-momentum across a constant-pressure shear layer - consists of nothing
+    but the round-off of these terms in BOTH implementations, so its error is judged against this scale."""
+    n_sp = u.shape[1] // 5 if u.shape[1] % 5 == 0 else (u.shape[1] - 8) // 5
+    amp = 2.0 * dim * np.abs(D).max() / min(h)
+    out = np.zeros(u.shape[1])
+    for s in range(n_sp):
+        q = u[:, 5 * s:5 * s + 5, :]
+        rho, E = q[:, 0], q[:, 4]
+        vel = [q[:, 1 + d] / rho for d in range(3)]
+        p = (gamma - 1) * (E - 0.5 * rho * sum(v * v for v in vel))
+        F = np.zeros(q.shape)
+        for d in range(dim):
+            F[:, 0] = np.maximum(F[:, 0], np.abs(rho * vel[d]))
+            for e in range(3):
+                F[:, 1 + e] = np.maximum(F[:, 1 + e], np.abs(rho * vel[d] * vel[e]) + (p if e == d else 0.0))
+            F[:, 4] = np.maximum(F[:, 4], np.abs(vel[d] * (E + p)))
+        for c in range(5):
+            out[5 * s + c] = amp * np.linalg.norm(F[:, c, :])
+    return out
+
+
+def rel_l2_guarded(got, want, scale, kappa=1e-2):
+    """||got - want||_2 / max(||want||_2, kappa * scale) per component (see summand_scale)."""
+    out = []
+    for c in range(want.shape[1]):
+        num = np.linalg.norm(got[:, c, :] - want[:, c, :])
+        den = max(np.linalg.norm(want[:, c, :]), kappa * scale[c])
+        out.append(num / den if den > 0 else num)
+    return np.array(out)

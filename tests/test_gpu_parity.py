@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from oracle import Oracle
-from tests import cases
+import dgsem_cases as cases
 from warpii_b200 import BC_INFLOW, BC_OUTFLOW, BC_WALL, BoxSolver
 
 pytestmark = pytest.mark.gpu
@@ -39,9 +39,13 @@ def check_rhs(o, g, u, tol=RHS_TOL):
     g.rhs(1, 0)
     got = g.download(1)
     want, _ = o.rhs(u)
-    err = cases.rel_l2_per_component(got, want)
     assert np.isfinite(got).all()
-    assert (err <= tol).all(), f"relative L2 per component {err}"
+    # relative L2 per component; components that are pure cancellation noise in both implementations are
+    # measured against 1e-2 of the magnitude of the differenced terms instead of against ~0 (dgsem_cases.py)
+    h = [(o_r - o_l) / n for o_l, o_r, n in zip(o.left, o.right, o.nx)]
+    scale = cases.summand_scale(u, o.gamma, o.dim, h, oracle.diff_matrix(o.p + 1))
+    err = cases.rel_l2_guarded(got, want, scale)
+    assert (err <= tol).all(), f"relative L2 per component {err} (plain: {cases.rel_l2_per_component(got, want)})"
     return err
 
 
@@ -247,7 +251,7 @@ def test_reference_periodic_1d_conservation():
 
 def test_reference_freestream_1d_convergence():
     """test/input_test.cc:18-66 through the GPU path."""
-    from tests.test_oracle_golden import _l2_error_density
+    from test_oracle_golden import _l2_error_density
     errs = []
     for nx in (20, 30):
         o, g = make_pair(1, 2, [nx], [0.0], [1.0], gamma=1.6666666666667)
