@@ -85,6 +85,10 @@ typedef struct warpii_gpu_halo {
 
 const char* warpii_gpu_last_error(void);
 int warpii_gpu_abi_version(void);
+/* Number of consecutive elements one thread block of the stage kernel works on.  Purely a performance hint for
+ * the host's element ordering: faces between two elements of the same group of this many consecutive elements
+ * are evaluated once, so compact patches (e.g. 4x4 in 2D) should be numbered consecutively.  Any ordering is correct. */
+int warpii_gpu_elems_per_block(int dim, int fe_degree);
 
 /* -- lifetime -------------------------------------------------------------- */
 int warpii_gpu_create(const warpii_gpu_mesh* mesh, int device, warpii_gpu_ctx** out);

@@ -75,6 +75,7 @@ int warpii_host_advance(warpii_step_fn step, double t_end, warpii_dt_fn recommen
  * Pass NULL output pointers to query sizes through the counts array:
  * counts = {n_local, n_interface, n_ghost_faces, n_boundary_faces, n_peers, n_send}. */
 int warpii_host_box_tables(int dim, const int32_t* nx, const int32_t* periodic, int rank, int n_ranks,
+                           int elems_per_block /* patch size of the element numbering, 1 = lexicographic */,
                            int64_t counts[6], int64_t* local_to_global, int32_t* face_neighbor,
                            int32_t* bf_elem, int32_t* bf_side, int32_t* bf_id, int32_t* peer_rank,
                            int64_t* send_offset, int64_t* recv_offset, int32_t* send_elem, int32_t* send_side,

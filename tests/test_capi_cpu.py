@@ -157,9 +157,10 @@ def test_box_tables_single_rank(dim, nx, periodic):
 @pytest.mark.parametrize("dim,nx,periodic,R", [(1, [8], [1], 2), (2, [4, 6], [1, 1], 3), (2, [3, 4], [1, 0], 2),
                                                (3, [3, 3, 8], [1, 1, 1], 4), (3, [2, 3, 2], [1, 1, 1], 2),
                                                (3, [4, 4, 8], [1, 1, 1], 8)])
-def test_box_tables_partition_is_consistent(dim, nx, periodic, R):
+@pytest.mark.parametrize("group", [1, 4])
+def test_box_tables_partition_is_consistent(dim, nx, periodic, R, group):
     """Every element owned once; ghost slots of rank a pair up with the send list of the peer, in the same order."""
-    tabs = [box_tables(dim, nx, periodic, r, R) for r in range(R)]
+    tabs = [box_tables(dim, nx, periodic, r, R, group=group) for r in range(R)]
     n = int(np.prod(nx))
     owned = np.concatenate([t["local_to_global"] for t in tabs])
     assert sorted(owned.tolist()) == list(range(n))
@@ -189,6 +190,20 @@ def test_box_tables_partition_is_consistent(dim, nx, periodic, R):
             assert np.array_equal(sent_g, t["ghost_global_elem"][mine])
             assert np.array_equal(tp["send_side"][theirs], t["ghost_side"][mine])
         del g2l
+
+
+def test_patch_numbering_groups_compact_patches():
+    """With group = 16 in 2D the first 16 device elements form a 4x4 patch, so 24 of their 64 faces are internal."""
+    t = box_tables(2, [8, 12], [1, 1], group=16)
+    l2g = t["local_to_global"]
+    assert sorted(l2g.tolist()) == list(range(96))
+    first = l2g[:16]
+    assert sorted((first % 8).tolist()) == sorted([0, 1, 2, 3] * 4) and sorted((first // 8).tolist()) == sorted([0, 1, 2, 3] * 4)
+    nb = t["face_neighbor"][:16]
+    assert int(((nb >= 0) & (nb < 16)).sum()) == 2 * 24
+    # a mesh that the patch shape does not divide is still a valid permutation
+    t = box_tables(3, [3, 5, 2], [1, 0, 1], group=8)
+    assert sorted(t["local_to_global"].tolist()) == list(range(30))
 
 
 # ---- N > 1 path on CPU: gloo, world size 2 ---------------------------------------------------------------------

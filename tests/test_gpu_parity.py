@@ -28,16 +28,16 @@ def make_pair(dim, p, nx, left, right, periodic=None, gamma=1.4, n_species=1, fi
     g = BoxSolver(dim, p, nx, left, right, periodic=periodic, gamma=gamma, n_species=n_species, fields_enabled=fields,
                   n_boundaries=nb, bc_kinds=bc)
     assert g.shape == o.shape
-    # single rank: device order == global lexicographic order
-    assert np.array_equal(g.local_to_global(), np.arange(o.n_elems))
-    assert np.allclose(g.node_coords(), o.node_coords(), rtol=0, atol=1e-15)
+    # single rank: the device numbers the elements patch by patch; l2g maps back to the oracle's lexicographic order
+    assert sorted(g.l2g.tolist()) == list(range(o.n_elems))
+    assert np.allclose(g.node_coords(), o.node_coords()[g.l2g], rtol=0, atol=1e-15)
     return o, g
 
 
 def check_rhs(o, g, u, tol=RHS_TOL):
-    g.upload(0, u)
+    g.upload_global(0, u)
     g.rhs(1, 0)
-    got = g.download(1)
+    got = g.download_global(1)
     want, _ = o.rhs(u)
     assert np.isfinite(got).all()
     # relative L2 per component; components that are pure cancellation noise in both implementations are
@@ -70,7 +70,7 @@ def test_one_rhs_periodic(dim, p, nx, left, right, ic, gamma):
     u = o.project(ic)
     check_rhs(o, g, u)
     # blending factors agree (all zero for these smooth states, but compare the tables anyway)
-    assert np.allclose(g.shock_indicator(0), o.alpha(u), rtol=0, atol=1e-12)
+    assert np.allclose(g.shock_indicator_global(0), o.alpha(u), rtol=0, atol=1e-12)
     g.close()
 
 
@@ -82,8 +82,8 @@ def test_sod_rhs_with_shock_capturing_and_outflow():
     u = o.project(cases.sod())
     a_ref = o.alpha(u)
     assert a_ref.max() > 0
-    g.upload(0, u)
-    a_gpu = g.shock_indicator(0)
+    g.upload_global(0, u)
+    a_gpu = g.shock_indicator_global(0)
     assert np.allclose(a_gpu, a_ref, rtol=1e-10, atol=1e-12)
     check_rhs(o, g, u)
     # after some steps the profile has a rarefaction, contact and shock: compare again there
@@ -97,10 +97,10 @@ def test_sod_full_run_config1():
     bc = [[BC_OUTFLOW, BC_OUTFLOW]]
     o, g = make_pair(1, 2, [200], [0.0], [1.0], periodic=[0], gamma=gamma, bc=bc)
     u = o.project(cases.sod())
-    g.set_state(u)
+    g.set_state_global(u)
     steps_g = g.solve(0.1)
     steps_o = o.solve(u, 0.1)
-    got = g.get_state()
+    got = g.get_state_global()
     assert steps_g == steps_o
     # A shock run is chaotic in the last bits (alpha switches); the profiles must still agree closely.
     err = cases.rel_l2_per_component(got, u)
@@ -118,7 +118,7 @@ def test_inflow_outflow_bif_and_balance():
     g.set_inflow(0, 0, q_in)
     u = o.project(cases.sine_wave())
     ic = o.global_integral(u)
-    g.set_state(u)
+    g.set_state_global(u)
     assert np.allclose(g.global_integral(0), ic, rtol=0, atol=1e-15)
     steps = g.solve(0.04)
     assert steps > 0
@@ -131,7 +131,7 @@ def test_inflow_outflow_bif_and_balance():
     steps_o = o.solve(u, 0.04, bif=bif_o)
     assert steps_o == steps
     assert np.allclose(bif, bif_o, rtol=1e-11, atol=1e-13)
-    assert (cases.rel_l2_per_component(g.get_state(), u)[[0, 1, 4]] < STEPS_TOL).all()
+    assert (cases.rel_l2_per_component(g.get_state_global(), u)[[0, 1, 4]] < STEPS_TOL).all()
     g.close()
 
 
@@ -144,7 +144,7 @@ def test_walls_2d_kelvin_helmholtz_rhs():
     u = o.project(cases.kelvin_helmholtz(k))
     check_rhs(o, g, u)
     a_ref = o.alpha(u)
-    assert np.allclose(g.shock_indicator(0), a_ref, rtol=1e-9, atol=1e-12)
+    assert np.allclose(g.shock_indicator_global(0), a_ref, rtol=1e-9, atol=1e-12)
     g.close()
 
 
@@ -170,9 +170,9 @@ def test_two_species_with_fields_rhs_and_step():
     u[:, 10:18, :] = rng.standard_normal(u[:, 10:18, :].shape)
     check_rhs(o, g, u)
     dt = 0.3 * o.recommend_dt(u)
-    g.upload(0, u)
+    g.upload_global(0, u)
     g.ssprk2_step(dt, 0.0)
-    got = g.download(0)
+    got = g.download_global(0)
     want = u.copy()
     o.ssprk2_step(want, dt, 0.0)
     assert (cases.rel_l2_per_component(got, want) < 1e-13).all()
@@ -184,7 +184,7 @@ def test_two_species_with_fields_rhs_and_step():
 def test_recommend_dt_parity(dim, p, nx, left, right, ic, gamma):
     o, g = make_pair(dim, p, nx, left, right, gamma=gamma)
     u = o.project(ic)
-    g.upload(0, u)
+    g.upload_global(0, u)
     want = o.recommend_dt(u)
     got = g.recommend_dt(0)
     assert abs(got - want) <= DT_TOL * want
@@ -206,12 +206,12 @@ def test_hundred_steps_vortex_2d():
     o, g = make_pair(2, 3, [16, 16], [0.0, -5.0], [10.0, 5.0], gamma=gamma, threads=8)
     u = o.project(cases.isentropic_vortex(gamma))
     ic = o.global_integral(u)
-    g.set_state(u)
+    g.set_state_global(u)
     t, steps = g.advance_to(0.0, 1e9, max_steps=100)
     assert steps == 100
     so = o.solve(u, t, max_steps=100)
     assert so == 100
-    got = g.get_state()
+    got = g.get_state_global()
     err = cases.rel_l2_per_component(got, u)
     assert (err[[0, 1, 2, 4]] <= STEPS_TOL).all(), err
     now = g.global_integral(0)
@@ -225,10 +225,10 @@ def test_hundred_steps_3d():
     o, g = make_pair(3, 3, [4, 4, 4], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], gamma=gamma, threads=8)
     u = o.project(cases.smooth_blob_3d(0.1))
     ic = o.global_integral(u)
-    g.set_state(u)
+    g.set_state_global(u)
     t, steps = g.advance_to(0.0, 1e9, max_steps=100)
     o.solve(u, t, max_steps=100)
-    err = cases.rel_l2_per_component(g.get_state(), u)
+    err = cases.rel_l2_per_component(g.get_state_global(), u)
     assert (err <= STEPS_TOL).all(), err
     now = g.global_integral(0)
     for c in range(5):
@@ -240,7 +240,7 @@ def test_reference_periodic_1d_conservation():
     """test/conservation_test.cc:45-83 through the GPU path: one p=4 cell, periodic onto itself."""
     o, g = make_pair(1, 4, [1], [0.0], [1.0], gamma=1.6666666666667)
     u = o.project(cases.sine_wave())
-    g.set_state(u)
+    g.set_state_global(u)
     ic = g.global_integral(0)
     assert g.solve(0.04) > 0
     now = g.global_integral(0)
@@ -255,9 +255,9 @@ def test_reference_freestream_1d_convergence():
     errs = []
     for nx in (20, 30):
         o, g = make_pair(1, 2, [nx], [0.0], [1.0], gamma=1.6666666666667)
-        g.set_state(o.project(cases.sine_wave()))
+        g.set_state_global(o.project(cases.sine_wave()))
         g.solve(0.04)
-        errs.append(_l2_error_density(o, g.get_state(), lambda x: 1 + 0.6 * np.sin(2 * np.pi * (x - 0.04)), 2))
+        errs.append(_l2_error_density(o, g.get_state_global(), lambda x: 1 + 0.6 * np.sin(2 * np.pi * (x - 0.04)), 2))
         g.close()
     assert abs(errs[1]) < 1e-4
     assert abs(errs[0] / errs[1] - 1.5 ** 3) < 1.0
@@ -266,7 +266,7 @@ def test_reference_freestream_1d_convergence():
 def test_solver_callbacks_and_step_count():
     """FiveMomentDGSolver::solve + advance(): the writeout callback fires at the frame times and at t_end."""
     o, g = make_pair(1, 2, [10], [0.0], [1.0], gamma=1.6666666666667)
-    g.set_state(o.project(cases.sine_wave()))
+    g.set_state_global(o.project(cases.sine_wave()))
     times = []
     steps = g.solve(0.05, callback=times.append, callback_interval=0.01)
     assert steps >= 5
@@ -293,22 +293,23 @@ def test_full_size_c2_properties():
     n = 512
     g = BoxSolver(2, 3, [n, n], [0.0, -5.0], [10.0, 5.0], gamma=gamma)
     xyz = g.node_coords()
-    u0 = cases.to_state(cases.isentropic_vortex(gamma)(xyz), gamma)
-    g.set_state(u0)
+    u0 = np.empty(g.shape)
+    u0[g.l2g] = cases.to_state(cases.isentropic_vortex(gamma)(xyz), gamma)   # global (lexicographic) element order
+    g.set_state_global(u0)
     ic = g.global_integral(0)
     t, steps = g.advance_to(0.0, 1e9, max_steps=10)
     assert steps == 10
     now = g.global_integral(0)
     for c in (0, 1, 2, 4):
         assert abs(now[c] - ic[c]) <= 2e-12 * max(1.0, abs(ic[c])), (c, now[c] - ic[c])
-    u10 = g.get_state()
+    u10 = g.get_state_global()
     assert np.isfinite(u10).all()
     # translation invariance: shifting the initial state by 64 elements in x and 32 in y shifts the answer, bit for bit
     sx, sy = 64, 32
     shifted = np.roll(np.roll(u0.reshape(n, n, 5, 16), sy, axis=0), sx, axis=1).reshape(u0.shape)
-    g.set_state(shifted)
+    g.set_state_global(shifted)
     g.advance_to(0.0, 1e9, max_steps=10)
-    u10s = g.get_state()
+    u10s = g.get_state_global()
     back = np.roll(np.roll(u10s.reshape(n, n, 5, 16), -sy, axis=0), -sx, axis=1).reshape(u0.shape)
     assert np.array_equal(back, u10)
     # free stream: a uniform state has zero residual up to round-off of the flux differences

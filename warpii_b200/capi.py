@@ -133,15 +133,19 @@ def host_advance(step, t_end, recommend_dt, callbacks):
     _check(L.warpii_host_advance(s, t_end, d, n, _ptr(iv), pz.ctypes.data_as(_i32p), pf.ctypes.data_as(_i32p), cb, None), host=True)
 
 
-def box_tables(dim, nx, periodic, rank=0, n_ranks=1):
-    """Mesh tables of one rank (no GPU needed): dict of numpy arrays."""
+def elems_per_block(dim, fe_degree):
+    return lib().warpii_gpu_elems_per_block(dim, fe_degree)
+
+
+def box_tables(dim, nx, periodic, rank=0, n_ranks=1, group=1):
+    """Mesh tables of one rank (no GPU needed): dict of numpy arrays.  group = patch size of the numbering."""
     L = lib()
-    L.warpii_host_box_tables.argtypes = [C.c_int, _i32p, _i32p, C.c_int, C.c_int, _i64p, _i64p, _i32p, _i32p, _i32p, _i32p,
-                                         _i32p, _i64p, _i64p, _i32p, _i32p, _i64p, _i32p]
+    L.warpii_host_box_tables.argtypes = [C.c_int, _i32p, _i32p, C.c_int, C.c_int, C.c_int, _i64p, _i64p, _i32p, _i32p, _i32p,
+                                         _i32p, _i32p, _i64p, _i64p, _i32p, _i32p, _i64p, _i32p]
     nx_a, per_a = _arr32(nx), _arr32([int(bool(p)) for p in periodic])
     counts = np.zeros(6, dtype=np.int64)
     none32, none64 = C.cast(None, _i32p), C.cast(None, _i64p)
-    _check(L.warpii_host_box_tables(dim, nx_a.ctypes.data_as(_i32p), per_a.ctypes.data_as(_i32p), rank, n_ranks,
+    _check(L.warpii_host_box_tables(dim, nx_a.ctypes.data_as(_i32p), per_a.ctypes.data_as(_i32p), rank, n_ranks, group,
                                     counts.ctypes.data_as(_i64p), none64, none32, none32, none32, none32, none32, none64,
                                     none64, none32, none32, none64, none32), host=True)
     n_local, n_iface, n_ghost, n_bf, n_peers, n_send = [int(v) for v in counts]
@@ -157,7 +161,7 @@ def box_tables(dim, nx, periodic, rank=0, n_ranks=1):
     }
     p32 = lambda k: t[k].ctypes.data_as(_i32p)
     p64 = lambda k: t[k].ctypes.data_as(_i64p)
-    _check(L.warpii_host_box_tables(dim, nx_a.ctypes.data_as(_i32p), per_a.ctypes.data_as(_i32p), rank, n_ranks,
+    _check(L.warpii_host_box_tables(dim, nx_a.ctypes.data_as(_i32p), per_a.ctypes.data_as(_i32p), rank, n_ranks, group,
                                     counts.ctypes.data_as(_i64p), p64("local_to_global"), p32("face_neighbor"), p32("bf_elem"),
                                     p32("bf_side"), p32("bf_id"), p32("peer_rank"), p64("send_offset"), p64("recv_offset"),
                                     p32("send_elem"), p32("send_side"), p64("ghost_global_elem"), p32("ghost_side")), host=True)
@@ -195,6 +199,36 @@ class BoxSolver:
         self.NN = L.warpii_box_solver_nodes_per_elem(h)
         self.shape = (self.n_elems, self.nc, self.NN)
         self.n_dofs = self.n_elems * self.nc * self.NN
+        self.l2g = self.local_to_global()   # device order -> global lexicographic element index
+
+    # ---- global (lexicographic) element order <-> this rank's device order -----------------------------
+    def upload_global(self, vec, u_global):
+        self.upload(vec, np.ascontiguousarray(u_global[self.l2g]))
+
+    def download_global(self, vec, out=None):
+        """Scatter this rank's elements into a global-order array (other ranks' elements are left untouched)."""
+        u = self.download(vec)
+        if out is None:
+            assert self.n_elems == int(self.l2g.max()) + 1, "pass `out` on a sharded run"
+            out = np.empty_like(u)
+        out[self.l2g] = u
+        return out
+
+    def set_state_global(self, u_global):
+        self.set_state(np.ascontiguousarray(u_global[self.l2g]))
+
+    def get_state_global(self, out=None):
+        u = self.get_state()
+        if out is None:
+            out = np.empty_like(u)
+        out[self.l2g] = u
+        return out
+
+    def shock_indicator_global(self, vec=0):
+        a = self.shock_indicator(vec)
+        out = np.empty_like(a)
+        out[self.l2g] = a
+        return out
 
     def close(self):
         if getattr(self, "h", None):

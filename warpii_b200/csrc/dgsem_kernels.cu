@@ -12,14 +12,27 @@
 
 namespace wgpu {
 
-__host__ __device__ constexpr int ipow_c(int b, int e) { return e == 0 ? 1 : b * ipow_c(b, e - 1); }
-
 template <int DIM, int NP>
 struct Geo {
-    static constexpr int NN = ipow_c(NP, DIM);        // nodes per element
-    static constexpr int NF = ipow_c(NP, DIM - 1);    // nodes per face
-    static constexpr int EPB = (128 / NN) > 0 ? (128 / NN) : 1;   // elements per block
-    static constexpr int THREADS = EPB * NN;
+    static constexpr int NN = ipow_c(NP, DIM);          // nodes per element
+    static constexpr int NF = ipow_c(NP, DIM - 1);      // nodes per face
+    static constexpr int G = elems_per_block(DIM, NP);  // elements per block
+    static constexpr int NODES = NN * G;                // nodes (= threads) per block
+    static constexpr int NFACE = 2 * DIM;
+    static constexpr int NSLOT = G * NFACE * NF;        // face-node result slots per block
+    static constexpr int THREADS = NODES;
+    // dynamic shared memory, in doubles
+    static constexpr int OFF_D = 0;
+    static constexpr int OFF_V = OFF_D + NP * NP;
+    static constexpr int OFF_W = OFF_V + NP * NP;
+    static constexpr int OFF_P = OFF_W + 8;                 // [kPrim][NODES]
+    static constexpr int OFF_A = OFF_P + kPrim * NODES;     // indicator scratch
+    static constexpr int OFF_B = OFF_A + NODES;
+    static constexpr int OFF_FACE = OFF_B + NODES;          // [5][NSLOT]
+    static constexpr int OFF_G = OFF_FACE + 5 * NSLOT;      // [5][NODES] subcell interface fluxes
+    static constexpr int OFF_ALPHA = OFF_G + 5 * NODES;     // [G]
+    static constexpr int OFF_RED = OFF_ALPHA + G;           // [32]
+    static constexpr int SMEM_DOUBLES = OFF_RED + 32;
 };
 
 __device__ __forceinline__ int stride_of(const int NP, const int d) { return d == 0 ? 1 : (d == 1 ? NP : NP * NP); }
@@ -30,6 +43,15 @@ __device__ __forceinline__ int face_node_index(const int d, const int i0, const 
     if (DIM == 1) return 0;
     if (DIM == 2) return d == 0 ? i1 : i0;
     return d == 0 ? (i1 + NP * i2) : (d == 1 ? (i0 + NP * i2) : (i0 + NP * i1));
+}
+// inverse: element-local node index of face node t on face (d, side)
+template <int DIM, int NP>
+__device__ __forceinline__ int node_of_face_node(const int d, const int side, const int t) {
+    const int e = side ? NP - 1 : 0;
+    if (DIM == 1) return e;
+    if (DIM == 2) return d == 0 ? (e + NP * t) : (t + NP * e);
+    const int t0 = t % NP, t1 = t / NP;
+    return d == 0 ? (e + NP * (t0 + NP * t1)) : (d == 1 ? (t0 + NP * (e + NP * t1)) : (t0 + NP * (t1 + NP * e)));
 }
 
 __device__ __forceinline__ double block_max(double v, double* s_red) {
@@ -44,50 +66,67 @@ __device__ __forceinline__ double block_max(double v, double* s_red) {
     return r;
 }
 
-// persson_peraire_shock_indicator.h:96-122 given the two modal energies
-__device__ __forceinline__ double blending_from_energies(const double g0, const double g1, const int NP) {
+// persson_peraire_shock_indicator.h:96-122 given the two modal energies; T and s/T are host constants
+__device__ __forceinline__ double blending_from_energies(const double g0, const double g1, const double T, const double sT) {
     const double n0 = sqrt(g0), n1 = sqrt(g1);
-    double total = 0.0, total_m1 = 0.0, top_m1 = 0.0;
-    if (n0 > 1e-10) { const double e = n0 * n0; total += e; total_m1 += e; }
-    if (n1 > 1e-10) { const double e = n1 * n1; top_m1 += e; total_m1 += e; total += e; }
-    const double E = fmax(0.0 / total, top_m1 / total_m1);
-    const double T = 0.5 * pow(10.0, -1.8 * pow((double)NP, 0.25));
-    const double s = 9.21024;
-    double alpha = 1.0 / (1.0 + exp(-s / T * (E - T)));
+    double total_m1 = 0.0, top_m1 = 0.0;
+    if (n0 > 1e-10) total_m1 += n0 * n0;
+    if (n1 > 1e-10) { const double e = n1 * n1; top_m1 += e; total_m1 += e; }
+    const double E = fmax(0.0, top_m1 / total_m1);
+    double alpha = 1.0 / (1.0 + exp(-sT * (E - T)));
     if (alpha < 1e-3) alpha = 0.0;
     else if (alpha > 0.5) alpha = 0.5;
     return alpha;
 }
 
+__device__ __forceinline__ Prim load_prim(const double* sP, const int nodes, const int n) {
+    Prim o;
+    o.rho = sP[0 * nodes + n];  o.u0 = sP[1 * nodes + n];   o.u1 = sP[2 * nodes + n];    o.u2 = sP[3 * nodes + n];
+    o.beta = sP[4 * nodes + n]; o.lrho = sP[5 * nodes + n]; o.lbeta = sP[6 * nodes + n]; o.p = sP[7 * nodes + n];
+    o.H = sP[8 * nodes + n];    o.lam = sP[9 * nodes + n];  o.ib = sP[10 * nodes + n];
+    return o;
+}
+
 template <int DIM, int NP>
 __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS) stage_kernel(const StageParams P) {
-    using G = Geo<DIM, NP>;
-    constexpr int NN = G::NN, NF = G::NF, EPB = G::EPB;
+    using GEO = Geo<DIM, NP>;
+    constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G, NODES = GEO::NODES, NFACE = GEO::NFACE, NSLOT = GEO::NSLOT;
 
-    __shared__ double sD[NP * NP], sW[NP], sV[NP * NP];
-    __shared__ double sPrim[EPB][8][NN];
-    __shared__ double sA[EPB][NN], sB[EPB][NN];     // indicator scratch
-    __shared__ double sG[EPB][5][NN];               // subcell interface fluxes
-    __shared__ double sAlpha[EPB];
-    __shared__ double sRed[32];
+    extern __shared__ double smem[];
+    double* const sD = smem + GEO::OFF_D;
+    double* const sV = smem + GEO::OFF_V;
+    double* const sW = smem + GEO::OFF_W;
+    double* const sP = smem + GEO::OFF_P;
+    double* const sA = smem + GEO::OFF_A;
+    double* const sB = smem + GEO::OFF_B;
+    double* const sFace = smem + GEO::OFF_FACE;
+    double* const sG = smem + GEO::OFF_G;
+    double* const sAlpha = smem + GEO::OFF_ALPHA;
+    double* const sRed = smem + GEO::OFF_RED;
 
     const int tid = threadIdx.x;
     const int le = tid / NN;
     const int j = tid - le * NN;
     const int i0 = j % NP, i1 = (DIM > 1) ? (j / NP) % NP : 0, i2 = (DIM > 2) ? j / (NP * NP) : 0;
     const int idx[3] = {i0, i1, i2};
-    const int64_t e = P.elem_begin + (int64_t)blockIdx.x * EPB + le;
+    const int64_t e0 = P.elem_begin + (int64_t)blockIdx.x * G;
+    const int64_t e = e0 + le;
     const bool active = e < P.elem_end;
+    const int64_t bl = P.block_begin + blockIdx.x;
+    const int n_face_tasks = P.face_count[bl] * NF;
+    const int32_t* const flist = P.face_list + bl * (G * NFACE);
 
-    for (int i = tid; i < NP * NP; i += blockDim.x) { sD[i] = P.T.D[i]; sV[i] = P.T.V[i]; }
-    for (int i = tid; i < NP; i += blockDim.x) sW[i] = P.T.w[i];
+    for (int i = tid; i < NP * NP; i += NODES) { sD[i] = P.T.D[i]; sV[i] = P.T.V[i]; }
+    for (int i = tid; i < NP; i += NODES) sW[i] = P.T.w[i];
 
     const double gamma = P.gamma, gm1 = P.gamma - 1.0;
+    const double hig = 0.5 / gm1;   // 1 / (2 (gamma - 1))
     const int nc = P.nc;
     double vmax_local = 0.0;
 
     for (int sp = 0; sp < P.nsp; sp++) {
         __syncthreads();   // smem reuse across species (and table load)
+        // ---- node phase: load, primitives, logs, wave speed ----------------------------------------
         const size_t off = ((size_t)e * nc + 5 * sp) * NN + j;
         double q[5] = {1.0, 0.0, 0.0, 0.0, 1.0};
         if (active) {
@@ -95,52 +134,100 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS) stage_kernel(const Stag
             for (int c = 0; c < 5; c++) q[c] = P.u[off + (size_t)c * NN];
         }
         const Prim me = make_prim(q[0], q[1], q[2], q[3], q[4], gamma);
-        sPrim[le][0][j] = me.rho;  sPrim[le][1][j] = me.u0;   sPrim[le][2][j] = me.u1;    sPrim[le][3][j] = me.u2;
-        sPrim[le][4][j] = me.beta; sPrim[le][5][j] = me.lrho; sPrim[le][6][j] = me.lbeta; sPrim[le][7][j] = me.p;
-        sA[le][j] = me.p * me.rho;   // indicator variable, fluid_flux_es_dgsem_operator.h:286-290
+        sP[0 * NODES + tid] = me.rho;  sP[1 * NODES + tid] = me.u0;   sP[2 * NODES + tid] = me.u1;    sP[3 * NODES + tid] = me.u2;
+        sP[4 * NODES + tid] = me.beta; sP[5 * NODES + tid] = me.lrho; sP[6 * NODES + tid] = me.lbeta; sP[7 * NODES + tid] = me.p;
+        sP[8 * NODES + tid] = me.H;    sP[9 * NODES + tid] = me.lam;  sP[10 * NODES + tid] = me.ib;
+        sA[tid] = me.p * me.rho;   // indicator variable, fluid_flux_es_dgsem_operator.h:286-290
         __syncthreads();
+
+        // ---- face phase: compact list of the block's faces; internal ones serve both elements ----------
+        for (int k = tid; k < n_face_tasks; k += NODES) {
+            const int fi = k / NF, t = k - fi * NF;
+            const int32_t desc = flist[fi];
+            const int fle = desc & 255, f = (desc >> 8) & 15, kind = (desc >> 12) & 3, nle = (desc >> 16) & 255;
+            const int d = f >> 1, side = f & 1;
+            const int slot = (fle * NFACE + f) * NF + t;
+            if (kind == kFaceBoundary) {
+                const int v = P.nbr[(size_t)(e0 + fle) * NFACE + f];
+                const size_t offb = (((size_t)(-1 - v) * P.nsp + sp) * 5) * NF + t;
+#pragma unroll
+                for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot] = P.bres[offb + (size_t)c * NF];
+                continue;
+            }
+            const Prim a = load_prim(sP, NODES, fle * NN + node_of_face_node<DIM, NP>(d, side, t));
+            Prim b;
+            if (kind == kFaceInternal) {
+                b = load_prim(sP, NODES, nle * NN + node_of_face_node<DIM, NP>(d, 1 - side, t));
+            } else {
+                const int v = P.nbr[(size_t)(e0 + fle) * NFACE + f];
+                double qn[5];
+                if (kind == kFaceElem) {
+                    const size_t offn = ((size_t)v * nc + 5 * sp) * NN + node_of_face_node<DIM, NP>(d, 1 - side, t);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) qn[c] = P.u[offn + (size_t)c * NN];
+                } else {
+                    const size_t offg = ((size_t)(v - P.n_elems) * (5 * P.nsp) + 5 * sp) * NF + t;
+#pragma unroll
+                    for (int c = 0; c < 5; c++) qn[c] = P.ghost[offg + (size_t)c * NF];
+                }
+                b = make_prim(qn[0], qn[1], qn[2], qn[3], qn[4], gamma);
+            }
+            const double sgn = side ? 1.0 : -1.0;
+            const double cf = P.inv_hw[d];
+            double Fs[5], Fm[5];
+            es_flux_d<DIM>(d, a, b, sgn, hig, Fs);
+            phys_flux_d<DIM>(d, a, Fm);
+#pragma unroll
+            for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot] = cf * (sgn * Fm[c] - Fs[c]);
+            if (kind == kFaceInternal) {
+                // the neighbour's side of the same face: n' = -n, f*(b,a,n') = -f*(a,b,n) exactly
+                double Fn[5];
+                phys_flux_d<DIM>(d, b, Fn);
+                const int slot2 = (nle * NFACE + (f ^ 1)) * NF + t;
+#pragma unroll
+                for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot2] = cf * (Fs[c] - sgn * Fn[c]);
+            }
+        }
 
         // ---- shock indicator: sum-factorised Legendre analysis of p*rho ------------------------------
         {
-            double (*src)[NN] = sA;
-            double (*dstb)[NN] = sB;
+            double* src = sA;
+            double* dstb = sB;
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
                 const int st = stride_of(NP, d);
-                const int base = j - idx[d] * st;
+                const int base = tid - idx[d] * st;
                 double acc = 0.0;
 #pragma unroll
-                for (int m = 0; m < NP; m++) acc += sV[idx[d] * NP + m] * src[le][base + m * st];
-                dstb[le][j] = acc;
+                for (int m = 0; m < NP; m++) acc += sV[idx[d] * NP + m] * src[base + m * st];
+                dstb[tid] = acc;
                 __syncthreads();
-                double (*t)[NN] = src; src = dstb; dstb = t;
+                double* t = src; src = dstb; dstb = t;
             }
             // src holds the modal coefficients c_k at k = (i0,i1,i2)
-            const double ck = src[le][j];
-            const bool shell = (i0 == NP - 1) || (i1 == NP - 1) || (i2 == NP - 1);
+            const double ck = src[tid];
             // two-level fixed-order sums: along i0, then over the remaining NP^(DIM-1) partials
-            dstb[le][j] = ck * ck;
+            dstb[tid] = ck * ck;
             __syncthreads();
             if (i0 == 0) {
                 double g0 = 0.0, g1 = 0.0;
                 const bool row_shell = (i1 == NP - 1) || (i2 == NP - 1);
 #pragma unroll
                 for (int m = 0; m < NP; m++) {
-                    const double v = dstb[le][j + m];
+                    const double v = dstb[tid + m];
                     if (row_shell || m == NP - 1) g1 += v; else g0 += v;
                 }
-                src[le][j] = g0;
-                src[le][j + 1] = g1;   // NP >= 2
+                src[tid] = g0;
+                src[tid + 1] = g1;   // NP >= 2
             }
             __syncthreads();
             if (j == 0) {
                 double g0 = 0.0, g1 = 0.0;
-                for (int r = 0; r < NF; r++) { g0 += src[le][r * NP]; g1 += src[le][r * NP + 1]; }
-                const double al = blending_from_energies(g0, g1, NP);
+                for (int r = 0; r < NF; r++) { g0 += src[tid + r * NP]; g1 += src[tid + r * NP + 1]; }
+                const double al = blending_from_energies(g0, g1, P.ind_T, P.ind_sT);
                 sAlpha[le] = al;
                 if (active && P.alpha_out) P.alpha_out[(size_t)e * P.nsp + sp] = al;
             }
-            (void)shell;
             __syncthreads();
         }
         const double alpha = sAlpha[le];
@@ -152,7 +239,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS) stage_kernel(const Stag
         for (int d = 0; d < DIM; d++) {
             const int st = stride_of(NP, d);
             const int jd = idx[d];
-            const int base = j - jd * st;
+            const int base = tid - jd * st;
             double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int l = 0; l < NP; l++) {
@@ -160,13 +247,10 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS) stage_kernel(const Stag
                 double F[5];
                 if (l == jd) {
                     if (djl == 0.0) continue;    // interior diagonal of the GLL derivative matrix vanishes
-                    phys_flux_d<DIM>(d, me, q[4], F);   // F#(u,u) = f(u)
+                    phys_flux_d<DIM>(d, me, F);   // F#(u,u) = f(u)
                 } else {
-                    const int ql = base + l * st;
-                    Prim o;
-                    o.rho = sPrim[le][0][ql];  o.u0 = sPrim[le][1][ql];   o.u1 = sPrim[le][2][ql];    o.u2 = sPrim[le][3][ql];
-                    o.beta = sPrim[le][4][ql]; o.lrho = sPrim[le][5][ql]; o.lbeta = sPrim[le][6][ql]; o.p = sPrim[le][7][ql];
-                    ec_flux_d<DIM>(d, me, o, gm1, F);
+                    const Prim o = load_prim(sP, NODES, base + l * st);
+                    ec_flux_d<DIM>(d, me, o, hig, F);
                 }
 #pragma unroll
                 for (int c = 0; c < 5; c++) acc[c] += djl * F[c];
@@ -188,24 +272,21 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS) stage_kernel(const Stag
                 const int jd = idx[d];
                 const bool on = active && alpha > 0.0;
                 if (on && jd < NP - 1) {
-                    const int qr = j + st;
-                    Prim o;
-                    o.rho = sPrim[le][0][qr];  o.u0 = sPrim[le][1][qr];   o.u1 = sPrim[le][2][qr];    o.u2 = sPrim[le][3][qr];
-                    o.beta = sPrim[le][4][qr]; o.lrho = sPrim[le][5][qr]; o.lbeta = sPrim[le][6][qr]; o.p = sPrim[le][7][qr];
+                    const Prim o = load_prim(sP, NODES, tid + st);
                     double F[5];
-                    es_flux_d<DIM>(d, me, o, 1.0, gamma, F);
+                    es_flux_d<DIM>(d, me, o, 1.0, hig, F);
 #pragma unroll
-                    for (int c = 0; c < 5; c++) sG[le][c][j] = F[c];
+                    for (int c = 0; c < 5; c++) sG[c * NODES + tid] = F[c];
                 }
                 __syncthreads();
                 if (on) {
                     double Fp[5];
-                    phys_flux_d<DIM>(d, me, q[4], Fp);
+                    phys_flux_d<DIM>(d, me, Fp);
                     const double cf = alpha * P.inv_h[d] / sW[jd];
 #pragma unroll
                     for (int c = 0; c < 5; c++) {
-                        const double left = (jd == 0) ? Fp[c] : sG[le][c][j - st];
-                        const double right = (jd == NP - 1) ? Fp[c] : sG[le][c][j];
+                        const double left = (jd == 0) ? Fp[c] : sG[c * NODES + tid - st];
+                        const double right = (jd == NP - 1) ? Fp[c] : sG[c * NODES + tid];
                         r[c] += cf * (left - right);
                     }
                 }
@@ -213,43 +294,19 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS) stage_kernel(const Stag
             }
         }
 
-        // ---- faces (gather form: this element's side of every face) ------------------------------------
-        if (active) {
+        // ---- collect this node's face contributions (written by the face phase; barriers above order them) --
 #pragma unroll
-            for (int d = 0; d < DIM; d++) {
-                const int st = stride_of(NP, d);
+        for (int d = 0; d < DIM; d++) {
+            const int t = face_node_index<DIM, NP>(d, i0, i1, i2);
+            if (idx[d] == 0) {
+                const int slot = (le * NFACE + 2 * d) * NF + t;
 #pragma unroll
-                for (int side = 0; side < 2; side++) {
-                    if (idx[d] != (side ? NP - 1 : 0)) continue;
-                    const int f = 2 * d + side;
-                    const int v = P.nbr[(size_t)e * (2 * DIM) + f];
-                    const int t = face_node_index<DIM, NP>(d, i0, i1, i2);
-                    if (v >= 0) {
-                        double qn[5];
-                        if (v < P.n_elems) {
-                            const int jn = j + (side ? -(NP - 1) : (NP - 1)) * st;
-                            const size_t offn = ((size_t)v * nc + 5 * sp) * NN + jn;
+                for (int c = 0; c < 5; c++) r[c] += sFace[c * NSLOT + slot];
+            }
+            if (idx[d] == NP - 1) {
+                const int slot = (le * NFACE + 2 * d + 1) * NF + t;
 #pragma unroll
-                            for (int c = 0; c < 5; c++) qn[c] = P.u[offn + (size_t)c * NN];
-                        } else {
-                            const size_t offg = ((size_t)(v - P.n_elems) * (5 * P.nsp) + 5 * sp) * NF + t;
-#pragma unroll
-                            for (int c = 0; c < 5; c++) qn[c] = P.ghost[offg + (size_t)c * NF];
-                        }
-                        const Prim o = make_prim(qn[0], qn[1], qn[2], qn[3], qn[4], gamma);
-                        const double sgn = side ? 1.0 : -1.0;
-                        double Fs[5], Fm[5];
-                        es_flux_d<DIM>(d, me, o, sgn, gamma, Fs);
-                        phys_flux_d<DIM>(d, me, q[4], Fm);
-                        const double cf = P.inv_hw[d];
-#pragma unroll
-                        for (int c = 0; c < 5; c++) r[c] += cf * (sgn * Fm[c] - Fs[c]);
-                    } else {
-                        const size_t offb = (((size_t)(-1 - v) * P.nsp + sp) * 5) * NF + t;
-#pragma unroll
-                        for (int c = 0; c < 5; c++) r[c] += P.bres[offb + (size_t)c * NF];
-                    }
-                }
+                for (int c = 0; c < 5; c++) r[c] += sFace[c * NSLOT + slot];
             }
         }
 
@@ -486,13 +543,6 @@ __global__ void pack_kernel(const double* __restrict__ u, const int32_t* __restr
     }
 }
 
-__global__ void gather_kernel(const double* __restrict__ src, const int64_t* __restrict__ index, double* __restrict__ dst, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[index[i]];
-}
-__global__ void scatter_kernel(const double* __restrict__ src, const int64_t* __restrict__ index, double* __restrict__ dst, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[index[i]] = src[i];
-}
-
 // --------------------------------------------------------------------------------------------------------
 // host-side dispatch over (dim, Np)
 // --------------------------------------------------------------------------------------------------------
@@ -510,14 +560,34 @@ __global__ void scatter_kernel(const double* __restrict__ src, const int64_t* __
         }                                                                                \
     } while (0)
 
+int stage_smem_bytes(int dim, int Np) {
+    int bytes = 0;
+#define CALL(D_, N_) { bytes = Geo<D_, N_>::SMEM_DOUBLES * (int)sizeof(double); }
+    WGPU_DISPATCH(dim, Np, CALL);
+#undef CALL
+    return bytes;
+}
+
+int prepare_kernels(int dim, int Np) {
+    cudaError_t err = cudaSuccess;
+#define CALL(D_, N_)                                                                                         \
+    {                                                                                                        \
+        err = cudaFuncSetAttribute(stage_kernel<D_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                   Geo<D_, N_>::SMEM_DOUBLES * (int)sizeof(double));                         \
+    }
+    WGPU_DISPATCH(dim, Np, CALL);
+#undef CALL
+    return err == cudaSuccess ? 0 : 1;
+}
+
 void launch_stage(int dim, int Np, const StageParams& P, cudaStream_t s) {
     const int64_t n = P.elem_end - P.elem_begin;
     if (n <= 0) return;
-#define CALL(D_, N_)                                                                      \
-    {                                                                                     \
-        using G = Geo<D_, N_>;                                                            \
-        const int64_t blocks = (n + G::EPB - 1) / G::EPB;                                 \
-        stage_kernel<D_, N_><<<(unsigned)blocks, G::THREADS, 0, s>>>(P);                  \
+#define CALL(D_, N_)                                                                                         \
+    {                                                                                                        \
+        using GEO = Geo<D_, N_>;                                                                             \
+        const int64_t blocks = (n + GEO::G - 1) / GEO::G;                                                    \
+        stage_kernel<D_, N_><<<(unsigned)blocks, GEO::THREADS, GEO::SMEM_DOUBLES * sizeof(double), s>>>(P);  \
     }
     WGPU_DISPATCH(dim, Np, CALL);
 #undef CALL
@@ -564,13 +634,6 @@ void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, con
 #define CALL(D_, N_) { pack_kernel<D_, N_><<<148 * 4, 256, 0, s>>>(u, send_elem, send_side, n_send, nc, nsp, sendbuf); }
     WGPU_DISPATCH(dim, Np, CALL);
 #undef CALL
-}
-
-void launch_gather(const double* src, const int64_t* index, double* dst, int64_t n, cudaStream_t s) {
-    if (n > 0) gather_kernel<<<148 * 8, 256, 0, s>>>(src, index, dst, n);
-}
-void launch_scatter(const double* src, const int64_t* index, double* dst, int64_t n, cudaStream_t s) {
-    if (n > 0) scatter_kernel<<<148 * 8, 256, 0, s>>>(src, index, dst, n);
 }
 
 }  // namespace wgpu

@@ -8,6 +8,23 @@ namespace wgpu {
 
 constexpr int kMaxNp = 7;   // fe_degree <= 6 (five_moment.h:116)
 
+__host__ __device__ constexpr int ipow_c(int b, int e) { return e == 0 ? 1 : b * ipow_c(b, e - 1); }
+
+// Elements per thread block ("patch"): the largest power of two that keeps a block at <= 256 nodes (= threads).
+// Faces between two elements of one block are evaluated once and serve both sides.
+__host__ __device__ constexpr int elems_per_block(int dim, int np) {
+    int g = 1;
+    while (2 * g * ipow_c(np, dim) <= 256) g *= 2;
+    return g;
+}
+
+// Per-block face work list entry (built once on the host from the face-pair table):
+//   bits 0-7 local element, 8-11 local face, 12-13 kind, 16-23 local neighbour element (internal faces)
+enum FaceKind { kFaceInternal = 0, kFaceElem = 1, kFaceGhost = 2, kFaceBoundary = 3 };
+__host__ __device__ constexpr int32_t face_desc(int le, int f, int kind, int nle) {
+    return (int32_t)(le | (f << 8) | (kind << 12) | (nle << 16));
+}
+
 // 1-D reference-element tables (Gauss-Lobatto on [0,1]); filled by reference_element.hpp on the host.
 struct ElemTables {
     double D[kMaxNp * kMaxNp];    // D[j*Np+l] = l_l'(x_j)
@@ -19,11 +36,14 @@ struct StageParams {
     const double* u;              // input state  [elem][comp][node]
     double* dst;                  // output state (same layout); dst != u
     const int32_t* nbr;           // [n_elems][2*dim] face-pair table (warpii_gpu.h)
+    const int32_t* face_list;     // [n_blocks][G*2*dim] compact face work list of every block
+    const int32_t* face_count;    // [n_blocks] {entries, of which internal (listed first)}
     const double* ghost;          // [n_ghost][5*nsp][nF] received face traces
     const double* bres;           // [n_bfaces][nsp][5][nF] boundary-face rate contributions (boundary kernel)
     double* alpha_out;            // optional [n_elems][nsp]
     unsigned long long* vmax;     // optional: max transport speed of dst (bits of a non-negative double)
-    int64_t elem_begin, elem_end; // element range of this launch
+    int64_t elem_begin, elem_end; // element range of this launch (elem_begin is a multiple of the block's range start)
+    int64_t block_begin;          // index of the first block of this range in face_list / face_count
     int64_t n_elems;
     int32_t nc, nsp;
     int32_t mode;                 // 0: dst = beta*dst + a*(u + dt*rate); 1: dst = rate
@@ -31,6 +51,7 @@ struct StageParams {
     double inv_h[3];              // 1/h_d
     double inv_hw[3];             // 1/(h_d * w_0): face lifting factor (face JxW / cell JxW on a Cartesian cell)
     double max_eig;               // sqrt(lambda_max(J^-T J^-1)), :487-502 of the reference operator
+    double ind_T, ind_sT;         // shock-indicator threshold T(Np) and gain s/T (persson_peraire_shock_indicator.h:110-112)
     ElemTables T;
 };
 
@@ -53,6 +74,8 @@ struct BoundaryParams {
     double Ig[(kMaxNp + 1) * kMaxNp];   // Ig[q*Np+i] = l_i(xg_q)
 };
 
+int stage_smem_bytes(int dim, int Np);
+int prepare_kernels(int dim, int Np);   // opt in to the dynamic shared memory the stage kernel needs; 0 on success
 void launch_stage(int dim, int Np, const StageParams& P, cudaStream_t s);
 void launch_boundary(int dim, int Np, const BoundaryParams& P, cudaStream_t s);
 // bif_rate[n_boundaries*5] = sum over faces/species of bflux (fixed order); then the stage update of the
@@ -69,7 +92,5 @@ void launch_integral(int dim, int Np, const double* u, int64_t n_elems, int nc, 
 // halo: sendbuf[i][5*nsp][nF] = trace of (send_elem[i], send_side[i])
 void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, const int32_t* send_side,
                  int64_t n_send, int nc, int nsp, double* sendbuf, cudaStream_t s);
-void launch_gather(const double* src, const int64_t* index, double* dst, int64_t n, cudaStream_t s);   // dst[i] = src[index[i]]
-void launch_scatter(const double* src, const int64_t* index, double* dst, int64_t n, cudaStream_t s);  // dst[index[i]] = src[i]
 
 }  // namespace wgpu

@@ -26,7 +26,10 @@ struct BoxDescription {
 
 class BoxMeshTables {
    public:
-    BoxMeshTables(const BoxDescription& box, int rank = 0, int n_ranks = 1) : box_(box), rank_(rank), n_ranks_(n_ranks) {
+    // elems_per_block: warpii_gpu_elems_per_block(dim, fe_degree); owned elements are numbered patch by patch
+    // (patches of that many elements, as cubic as powers of two allow) so that most faces are block-internal.
+    BoxMeshTables(const BoxDescription& box, int rank = 0, int n_ranks = 1, int elems_per_block = 1)
+        : box_(box), rank_(rank), n_ranks_(n_ranks), group_(elems_per_block < 1 ? 1 : elems_per_block) {
         if (box.dim < 1 || box.dim > 3) throw std::invalid_argument("n_dims must be 1, 2, or 3");
         for (int d = 0; d < box.dim; d++) {
             if (box.nx[d] < 1) throw std::invalid_argument("nx must be positive");
@@ -140,6 +143,29 @@ class BoxMeshTables {
             }
             (touches ? iface : inner).push_back(g);
         }
+        // patch-major numbering inside each group: key = (patch index, index within the patch), x fastest in both
+        int shape[3] = {1, 1, 1};
+        for (int g = group_, d = 0; g > 1; g /= 2, d = (d + 1) % box_.dim) shape[d] *= 2;
+        auto patch_key = [&](int64_t g) {
+            int idx[3];
+            elem_multi_index(g, idx);
+            int64_t patch = 0, within = 0;
+            for (int d = box_.dim - 1; d >= 0; d--) {
+                patch = patch * ((box_.nx[d] + shape[d] - 1) / shape[d]) + idx[d] / shape[d];
+                within = within * shape[d] + idx[d] % shape[d];
+            }
+            return patch * group_ + within;
+        };
+        auto sort_by_patch = [&](std::vector<int64_t>& v) {
+            std::vector<std::pair<int64_t, int64_t>> keyed(v.size());
+            for (size_t i = 0; i < v.size(); i++) keyed[i] = {patch_key(v[i]), v[i]};
+            std::sort(keyed.begin(), keyed.end());
+            for (size_t i = 0; i < v.size(); i++) v[i] = keyed[i].second;
+        };
+        if (group_ > 1) {
+            sort_by_patch(iface);
+            sort_by_patch(inner);
+        }
         n_interface_ = (int64_t)iface.size();
         local_to_global_ = iface;
         local_to_global_.insert(local_to_global_.end(), inner.begin(), inner.end());
@@ -219,7 +245,7 @@ class BoxMeshTables {
     }
 
     BoxDescription box_;
-    int rank_, n_ranks_;
+    int rank_, n_ranks_, group_;
     int64_t n_ghost_ = 0, n_interface_ = 0;
     std::vector<int64_t> local_to_global_;
     std::vector<int32_t> face_neighbor_, bf_elem_, bf_side_, bf_id_;

@@ -25,7 +25,8 @@ class FiveMomentGpuSolver {
     FiveMomentGpuSolver(const BoxDescription& box, int fe_degree, int n_species, bool fields_enabled, double gas_gamma,
                         double t_end, int n_boundaries, std::vector<SpeciesBC> bcs, int rank, int n_ranks, int device)
         : t_end_(t_end), fe_degree_(fe_degree), n_species_(n_species), fields_enabled_(fields_enabled), gas_gamma_(gas_gamma),
-          n_boundaries_(n_boundaries), bcs_(std::move(bcs)), device_(device), tables_(box, rank, n_ranks), element_(fe_degree) {
+          n_boundaries_(n_boundaries), bcs_(std::move(bcs)), device_(device),
+          tables_(box, rank, n_ranks, warpii_gpu_elems_per_block(box.dim, fe_degree)), element_(fe_degree) {
         nc_ = 5 * n_species + (fields_enabled ? 8 : 0);
         nn_ = 1;
         for (int d = 0; d < box.dim; d++) nn_ *= fe_degree + 1;

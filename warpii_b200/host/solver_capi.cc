@@ -149,7 +149,7 @@ int warpii_host_advance(warpii_step_fn step, double t_end, warpii_dt_fn recommen
     })
 }
 
-int warpii_host_box_tables(int dim, const int32_t* nx, const int32_t* periodic, int rank, int n_ranks, int64_t counts[6],
+int warpii_host_box_tables(int dim, const int32_t* nx, const int32_t* periodic, int rank, int n_ranks, int elems_per_block, int64_t counts[6],
                            int64_t* local_to_global, int32_t* face_neighbor, int32_t* bf_elem, int32_t* bf_side, int32_t* bf_id,
                            int32_t* peer_rank, int64_t* send_offset, int64_t* recv_offset, int32_t* send_elem, int32_t* send_side,
                            int64_t* ghost_global_elem, int32_t* ghost_side) {
@@ -162,7 +162,7 @@ int warpii_host_box_tables(int dim, const int32_t* nx, const int32_t* periodic, 
             box.right[d] = 1.0;
             box.periodic[d] = periodic ? periodic[d] != 0 : true;
         }
-        BoxMeshTables t(box, rank, n_ranks);
+        BoxMeshTables t(box, rank, n_ranks, elems_per_block);
         counts[0] = t.n_local();
         counts[1] = t.n_interface();
         counts[2] = t.n_ghost_faces();
