@@ -1,0 +1,236 @@
+// Auxiliary kernels of the ES-DGSEM path for sm_100a: boundary faces, boundary-integrated-flux update, stand-alone
+// CFL reduction, global integrals, halo packing.  The hot kernel is in dgsem_stage_kernel.cu.
+#include "dgsem_common.cuh"
+#include "dgsem_physics.cuh"
+
+namespace wgpu {
+
+// --------------------------------------------------------------------------------------------------------
+// Boundary faces (fluid_flux_es_dgsem_operator.h:344-440): Gauss(p+2) face quadrature, ghost state by
+// boundary kind, Lax-Friedrichs flux; one thread per (boundary face, species).  Emits the rate contribution
+// per face node (already divided by the cell's diagonal mass) and the integrated numerical flux.
+// --------------------------------------------------------------------------------------------------------
+template <int DIM, int NP>
+__global__ void boundary_kernel(const BoundaryParams P) {
+    constexpr int NN = ipow_c(NP, DIM), NF = ipow_c(NP, DIM - 1), NG1 = NP + 1, NG = ipow_c(NG1, DIM - 1);
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= P.n_bfaces * P.nsp) return;
+    const int64_t bf = gid / P.nsp;
+    const int sp = (int)(gid - bf * P.nsp);
+    const int e = P.bf_elem[bf], f = P.bf_side[bf], bid = P.bf_id[bf];
+    const int d = f / 2, side = f % 2;
+    const double sgn = side ? 1.0 : -1.0;
+    const int kind = P.bc_kind[sp * P.n_boundaries + bid];
+    const int st = stride_of(NP, d);
+
+    double area = 1.0;
+    for (int a = 0; a < DIM; a++) if (a != d) area *= P.h[a];
+
+    double acc[5][NF];
+#pragma unroll
+    for (int c = 0; c < 5; c++)
+        for (int t = 0; t < NF; t++) acc[c][t] = 0.0;
+    double bsum[5] = {0, 0, 0, 0, 0};
+
+    for (int g = 0; g < NG; g++) {
+        const int g0 = g % NG1, g1 = (g / NG1) % NG1;
+        double wm[5] = {0, 0, 0, 0, 0};
+        for (int t = 0; t < NF; t++) {
+            const int t0 = t % NP, t1 = (t / NP) % NP;
+            double phi = 1.0;
+            if (DIM >= 2) phi *= P.Ig[g0 * NP + t0];
+            if (DIM >= 3) phi *= P.Ig[g1 * NP + t1];
+            // node of face node t: tangential dims in increasing order
+            int id[3] = {0, 0, 0};
+            {
+                int tt[2] = {t0, t1}, k = 0;
+                for (int a = 0; a < DIM; a++) { if (a == d) continue; id[a] = tt[k++]; }
+                id[d] = side ? NP - 1 : 0;
+            }
+            const int node = id[0] + NP * (id[1] + NP * id[2]);
+            const size_t off = ((size_t)e * P.nc + 5 * sp) * NN + node;
+            for (int c = 0; c < 5; c++) wm[c] += phi * P.u[off + (size_t)c * NN];
+        }
+        double wp[5];
+        if (kind == 2) {   // inflow: prescribed conserved state
+            for (int c = 0; c < 5; c++) wp[c] = P.inflow[((size_t)sp * P.n_boundaries + bid) * 5 + c];
+        } else if (kind == 1) {   // (supersonic) outflow
+            for (int c = 0; c < 5; c++) wp[c] = wm[c];
+        } else {   // wall: reflect the normal momentum over the first dim components, zero the rest
+            const double rho_u_dot_n = wm[1 + d] * sgn;
+            wp[0] = wm[0];
+            for (int a = 0; a < 3; a++) wp[a + 1] = (a < DIM) ? wm[a + 1] : 0.0;
+            wp[1 + d] = wm[1 + d] - 2.0 * rho_u_dot_n * sgn;
+            wp[4] = wm[4];
+        }
+        double Fs[5], Fm[5];
+        lf_flux_d<DIM>(d, sgn, wm, wp, P.gamma, Fs, Fm);
+        double wq = 1.0;
+        if (DIM >= 2) wq *= P.wg[g0];
+        if (DIM >= 3) wq *= P.wg[g1];
+        for (int c = 0; c < 5; c++) bsum[c] += Fs[c] * (area * wq);
+        for (int t = 0; t < NF; t++) {
+            const int t0 = t % NP, t1 = (t / NP) % NP;
+            double phi = 1.0;
+            if (DIM >= 2) phi *= P.Ig[g0 * NP + t0];
+            if (DIM >= 3) phi *= P.Ig[g1 * NP + t1];
+            for (int c = 0; c < 5; c++) acc[c][t] += phi * ((Fm[c] - Fs[c]) * wq);
+        }
+    }
+    // divide by the cell mass at the face node: Jdet * w_end * wF_t  (area / Jdet = 1/h_d)
+    for (int t = 0; t < NF; t++) {
+        const int t0 = t % NP, t1 = (t / NP) % NP;
+        double wF = 1.0;
+        if (DIM >= 2) wF *= P.w[t0];
+        if (DIM >= 3) wF *= P.w[t1];
+        const double cf = P.inv_h[d] / (P.w[0] * wF);
+        for (int c = 0; c < 5; c++) P.bres[((size_t)(bf * P.nsp + sp) * 5 + c) * NF + t] = acc[c][t] * cf;
+    }
+    for (int c = 0; c < 5; c++) P.bflux[(size_t)(bf * P.nsp + sp) * 5 + c] = bsum[c];
+    (void)st;
+}
+
+// one block; fixed summation order => deterministic boundary-integrated fluxes
+__global__ void bif_update_kernel(const double* bflux, const int32_t* bf_id, int64_t n_bfaces, int nsp,
+                                  int n_boundaries, double* bif_dst, const double* bif_u, double dt, double a,
+                                  double beta, int mode) {
+    const int i = threadIdx.x;   // i = bid*5 + c
+    if (i >= n_boundaries * 5) return;
+    const int bid = i / 5, c = i % 5;
+    double rate = 0.0;
+    for (int64_t bf = 0; bf < n_bfaces; bf++) {
+        if (bf_id[bf] != bid) continue;
+        for (int sp = 0; sp < nsp; sp++) rate += bflux[(size_t)(bf * nsp + sp) * 5 + c];
+    }
+    if (mode == 1) { bif_dst[i] = rate; return; }
+    double v = beta * bif_dst[i] + (a * dt) * rate;
+    v = v + a * bif_u[i];
+    bif_dst[i] = v;
+}
+
+template <int DIM, int NP>
+__global__ void cfl_kernel(const double* __restrict__ u, int64_t n_elems, int nc, int nsp, double gamma,
+                           double ih0, double ih1, double ih2, double max_eig, unsigned long long* vmax) {
+    constexpr int NN = ipow_c(NP, DIM);
+    __shared__ double sRed[32];
+    const int64_t total = n_elems * nsp * NN;
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % NN);
+        const int64_t es = i / NN;
+        const int sp = (int)(es % nsp);
+        const int64_t e = es / nsp;
+        const size_t off = ((size_t)e * nc + 5 * sp) * NN + j;
+        const double q0 = u[off], q1 = u[off + NN], q2 = u[off + 2 * (size_t)NN], q3 = u[off + 3 * (size_t)NN],
+                     q4 = u[off + 4 * (size_t)NN];
+        const double inv = 1.0 / q0;
+        const double sm = q1 * q1 + q2 * q2 + q3 * q3;
+        const double pr = (gamma - 1.0) * (q4 - sm * (0.5 * inv));
+        double conv = fabs(q1 * inv) * ih0;
+        if (DIM > 1) conv = fmax(conv, fabs(q2 * inv) * ih1);
+        if (DIM > 2) conv = fmax(conv, fabs(q3 * inv) * ih2);
+        m = fmax(m, max_eig * sqrt(gamma * pr * inv) + conv);
+    }
+    m = block_max(m, sRed);
+    if (threadIdx.x == 0) atomicMax(vmax, (unsigned long long)__double_as_longlong(m));
+}
+
+template <int DIM, int NP>
+__global__ void integral_partial_kernel(const double* __restrict__ u, int64_t n_elems, int nc, int species,
+                                        double Jdet, const double* __restrict__ w1, double* partial) {
+    // each block owns a contiguous element range; thread 0..4 = component; fixed order within the block
+    constexpr int NN = ipow_c(NP, DIM);
+    const int c = threadIdx.x;
+    if (c >= 5) return;
+    const int64_t per = (n_elems + gridDim.x - 1) / gridDim.x;
+    const int64_t e0 = blockIdx.x * per, e1 = (e0 + per < n_elems) ? e0 + per : n_elems;
+    double s = 0.0;
+    for (int64_t e = e0; e < e1; e++) {
+        const double* ue = u + ((size_t)e * nc + 5 * species + c) * NN;
+        double cell = 0.0;
+        for (int j = 0; j < NN; j++) {
+            double wj = w1[j % NP];
+            if (DIM > 1) wj *= w1[(j / NP) % NP];
+            if (DIM > 2) wj *= w1[j / (NP * NP)];
+            cell += ue[j] * (Jdet * wj);
+        }
+        s += cell;
+    }
+    partial[(size_t)blockIdx.x * 5 + c] = s;
+}
+__global__ void integral_final_kernel(const double* partial, int n_blocks, double* out) {
+    const int c = threadIdx.x;
+    if (c >= 5) return;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; b++) s += partial[(size_t)b * 5 + c];
+    out[c] = s;
+}
+
+template <int DIM, int NP>
+__global__ void pack_kernel(const double* __restrict__ u, const int32_t* __restrict__ send_elem,
+                            const int32_t* __restrict__ send_side, int64_t n_send, int nc, int nsp,
+                            double* __restrict__ sendbuf) {
+    constexpr int NN = ipow_c(NP, DIM), NF = ipow_c(NP, DIM - 1);
+    const int ncf = 5 * nsp;
+    const int64_t total = n_send * ncf * NF;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % NF);
+        const int c = (int)((i / NF) % ncf);
+        const int64_t s = i / ((int64_t)NF * ncf);
+        const int e = send_elem[s], f = send_side[s];
+        const int d = f / 2, side = f % 2;
+        int id[3] = {0, 0, 0};
+        {
+            int tt[2] = {t % NP, (t / NP) % NP}, k = 0;
+            for (int a = 0; a < DIM; a++) { if (a == d) continue; id[a] = tt[k++]; }
+            id[d] = side ? NP - 1 : 0;
+        }
+        const int node = id[0] + NP * (id[1] + NP * id[2]);
+        sendbuf[i] = u[((size_t)e * nc + c) * NN + node];
+    }
+}
+
+void launch_boundary(int dim, int Np, const BoundaryParams& P, cudaStream_t s) {
+    const int64_t n = P.n_bfaces * P.nsp;
+    if (n <= 0) return;
+#define CALL(D_, N_) { boundary_kernel<D_, N_><<<(unsigned)((n + 63) / 64), 64, 0, s>>>(P); }
+    WGPU_DISPATCH(dim, Np, CALL);
+#undef CALL
+}
+
+void launch_bif_update(const double* bflux, const int32_t* bf_id, int64_t n_bfaces, int nsp, int n_boundaries,
+                       double* bif_dst, const double* bif_u, double dt, double a, double beta, int mode,
+                       cudaStream_t s) {
+    if (n_boundaries <= 0) return;
+    bif_update_kernel<<<1, ((n_boundaries * 5 + 31) / 32) * 32, 0, s>>>(bflux, bf_id, n_bfaces, nsp, n_boundaries,
+                                                                          bif_dst, bif_u, dt, a, beta, mode);
+}
+
+void launch_cfl(int dim, int Np, const double* u, int64_t n_elems, int nc, int nsp, double gamma,
+                const double* inv_h, double max_eig, unsigned long long* vmax, cudaStream_t s) {
+    if (n_elems <= 0) return;
+#define CALL(D_, N_) { cfl_kernel<D_, N_><<<148 * 8, 256, 0, s>>>(u, n_elems, nc, nsp, gamma, inv_h[0], inv_h[1], inv_h[2], max_eig, vmax); }
+    WGPU_DISPATCH(dim, Np, CALL);
+#undef CALL
+}
+
+int integral_blocks(int64_t n_elems) { return (int)(n_elems < 1184 ? (n_elems > 0 ? n_elems : 1) : 1184); }
+
+void launch_integral(int dim, int Np, const double* u, int64_t n_elems, int nc, int species, double Jdet,
+                     const double* w, double* partial, double* out, cudaStream_t s) {
+    const int nb = integral_blocks(n_elems);
+#define CALL(D_, N_) { integral_partial_kernel<D_, N_><<<nb, 32, 0, s>>>(u, n_elems, nc, species, Jdet, w, partial); }
+    WGPU_DISPATCH(dim, Np, CALL);
+#undef CALL
+    integral_final_kernel<<<1, 32, 0, s>>>(partial, nb, out);
+}
+
+void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, const int32_t* send_side,
+                 int64_t n_send, int nc, int nsp, double* sendbuf, cudaStream_t s) {
+    if (n_send <= 0) return;
+#define CALL(D_, N_) { pack_kernel<D_, N_><<<148 * 4, 256, 0, s>>>(u, send_elem, send_side, n_send, nc, nsp, sendbuf); }
+    WGPU_DISPATCH(dim, Np, CALL);
+#undef CALL
+}
+
+}  // namespace wgpu

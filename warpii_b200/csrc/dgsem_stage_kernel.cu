@@ -1,0 +1,427 @@
+// The fused ES-DGSEM stage kernel for sm_100a (FP64 on the CUDA cores).
+//
+// One launch does, for every element, what the reference does in separate global sweeps
+// (fluid_flux_es_dgsem_operator.h:127-214): gather, shock indicator (persson_peraire_shock_indicator.h),
+// split-form volume term (split_form_volume_flux.h), subcell-FV blend (subcell_finite_volume_flux.h), both
+// sides' face lifting (:301-342), inverse diagonal mass, the RK stage update and (optionally) the CFL
+// reduction of the updated state (:450-514): one HBM read of u, one write of dst.
+//
+// Work decomposition inside a block (a patch of G elements, NODES = G * Np^dim threads):
+//   node phase   one thread per node: load the 5 conserved values (coalesced), form the node's primitives,
+//                logarithms and wave speed once, park them in shared memory;
+//   indicator    sum-factorised Legendre analysis of p*rho in shared memory, alpha of all G elements by one warp;
+//   task phase   a flat list of independent tasks spread over all threads:
+//                  - every UNORDERED node pair (j,l) of every pencil once (the two-point flux is symmetric), flux
+//                    into shared memory; the pairs (j,j+1) also carry the dissipation needed by the subcell FV
+//                    scheme when the element's alpha > 0;
+//                  - every face node of the block's compact face list once; faces between two elements of the
+//                    block serve both of them;
+//   node phase 2 gather D-weighted pair fluxes, FV differences and face terms, scale, update, store, CFL.
+#include "dgsem_common.cuh"
+#include "dgsem_physics.cuh"
+
+namespace wgpu {
+
+template <int DIM, int NP>
+struct Geo {
+    static constexpr int NN = ipow_c(NP, DIM);          // nodes per element
+    static constexpr int NF = ipow_c(NP, DIM - 1);      // nodes per face = pencils per direction
+    static constexpr int G = elems_per_block(DIM, NP);  // elements per block
+    static constexpr int NODES = NN * G;                // nodes (= threads) per block
+    static constexpr int NFACE = 2 * DIM;
+    static constexpr int NSLOT = G * NFACE * NF;        // face-node result slots per block
+    static constexpr int NPAIR = NP * (NP - 1) / 2;     // unordered node pairs per pencil; ids 0..NP-2 are (j, j+1)
+    static constexpr int PPE = DIM * NF * NPAIR;        // pair tasks per element
+    static constexpr int NPB = G * PPE;                 // pair tasks per block
+    static constexpr int NADJ = G * DIM * NF * (NP - 1);   // adjacent pairs per block (subcell interfaces)
+    static constexpr int THREADS = NODES;
+    static constexpr int MIN_BLOCKS = (512 / THREADS) > 0 ? (512 / THREADS) : 1;
+    // dynamic shared memory, in doubles
+    static constexpr int OFF_D = 0;
+    static constexpr int OFF_V = OFF_D + NP * NP;
+    static constexpr int OFF_W = OFF_V + NP * NP;
+    static constexpr int OFF_TAB = OFF_W + 8;                   // int tables: pair -> (j,l), (j,l) -> pair
+    static constexpr int OFF_P = OFF_TAB + (NPAIR + NP * NP + 1) / 2 + 1;   // [kPrim][NODES]
+    static constexpr int OFF_PAIR = OFF_P + kPrim * NODES;      // [5][NPB] pair fluxes; indicator scratch aliases it
+    static constexpr int OFF_DISS = OFF_PAIR + 5 * NPB;         // [5][NADJ] dissipation of adjacent pairs
+    static constexpr int OFF_FACE = OFF_DISS + 5 * NADJ;        // [5][NSLOT]
+    static constexpr int OFF_ALPHA = OFF_FACE + 5 * NSLOT;      // [G]
+    static constexpr int OFF_RED = OFF_ALPHA + G;               // [32]
+    static constexpr int SMEM_DOUBLES = OFF_RED + 32;
+    static_assert(5 * NPB >= 2 * NODES, "indicator scratch must fit in the pair-flux area");
+};
+
+// persson_peraire_shock_indicator.h:96-122 given the two modal energies; T and s/T are host constants
+__device__ __forceinline__ double blending_from_energies(const double g0, const double g1, const double T, const double sT) {
+    const double n0 = sqrt(g0), n1 = sqrt(g1);
+    double total_m1 = 0.0, top_m1 = 0.0;
+    if (n0 > 1e-10) total_m1 += n0 * n0;
+    if (n1 > 1e-10) { const double e = n1 * n1; top_m1 += e; total_m1 += e; }
+    const double E = fmax(0.0, top_m1 / total_m1);
+    double alpha = 1.0 / (1.0 + exp(-sT * (E - T)));
+    if (alpha < 1e-3) alpha = 0.0;
+    else if (alpha > 0.5) alpha = 0.5;
+    return alpha;
+}
+
+__device__ __forceinline__ Prim load_prim(const double* sP, const int nodes, const int n) {
+    Prim o;
+    o.rho = sP[0 * nodes + n];  o.u0 = sP[1 * nodes + n];   o.u1 = sP[2 * nodes + n];    o.u2 = sP[3 * nodes + n];
+    o.beta = sP[4 * nodes + n]; o.lrho = sP[5 * nodes + n]; o.lbeta = sP[6 * nodes + n]; o.p = sP[7 * nodes + n];
+    o.H = sP[8 * nodes + n];    o.q2 = sP[9 * nodes + n];   o.lam = sP[10 * nodes + n];  o.ib = sP[11 * nodes + n];
+    return o;
+}
+
+// pencil number (0..NF-1) of node (i0,i1,i2) in direction d == its tangential index
+// first node of pencil pe in direction d
+template <int DIM, int NP>
+__device__ __forceinline__ int pencil_first_node(const int d, const int pe) {
+    if (DIM == 1) return 0;
+    if (DIM == 2) return d == 0 ? NP * pe : pe;
+    const int t0 = pe % NP, t1 = pe / NP;
+    return d == 0 ? NP * (t0 + NP * t1) : (d == 1 ? (t0 + NP * NP * t1) : (t0 + NP * t1));
+}
+
+template <int DIM, int NP>
+__global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCKS) stage_kernel(const StageParams P) {
+    using GEO = Geo<DIM, NP>;
+    constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G, NODES = GEO::NODES, NFACE = GEO::NFACE, NSLOT = GEO::NSLOT;
+    constexpr int NPAIR = GEO::NPAIR, PPE = GEO::PPE, NPB = GEO::NPB, NADJ = GEO::NADJ;
+
+    extern __shared__ double smem[];
+    double* const sD = smem + GEO::OFF_D;
+    double* const sV = smem + GEO::OFF_V;
+    double* const sW = smem + GEO::OFF_W;
+    int* const sPairJL = reinterpret_cast<int*>(smem + GEO::OFF_TAB);   // [NPAIR]: j | l << 8
+    int* const sPairId = sPairJL + NPAIR;                               // [NP*NP]: pair id of (a, b), a != b
+    double* const sP = smem + GEO::OFF_P;
+    double* const sPair = smem + GEO::OFF_PAIR;
+    double* const sA = sPair;            // indicator scratch (dead before the task phase writes pair fluxes)
+    double* const sB = sPair + NODES;
+    double* const sDiss = smem + GEO::OFF_DISS;
+    double* const sFace = smem + GEO::OFF_FACE;
+    double* const sAlpha = smem + GEO::OFF_ALPHA;
+    double* const sRed = smem + GEO::OFF_RED;
+
+    const int tid = threadIdx.x;
+    const int le = tid / NN;
+    const int j = tid - le * NN;
+    const int i0 = j % NP, i1 = (DIM > 1) ? (j / NP) % NP : 0, i2 = (DIM > 2) ? j / (NP * NP) : 0;
+    const int idx[3] = {i0, i1, i2};
+    const int64_t e0 = P.elem_begin + (int64_t)blockIdx.x * G;
+    const int64_t e = e0 + le;
+    const bool active = e < P.elem_end;
+    const int n_active = (int)((P.elem_end - e0) < G ? (P.elem_end - e0) : G);
+    const int64_t bl = P.block_begin + blockIdx.x;
+    const int n_face_tasks = P.face_count[bl] * NF;
+    const int32_t* const flist = P.face_list + bl * (G * NFACE);
+
+    for (int i = tid; i < NP * NP; i += NODES) { sD[i] = P.T.D[i]; sV[i] = P.T.V[i]; }
+    for (int i = tid; i < NP; i += NODES) sW[i] = P.T.w[i];
+    // pair numbering of a pencil: ids 0..NP-2 are the adjacent pairs (j, j+1), the rest follow in (j, l) order
+    for (int i = tid; i < NP * NP; i += NODES) {
+        const int a = i / NP, b = i % NP;
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        int id = 0;
+        if (hi == lo + 1) id = lo;
+        else if (hi > lo + 1) {
+            id = NP - 1;
+            for (int jj = 0; jj < lo; jj++) id += (NP - 2 - jj) > 0 ? (NP - 2 - jj) : 0;
+            id += hi - lo - 2;
+        }
+        sPairId[i] = id;
+        if (a < b) sPairJL[id] = a | (b << 8);
+    }
+
+    const double gamma = P.gamma, gm1 = P.gamma - 1.0;
+    const double hig = 0.5 / gm1;   // 1 / (2 (gamma - 1))
+    const int nc = P.nc;
+    double vmax_local = 0.0;
+
+    for (int sp = 0; sp < P.nsp; sp++) {
+        __syncthreads();   // shared-memory reuse across species (and the table fill above)
+        // ---- node phase: load, primitives, logs, wave speed ----------------------------------------------
+        const size_t off = ((size_t)e * nc + 5 * sp) * NN + j;
+        double q[5] = {1.0, 0.0, 0.0, 0.0, 1.0};
+        if (active) {
+#pragma unroll
+            for (int c = 0; c < 5; c++) q[c] = P.u[off + (size_t)c * NN];
+        }
+        const Prim me = make_prim(q[0], q[1], q[2], q[3], q[4], gamma);
+        sP[0 * NODES + tid] = me.rho;  sP[1 * NODES + tid] = me.u0;  sP[2 * NODES + tid] = me.u1;    sP[3 * NODES + tid] = me.u2;
+        sP[4 * NODES + tid] = me.beta; sP[5 * NODES + tid] = me.lrho; sP[6 * NODES + tid] = me.lbeta; sP[7 * NODES + tid] = me.p;
+        sP[8 * NODES + tid] = me.H;    sP[9 * NODES + tid] = me.q2;  sP[10 * NODES + tid] = me.lam;  sP[11 * NODES + tid] = me.ib;
+        sA[tid] = me.p * me.rho;   // indicator variable, fluid_flux_es_dgsem_operator.h:286-290
+        __syncthreads();
+
+        // ---- shock indicator: sum-factorised Legendre analysis of p*rho --------------------------------------
+        {
+            double* src = sA;
+            double* dstb = sB;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                const int st = stride_of(NP, d);
+                const int base = tid - idx[d] * st;
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m < NP; m++) acc += sV[idx[d] * NP + m] * src[base + m * st];
+                dstb[tid] = acc;
+                __syncthreads();
+                double* t = src; src = dstb; dstb = t;
+            }
+            // src holds the modal coefficients c_k at k = (i0,i1,i2); fixed-order sums: along i0, then the rest
+            const double ck = src[tid];
+            dstb[tid] = ck * ck;
+            __syncthreads();
+            if (i0 == 0) {
+                double g0 = 0.0, g1 = 0.0;
+                const bool row_shell = (i1 == NP - 1) || (i2 == NP - 1);
+#pragma unroll
+                for (int m = 0; m < NP; m++) {
+                    const double v = dstb[tid + m];
+                    if (row_shell || m == NP - 1) g1 += v; else g0 += v;
+                }
+                src[tid] = g0;
+                src[tid + 1] = g1;   // NP >= 2
+            }
+            __syncthreads();
+            if (tid < G) {   // one (part of a) warp evaluates the logistic blend of all elements of the block
+                double g0 = 0.0, g1 = 0.0;
+                const int b0 = tid * NN;
+                for (int r = 0; r < NF; r++) { g0 += src[b0 + r * NP]; g1 += src[b0 + r * NP + 1]; }
+                const double al = blending_from_energies(g0, g1, P.ind_T, P.ind_sT);
+                sAlpha[tid] = al;
+                if (tid < n_active && P.alpha_out) P.alpha_out[(size_t)(e0 + tid) * P.nsp + sp] = al;
+            }
+            __syncthreads();
+        }
+        const double alpha = sAlpha[le];
+
+        // ---- task phase ---------------------------------------------------------------------------------------
+        // (a) unordered node pairs of every pencil: symmetric two-point flux, once
+        for (int k = tid; k < NPB; k += NODES) {
+            const int ple = k / PPE;
+            int rem = k - ple * PPE;
+            const int d = rem / (NF * NPAIR);
+            rem -= d * (NF * NPAIR);
+            const int pe = rem / NPAIR, pid = rem - pe * NPAIR;
+            const int jl = sPairJL[pid];
+            const int st = stride_of(NP, d);
+            const int n0 = ple * NN + pencil_first_node<DIM, NP>(d, pe);
+            const Prim a = load_prim(sP, NODES, n0 + (jl & 255) * st);
+            const Prim b = load_prim(sP, NODES, n0 + (jl >> 8) * st);
+            double F[5], ibl;
+            ec_flux_d<DIM>(d, a, b, hig, F, ibl);
+#pragma unroll
+            for (int c = 0; c < 5; c++) sPair[c * NPB + k] = F[c];
+            if (pid < NP - 1 && sAlpha[ple] > 0.0) {   // subcell interface (j, j+1): dissipation for the FV blend
+                double Dv[5];
+                es_dissipation(a, b, ibl, hig, Dv);
+                const int slot = ((ple * DIM + d) * NF + pe) * (NP - 1) + pid;
+#pragma unroll
+                for (int c = 0; c < 5; c++) sDiss[c * NADJ + slot] = Dv[c];
+            }
+        }
+        // (b) face nodes of the block's compact face list; faces inside the block serve both elements
+        for (int k = tid; k < n_face_tasks; k += NODES) {
+            const int fi = k / NF, t = k - fi * NF;
+            const int32_t desc = flist[fi];
+            const int fle = desc & 255, f = (desc >> 8) & 15, kind = (desc >> 12) & 3, nle = (desc >> 16) & 255;
+            const int d = f >> 1, side = f & 1;
+            const int slot = (fle * NFACE + f) * NF + t;
+            if (kind == kFaceBoundary) {
+                const int v = P.nbr[(size_t)(e0 + fle) * NFACE + f];
+                const size_t offb = (((size_t)(-1 - v) * P.nsp + sp) * 5) * NF + t;
+#pragma unroll
+                for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot] = P.bres[offb + (size_t)c * NF];
+                continue;
+            }
+            const Prim a = load_prim(sP, NODES, fle * NN + node_of_face_node<DIM, NP>(d, side, t));
+            Prim b;
+            if (kind == kFaceInternal) {
+                b = load_prim(sP, NODES, nle * NN + node_of_face_node<DIM, NP>(d, 1 - side, t));
+            } else {
+                const int v = P.nbr[(size_t)(e0 + fle) * NFACE + f];
+                double qn[5];
+                if (kind == kFaceElem) {
+                    const size_t offn = ((size_t)v * nc + 5 * sp) * NN + node_of_face_node<DIM, NP>(d, 1 - side, t);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) qn[c] = P.u[offn + (size_t)c * NN];
+                } else {
+                    const size_t offg = ((size_t)(v - P.n_elems) * (5 * P.nsp) + 5 * sp) * NF + t;
+#pragma unroll
+                    for (int c = 0; c < 5; c++) qn[c] = P.ghost[offg + (size_t)c * NF];
+                }
+                b = make_prim(qn[0], qn[1], qn[2], qn[3], qn[4], gamma);
+            }
+            const double sgn = side ? 1.0 : -1.0;
+            const double cf = P.inv_hw[d];
+            double Fe[5], Dv[5], Fm[5], ibl;
+            ec_flux_d<DIM>(d, a, b, hig, Fe, ibl);
+            es_dissipation(a, b, ibl, hig, Dv);
+            phys_flux_d<DIM>(d, a, Fm);
+            // (f(u_m).n - f*) / (h_d w_0) with f* = sgn F# - D   (fluid_flux_es_dgsem_operator.h:318-333)
+#pragma unroll
+            for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot] = cf * (sgn * (Fm[c] - Fe[c]) + Dv[c]);
+            if (kind == kFaceInternal) {
+                // the neighbour's side of the same face: n' = -n, f*(b,a,n') = -f*(a,b,n) exactly
+                double Fn[5];
+                phys_flux_d<DIM>(d, b, Fn);
+                const int slot2 = (nle * NFACE + (f ^ 1)) * NF + t;
+#pragma unroll
+                for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot2] = cf * (sgn * (Fe[c] - Fn[c]) - Dv[c]);
+            }
+        }
+        __syncthreads();
+
+        // ---- node phase 2: assemble the rate of this node ----------------------------------------------------
+        double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        // split-form volume term: (1-alpha) * sum_d (-2/h_d) sum_l D[j_d][l] F#_d(u_j,u_l)   (split_form_volume_flux.h:68-98)
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            const int jd = idx[d];
+            const int pe = face_node_index<DIM, NP>(d, i0, i1, i2);
+            const int kbase = (le * DIM + d) * (NF * NPAIR) + pe * NPAIR;
+            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            const double djj = sD[jd * NP + jd];
+            if (djj != 0.0) {   // F#(u,u) = f(u); the interior diagonal of the GLL derivative matrix vanishes
+                double Fp[5];
+                phys_flux_d<DIM>(d, me, Fp);
+#pragma unroll
+                for (int c = 0; c < 5; c++) acc[c] = djj * Fp[c];
+            }
+#pragma unroll
+            for (int l = 0; l < NP; l++) {
+                if (l == jd) continue;
+                const double djl = sD[jd * NP + l];
+                const int k = kbase + sPairId[jd * NP + l];
+#pragma unroll
+                for (int c = 0; c < 5; c++) acc[c] += djl * sPair[c * NPB + k];
+            }
+            const double s = -2.0 * P.inv_h[d];
+#pragma unroll
+            for (int c = 0; c < 5; c++) r[c] += s * acc[c];
+        }
+        if (alpha > 0.0) {
+            const double oma = 1.0 - alpha;
+#pragma unroll
+            for (int c = 0; c < 5; c++) r[c] *= oma;
+            // subcell finite-volume blend (subcell_finite_volume_flux.h:75-158): interface flux = F# - D
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                const int jd = idx[d];
+                const int pe = face_node_index<DIM, NP>(d, i0, i1, i2);
+                const int kbase = (le * DIM + d) * (NF * NPAIR) + pe * NPAIR;    // adjacent pairs are ids 0..NP-2
+                const int abase = ((le * DIM + d) * NF + pe) * (NP - 1);
+                double Fp[5];
+                phys_flux_d<DIM>(d, me, Fp);
+                const double cf = alpha * P.inv_h[d] / sW[jd];
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    const double left = (jd == 0) ? Fp[c] : sPair[c * NPB + kbase + jd - 1] - sDiss[c * NADJ + abase + jd - 1];
+                    const double right = (jd == NP - 1) ? Fp[c] : sPair[c * NPB + kbase + jd] - sDiss[c * NADJ + abase + jd];
+                    r[c] += cf * (left - right);
+                }
+            }
+        }
+        // faces
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            const int t = face_node_index<DIM, NP>(d, i0, i1, i2);
+            if (idx[d] == 0) {
+                const int slot = (le * NFACE + 2 * d) * NF + t;
+#pragma unroll
+                for (int c = 0; c < 5; c++) r[c] += sFace[c * NSLOT + slot];
+            }
+            if (idx[d] == NP - 1) {
+                const int slot = (le * NFACE + 2 * d + 1) * NF + t;
+#pragma unroll
+                for (int c = 0; c < 5; c++) r[c] += sFace[c * NSLOT + slot];
+            }
+        }
+
+        // ---- inverse mass is folded into the factors above; stage update ------------------------------------
+        if (active) {
+            double qn[5];
+            if (P.mode == 1) {
+#pragma unroll
+                for (int c = 0; c < 5; c++) qn[c] = r[c];
+            } else if (P.beta == 0.0) {
+#pragma unroll
+                for (int c = 0; c < 5; c++) qn[c] = P.a * (q[c] + P.dt * r[c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 5; c++) qn[c] = P.beta * P.dst[off + (size_t)c * NN] + P.a * (q[c] + P.dt * r[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 5; c++) P.dst[off + (size_t)c * NN] = qn[c];
+
+            if (P.vmax && P.mode == 0) {
+                // compute_cell_transport_speed (:450-514) of the updated state
+                const double inv = rcp_pos(qn[0]);
+                const double sm = qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3];
+                const double pr = gm1 * (qn[4] - sm * (0.5 * inv));
+                double conv = fabs(qn[1] * inv) * P.inv_h[0];
+                if (DIM > 1) conv = fmax(conv, fabs(qn[2] * inv) * P.inv_h[1]);
+                if (DIM > 2) conv = fmax(conv, fabs(qn[3] * inv) * P.inv_h[2]);
+                const double cs = sqrt(gamma * pr * inv);
+                vmax_local = fmax(vmax_local, P.max_eig * cs + conv);
+            }
+        }
+    }
+
+    // ---- field components are carried through unchanged by this operator -----------------
+    if (active && nc > 5 * P.nsp) {
+        for (int c = 5 * P.nsp; c < nc; c++) {
+            const size_t off = ((size_t)e * nc + c) * NN + j;
+            double v;
+            if (P.mode == 1) v = 0.0;
+            else if (P.beta == 0.0) v = P.a * P.u[off];
+            else v = P.beta * P.dst[off] + P.a * P.u[off];
+            P.dst[off] = v;
+        }
+    }
+
+    if (P.vmax && P.mode == 0) {
+        const double m = block_max(vmax_local, sRed);
+        if (tid == 0) atomicMax(P.vmax, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+int stage_smem_bytes(int dim, int Np) {
+    int bytes = 0;
+#define CALL(D_, N_) { bytes = Geo<D_, N_>::SMEM_DOUBLES * (int)sizeof(double); }
+    WGPU_DISPATCH(dim, Np, CALL);
+#undef CALL
+    return bytes;
+}
+
+int prepare_kernels(int dim, int Np) {
+    cudaError_t err = cudaSuccess;
+#define CALL(D_, N_)                                                                                         \
+    {                                                                                                        \
+        err = cudaFuncSetAttribute(stage_kernel<D_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                   Geo<D_, N_>::SMEM_DOUBLES * (int)sizeof(double));                         \
+        if (err == cudaSuccess)                                                                              \
+            err = cudaFuncSetAttribute(stage_kernel<D_, N_>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                       cudaSharedmemCarveoutMaxShared);                                      \
+    }
+    WGPU_DISPATCH(dim, Np, CALL);
+#undef CALL
+    return err == cudaSuccess ? 0 : 1;
+}
+
+void launch_stage(int dim, int Np, const StageParams& P, cudaStream_t s) {
+    const int64_t n = P.elem_end - P.elem_begin;
+    if (n <= 0) return;
+#define CALL(D_, N_)                                                                                         \
+    {                                                                                                        \
+        using GEO = Geo<D_, N_>;                                                                             \
+        const int64_t blocks = (n + GEO::G - 1) / GEO::G;                                                    \
+        stage_kernel<D_, N_><<<(unsigned)blocks, GEO::THREADS, GEO::SMEM_DOUBLES * sizeof(double), s>>>(P);  \
+    }
+    WGPU_DISPATCH(dim, Np, CALL);
+#undef CALL
+}
+
+}  // namespace wgpu
