@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             const Prim a = load_prim(sP, NODES, n0 + (jl & 255) * st);
             const Prim b = load_prim(sP, NODES, n0 + (jl >> 8) * st);
             double F[5], ibl;
-            ec_flux_d<DIM>(d, a, b, hig, F, ibl);
+            ec_flux_d(d, a, b, hig, F, ibl);
 #pragma unroll
             for (int c = 0; c < 5; c++) sPair[c * NPB + k] = F[c];
             if (pid < NP - 1 && sAlpha[ple] > 0.0) {   // subcell interface (j, j+1): dissipation for the FV blend
@@ -257,16 +257,16 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             const double sgn = side ? 1.0 : -1.0;
             const double cf = P.inv_hw[d];
             double Fe[5], Dv[5], Fm[5], ibl;
-            ec_flux_d<DIM>(d, a, b, hig, Fe, ibl);
+            ec_flux_d(d, a, b, hig, Fe, ibl);
             es_dissipation(a, b, ibl, hig, Dv);
-            phys_flux_d<DIM>(d, a, Fm);
+            phys_flux_d(d, a, Fm);
             // (f(u_m).n - f*) / (h_d w_0) with f* = sgn F# - D   (fluid_flux_es_dgsem_operator.h:318-333)
 #pragma unroll
             for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot] = cf * (sgn * (Fm[c] - Fe[c]) + Dv[c]);
             if (kind == kFaceInternal) {
                 // the neighbour's side of the same face: n' = -n, f*(b,a,n') = -f*(a,b,n) exactly
                 double Fn[5];
-                phys_flux_d<DIM>(d, b, Fn);
+                phys_flux_d(d, b, Fn);
                 const int slot2 = (nle * NFACE + (f ^ 1)) * NF + t;
 #pragma unroll
                 for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot2] = cf * (sgn * (Fe[c] - Fn[c]) - Dv[c]);
@@ -286,17 +286,17 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             const double djj = sD[jd * NP + jd];
             if (djj != 0.0) {   // F#(u,u) = f(u); the interior diagonal of the GLL derivative matrix vanishes
                 double Fp[5];
-                phys_flux_d<DIM>(d, me, Fp);
+                phys_flux_d(d, me, Fp);
 #pragma unroll
                 for (int c = 0; c < 5; c++) acc[c] = djj * Fp[c];
             }
 #pragma unroll
             for (int l = 0; l < NP; l++) {
-                if (l == jd) continue;
-                const double djl = sD[jd * NP + l];
+                // branch-free: the l == j_d slot re-reads pair 0 with weight 0 (its term was added above)
+                const double djl = (l == jd) ? 0.0 : sD[jd * NP + l];
                 const int k = kbase + sPairId[jd * NP + l];
 #pragma unroll
-                for (int c = 0; c < 5; c++) acc[c] += djl * sPair[c * NPB + k];
+                for (int c = 0; c < 5; c++) acc[c] = fma(djl, sPair[c * NPB + k], acc[c]);
             }
             const double s = -2.0 * P.inv_h[d];
 #pragma unroll
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 const int kbase = (le * DIM + d) * (NF * NPAIR) + pe * NPAIR;    // adjacent pairs are ids 0..NP-2
                 const int abase = ((le * DIM + d) * NF + pe) * (NP - 1);
                 double Fp[5];
-                phys_flux_d<DIM>(d, me, Fp);
+                phys_flux_d(d, me, Fp);
                 const double cf = alpha * P.inv_h[d] / sW[jd];
 #pragma unroll
                 for (int c = 0; c < 5; c++) {
