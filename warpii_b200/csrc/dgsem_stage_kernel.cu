@@ -8,19 +8,22 @@
 //
 // Work decomposition inside a block (a patch of G elements, NODES = G * Np^dim threads):
 //   node phase   one thread per node: load the 5 conserved values (coalesced), form the node's primitives,
-//                logarithms and wave speed once, park them in shared memory;
+//                logarithms and wave speed once, park them in shared memory (node-major, 16-byte vector access);
 //   indicator    sum-factorised Legendre analysis of p*rho in shared memory, alpha of all G elements by one warp;
-//   task phase   a flat list of independent tasks spread over all threads:
+//   task phase   independent tasks spread over all threads:
 //                  - every UNORDERED node pair (j,l) of every pencil once (the two-point flux is symmetric), flux
-//                    into shared memory; the pairs (j,j+1) also carry the dissipation needed by the subcell FV
-//                    scheme when the element's alpha > 0;
+//                    into shared memory;
 //                  - every face node of the block's compact face list once; faces between two elements of the
 //                    block serve both of them;
-//   node phase 2 gather D-weighted pair fluxes, FV differences and face terms, scale, update, store, CFL.
+//   node phase 2 gather D-weighted pair fluxes, FV differences (only where alpha > 0) and face terms, update,
+//                store, CFL.
 #include "dgsem_common.cuh"
 #include "dgsem_physics.cuh"
 
 namespace wgpu {
+
+constexpr int kPS = 14;   // doubles per node in the shared primitive table (12 used; 14 keeps 16-byte loads conflict-free)
+constexpr int kFS = 6;    // doubles per flux record (5 used)
 
 template <int DIM, int NP>
 struct Geo {
@@ -32,23 +35,22 @@ struct Geo {
     static constexpr int NSLOT = G * NFACE * NF;        // face-node result slots per block
     static constexpr int NPAIR = NP * (NP - 1) / 2;     // unordered node pairs per pencil; ids 0..NP-2 are (j, j+1)
     static constexpr int PPE = DIM * NF * NPAIR;        // pair tasks per element
-    static constexpr int NPB = G * PPE;                 // pair tasks per block
-    static constexpr int NADJ = G * DIM * NF * (NP - 1);   // adjacent pairs per block (subcell interfaces)
+    static constexpr int ROUNDS = (PPE + NN - 1) / NN;  // pair tasks per thread (last round may be partial)
     static constexpr int THREADS = NODES;
     static constexpr int MIN_BLOCKS = (512 / THREADS) > 0 ? (512 / THREADS) : 1;
-    // dynamic shared memory, in doubles
+    // dynamic shared memory, in doubles (every offset even => 16-byte aligned)
+    static constexpr int even(int x) { return (x + 1) & ~1; }
     static constexpr int OFF_D = 0;
-    static constexpr int OFF_V = OFF_D + NP * NP;
-    static constexpr int OFF_W = OFF_V + NP * NP;
-    static constexpr int OFF_TAB = OFF_W + 8;                   // int tables: pair -> (j,l), (j,l) -> pair
-    static constexpr int OFF_P = OFF_TAB + (NPAIR + NP * NP + 1) / 2 + 1;   // [kPrim][NODES]
-    static constexpr int OFF_PAIR = OFF_P + kPrim * NODES;      // [5][NPB] pair fluxes; indicator scratch aliases it
-    static constexpr int OFF_DISS = OFF_PAIR + 5 * NPB;         // [5][NADJ] dissipation of adjacent pairs
-    static constexpr int OFF_FACE = OFF_DISS + 5 * NADJ;        // [5][NSLOT]
-    static constexpr int OFF_ALPHA = OFF_FACE + 5 * NSLOT;      // [G]
-    static constexpr int OFF_RED = OFF_ALPHA + G;               // [32]
+    static constexpr int OFF_V = even(OFF_D + NP * NP);
+    static constexpr int OFF_W = even(OFF_V + NP * NP);
+    static constexpr int OFF_TAB = OFF_W + 8;                               // int tables: pair -> (j,l), (j,l) -> pair
+    static constexpr int OFF_P = even(OFF_TAB + (NPAIR + NP * NP + 1) / 2 + 1);   // [NODES][kPS]
+    static constexpr int OFF_PAIR = OFF_P + kPS * NODES;                    // [G*PPE][kFS]; indicator scratch aliases it
+    static constexpr int OFF_FACE = OFF_PAIR + kFS * G * PPE;               // [NSLOT][kFS]
+    static constexpr int OFF_ALPHA = OFF_FACE + kFS * NSLOT;                // [G]
+    static constexpr int OFF_RED = even(OFF_ALPHA + G);                     // [32]
     static constexpr int SMEM_DOUBLES = OFF_RED + 32;
-    static_assert(5 * NPB >= 2 * NODES, "indicator scratch must fit in the pair-flux area");
+    static_assert(kFS * G * PPE >= 2 * NODES, "indicator scratch must fit in the pair-flux area");
 };
 
 // persson_peraire_shock_indicator.h:96-122 given the two modal energies; T and s/T are host constants
@@ -64,16 +66,46 @@ __device__ __forceinline__ double blending_from_energies(const double g0, const 
     return alpha;
 }
 
-__device__ __forceinline__ Prim load_prim(const double* sP, const int nodes, const int n) {
+// node record: [rho u0 | u1 u2 | beta lrho | lbeta q2 | p H | lam ib | - -]
+__device__ __forceinline__ void store_prim(double* sP, const int n, const Prim& P) {
+    double2* r = reinterpret_cast<double2*>(sP + n * kPS);
+    r[0] = make_double2(P.rho, P.u0);
+    r[1] = make_double2(P.u1, P.u2);
+    r[2] = make_double2(P.beta, P.lrho);
+    r[3] = make_double2(P.lbeta, P.q2);
+    r[4] = make_double2(P.p, P.H);
+    r[5] = make_double2(P.lam, P.ib);
+}
+// the 8 fields the entropy-conserving flux needs
+__device__ __forceinline__ Prim load_prim_ec(const double* sP, const int n) {
+    const double2* r = reinterpret_cast<const double2*>(sP + n * kPS);
+    const double2 a = r[0], b = r[1], c = r[2], d = r[3];
     Prim o;
-    o.rho = sP[0 * nodes + n];  o.u0 = sP[1 * nodes + n];   o.u1 = sP[2 * nodes + n];    o.u2 = sP[3 * nodes + n];
-    o.beta = sP[4 * nodes + n]; o.lrho = sP[5 * nodes + n]; o.lbeta = sP[6 * nodes + n]; o.p = sP[7 * nodes + n];
-    o.H = sP[8 * nodes + n];    o.q2 = sP[9 * nodes + n];   o.lam = sP[10 * nodes + n];  o.ib = sP[11 * nodes + n];
+    o.rho = a.x; o.u0 = a.y; o.u1 = b.x; o.u2 = b.y; o.beta = c.x; o.lrho = c.y; o.lbeta = d.x; o.q2 = d.y;
+    o.p = 0.0; o.H = 0.0; o.lam = 0.0; o.ib = 0.0;
     return o;
 }
+__device__ __forceinline__ Prim load_prim(const double* sP, const int n) {
+    const double2* r = reinterpret_cast<const double2*>(sP + n * kPS);
+    const double2 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5];
+    Prim o;
+    o.rho = a.x; o.u0 = a.y; o.u1 = b.x; o.u2 = b.y; o.beta = c.x; o.lrho = c.y; o.lbeta = d.x; o.q2 = d.y;
+    o.p = e.x; o.H = e.y; o.lam = f.x; o.ib = f.y;
+    return o;
+}
+__device__ __forceinline__ void store_flux(double* rec, const double F[5]) {
+    double2* r = reinterpret_cast<double2*>(rec);
+    r[0] = make_double2(F[0], F[1]);
+    r[1] = make_double2(F[2], F[3]);
+    rec[4] = F[4];
+}
+__device__ __forceinline__ void load_flux(const double* rec, double F[5]) {
+    const double2* r = reinterpret_cast<const double2*>(rec);
+    const double2 a = r[0], b = r[1];
+    F[0] = a.x; F[1] = a.y; F[2] = b.x; F[3] = b.y; F[4] = rec[4];
+}
 
-// pencil number (0..NF-1) of node (i0,i1,i2) in direction d == its tangential index
-// first node of pencil pe in direction d
+// first node of pencil pe (= tangential index) in direction d
 template <int DIM, int NP>
 __device__ __forceinline__ int pencil_first_node(const int d, const int pe) {
     if (DIM == 1) return 0;
@@ -85,10 +117,10 @@ __device__ __forceinline__ int pencil_first_node(const int d, const int pe) {
 template <int DIM, int NP>
 __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCKS) stage_kernel(const StageParams P) {
     using GEO = Geo<DIM, NP>;
-    constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G, NODES = GEO::NODES, NFACE = GEO::NFACE, NSLOT = GEO::NSLOT;
-    constexpr int NPAIR = GEO::NPAIR, PPE = GEO::PPE, NPB = GEO::NPB, NADJ = GEO::NADJ;
+    constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G, NODES = GEO::NODES, NFACE = GEO::NFACE;
+    constexpr int NPAIR = GEO::NPAIR, PPE = GEO::PPE, ROUNDS = GEO::ROUNDS;
 
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     double* const sD = smem + GEO::OFF_D;
     double* const sV = smem + GEO::OFF_V;
     double* const sW = smem + GEO::OFF_W;
@@ -98,7 +130,6 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
     double* const sPair = smem + GEO::OFF_PAIR;
     double* const sA = sPair;            // indicator scratch (dead before the task phase writes pair fluxes)
     double* const sB = sPair + NODES;
-    double* const sDiss = smem + GEO::OFF_DISS;
     double* const sFace = smem + GEO::OFF_FACE;
     double* const sAlpha = smem + GEO::OFF_ALPHA;
     double* const sRed = smem + GEO::OFF_RED;
@@ -147,11 +178,11 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
 #pragma unroll
             for (int c = 0; c < 5; c++) q[c] = P.u[off + (size_t)c * NN];
         }
-        const Prim me = make_prim(q[0], q[1], q[2], q[3], q[4], gamma);
-        sP[0 * NODES + tid] = me.rho;  sP[1 * NODES + tid] = me.u0;  sP[2 * NODES + tid] = me.u1;    sP[3 * NODES + tid] = me.u2;
-        sP[4 * NODES + tid] = me.beta; sP[5 * NODES + tid] = me.lrho; sP[6 * NODES + tid] = me.lbeta; sP[7 * NODES + tid] = me.p;
-        sP[8 * NODES + tid] = me.H;    sP[9 * NODES + tid] = me.q2;  sP[10 * NODES + tid] = me.lam;  sP[11 * NODES + tid] = me.ib;
-        sA[tid] = me.p * me.rho;   // indicator variable, fluid_flux_es_dgsem_operator.h:286-290
+        {
+            const Prim me = make_prim(q[0], q[1], q[2], q[3], q[4], gamma);
+            store_prim(sP, tid, me);
+            sA[tid] = me.p * me.rho;   // indicator variable, fluid_flux_es_dgsem_operator.h:286-290
+        }
         __syncthreads();
 
         // ---- shock indicator: sum-factorised Legendre analysis of p*rho --------------------------------------
@@ -195,31 +226,24 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             }
             __syncthreads();
         }
-        const double alpha = sAlpha[le];
 
         // ---- task phase ---------------------------------------------------------------------------------------
-        // (a) unordered node pairs of every pencil: symmetric two-point flux, once
-        for (int k = tid; k < NPB; k += NODES) {
-            const int ple = k / PPE;
-            int rem = k - ple * PPE;
-            const int d = rem / (NF * NPAIR);
-            rem -= d * (NF * NPAIR);
-            const int pe = rem / NPAIR, pid = rem - pe * NPAIR;
-            const int jl = sPairJL[pid];
-            const int st = stride_of(NP, d);
-            const int n0 = ple * NN + pencil_first_node<DIM, NP>(d, pe);
-            const Prim a = load_prim(sP, NODES, n0 + (jl & 255) * st);
-            const Prim b = load_prim(sP, NODES, n0 + (jl >> 8) * st);
-            double F[5], ibl;
-            ec_flux_d(d, a, b, hig, F, ibl);
+        // (a) unordered node pairs of the pencils of this thread's element: symmetric two-point flux, once
 #pragma unroll
-            for (int c = 0; c < 5; c++) sPair[c * NPB + k] = F[c];
-            if (pid < NP - 1 && sAlpha[ple] > 0.0) {   // subcell interface (j, j+1): dissipation for the FV blend
-                double Dv[5];
-                es_dissipation(a, b, ibl, hig, Dv);
-                const int slot = ((ple * DIM + d) * NF + pe) * (NP - 1) + pid;
-#pragma unroll
-                for (int c = 0; c < 5; c++) sDiss[c * NADJ + slot] = Dv[c];
+        for (int r = 0; r < ROUNDS; r++) {
+            const int p = r * NN + j;
+            if (PPE % NN == 0 || p < PPE) {
+                const int d = p / (NF * NPAIR);
+                const int rem = p - d * (NF * NPAIR);
+                const int pe = rem / NPAIR, pid = rem - pe * NPAIR;
+                const int jl = sPairJL[pid];
+                const int st = stride_of(NP, d);
+                const int n0 = le * NN + pencil_first_node<DIM, NP>(d, pe);
+                const Prim a = load_prim_ec(sP, n0 + (jl & 255) * st);
+                const Prim b = load_prim_ec(sP, n0 + (jl >> 8) * st);
+                double F[5], ibl;
+                ec_flux_d(d, a, b, hig, F, ibl);
+                store_flux(sPair + (le * PPE + p) * kFS, F);
             }
         }
         // (b) face nodes of the block's compact face list; faces inside the block serve both elements
@@ -228,18 +252,20 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             const int32_t desc = flist[fi];
             const int fle = desc & 255, f = (desc >> 8) & 15, kind = (desc >> 12) & 3, nle = (desc >> 16) & 255;
             const int d = f >> 1, side = f & 1;
-            const int slot = (fle * NFACE + f) * NF + t;
+            double* const rec = sFace + ((fle * NFACE + f) * NF + t) * kFS;
             if (kind == kFaceBoundary) {
                 const int v = P.nbr[(size_t)(e0 + fle) * NFACE + f];
                 const size_t offb = (((size_t)(-1 - v) * P.nsp + sp) * 5) * NF + t;
+                double Fb[5];
 #pragma unroll
-                for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot] = P.bres[offb + (size_t)c * NF];
+                for (int c = 0; c < 5; c++) Fb[c] = P.bres[offb + (size_t)c * NF];
+                store_flux(rec, Fb);
                 continue;
             }
-            const Prim a = load_prim(sP, NODES, fle * NN + node_of_face_node<DIM, NP>(d, side, t));
+            const Prim a = load_prim(sP, fle * NN + node_of_face_node<DIM, NP>(d, side, t));
             Prim b;
             if (kind == kFaceInternal) {
-                b = load_prim(sP, NODES, nle * NN + node_of_face_node<DIM, NP>(d, 1 - side, t));
+                b = load_prim(sP, nle * NN + node_of_face_node<DIM, NP>(d, 1 - side, t));
             } else {
                 const int v = P.nbr[(size_t)(e0 + fle) * NFACE + f];
                 double qn[5];
@@ -261,30 +287,34 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             es_dissipation(a, b, ibl, hig, Dv);
             phys_flux_d(d, a, Fm);
             // (f(u_m).n - f*) / (h_d w_0) with f* = sgn F# - D   (fluid_flux_es_dgsem_operator.h:318-333)
+            double R[5];
 #pragma unroll
-            for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot] = cf * (sgn * (Fm[c] - Fe[c]) + Dv[c]);
+            for (int c = 0; c < 5; c++) R[c] = cf * (sgn * (Fm[c] - Fe[c]) + Dv[c]);
+            store_flux(rec, R);
             if (kind == kFaceInternal) {
                 // the neighbour's side of the same face: n' = -n, f*(b,a,n') = -f*(a,b,n) exactly
                 double Fn[5];
                 phys_flux_d(d, b, Fn);
-                const int slot2 = (nle * NFACE + (f ^ 1)) * NF + t;
 #pragma unroll
-                for (int c = 0; c < 5; c++) sFace[c * NSLOT + slot2] = cf * (sgn * (Fe[c] - Fn[c]) - Dv[c]);
+                for (int c = 0; c < 5; c++) R[c] = cf * (sgn * (Fe[c] - Fn[c]) - Dv[c]);
+                store_flux(sFace + ((nle * NFACE + (f ^ 1)) * NF + t) * kFS, R);
             }
         }
         __syncthreads();
 
         // ---- node phase 2: assemble the rate of this node ----------------------------------------------------
+        const double alpha = sAlpha[le];
+        const Prim me = load_prim(sP, tid);
         double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         // split-form volume term: (1-alpha) * sum_d (-2/h_d) sum_l D[j_d][l] F#_d(u_j,u_l)   (split_form_volume_flux.h:68-98)
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
             const int jd = idx[d];
             const int pe = face_node_index<DIM, NP>(d, i0, i1, i2);
-            const int kbase = (le * DIM + d) * (NF * NPAIR) + pe * NPAIR;
-            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            const double djj = sD[jd * NP + jd];
-            if (djj != 0.0) {   // F#(u,u) = f(u); the interior diagonal of the GLL derivative matrix vanishes
+            const double* const prec = sPair + (le * PPE + d * (NF * NPAIR) + pe * NPAIR) * kFS;
+            double acc[5];
+            {   // F#(u,u) = f(u); its weight D[j][j] vanishes except at the two end nodes
+                const double djj = sD[jd * NP + jd];
                 double Fp[5];
                 phys_flux_d(d, me, Fp);
 #pragma unroll
@@ -294,49 +324,65 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             for (int l = 0; l < NP; l++) {
                 // branch-free: the l == j_d slot re-reads pair 0 with weight 0 (its term was added above)
                 const double djl = (l == jd) ? 0.0 : sD[jd * NP + l];
-                const int k = kbase + sPairId[jd * NP + l];
+                double F[5];
+                load_flux(prec + sPairId[jd * NP + l] * kFS, F);
 #pragma unroll
-                for (int c = 0; c < 5; c++) acc[c] = fma(djl, sPair[c * NPB + k], acc[c]);
+                for (int c = 0; c < 5; c++) acc[c] = fma(djl, F[c], acc[c]);
             }
             const double s = -2.0 * P.inv_h[d];
 #pragma unroll
-            for (int c = 0; c < 5; c++) r[c] += s * acc[c];
+            for (int c = 0; c < 5; c++) r[c] = fma(s, acc[c], r[c]);
         }
         if (alpha > 0.0) {
             const double oma = 1.0 - alpha;
 #pragma unroll
             for (int c = 0; c < 5; c++) r[c] *= oma;
-            // subcell finite-volume blend (subcell_finite_volume_flux.h:75-158): interface flux = F# - D
+            // subcell finite-volume blend (subcell_finite_volume_flux.h:75-158).  Interface flux between subcells
+            // i and i+1 = F#(u_i,u_{i+1}) - D(u_i,u_{i+1}); F# is the pair flux already in shared memory (adjacent
+            // pairs are ids 0..NP-2), the dissipation is formed here because few elements need it.
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
                 const int jd = idx[d];
+                const int st = stride_of(NP, d);
                 const int pe = face_node_index<DIM, NP>(d, i0, i1, i2);
-                const int kbase = (le * DIM + d) * (NF * NPAIR) + pe * NPAIR;    // adjacent pairs are ids 0..NP-2
-                const int abase = ((le * DIM + d) * NF + pe) * (NP - 1);
-                double Fp[5];
+                const double* const prec = sPair + (le * PPE + d * (NF * NPAIR) + pe * NPAIR) * kFS;
+                double Fp[5], left[5], right[5];
                 phys_flux_d(d, me, Fp);
+#pragma unroll
+                for (int c = 0; c < 5; c++) { left[c] = Fp[c]; right[c] = Fp[c]; }
+                if (jd > 0) {
+                    const Prim o = load_prim(sP, tid - st);
+                    double Fd[5], Dv[5], ibl;
+                    ec_flux_d(d, o, me, hig, Fd, ibl);   // only for 1/beta_ln; the flux itself comes from the table
+                    es_dissipation(o, me, ibl, hig, Dv);
+                    load_flux(prec + (jd - 1) * kFS, Fd);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) left[c] = Fd[c] - Dv[c];
+                }
+                if (jd < NP - 1) {
+                    const Prim o = load_prim(sP, tid + st);
+                    double Fd[5], Dv[5], ibl;
+                    ec_flux_d(d, me, o, hig, Fd, ibl);
+                    es_dissipation(me, o, ibl, hig, Dv);
+                    load_flux(prec + jd * kFS, Fd);
+#pragma unroll
+                    for (int c = 0; c < 5; c++) right[c] = Fd[c] - Dv[c];
+                }
                 const double cf = alpha * P.inv_h[d] / sW[jd];
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
-                    const double left = (jd == 0) ? Fp[c] : sPair[c * NPB + kbase + jd - 1] - sDiss[c * NADJ + abase + jd - 1];
-                    const double right = (jd == NP - 1) ? Fp[c] : sPair[c * NPB + kbase + jd] - sDiss[c * NADJ + abase + jd];
-                    r[c] += cf * (left - right);
-                }
+                for (int c = 0; c < 5; c++) r[c] += cf * (left[c] - right[c]);
             }
         }
         // faces
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
             const int t = face_node_index<DIM, NP>(d, i0, i1, i2);
-            if (idx[d] == 0) {
-                const int slot = (le * NFACE + 2 * d) * NF + t;
+            if (idx[d] == 0 || idx[d] == NP - 1) {   // NP >= 2: a node is on at most one face per direction
+                const int f = 2 * d + (idx[d] == 0 ? 0 : 1);
+                double F[5];
+                load_flux(sFace + ((le * NFACE + f) * NF + t) * kFS, F);
 #pragma unroll
-                for (int c = 0; c < 5; c++) r[c] += sFace[c * NSLOT + slot];
-            }
-            if (idx[d] == NP - 1) {
-                const int slot = (le * NFACE + 2 * d + 1) * NF + t;
-#pragma unroll
-                for (int c = 0; c < 5; c++) r[c] += sFace[c * NSLOT + slot];
+                for (int c = 0; c < 5; c++) r[c] += F[c];
             }
         }
 
