@@ -159,6 +159,15 @@ int warpii_gpu_stage_timing(warpii_gpu_ctx* ctx, int enable, double* ms_total, i
 /* the CUDA stream (cudaStream_t) all work of this context is issued on */
 int warpii_gpu_stream(warpii_gpu_ctx* ctx, void** stream_out);
 
+/* -- point physics on the device, for known-answer tests ------------------------------------------------
+ * For n state pairs (qa[i], qb[i]) of 5 conserved values: the direction-d entropy-conserving flux
+ * (euler_CH_EC_flux, euler.h:186-228) and the entropy-dissipating flux across a face with normal +e_d
+ * (euler_CH_entropy_dissipating_flux, :232-284), evaluated by the same device functions the stage kernel uses.
+ * prim_out (nullable) receives the 12 per-node quantities of qa[i]: rho,u0,u1,u2,beta,log rho,log beta,|u|^2,p,E+p,
+ * |u|+c, 1/beta.  Needs no context. */
+int warpii_gpu_point_fluxes(int device, int n, const double* qa, const double* qb, int d, double gamma,
+                            double* ec_out, double* es_out, double* prim_out);
+
 #ifdef __cplusplus
 }
 #endif

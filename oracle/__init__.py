@@ -24,7 +24,7 @@ _up = C.POINTER(C.c_uint)
 def build(force=False):
     """Compile the oracle (and oracle/_ref when /root/reference exists)."""
     if force or not os.path.exists(_LIB_PATH) or (
-            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "dgsem_oracle.cc"))):
+            os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("dgsem_oracle.cc", "det_log.h"))):
         subprocess.check_call(["make", "-C", _HERE, "_build/liboracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir("/root/reference/src"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
@@ -49,6 +49,9 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.orc_ln_avg.restype = C.c_double
         L.orc_ln_avg.argtypes = [C.c_double, C.c_double]
+        L.orc_det_log.restype = C.c_double
+        L.orc_det_log.argtypes = [C.c_double]
+        L.orc_set_log_impl.argtypes = [C.c_int]
         L.orc_pressure.restype = C.c_double
         L.orc_pressure.argtypes = [_dp, C.c_double]
         L.orc_euler_flux.argtypes = [C.c_int, _dp, C.c_double, _dp]
@@ -127,6 +130,15 @@ def advance(step, t_end, recommend_dt, callbacks):
 
 
 # ---- point physics helpers -------------------------------------------------
+def set_log_impl(deterministic):
+    """1: oracle/det_log.h inside ln_avg (default), 0: libm's log like the reference."""
+    lib().orc_set_log_impl(int(bool(deterministic)))
+
+
+def det_log(x):
+    return lib().orc_det_log(float(x))
+
+
 def ln_avg(a, b):
     return lib().orc_ln_avg(a, b)
 

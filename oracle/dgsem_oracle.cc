@@ -9,6 +9,7 @@
 // -ffp-contract=off so no FMA contraction sneaks in.
 // ============================================================================
 #include "dgsem_oracle.h"
+#include "det_log.h"
 
 #include <algorithm>
 #include <cmath>
@@ -27,9 +28,14 @@ namespace {
 // Point physics.  State q = [rho, mx, my, mz, E] (always three momenta).
 // ---------------------------------------------------------------------------
 
+// The reference calls std::log here.  1 = the deterministic logarithm of oracle/det_log.h (default: it is what makes
+// a 1e-12 comparison with another platform meaningful, see that header), 0 = this platform's libm.
+int g_log_impl = 1;
+inline double olog(double x) { return g_log_impl ? detlog::det_log(x) : std::log(x); }
+
 // src/five_moment/euler.h:118-125
 inline double ln_avg(double a, double b) {
-    double diff_log = std::fabs(std::log(b) - std::log(a));
+    double diff_log = std::fabs(olog(b) - olog(a));
     const double C = 1e6;
     double lhs = std::fmax(C * std::fabs(b - a), b + a);
     double denom = std::fmax(C * diff_log, 2.0);
@@ -840,6 +846,9 @@ void advance(const std::function<bool(double, double)>& step, double t_end, cons
 extern "C" {
 
 double orc_ln_avg(double a, double b) { return ln_avg(a, b); }
+void orc_set_log_impl(int deterministic) { g_log_impl = deterministic ? 1 : 0; }
+int orc_get_log_impl(void) { return g_log_impl; }
+double orc_det_log(double x) { return detlog::det_log(x); }
 double orc_pressure(const double q[5], double gamma) { return pressure(q, gamma); }
 
 #define DIM_DISPATCH(dim, CALL1, CALL2, CALL3) \

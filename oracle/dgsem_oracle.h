@@ -31,6 +31,10 @@ extern "C" {
 
 // ---- point physics (reference: src/five_moment/euler.h) --------------------
 double orc_ln_avg(double a, double b);                                   // euler.h:118-125
+// logarithm used inside ln_avg: 1 = oracle/det_log.h (default; bit-identical to the device's), 0 = libm like the reference
+void orc_set_log_impl(int deterministic);
+int orc_get_log_impl(void);
+double orc_det_log(double x);
 double orc_pressure(const double q[5], double gamma);                    // euler.h:32-44
 void orc_euler_flux(int dim, const double q[5], double gamma, double* F /*[5][dim]*/);   // :46-63
 void orc_lf_flux(int dim, const double qin[5], const double qout[5], const double* n,

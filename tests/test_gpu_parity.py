@@ -61,6 +61,12 @@ RHS_CASES = [
     (3, 4, [4, 4, 4], [0.0, -5.0, -5.0], [10.0, 5.0, 5.0], cases.isentropic_vortex(), 1.4),
     (3, 2, [6, 6, 3], [0.0, 0.0, 0.0], [1.0, 2.0, 1.0], cases.smooth_blob_3d(0.1), 1.4),
     (3, 6, [2, 2, 2], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], cases.smooth_blob_3d(0.1), 5.0 / 3.0),
+    # fine meshes: neighbouring states nearly equal => ln_avg and the flux differences are at their worst conditioning
+    # (h of the 512^2 / 128^3 BASELINE configs is reached at 128^2 / 32^3 on a quarter / a 64th of the domain)
+    (2, 3, [128, 128], [0.0, -5.0], [10.0, 5.0], cases.isentropic_vortex(), 1.4),
+    (2, 3, [128, 128], [2.5, -1.25], [5.0, 1.25], cases.isentropic_vortex(), 1.4),
+    (3, 4, [8, 8, 8], [4.0, -0.5, -0.5], [5.0, 0.5, 0.5], cases.isentropic_vortex(), 1.4),
+    (3, 3, [16, 16, 16], [0.0, -5.0, -5.0], [10.0, 5.0, 5.0], cases.isentropic_vortex(), 1.4),
 ]
 
 

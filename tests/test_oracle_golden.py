@@ -416,3 +416,51 @@ def test_freestream_2d_smoke():
     o.solve(u, 0.1, max_steps=30)
     assert np.isfinite(u).all()
     assert np.allclose(o.global_integral(u)[:3], ic[:3], atol=1e-12)
+
+
+# --------------------------------------------------------------------------- the logarithm inside ln_avg
+def test_det_log_is_a_faithful_logarithm():
+    """oracle/det_log.h (== warpii_b200/csrc/det_log.cuh) is within 1 ulp of libm everywhere it is used."""
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(0.05, 5, 20000), np.exp(rng.uniform(-30, 30, 10000)),
+                         1 + rng.uniform(-1e-3, 1e-3, 10000), [1.0, 0.5, 2.0, 1e-300, 1e300]])
+    d = np.array([oracle.det_log(x) for x in xs])
+    ref = np.log(xs.astype(np.longdouble))
+    ulp = np.spacing(np.abs(np.log(xs)))
+    ulp[ulp == 0] = np.spacing(1e-300)
+    assert np.max(np.abs((d - ref).astype(np.float64)) / ulp) < 1.0
+    assert oracle.det_log(1.0) == 0.0
+    # special arguments are delegated to libm
+    assert np.isnan(oracle.det_log(-1.0)) and oracle.det_log(0.0) == -np.inf
+
+
+@pytest.mark.parametrize("det", [0, 1])
+def test_goldens_hold_with_either_logarithm(det):
+    """The reference's known-answer vectors do not depend on which faithful log is used."""
+    oracle.set_log_impl(det)
+    try:
+        test_ln_avg_goldens()
+        test_ec_flux_goldens()
+        test_es_flux_goldens()
+    finally:
+        oracle.set_log_impl(1)
+
+
+def test_libm_sensitivity():
+    """Why the parity runs pin the logarithm: on a fine mesh the reference algorithm's RHS moves by far more than
+    1e-12 when log() changes in the last bit (here: glibc's log vs det_log, which agree to 1 ulp).  The energy
+    equation, fed by ln_avg(beta), is the most sensitive."""
+    g = 1.4
+    o = Oracle(2, 3, [128, 128], [2.5, -1.25], [5.0, 1.25], gamma=g, threads=8)   # h of BASELINE config 2
+    ic = lambda xyz: __import__("dgsem_cases").isentropic_vortex(g)(xyz)
+    u = o.project(ic)
+    try:
+        oracle.set_log_impl(0)
+        r_libm, _ = o.rhs(u)
+        oracle.set_log_impl(1)
+        r_det, _ = o.rhs(u)
+    finally:
+        oracle.set_log_impl(1)
+    rel = np.array([np.linalg.norm(r_libm[:, c] - r_det[:, c]) / max(np.linalg.norm(r_det[:, c]), 1e-300) for c in (0, 1, 2, 4)])
+    assert rel.max() > 1e-12, rel          # the two CPU runs differ by more than the GPU tolerance ...
+    assert rel.max() < 1e-7, rel           # ... but only by amplified last-bit noise

@@ -19,7 +19,8 @@ class WarpiiGpuError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libwarpii_b200.so")
+    # WARPII_B200_LIB selects another BUILD of the same library (tuning experiments); never a different backend
+    return os.environ.get("WARPII_B200_LIB") or os.path.join(_HERE, "lib", "libwarpii_b200.so")
 
 
 _lib = None
@@ -348,3 +349,15 @@ class BoxSolver:
         p = C.c_void_p()
         _check(lib().warpii_gpu_stream(self.ctx, C.byref(p)))
         return p.value
+
+
+def point_fluxes(qa, qb, d, gamma, device=0):
+    """Device evaluation of the EC flux (direction d) and the ES flux (normal +e_d) for state pairs; see warpii_gpu.h."""
+    qa = np.ascontiguousarray(qa, dtype=np.float64).reshape(-1, 5)
+    qb = np.ascontiguousarray(qb, dtype=np.float64).reshape(-1, 5)
+    n = qa.shape[0]
+    ec, es, prim = np.zeros((n, 5)), np.zeros((n, 5)), np.zeros((n, 12))
+    L = lib()
+    L.warpii_gpu_point_fluxes.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_double, _dp, _dp, _dp]
+    _check(L.warpii_gpu_point_fluxes(device, n, _ptr(qa), _ptr(qb), d, gamma, _ptr(ec), _ptr(es), _ptr(prim)))
+    return ec, es, prim

@@ -234,3 +234,28 @@ void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, con
 }
 
 }  // namespace wgpu
+
+// ---- point physics on the device, for known-answer tests (the reference's euler_test.cc goldens) -----------------
+namespace wgpu {
+__global__ void point_flux_kernel(int n, const double* qa, const double* qb, int d, double gamma, double* ec,
+                                  double* es, double* prim) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* a5 = qa + 5 * i;
+    const double* b5 = qb + 5 * i;
+    const Prim a = make_prim(a5[0], a5[1], a5[2], a5[3], a5[4], gamma);
+    const Prim b = make_prim(b5[0], b5[1], b5[2], b5[3], b5[4], gamma);
+    const double hig = 0.5 / (gamma - 1.0);
+    double F[5], Dv[5], ibl;
+    ec_flux_d(d, a, b, hig, F, ibl);
+    es_dissipation(a, b, ibl, hig, Dv);
+    for (int c = 0; c < 5; c++) { ec[5 * i + c] = F[c]; es[5 * i + c] = F[c] - Dv[c]; }
+    double* p = prim + 12 * i;
+    p[0] = a.rho; p[1] = a.u0; p[2] = a.u1; p[3] = a.u2; p[4] = a.beta; p[5] = a.lrho; p[6] = a.lbeta; p[7] = a.q2;
+    p[8] = a.p; p[9] = a.H; p[10] = a.lam; p[11] = a.ib;
+}
+void launch_point_flux(int n, const double* qa, const double* qb, int d, double gamma, double* ec, double* es,
+                       double* prim, cudaStream_t s) {
+    if (n > 0) point_flux_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, qa, qb, d, gamma, ec, es, prim);
+}
+}  // namespace wgpu

@@ -12,9 +12,12 @@ __host__ __device__ constexpr int ipow_c(int b, int e) { return e == 0 ? 1 : b *
 
 // Elements per thread block ("patch"): the largest power of two that keeps a block at <= 256 nodes (= threads).
 // Faces between two elements of one block are evaluated once and serve both sides.
+#ifndef WGPU_BLOCK_NODES
+#define WGPU_BLOCK_NODES 256
+#endif
 __host__ __device__ constexpr int elems_per_block(int dim, int np) {
     int g = 1;
-    while (2 * g * ipow_c(np, dim) <= 256) g *= 2;
+    while (2 * g * ipow_c(np, dim) <= WGPU_BLOCK_NODES) g *= 2;
     return g;
 }
 

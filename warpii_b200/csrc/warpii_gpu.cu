@@ -777,3 +777,27 @@ int warpii_gpu_stream(warpii_gpu_ctx* c, void** stream_out) {
 }
 
 }  // extern "C"
+
+namespace wgpu {
+void launch_point_flux(int n, const double* qa, const double* qb, int d, double gamma, double* ec, double* es,
+                       double* prim, cudaStream_t s);
+}
+
+extern "C" int warpii_gpu_point_fluxes(int device, int n, const double* qa, const double* qb, int d, double gamma,
+                                       double* ec_out, double* es_out, double* prim_out) {
+    if (n <= 0) return 0;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail("no CUDA device available");
+    CUDA_OK(cudaSetDevice(device));
+    double *dqa = nullptr, *dqb = nullptr, *dec = nullptr, *des = nullptr, *dpr = nullptr;
+    if (upload(&dqa, qa, (size_t)5 * n) || upload(&dqb, qb, (size_t)5 * n) || upload<double>(&dec, nullptr, (size_t)5 * n) ||
+        upload<double>(&des, nullptr, (size_t)5 * n) || upload<double>(&dpr, nullptr, (size_t)12 * n))
+        return 1;
+    wgpu::launch_point_flux(n, dqa, dqb, d, gamma, dec, des, dpr, nullptr);
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(ec_out, dec, (size_t)5 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(es_out, des, (size_t)5 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (prim_out) CUDA_OK(cudaMemcpy(prim_out, dpr, (size_t)12 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dqa); cudaFree(dqb); cudaFree(dec); cudaFree(des); cudaFree(dpr);
+    return 0;
+}
