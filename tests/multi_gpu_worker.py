@@ -1,0 +1,77 @@
+"""Worker of tests/test_gpu_multi.py: one rank per GPU (torch.distributed.run), element-sharded run against the
+global CPU oracle.  Exits non-zero on any mismatch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import dgsem_cases as cases  # noqa: E402
+from oracle import Oracle  # noqa: E402
+from warpii_b200 import BoxSolver, nccl_unique_id  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def fresh_id():
+        # one NCCL unique id per communicator: created on rank 0 through the ABI, broadcast by the caller
+        t = torch.tensor(list(nccl_unique_id()) if rank == 0 else [0] * 128, dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().tolist())
+
+    for (dim, p, nx, left, right, ic, gamma) in [
+        (2, 3, [8, 12], [0.0, -5.0], [10.0, 5.0], cases.isentropic_vortex(1.4), 1.4),
+        (3, 2, [4, 4, 6], [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], cases.smooth_blob_3d(0.1), 5.0 / 3.0),
+        (1, 3, [16], [0.0], [1.0], cases.sine_wave(), 5.0 / 3.0),
+    ]:
+        o = Oracle(dim, p, nx, left, right, gamma=gamma, threads=4)
+        u = o.project(ic)
+        g = BoxSolver(dim, p, nx, left, right, gamma=gamma, rank=rank, n_ranks=world, device=local)
+        g.attach_comm(fresh_id())
+        assert g.n_elems < o.n_elems
+        # one RHS with halo exchange
+        g.upload_global(0, u)
+        g.rhs(1, 0)
+        got = g.download(1)
+        want, _ = o.rhs(u)
+        err = cases.rel_l2_per_component(got, want[g.l2g])
+        assert (err <= 1e-12).all(), (rank, dim, err)
+        # dt: max over ranks (NCCL all-reduce) equals the global oracle value
+        dt = g.recommend_dt(0)
+        assert abs(dt - o.recommend_dt(u)) <= 1e-13 * dt, (dt, o.recommend_dt(u))
+        # global integrals are summed over ranks
+        assert np.allclose(g.global_integral(0), o.global_integral(u), rtol=1e-13, atol=1e-13)
+        # 20 steps: every rank takes the same dt sequence; conservation and parity
+        ic_int = o.global_integral(u)
+        t, steps = g.advance_to(0.0, 1e9, max_steps=20)
+        o.solve(u, t, max_steps=20)
+        got = g.download(0)
+        err = cases.rel_l2_per_component(got, u[g.l2g])
+        assert (err <= 1e-11).all(), (rank, dim, err)
+        now = g.global_integral(0)
+        assert np.allclose(now, ic_int, rtol=1e-12, atol=1e-12)
+        # the sharded result is bit-identical to the single-GPU result of the same library
+        if rank == 0:
+            g1 = BoxSolver(dim, p, nx, left, right, gamma=gamma, device=local)
+            g1.upload_global(0, o.project(ic))
+            g1.advance_to(0.0, 1e9, max_steps=20)
+            single = g1.download_global(0)
+            assert np.array_equal(single[g.l2g], got), "sharded and single-GPU runs differ"
+            g1.close()
+        g.close()
+        dist.barrier()
+    dist.destroy_process_group()
+    print(f"rank {rank}: multi-GPU parity ok")
+
+
+if __name__ == "__main__":
+    main()
