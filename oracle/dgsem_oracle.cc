@@ -37,8 +37,9 @@ inline double olog(double x) { return g_log_impl ? detlog::det_log(x) : std::log
 inline double ln_avg(double a, double b) {
     double diff_log = std::fabs(olog(b) - olog(a));
     const double C = 1e6;
-    double lhs = std::fmax(C * std::fabs(b - a), b + a);
-    double denom = std::fmax(C * diff_log, 2.0);
+    // std::max, not fmax: a NaN logarithm (negative pressure) must poison the flux as it does in the reference
+    double lhs = std::max(C * std::fabs(b - a), b + a);
+    double denom = std::max(C * diff_log, 2.0);
     return lhs / denom;
 }
 
