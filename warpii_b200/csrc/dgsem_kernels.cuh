@@ -21,13 +21,6 @@ __host__ __device__ constexpr int elems_per_block(int dim, int np) {
     return g;
 }
 
-// Per-block face work list entry (built once on the host from the face-pair table):
-//   bits 0-7 local element, 8-11 local face, 12-13 kind, 16-23 local neighbour element (internal faces)
-enum FaceKind { kFaceInternal = 0, kFaceElem = 1, kFaceGhost = 2, kFaceBoundary = 3 };
-__host__ __device__ constexpr int32_t face_desc(int le, int f, int kind, int nle) {
-    return (int32_t)(le | (f << 8) | (kind << 12) | (nle << 16));
-}
-
 // 1-D reference-element tables (Gauss-Lobatto on [0,1]); filled by reference_element.hpp on the host.
 struct ElemTables {
     double D[kMaxNp * kMaxNp];    // D[j*Np+l] = l_l'(x_j)
@@ -39,14 +32,11 @@ struct StageParams {
     const double* u;              // input state  [elem][comp][node]
     double* dst;                  // output state (same layout); dst != u
     const int32_t* nbr;           // [n_elems][2*dim] face-pair table (warpii_gpu.h)
-    const int32_t* face_list;     // [n_blocks][G*2*dim] compact face work list of every block
-    const int32_t* face_count;    // [n_blocks] {entries, of which internal (listed first)}
     const double* ghost;          // [n_ghost][5*nsp][nF] received face traces
     const double* bres;           // [n_bfaces][nsp][5][nF] boundary-face rate contributions (boundary kernel)
     double* alpha_out;            // optional [n_elems][nsp]
     unsigned long long* vmax;     // optional: max transport speed of dst (bits of a non-negative double)
-    int64_t elem_begin, elem_end; // element range of this launch (elem_begin is a multiple of the block's range start)
-    int64_t block_begin;          // index of the first block of this range in face_list / face_count
+    int64_t elem_begin, elem_end; // element range of this launch
     int64_t n_elems;
     int32_t nc, nsp;
     int32_t mode;                 // 0: dst = beta*dst + a*(u + dt*rate); 1: dst = rate

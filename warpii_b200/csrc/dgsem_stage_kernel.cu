@@ -6,15 +6,17 @@
 // sides' face lifting (:301-342), inverse diagonal mass, the RK stage update and (optionally) the CFL
 // reduction of the updated state (:450-514): one HBM read of u, one write of dst.
 //
-// Work decomposition inside a block (a patch of G elements, NODES = G * Np^dim threads):
-//   node phase   one thread per node: load the 5 conserved values (coalesced), form the node's primitives,
-//                logarithms and wave speed once, park them in shared memory (node-major, 16-byte vector access);
-//   indicator    sum-factorised Legendre analysis of p*rho in shared memory, alpha of all G elements by one warp;
-//   task phase   independent tasks spread over all threads:
-//                  - every UNORDERED node pair (j,l) of every pencil once (the two-point flux is symmetric), flux
-//                    into shared memory;
-//                  - every face node of the block's compact face list once; faces between two elements of the
-//                    block serve both of them;
+// Work decomposition inside a block (a patch of G elements, NODES = G * Np^dim threads, one thread per node):
+//   node phase   load the 5 conserved values (coalesced), form the node's primitives, logarithms and wave speed
+//                once, park them in shared memory (node-major, 16-byte vector access).  ONE block barrier: from here
+//                on a thread only reads the block's primitive table and writes its own element's scratch, so the
+//                rest is synchronised per GROUP (the warp(s) that hold whole elements: __syncwarp for Np^dim | 32, a
+//                named barrier for Np^dim a multiple of 32, the block barrier otherwise) and warps never wait for
+//                the slowest warp of the block;
+//   indicator    sum-factorised Legendre analysis of p*rho, alpha per element;
+//   task phase   the element's own threads share (a) every UNORDERED node pair (j,l) of its pencils once (the
+//                two-point flux is symmetric) and (b) its face nodes; a neighbour inside the patch is read from the
+//                shared primitive table, others are gathered from L2/HBM (or the NCCL ghost buffer);
 //   node phase 2 gather D-weighted pair fluxes, FV differences (only where alpha > 0) and face terms, update,
 //                store, CFL.
 #include "dgsem_common.cuh"
@@ -37,6 +39,8 @@ struct Geo {
     static constexpr int PPE = DIM * NF * NPAIR;        // pair tasks per element
     static constexpr int ROUNDS = (PPE + NN - 1) / NN;  // pair tasks per thread (last round may be partial)
     static constexpr int THREADS = NODES;
+    // threads that synchronise among themselves after the node phase: whole warps holding whole elements
+    static constexpr int GROUP = (32 % NN == 0 && NODES % 32 == 0) ? 32 : ((NN % 32 == 0 && NODES / NN <= 15) ? NN : NODES);
     static constexpr int MIN_BLOCKS = (512 / THREADS) > 0 ? (512 / THREADS) : 1;
     // dynamic shared memory, in doubles (every offset even => 16-byte aligned)
     static constexpr int even(int x) { return (x + 1) & ~1; }
@@ -45,21 +49,23 @@ struct Geo {
     static constexpr int OFF_W = even(OFF_V + NP * NP);
     static constexpr int OFF_TAB = OFF_W + 8;                               // int tables: pair -> (j,l), (j,l) -> pair
     static constexpr int OFF_P = even(OFF_TAB + (NPAIR + NP * NP + 1) / 2 + 1);   // [NODES][kPS]
-    static constexpr int OFF_PAIR = OFF_P + kPS * NODES;                    // [G*PPE][kFS]; indicator scratch aliases it
+    static constexpr int OFF_A = OFF_P + kPS * NODES;                       // [2][NODES] indicator scratch
+    static constexpr int OFF_PAIR = OFF_A + 2 * NODES;                      // [G*PPE][kFS]
     static constexpr int OFF_FACE = OFF_PAIR + kFS * G * PPE;               // [NSLOT][kFS]
     static constexpr int OFF_ALPHA = OFF_FACE + kFS * NSLOT;                // [G]
     static constexpr int OFF_RED = even(OFF_ALPHA + G);                     // [32]
     static constexpr int SMEM_DOUBLES = OFF_RED + 32;
-    static_assert(kFS * G * PPE >= 2 * NODES, "indicator scratch must fit in the pair-flux area");
 };
 
-// persson_peraire_shock_indicator.h:96-122 given the two modal energies; T and s/T are host constants
+// persson_peraire_shock_indicator.h:96-122 given the two modal energies g = (group norm)^2; T and s/T are host
+// constants.  A group whose norm is below 1e-10 is dropped (deal.II process_coefficients).  alpha < 1e-3 -> 0, which is
+// decided without the exponential for the (overwhelmingly common) smooth elements.
 __device__ __forceinline__ double blending_from_energies(const double g0, const double g1, const double T, const double sT) {
-    const double n0 = sqrt(g0), n1 = sqrt(g1);
-    double total_m1 = 0.0, top_m1 = 0.0;
-    if (n0 > 1e-10) total_m1 += n0 * n0;
-    if (n1 > 1e-10) { const double e = n1 * n1; top_m1 += e; total_m1 += e; }
-    const double E = fmax(0.0, top_m1 / total_m1);
+    const double e0 = g0 > 1e-20 ? g0 : 0.0, e1 = g1 > 1e-20 ? g1 : 0.0;
+    const double total = e0 + e1;
+    if (!(total > 0.0)) return 0.0;
+    const double E = e1 * rcp_pos(total);
+    if (sT * (T - E) > 6.95) return 0.0;          // 1/(1+exp(x)) < 1e-3  <=>  x > ln 999 = 6.9068
     double alpha = 1.0 / (1.0 + exp(-sT * (E - T)));
     if (alpha < 1e-3) alpha = 0.0;
     else if (alpha > 0.5) alpha = 0.5;
@@ -105,6 +111,13 @@ __device__ __forceinline__ void load_flux(const double* rec, double F[5]) {
     F[0] = a.x; F[1] = a.y; F[2] = b.x; F[3] = b.y; F[4] = rec[4];
 }
 
+template <int GROUP, int NODES>
+__device__ __forceinline__ void group_sync(const int tid) {
+    if (GROUP == 32) __syncwarp();
+    else if (GROUP == NODES) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / GROUP), "n"(GROUP) : "memory");
+}
+
 // first node of pencil pe (= tangential index) in direction d
 template <int DIM, int NP>
 __device__ __forceinline__ int pencil_first_node(const int d, const int pe) {
@@ -118,7 +131,7 @@ template <int DIM, int NP>
 __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCKS) stage_kernel(const StageParams P) {
     using GEO = Geo<DIM, NP>;
     constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G, NODES = GEO::NODES, NFACE = GEO::NFACE;
-    constexpr int NPAIR = GEO::NPAIR, PPE = GEO::PPE, ROUNDS = GEO::ROUNDS;
+    constexpr int NPAIR = GEO::NPAIR, PPE = GEO::PPE, ROUNDS = GEO::ROUNDS, GROUP = GEO::GROUP;
 
     extern __shared__ __align__(16) double smem[];
     double* const sD = smem + GEO::OFF_D;
@@ -128,8 +141,8 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
     int* const sPairId = sPairJL + NPAIR;                               // [NP*NP]: pair id of (a, b), a != b
     double* const sP = smem + GEO::OFF_P;
     double* const sPair = smem + GEO::OFF_PAIR;
-    double* const sA = sPair;            // indicator scratch (dead before the task phase writes pair fluxes)
-    double* const sB = sPair + NODES;
+    double* const sA = smem + GEO::OFF_A;   // indicator scratch; only the owning group touches its nodes' slots
+    double* const sB = sA + NODES;
     double* const sFace = smem + GEO::OFF_FACE;
     double* const sAlpha = smem + GEO::OFF_ALPHA;
     double* const sRed = smem + GEO::OFF_RED;
@@ -142,10 +155,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
     const int64_t e0 = P.elem_begin + (int64_t)blockIdx.x * G;
     const int64_t e = e0 + le;
     const bool active = e < P.elem_end;
-    const int n_active = (int)((P.elem_end - e0) < G ? (P.elem_end - e0) : G);
-    const int64_t bl = P.block_begin + blockIdx.x;
-    const int n_face_tasks = P.face_count[bl] * NF;
-    const int32_t* const flist = P.face_list + bl * (G * NFACE);
+    const int64_t e_hi = (e0 + G < P.elem_end) ? e0 + G : P.elem_end;   // elements [e0, e_hi) have primitives in shared memory
 
     for (int i = tid; i < NP * NP; i += NODES) { sD[i] = P.T.D[i]; sV[i] = P.T.V[i]; }
     for (int i = tid; i < NP; i += NODES) sW[i] = P.T.w[i];
@@ -185,7 +195,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
         }
         __syncthreads();
 
-        // ---- shock indicator: sum-factorised Legendre analysis of p*rho --------------------------------------
+        // ---- shock indicator: sum-factorised Legendre analysis of p*rho (group-local from here on) ------------
         {
             double* src = sA;
             double* dstb = sB;
@@ -197,13 +207,13 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
 #pragma unroll
                 for (int m = 0; m < NP; m++) acc += sV[idx[d] * NP + m] * src[base + m * st];
                 dstb[tid] = acc;
-                __syncthreads();
+                group_sync<GROUP, NODES>(tid);
                 double* t = src; src = dstb; dstb = t;
             }
             // src holds the modal coefficients c_k at k = (i0,i1,i2); fixed-order sums: along i0, then the rest
             const double ck = src[tid];
             dstb[tid] = ck * ck;
-            __syncthreads();
+            group_sync<GROUP, NODES>(tid);
             if (i0 == 0) {
                 double g0 = 0.0, g1 = 0.0;
                 const bool row_shell = (i1 == NP - 1) || (i2 == NP - 1);
@@ -215,16 +225,15 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 src[tid] = g0;
                 src[tid + 1] = g1;   // NP >= 2
             }
-            __syncthreads();
-            if (tid < G) {   // one (part of a) warp evaluates the logistic blend of all elements of the block
+            group_sync<GROUP, NODES>(tid);
+            if (j == 0) {
                 double g0 = 0.0, g1 = 0.0;
-                const int b0 = tid * NN;
-                for (int r = 0; r < NF; r++) { g0 += src[b0 + r * NP]; g1 += src[b0 + r * NP + 1]; }
+                for (int r = 0; r < NF; r++) { g0 += src[tid + r * NP]; g1 += src[tid + r * NP + 1]; }
                 const double al = blending_from_energies(g0, g1, P.ind_T, P.ind_sT);
-                sAlpha[tid] = al;
-                if (tid < n_active && P.alpha_out) P.alpha_out[(size_t)(e0 + tid) * P.nsp + sp] = al;
+                sAlpha[le] = al;
+                if (active && P.alpha_out) P.alpha_out[(size_t)e * P.nsp + sp] = al;
             }
-            __syncthreads();
+            group_sync<GROUP, NODES>(tid);
         }
 
         // ---- task phase ---------------------------------------------------------------------------------------
@@ -246,15 +255,13 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 store_flux(sPair + (le * PPE + p) * kFS, F);
             }
         }
-        // (b) face nodes of the block's compact face list; faces inside the block serve both elements
-        for (int k = tid; k < n_face_tasks; k += NODES) {
-            const int fi = k / NF, t = k - fi * NF;
-            const int32_t desc = flist[fi];
-            const int fle = desc & 255, f = (desc >> 8) & 15, kind = (desc >> 12) & 3, nle = (desc >> 16) & 255;
+        // (b) the element's face nodes: its own side of every face (gather form, no atomics)
+        for (int ft = j; ft < NFACE * NF; ft += NN) {
+            const int f = ft / NF, t = ft - f * NF;
             const int d = f >> 1, side = f & 1;
-            double* const rec = sFace + ((fle * NFACE + f) * NF + t) * kFS;
-            if (kind == kFaceBoundary) {
-                const int v = P.nbr[(size_t)(e0 + fle) * NFACE + f];
+            double* const rec = sFace + ((le * NFACE + f) * NF + t) * kFS;
+            const int v = active ? P.nbr[(size_t)e * NFACE + f] : (int)e0;
+            if (v < 0) {   // domain boundary: rate contribution prepared by boundary_kernel
                 const size_t offb = (((size_t)(-1 - v) * P.nsp + sp) * 5) * NF + t;
                 double Fb[5];
 #pragma unroll
@@ -262,15 +269,15 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 store_flux(rec, Fb);
                 continue;
             }
-            const Prim a = load_prim(sP, fle * NN + node_of_face_node<DIM, NP>(d, side, t));
+            const Prim a = load_prim(sP, le * NN + node_of_face_node<DIM, NP>(d, side, t));
+            const int nn = node_of_face_node<DIM, NP>(d, 1 - side, t);
             Prim b;
-            if (kind == kFaceInternal) {
-                b = load_prim(sP, nle * NN + node_of_face_node<DIM, NP>(d, 1 - side, t));
+            if (v >= e0 && v < e_hi) {   // neighbour inside the patch: its primitives are in shared memory
+                b = load_prim(sP, (int)(v - e0) * NN + nn);
             } else {
-                const int v = P.nbr[(size_t)(e0 + fle) * NFACE + f];
                 double qn[5];
-                if (kind == kFaceElem) {
-                    const size_t offn = ((size_t)v * nc + 5 * sp) * NN + node_of_face_node<DIM, NP>(d, 1 - side, t);
+                if (v < P.n_elems) {
+                    const size_t offn = ((size_t)v * nc + 5 * sp) * NN + nn;
 #pragma unroll
                     for (int c = 0; c < 5; c++) qn[c] = P.u[offn + (size_t)c * NN];
                 } else {
@@ -291,16 +298,8 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
 #pragma unroll
             for (int c = 0; c < 5; c++) R[c] = cf * (sgn * (Fm[c] - Fe[c]) + Dv[c]);
             store_flux(rec, R);
-            if (kind == kFaceInternal) {
-                // the neighbour's side of the same face: n' = -n, f*(b,a,n') = -f*(a,b,n) exactly
-                double Fn[5];
-                phys_flux_d(d, b, Fn);
-#pragma unroll
-                for (int c = 0; c < 5; c++) R[c] = cf * (sgn * (Fe[c] - Fn[c]) - Dv[c]);
-                store_flux(sFace + ((nle * NFACE + (f ^ 1)) * NF + t) * kFS, R);
-            }
         }
-        __syncthreads();
+        group_sync<GROUP, NODES>(tid);
 
         // ---- node phase 2: assemble the rate of this node ----------------------------------------------------
         const double alpha = sAlpha[le];

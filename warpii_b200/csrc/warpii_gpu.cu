@@ -106,9 +106,6 @@ struct warpii_gpu_ctx {
     std::vector<double*> vec;
     std::vector<double*> bif;
     unsigned long long* d_vmax = nullptr;   // one slot per vector
-    std::vector<int32_t> h_nbr;             // host copy of the face-pair table (block work lists are rebuilt when a halo is attached)
-    int32_t *d_face_list = nullptr, *d_face_count = nullptr;
-    int64_t n_blocks_first = 0;             // blocks covering [0, n_interface) (0 without a halo)
     double ind_T = 0, ind_sT = 0;
     std::vector<char> vmax_valid;
     double* h_pin = nullptr;                // pinned staging, n_dofs doubles (lazy)
@@ -156,56 +153,11 @@ int get_events(warpii_gpu_ctx* c, cudaEvent_t* a, cudaEvent_t* b) {
     return 0;
 }
 
-// Per-block face work lists: every face of the block's elements exactly once, faces between two elements of the
-// same block first (they are evaluated once and serve both sides).  Blocks never straddle n_interface, so the
-// interface and interior launches of a sharded run each see whole blocks.
-int build_block_lists(warpii_gpu_ctx* c) {
-    const int G = elems_per_block(c->dim, c->Np), nf = 2 * c->dim;
-    std::vector<std::pair<int64_t, int64_t>> ranges;
-    if (c->n_interface > 0) ranges.push_back({0, c->n_interface});
-    ranges.push_back({c->n_interface, c->n_elems});
-    std::vector<int32_t> list, count;
-    c->n_blocks_first = 0;
-    for (size_t r = 0; r < ranges.size(); r++) {
-        const int64_t b0 = ranges[r].first, b1 = ranges[r].second;
-        const int64_t nb = (b1 - b0 + G - 1) / G;
-        if (r == 0 && ranges.size() > 1) c->n_blocks_first = nb;
-        for (int64_t b = 0; b < nb; b++) {
-            const int64_t s0 = b0 + b * G, s1 = std::min<int64_t>(s0 + G, b1);
-            std::vector<int32_t> internal, other;
-            for (int64_t e = s0; e < s1; e++)
-                for (int f = 0; f < nf; f++) {
-                    const int64_t v = c->h_nbr[(size_t)e * nf + f];
-                    const int le = (int)(e - s0);
-                    if (v < 0) other.push_back(face_desc(le, f, kFaceBoundary, 0));
-                    else if (v >= c->n_elems) other.push_back(face_desc(le, f, kFaceGhost, 0));
-                    else if (v >= s0 && v < s1) {
-                        if (e < v || (e == v && (f & 1) == 0)) internal.push_back(face_desc(le, f, kFaceInternal, (int)(v - s0)));
-                    } else other.push_back(face_desc(le, f, kFaceElem, 0));
-                }
-            count.push_back((int32_t)(internal.size() + other.size()));
-            const size_t base = list.size();
-            list.resize(base + (size_t)G * nf, 0);
-            std::copy(internal.begin(), internal.end(), list.begin() + base);
-            std::copy(other.begin(), other.end(), list.begin() + base + internal.size());
-        }
-    }
-    cudaFree(c->d_face_list);
-    cudaFree(c->d_face_count);
-    c->d_face_list = c->d_face_count = nullptr;
-    if (upload(&c->d_face_list, list.data(), list.size())) return 1;
-    if (upload(&c->d_face_count, count.data(), count.size())) return 1;
-    return 0;
-}
-
 StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double beta, int mode, bool fuse_cfl) {
     StageParams P;
     P.u = c->vec[u];
     P.dst = c->vec[dst];
     P.nbr = c->d_nbr;
-    P.face_list = c->d_face_list;
-    P.face_count = c->d_face_count;
-    P.block_begin = 0;
     P.ind_T = c->ind_T;
     P.ind_sT = c->ind_sT;
     P.ghost = c->d_ghost;
@@ -276,13 +228,11 @@ int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double bet
         // interior elements while the traces are in flight, then the interface elements
         P.elem_begin = c->n_interface;
         P.elem_end = c->n_elems;
-        P.block_begin = c->n_blocks_first;
         launch_stage(c->dim, c->Np, P, c->stream);
         if (P.elem_end > P.elem_begin) c->launches++;
         CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_recv, 0));
         P.elem_begin = 0;
         P.elem_end = c->n_interface;
-        P.block_begin = 0;
         launch_stage(c->dim, c->Np, P, c->stream);
         if (P.elem_end > P.elem_begin) c->launches++;
     } else {
@@ -443,11 +393,10 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
         return 1;
     }
 
-    c->h_nbr.assign(m->face_neighbor, m->face_neighbor + (size_t)c->n_elems * nf);
     // persson_peraire_shock_indicator.h:110-112
     c->ind_T = 0.5 * std::pow(10.0, -1.8 * std::pow((double)c->Np, 0.25));
     c->ind_sT = 9.21024 / c->ind_T;
-    if (build_block_lists(c) || prepare_kernels(c->dim, c->Np)) {
+    if (prepare_kernels(c->dim, c->Np)) {
         std::string keep = g_last_error.empty() ? std::string("kernel preparation failed") : g_last_error;
         warpii_gpu_destroy(c);
         g_last_error = keep;
@@ -489,7 +438,7 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     cudaFree(c->d_nbr); cudaFree(c->d_bf_elem); cudaFree(c->d_bf_side); cudaFree(c->d_bf_id); cudaFree(c->d_bc_kind);
     cudaFree(c->d_inflow); cudaFree(c->d_w); cudaFree(c->d_bres); cudaFree(c->d_bflux); cudaFree(c->d_ghost);
     cudaFree(c->d_sendbuf); cudaFree(c->d_partial); cudaFree(c->d_out5); cudaFree(c->d_alpha); cudaFree(c->d_vmax);
-    cudaFree(c->d_send_elem); cudaFree(c->d_send_side); cudaFree(c->d_face_list); cudaFree(c->d_face_count);
+    cudaFree(c->d_send_elem); cudaFree(c->d_send_side);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -698,9 +647,9 @@ int warpii_gpu_shock_indicator(warpii_gpu_ctx* c, int vec, double* alpha_out) {
         CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_recv, 0));
     }
     if (c->n_interface > 0) {
-        P.elem_begin = 0; P.elem_end = c->n_interface; P.block_begin = 0;
+        P.elem_begin = 0; P.elem_end = c->n_interface;
         launch_stage(c->dim, c->Np, P, c->stream);
-        P.elem_begin = c->n_interface; P.elem_end = c->n_elems; P.block_begin = c->n_blocks_first;
+        P.elem_begin = c->n_interface; P.elem_end = c->n_elems;
     }
     launch_stage(c->dim, c->Np, P, c->stream);
     c->launches++;
@@ -745,7 +694,6 @@ int warpii_gpu_attach_comm(warpii_gpu_ctx* c, const char id[WARPII_GPU_NCCL_ID_B
         if (upload(&c->d_send_elem, halo->send_elem, (size_t)c->n_send)) return 1;
         if (upload(&c->d_send_side, halo->send_side, (size_t)c->n_send)) return 1;
         if (upload<double>(&c->d_sendbuf, nullptr, (size_t)c->n_send * 5 * c->nsp * c->NF)) return 1;
-        if (build_block_lists(c)) return 1;
     }
     return 0;
 }
