@@ -10,10 +10,11 @@ constexpr int kMaxNp = 7;   // fe_degree <= 6 (five_moment.h:116)
 
 __host__ __device__ constexpr int ipow_c(int b, int e) { return e == 0 ? 1 : b * ipow_c(b, e - 1); }
 
-// Elements per thread block ("patch"): the largest power of two that keeps a block at <= 256 nodes (= threads).
-// Faces between two elements of one block are evaluated once and serve both sides.
+// Elements per thread block ("patch"): the largest power of two that keeps a block at <= 128 nodes (= threads); a
+// neighbour inside the patch is read from shared memory instead of being gathered and re-derived.  Measured on C2
+// (profiles/README.md): 64 -> 0.413 ms, 128 -> 0.416 ms, 256 -> 0.441 ms, 512 -> 0.486 ms per stage.
 #ifndef WGPU_BLOCK_NODES
-#define WGPU_BLOCK_NODES 256
+#define WGPU_BLOCK_NODES 128
 #endif
 __host__ __device__ constexpr int elems_per_block(int dim, int np) {
     int g = 1;
