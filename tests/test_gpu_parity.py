@@ -292,6 +292,27 @@ def test_error_conventions():
         BoxSolver(1, 2, [4], [0.0], [1.0], periodic=[0], n_boundaries=0)
 
 
+def test_unphysical_state_is_reported():
+    """The GPU analogue of --enable-fpe (fpe.cc:19-22): a negative pressure yields a NaN transport speed, and the time
+    loop stops with an error instead of marching on."""
+    from warpii_b200 import WarpiiGpuError
+    o, g = make_pair(2, 3, [8, 8], [0.0, -5.0], [10.0, 5.0], gamma=1.4)
+    u = o.project(cases.isentropic_vortex(1.4))
+    bad = u.copy()
+    bad[13, 4, 5] = 0.01          # total energy below the kinetic energy at one node
+    g.upload_global(0, bad)
+    assert np.isnan(g.max_transport_speed(0))
+    with pytest.raises(WarpiiGpuError):
+        g.advance_to(0.0, 1.0, max_steps=3)
+    # the fused reduction of the second stage reports it too
+    g.upload_global(0, u)
+    g.ssprk2_step(0.9, 0.0)       # far beyond the stable step: the state blows up
+    g.ssprk2_step(0.9, 0.9)
+    v = g.max_transport_speed(0)
+    assert not np.isfinite(v) or v > 1e3
+    g.close()
+
+
 # ---- full-size checks on the bench workload (size-independent properties; the oracle would take minutes here) ----
 def test_full_size_c2_properties():
     """BASELINE config 2 (512x512, p=3): conservation over steps, free-stream preservation, translation invariance."""

@@ -129,7 +129,7 @@ __global__ void cfl_kernel(const double* __restrict__ u, int64_t n_elems, int nc
         double conv = fabs(q1 * inv) * ih0;
         if (DIM > 1) conv = fmax(conv, fabs(q2 * inv) * ih1);
         if (DIM > 2) conv = fmax(conv, fabs(q3 * inv) * ih2);
-        m = fmax(m, max_eig * sqrt(gamma * pr * inv) + conv);
+        m = nan_max(m, max_eig * sqrt(gamma * pr * inv) + conv);   // NaN (negative pressure) is kept, see nan_max
     }
     m = block_max(m, sRed);
     if (threadIdx.x == 0) atomicMax(vmax, (unsigned long long)__double_as_longlong(m));

@@ -26,15 +26,18 @@ __device__ __forceinline__ int node_of_face_node(const int d, const int side, co
     return d == 0 ? (e + NP * (t0 + NP * t1)) : (d == 1 ? (t0 + NP * (e + NP * t1)) : (t0 + NP * (t1 + NP * e)));
 }
 
+// max that keeps a NaN once it has seen one (an unphysical state must surface as a NaN time step)
+__device__ __forceinline__ double nan_max(const double a, const double b) { return (b > a || b != b) ? b : a; }
+
 __device__ __forceinline__ double block_max(double v, double* s_red) {
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = nan_max(v, __shfl_xor_sync(0xffffffffu, v, o));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = (blockDim.x + 31) >> 5;
     __syncthreads();
     if (lane == 0) s_red[warp] = v;
     __syncthreads();
     double r = s_red[0];
-    for (int i = 1; i < nwarps; i++) r = fmax(r, s_red[i]);
+    for (int i = 1; i < nwarps; i++) r = nan_max(r, s_red[i]);
     return r;
 }
 

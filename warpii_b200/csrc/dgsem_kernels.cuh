@@ -42,6 +42,7 @@ struct StageParams {
     int32_t nc, nsp;
     int32_t mode;                 // 0: dst = beta*dst + a*(u + dt*rate); 1: dst = rate
     double gamma, dt, a, beta;
+    double hig;                   // 1 / (2 (gamma - 1))
     double inv_h[3];              // 1/h_d
     double inv_hw[3];             // 1/(h_d * w_0): face lifting factor (face JxW / cell JxW on a Cartesian cell)
     double max_eig;               // sqrt(lambda_max(J^-T J^-1)), :487-502 of the reference operator

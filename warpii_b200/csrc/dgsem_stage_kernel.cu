@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
     }
 
     const double gamma = P.gamma, gm1 = P.gamma - 1.0;
-    const double hig = 0.5 / gm1;   // 1 / (2 (gamma - 1))
+    const double hig = P.hig;   // 1 / (2 (gamma - 1)), formed on the host
     const int nc = P.nc;
     double vmax_local = 0.0;
 
@@ -409,8 +409,11 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 double conv = fabs(qn[1] * inv) * P.inv_h[0];
                 if (DIM > 1) conv = fmax(conv, fabs(qn[2] * inv) * P.inv_h[1]);
                 if (DIM > 2) conv = fmax(conv, fabs(qn[3] * inv) * P.inv_h[2]);
-                const double cs = sqrt(gamma * pr * inv);
-                vmax_local = fmax(vmax_local, P.max_eig * cs + conv);
+                const double c2 = gamma * pr * inv;
+                // a non-positive or NaN c^2 (unphysical state) must reach the host as a NaN speed, not be clamped
+                const double cs = (c2 > 0.0) ? sqrt_pos(c2) : sqrt(c2 - 1.0);
+                const double speed = P.max_eig * cs + conv;
+                vmax_local = (speed > vmax_local || speed != speed) ? speed : vmax_local;
             }
         }
     }

@@ -171,6 +171,7 @@ StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a,
     P.nsp = c->nsp;
     P.mode = mode;
     P.gamma = c->gamma;
+    P.hig = 0.5 / (c->gamma - 1.0);
     P.dt = dt;
     P.a = a;
     P.beta = beta;
