@@ -52,85 +52,64 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (NVML from a thread: one sample ~4 ms into the region, then every 50 ms; falls back to
-    `nvidia-smi -lms` if NVML is unavailable)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Clocks and throttle reasons for the timed region.
+
+    The SM clock DURING the region is measured on the device itself: while stage timing is on, the library enqueues a
+    40 us probe kernel after every batch of steps that compares clock64 with the global timer
+    (warpii_gpu_sm_clock_probes).  NVML / nvidia-smi are only queried immediately BEFORE and AFTER the region: a
+    single NVML query inside it stalled the 2-GPU NCCL run by ~6 ms (20 % of a 40-step region; measured, see
+    profiles/README.md), so in-region polling would make the number wrong rather than safe.  An average probe clock
+    equal to the maximum clock plus empty reason sets on both sides excludes a slowdown in between.
+    """
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
-        self.sm, self.reasons, self.sm_max, self.power = [], set(), None, []
-
-    def start(self):
+        self.index, self.nvml, self.reasons, self.sm_max, self.sm_nvml = index, None, set(), None, []
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nvml = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
-            return
         except Exception:
             self.nvml = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
 
-    def _poll(self):
-        n = self.nvml
-        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-        time.sleep(0.004)
-        while not self.stop_flag:
+    def poll(self):
+        """One NVML sample (call right before / right after the timed region, GPU still busy or just released)."""
+        if self.nvml:
+            n = self.nvml
             try:
-                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                self.sm_nvml.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
                 try:
                     r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for name, bit in bits.items():
+                for name, bit in self.BITS.items():
                     if r & bit:
                         self.reasons.add(name)
-                self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            # NVML queries take a driver lock for ~1 ms and stall this process's launches (measured: 10 ms polling cost
-            # 20 % of the 2-GPU step rate), so poll sparsely: once early in the timed region, then every 50 ms
-            time.sleep(0.05)
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.nvml:
-            self.stop_flag = True
-            self.t.join(timeout=2)
-            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
-                    "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
-                    "reasons": sorted(self.reasons), "source": "nvml"}
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                smax.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
+            return
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,"
+                                  "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+            r = [c.strip() for c in out.strip().split(",")]
+            self.sm_nvml.append(float(r[0]))
+            self.sm_max = float(r[1])
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
                 if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def result(self, probes_mhz):
+        probes = [float(v) for v in probes_mhz]
+        return {"sm_mhz": float(np.median(probes)) if probes else (float(np.median(self.sm_nvml)) if self.sm_nvml else None),
+                "sm_max_mhz": self.sm_max, "samples": len(probes), "sm_mhz_min": min(probes) if probes else None,
+                "sm_mhz_before_after_nvml": self.sm_nvml, "reasons": sorted(self.reasons),
+                "source": "device clock64/globaltimer probes inside the timed region; NVML before and after"}
 
 
 def build_ic(w, xyz):
@@ -258,11 +237,12 @@ def run_ours(args, w):
 
     # ---- device-resident throughput -----------------------------------------------------------------
     t = 0.0
-    t, _ = g.advance_to(t, 1e30, max_steps=args.warmup)
     sampler = ClockSampler(local_rank)
-    barrier()
+    t, _ = g.advance_to(t, 1e30, max_steps=max(args.warmup - 1, 1))
     if rank == 0 and not args.no_clocks:
-        sampler.start()
+        sampler.poll()      # under load (the warm-up steps), one more warm-up step and a barrier before the timed region
+    t, _ = g.advance_to(t, 1e30, max_steps=1)
+    barrier()
     g.stage_timing(True)
     launches0 = g.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -273,7 +253,10 @@ def run_ours(args, w):
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = g.launch_count() - launches0
     stage_ms, stage_n = g.stage_timing(False)
-    clocks = sampler.stop() if (rank == 0 and not args.no_clocks) else None
+    clocks = None
+    if rank == 0 and not args.no_clocks:
+        sampler.poll()
+        clocks = sampler.result(g.sm_clock_probes())
     assert steps == args.steps
     value = 2.0 * n_dofs_total * args.steps / (ms * 1e-3)
 

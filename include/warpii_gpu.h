@@ -156,6 +156,10 @@ int64_t warpii_gpu_launch_count(const warpii_gpu_ctx* ctx);
 /* device time in ms of the stage kernels launched since the last reset (CUDA events on the launching stream),
  * and how many there were; used by bench.py for the roofline line. */
 int warpii_gpu_stage_timing(warpii_gpu_ctx* ctx, int enable, double* ms_total, int64_t* n_launches);
+/* While stage timing is enabled, warpii_gpu_advance_to also measures the SM clock ON the device after every batch of
+ * steps (one thread compares clock64 with the global timer for 40 us).  Returns the MHz readings collected since the
+ * last call.  (NVML/nvidia-smi queries inside a timed region stall NCCL runs for milliseconds.) */
+int warpii_gpu_sm_clock_probes(warpii_gpu_ctx* ctx, double* mhz_out, int max_out, int* n_out);
 /* the CUDA stream (cudaStream_t) all work of this context is issued on */
 int warpii_gpu_stream(warpii_gpu_ctx* ctx, void** stream_out);
 

@@ -340,6 +340,15 @@ class BoxSolver:
         _check(lib().warpii_gpu_stage_timing(self.ctx, int(enable), C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def sm_clock_probes(self):
+        """SM clock readings (MHz) taken on the device after every batch of steps while stage timing was enabled."""
+        out = np.zeros(64)
+        n = C.c_int(0)
+        L = lib()
+        L.warpii_gpu_sm_clock_probes.argtypes = [C.c_void_p, _dp, C.c_int, C.POINTER(C.c_int)]
+        _check(L.warpii_gpu_sm_clock_probes(self.ctx, _ptr(out), 64, C.byref(n)))
+        return out[:n.value].tolist()
+
     def device_ptr(self, vec):
         p = C.c_void_p()
         _check(lib().warpii_gpu_device_ptr(self.ctx, vec, C.byref(p)))

@@ -92,8 +92,10 @@ __global__ void boundary_kernel(const BoundaryParams P) {
 
 // one block; fixed summation order => deterministic boundary-integrated fluxes
 __global__ void bif_update_kernel(const double* bflux, const int32_t* bf_id, int64_t n_bfaces, int nsp,
-                                  int n_boundaries, double* bif_dst, const double* bif_u, double dt, double a,
-                                  double beta, int mode) {
+                                  int n_boundaries, double* bif_dst, const double* bif_u, double dt_host,
+                                  const double* dt_dev, const int* skip_dev, double a, double beta, int mode) {
+    if (skip_dev && *skip_dev) return;
+    const double dt = dt_dev ? *dt_dev : dt_host;
     const int i = threadIdx.x;   // i = bid*5 + c
     if (i >= n_boundaries * 5) return;
     const int bid = i / 5, c = i % 5;
@@ -199,11 +201,11 @@ void launch_boundary(int dim, int Np, const BoundaryParams& P, cudaStream_t s) {
 }
 
 void launch_bif_update(const double* bflux, const int32_t* bf_id, int64_t n_bfaces, int nsp, int n_boundaries,
-                       double* bif_dst, const double* bif_u, double dt, double a, double beta, int mode,
-                       cudaStream_t s) {
+                       double* bif_dst, const double* bif_u, double dt, const double* dt_dev, const int* skip_dev, double a,
+                       double beta, int mode, cudaStream_t s) {
     if (n_boundaries <= 0) return;
     bif_update_kernel<<<1, ((n_boundaries * 5 + 31) / 32) * 32, 0, s>>>(bflux, bf_id, n_bfaces, nsp, n_boundaries,
-                                                                          bif_dst, bif_u, dt, a, beta, mode);
+                                                                          bif_dst, bif_u, dt, dt_dev, skip_dev, a, beta, mode);
 }
 
 void launch_cfl(int dim, int Np, const double* u, int64_t n_elems, int nc, int nsp, double gamma,
@@ -233,6 +235,56 @@ void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, con
 #undef CALL
 }
 
+}  // namespace wgpu
+
+// ---- device-resident clock (inner loop of advance(), timestepper.cc:34-42) ------------------------------------
+namespace wgpu {
+__global__ void clock_kernel(DevClock* ck, unsigned long long* vmax, int finalize) {
+    if (ck->pending) {   // book the step that has just been computed
+        ck->t += ck->dt;
+        ck->steps += 1;
+        ck->pending = 0;
+    }
+    if (ck->done) return;
+    if (!(ck->t < ck->t_stop - 1e-12) || (ck->max_steps > 0 && ck->steps >= ck->max_steps)) {
+        ck->done = 1;
+        ck->dt = 0.0;
+        return;
+    }
+    if (finalize) return;   // end of a batch: the next batch starts with a full call
+    double dt = ck->fixed_dt;
+    if (!(dt > 0.0)) {
+        const double v = __longlong_as_double((long long)*vmax);
+        dt = 0.5 / (v * ck->np * ck->np);   // fluid_flux_es_dgsem_operator.h:446-447
+    }
+    if (!(dt > 0.0) || isinf(dt) || isnan(dt)) {   // unphysical state: stop, the host reports it
+        ck->error = 1;
+        ck->done = 1;
+        ck->dt = dt;
+        return;
+    }
+    ck->dt = fmin(dt, ck->t_stop - ck->t);
+    ck->pending = 1;
+    *vmax = 0ull;   // the second stage of the coming step reduces the new maximum into it
+}
+void launch_clock(DevClock* clock, unsigned long long* vmax, int finalize, cudaStream_t s) {
+    clock_kernel<<<1, 1, 0, s>>>(clock, vmax, finalize);
+}
+}  // namespace wgpu
+
+// ---- SM clock measured ON the device (no NVML call inside a timed region: those stall NCCL runs for milliseconds) ----
+namespace wgpu {
+__global__ void sm_clock_probe_kernel(double* out_mhz) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    do {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < 40000ull);   // 40 us window
+    const long long c1 = clock64();
+    *out_mhz = (double)(c1 - c0) / (double)(t1 - t0) * 1e3;
+}
+void launch_sm_clock_probe(double* out_mhz, cudaStream_t s) { sm_clock_probe_kernel<<<1, 1, 0, s>>>(out_mhz); }
 }  // namespace wgpu
 
 // ---- point physics on the device, for known-answer tests (the reference's euler_test.cc goldens) -----------------

@@ -42,6 +42,8 @@ struct StageParams {
     int32_t nc, nsp;
     int32_t mode;                 // 0: dst = beta*dst + a*(u + dt*rate); 1: dst = rate
     double gamma, dt, a, beta;
+    const double* dt_dev;         // if non-null the time step is read from device memory (device-resident time loop)
+    const int* skip_dev;          // if non-null and *skip_dev != 0 the launch is a no-op (time loop already finished)
     double hig;                   // 1 / (2 (gamma - 1))
     double inv_h[3];              // 1/h_d
     double inv_hw[3];             // 1/(h_d * w_0): face lifting factor (face JxW / cell JxW on a Cartesian cell)
@@ -69,6 +71,20 @@ struct BoundaryParams {
     double Ig[(kMaxNp + 1) * kMaxNp];   // Ig[q*Np+i] = l_i(xg_q)
 };
 
+// Device-resident clock of warpii_gpu_advance_to: the inner loop of advance() (timestepper.cc:34-42) without a host
+// round trip per step.
+struct DevClock {
+    double t, dt, t_stop, fixed_dt;
+    long long steps, max_steps;
+    int done, error, pending, np;
+};
+// finalize != 0: only book the pending step (t += dt, steps++).  Otherwise also decide whether to continue and set the
+// next dt = min(fixed_dt or 0.5/(vmax np^2), t_stop - t), then clear *vmax for the fused reduction of the coming step.
+void launch_clock(DevClock* clock, unsigned long long* vmax, int finalize, cudaStream_t s);
+
+// one thread spins 40 us and reports (SM cycles / wall ns): the SM clock in MHz at that point of the stream
+void launch_sm_clock_probe(double* out_mhz, cudaStream_t s);
+
 int stage_smem_bytes(int dim, int Np);
 int prepare_kernels(int dim, int Np);   // opt in to the dynamic shared memory the stage kernel needs; 0 on success
 void launch_stage(int dim, int Np, const StageParams& P, cudaStream_t s);
@@ -76,8 +92,8 @@ void launch_boundary(int dim, int Np, const BoundaryParams& P, cudaStream_t s);
 // bif_rate[n_boundaries*5] = sum over faces/species of bflux (fixed order); then the stage update of the
 // boundary-integrated fluxes (fluid_flux_es_dgsem_operator.h:207-212)
 void launch_bif_update(const double* bflux, const int32_t* bf_id, int64_t n_bfaces, int nsp, int n_boundaries,
-                       double* bif_dst, const double* bif_u, double dt, double a, double beta, int mode,
-                       cudaStream_t s);
+                       double* bif_dst, const double* bif_u, double dt, const double* dt_dev, const int* skip_dev, double a,
+                       double beta, int mode, cudaStream_t s);
 void launch_cfl(int dim, int Np, const double* u, int64_t n_elems, int nc, int nsp, double gamma,
                 const double* inv_h, double max_eig, unsigned long long* vmax, cudaStream_t s);
 // deterministic two-pass reduction: out[5] = sum_e sum_j u * (Jdet * w_j); partial must hold 5*n_blocks doubles

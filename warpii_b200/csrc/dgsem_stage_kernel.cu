@@ -147,6 +147,9 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
     double* const sAlpha = smem + GEO::OFF_ALPHA;
     double* const sRed = smem + GEO::OFF_RED;
 
+    if (P.skip_dev && *P.skip_dev) return;   // uniform: the device-resident time loop has finished
+    const double dt = P.dt_dev ? *P.dt_dev : P.dt;
+
     const int tid = threadIdx.x;
     const int le = tid / NN;
     const int j = tid - le * NN;
@@ -393,10 +396,10 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 for (int c = 0; c < 5; c++) qn[c] = r[c];
             } else if (P.beta == 0.0) {
 #pragma unroll
-                for (int c = 0; c < 5; c++) qn[c] = P.a * (q[c] + P.dt * r[c]);
+                for (int c = 0; c < 5; c++) qn[c] = P.a * (q[c] + dt * r[c]);
             } else {
 #pragma unroll
-                for (int c = 0; c < 5; c++) qn[c] = P.beta * P.dst[off + (size_t)c * NN] + P.a * (q[c] + P.dt * r[c]);
+                for (int c = 0; c < 5; c++) qn[c] = P.beta * P.dst[off + (size_t)c * NN] + P.a * (q[c] + dt * r[c]);
             }
 #pragma unroll
             for (int c = 0; c < 5; c++) P.dst[off + (size_t)c * NN] = qn[c];

@@ -110,6 +110,10 @@ struct warpii_gpu_ctx {
     std::vector<char> vmax_valid;
     double* h_pin = nullptr;                // pinned staging, n_dofs doubles (lazy)
     double* h_small = nullptr;              // pinned, 64 doubles
+    DevClock* d_clock = nullptr;            // device-resident time loop state
+    DevClock* h_clock = nullptr;            // pinned mirror
+    double* d_probe = nullptr;              // SM clock probes (MHz), ring of 64
+    int n_probes = 0;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, n_ranks = 1;
@@ -170,6 +174,8 @@ StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a,
     P.nc = c->nc;
     P.nsp = c->nsp;
     P.mode = mode;
+    P.dt_dev = nullptr;
+    P.skip_dev = nullptr;
     P.gamma = c->gamma;
     P.hig = 0.5 / (c->gamma - 1.0);
     P.dt = dt;
@@ -203,7 +209,10 @@ int start_exchange(warpii_gpu_ctx* c, int u) {
     return 0;
 }
 
-int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double beta, int mode, bool fuse_cfl) {
+int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double beta, int mode, bool fuse_cfl,
+              bool device_clock = false) {
+    const double* dt_dev = device_clock ? &c->d_clock->dt : nullptr;
+    const int* skip_dev = device_clock ? &c->d_clock->done : nullptr;
     // boundary faces first: their contributions are consumed by the stage kernel
     if (c->n_bfaces > 0) {
         BoundaryParams B = c->B;
@@ -212,12 +221,15 @@ int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double bet
         c->launches++;
     }
     if (c->n_boundaries > 0) {
-        launch_bif_update(c->d_bflux, c->d_bf_id, c->n_bfaces, c->nsp, c->n_boundaries, c->bif[dst], c->bif[u], dt, a,
-                          beta, mode, c->stream);
+        launch_bif_update(c->d_bflux, c->d_bf_id, c->n_bfaces, c->nsp, c->n_boundaries, c->bif[dst], c->bif[u], dt, dt_dev,
+                          skip_dev, a, beta, mode, c->stream);
         c->launches++;
     }
-    if (fuse_cfl) CUDA_OK(cudaMemsetAsync(c->d_vmax + dst, 0, sizeof(unsigned long long), c->stream));
+    // (with the device clock, clock_kernel clears the slot after it has read the previous maximum)
+    if (fuse_cfl && !device_clock) CUDA_OK(cudaMemsetAsync(c->d_vmax + dst, 0, sizeof(unsigned long long), c->stream));
     StageParams P = stage_params(c, dst, u, dt, a, beta, mode, fuse_cfl);
+    P.dt_dev = dt_dev;
+    P.skip_dev = skip_dev;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->timing) {
         if (get_events(c, &e0, &e1)) return 1;
@@ -226,16 +238,20 @@ int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double bet
     const bool halo = c->comm && !c->peer_rank.empty();
     if (halo) {
         if (start_exchange(c, u)) return 1;
-        // interior elements while the traces are in flight, then the interface elements
+        // interior elements on the compute stream while the traces are in flight; the (few) interface elements follow the
+        // receive on the high-priority communication stream, so they slot in between the interior kernel's blocks
+        // instead of waiting for its tail.  The two launches write disjoint elements of dst.
+        StageParams Pi = P;
+        Pi.elem_begin = 0;
+        Pi.elem_end = c->n_interface;
+        launch_stage(c->dim, c->Np, Pi, c->comm_stream);
+        if (Pi.elem_end > Pi.elem_begin) c->launches++;
+        CUDA_OK(cudaEventRecord(c->ev_recv, c->comm_stream));
         P.elem_begin = c->n_interface;
         P.elem_end = c->n_elems;
         launch_stage(c->dim, c->Np, P, c->stream);
         if (P.elem_end > P.elem_begin) c->launches++;
         CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_recv, 0));
-        P.elem_begin = 0;
-        P.elem_end = c->n_interface;
-        launch_stage(c->dim, c->Np, P, c->stream);
-        if (P.elem_end > P.elem_begin) c->launches++;
     } else {
         launch_stage(c->dim, c->Np, P, c->stream);
         c->launches++;
@@ -357,8 +373,10 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
     if (m->bc_kind)
         for (size_t i = 0; i < (size_t)c->nsp * c->n_boundaries; i++) c->h_bc_kind[i] = m->bc_kind[i];
 
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_recv, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
@@ -387,6 +405,9 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
         rc |= upload<double>(&c->bif[v], nullptr, (size_t)5 * (c->n_boundaries > 0 ? c->n_boundaries : 1));
     }
     if (!rc && cudaMallocHost((void**)&c->h_small, 64 * sizeof(double)) != cudaSuccess) rc = fail("cudaMallocHost failed");
+    if (!rc && cudaMallocHost((void**)&c->h_clock, sizeof(DevClock)) != cudaSuccess) rc = fail("cudaMallocHost failed");
+    if (!rc && cudaMalloc((void**)&c->d_clock, sizeof(DevClock)) != cudaSuccess) rc = fail("cudaMalloc failed");
+    if (!rc && cudaMalloc((void**)&c->d_probe, 64 * sizeof(double)) != cudaSuccess) rc = fail("cudaMalloc failed");
     if (rc) {
         std::string keep = g_last_error;
         warpii_gpu_destroy(c);
@@ -442,6 +463,9 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     cudaFree(c->d_send_elem); cudaFree(c->d_send_side);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_small) cudaFreeHost(c->h_small);
+    if (c->h_clock) cudaFreeHost(c->h_clock);
+    cudaFree(c->d_clock);
+    cudaFree(c->d_probe);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->ev_pack) cudaEventDestroy(c->ev_pack);
     if (c->ev_recv) cudaEventDestroy(c->ev_recv);
@@ -575,25 +599,48 @@ int warpii_gpu_ssprk2_step(warpii_gpu_ctx* c, int solution, int f1, double dt, d
 int warpii_gpu_advance_to(warpii_gpu_ctx* c, int solution, int f1, double* t_inout, double t_stop, double fixed_dt,
                           int64_t max_steps, int64_t* steps_out) {
     if (check_vec(c, solution, "advance_to") || check_vec(c, f1, "advance_to")) return 1;
+    if (solution == f1) return fail("advance_to: solution and f1 must be different vectors");
     if (!t_inout) return fail("advance_to: null time pointer");
-    double t = *t_inout;
-    int64_t steps = 0;
-    while (t < t_stop - 1e-12) {   // timestepper.cc:34-42
-        double dt = fixed_dt;
-        if (!(fixed_dt > 0.0) && warpii_gpu_recommend_dt(c, solution, &dt)) return 1;
-        if (!(dt > 0.0) || !std::isfinite(dt)) {
-            *t_inout = t;
-            if (steps_out) *steps_out = steps;
-            return fail("advance_to: recommended dt = %g at t = %g (state is no longer physical)", dt, t);
-        }
-        dt = std::fmin(dt, t_stop - t);
-        if (warpii_gpu_ssprk2_step(c, solution, f1, dt, t)) return 1;
-        t += dt;
-        steps++;
-        if (max_steps > 0 && steps >= max_steps) break;
+    CUDA_OK(cudaSetDevice(c->device));
+    // The loop of timestepper.cc:34-42 with t, dt and the stop test resident on the device: steps are enqueued in
+    // batches and the host looks at the clock once per batch, so there is no host round trip (and no launch gap) per step.
+    if (!c->vmax_valid[solution]) {
+        CUDA_OK(cudaMemsetAsync(c->d_vmax + solution, 0, sizeof(unsigned long long), c->stream));
+        launch_cfl(c->dim, c->Np, c->vec[solution], c->n_elems, c->nc, c->nsp, c->gamma, c->inv_h, c->max_eig, c->d_vmax + solution, c->stream);
+        c->launches++;
+        c->vmax_valid[solution] = 1;
     }
-    *t_inout = t;
-    if (steps_out) *steps_out = steps;
+    if (c->comm && c->n_ranks > 1)   // max over ranks; idempotent if the slot already holds the global maximum
+        NCCL_OK(g_nccl.AllReduce(c->d_vmax + solution, c->d_vmax + solution, 1, ncclDouble, ncclMax, c->comm, c->stream));
+    DevClock* hc = c->h_clock;
+    *hc = DevClock{*t_inout, 0.0, t_stop, fixed_dt > 0.0 ? fixed_dt : 0.0, 0, max_steps > 0 ? max_steps : 0, 0, 0, 0, c->p + 1};
+    CUDA_OK(cudaMemcpyAsync(c->d_clock, hc, sizeof(DevClock), cudaMemcpyHostToDevice, c->stream));
+    const int batch = 8;
+    int64_t known_steps = 0;
+    for (;;) {
+        int n = batch;
+        if (max_steps > 0 && max_steps - known_steps < n) n = (int)(max_steps - known_steps);
+        for (int i = 0; i < n; i++) {
+            launch_clock(c->d_clock, c->d_vmax + solution, 0, c->stream);
+            if (run_stage(c, f1, solution, 0.0, 1.0, 0.0, 0, false, true)) return 1;        // rk.h:102-103
+            if (run_stage(c, solution, f1, 0.0, 0.5, 0.5, 0, true, true)) return 1;         // rk.h:104-105
+            if (c->comm && c->n_ranks > 1)
+                NCCL_OK(g_nccl.AllReduce(c->d_vmax + solution, c->d_vmax + solution, 1, ncclDouble, ncclMax, c->comm, c->stream));
+        }
+        launch_clock(c->d_clock, c->d_vmax + solution, 1, c->stream);   // book the last step of the batch, test for the end
+        if (c->timing && c->n_probes < 64) launch_sm_clock_probe(c->d_probe + c->n_probes++, c->stream);
+        c->launches += n + 1;
+        CUDA_OK(cudaMemcpyAsync(hc, c->d_clock, sizeof(DevClock), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        known_steps = hc->steps;
+        if (hc->done || hc->error || (max_steps > 0 && known_steps >= max_steps)) break;
+    }
+    c->vmax_valid[solution] = 1;
+    c->vmax_valid[f1] = 0;
+    *t_inout = hc->t;
+    if (steps_out) *steps_out = hc->steps;
+    if (hc->error)
+        return fail("advance_to: recommended dt = %g at t = %g (state is no longer physical)", hc->dt, hc->t);
     return 0;
 }
 
@@ -748,5 +795,15 @@ extern "C" int warpii_gpu_point_fluxes(int device, int n, const double* qa, cons
     CUDA_OK(cudaMemcpy(es_out, des, (size_t)5 * n * sizeof(double), cudaMemcpyDeviceToHost));
     if (prim_out) CUDA_OK(cudaMemcpy(prim_out, dpr, (size_t)12 * n * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(dqa); cudaFree(dqb); cudaFree(dec); cudaFree(des); cudaFree(dpr);
+    return 0;
+}
+
+extern "C" int warpii_gpu_sm_clock_probes(warpii_gpu_ctx* c, double* mhz_out, int max_out, int* n_out) {
+    if (!c || !n_out) return fail("null argument");
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    const int n = c->n_probes < max_out ? c->n_probes : max_out;
+    if (n > 0) CUDA_OK(cudaMemcpy(mhz_out, c->d_probe, n * sizeof(double), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    c->n_probes = 0;
     return 0;
 }
