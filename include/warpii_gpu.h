@@ -111,6 +111,15 @@ int warpii_gpu_device_ptr(warpii_gpu_ctx* ctx, int vec, void** out);
  * (fluid_flux_es_dgsem_operator.h:377-380).  Call again before a stage if the function depends on t
  * (the reference calls set_time(t) at :140-144). */
 int warpii_gpu_set_inflow(warpii_gpu_ctx* ctx, int species, int boundary_id, const double q[5]);
+/* Space-dependent inflow: the Function<dim> of EulerBCMap::get_inflow tabulated where the reference evaluates it,
+ * phi.quadrature_point(q) of every boundary face (fluid_flux_es_dgsem_operator.h:381-384):
+ * table[n_faces][points_per_face][5] conserved values for one species; faces in the order of
+ * warpii_gpu_mesh.boundary_face_*, points_per_face = (fe_degree+2)^(dim-1) Gauss points, tensor-ordered with the
+ * lower tangential dimension fastest.  Rows of faces whose condition is not Inflow are ignored.  Upload again before a
+ * stage when the function depends on t.  After the first table, warpii_gpu_set_inflow keeps working (it overwrites
+ * the rows of its boundary). */
+int warpii_gpu_n_boundary_points(const warpii_gpu_ctx* ctx, int64_t* n_faces_out, int* points_per_face_out);
+int warpii_gpu_set_inflow_table(warpii_gpu_ctx* ctx, int species, const double* table);
 
 /* -- the operator ----------------------------------------------------------------------------------
  * dst = beta*dst + alpha*(u + dt * M^-1 R(u)), and the same for the boundary-integrated fluxes

@@ -51,6 +51,18 @@ int warpii_box_solver_set_state(warpii_box_solver* s, const double* host);
 int warpii_box_solver_get_state(warpii_box_solver* s, double* host);
 int warpii_box_solver_set_inflow(warpii_box_solver* s, int species, int boundary_id, const double q[5]);
 
+/* Space/time-dependent inflow: q5 = fn(x[dim], t), the Function<dim> of EulerBCMap::set_inflow_boundary
+ * (bc_helper.h:52-64).  The host layer tabulates it at this rank's boundary quadrature points with the stage time before
+ * every stage (time_dependent != 0; the reference's set_time(t), fluid_flux_es_dgsem_operator.h:139-144) or once, and
+ * uploads the table through warpii_gpu_set_inflow_table. */
+typedef void (*warpii_inflow_fn)(const double* x, double t, double* q5, void* user);
+int warpii_box_solver_set_inflow_function(warpii_box_solver* s, int species, int boundary_id, warpii_inflow_fn fn,
+                                          void* user, int time_dependent);
+/* this rank's boundary faces: xyz[face][point][dim] of the quadrature points (Gauss(fe_degree+2)^(dim-1) per face) and
+ * the boundary id of every face, in the order of the inflow table; either output may be NULL */
+int64_t warpii_box_solver_n_boundary_faces(const warpii_box_solver* s);
+int warpii_box_solver_boundary_points(const warpii_box_solver* s, double* xyz, int32_t* face_boundary_id);
+
 /* attach the NCCL communicator (id from warpii_gpu_nccl_unique_id on rank 0, broadcast by the caller) */
 int warpii_box_solver_attach_comm(warpii_box_solver* s, const char id[WARPII_GPU_NCCL_ID_BYTES]);
 
@@ -62,6 +74,36 @@ int warpii_box_solver_solve(warpii_box_solver* s, double t_end, double fixed_dt,
 /* SSPRK2Integrator::evolve_one_time_step / operator.recommend_dt on the solver's own solution vector */
 int warpii_box_solver_step(warpii_box_solver* s, double dt, double t);
 int warpii_box_solver_recommend_dt(warpii_box_solver* s, double* dt_out);
+
+/* ---- the FiveMoment application driven by a WarpII input file ------------------------------------------------------
+ * Replaces Warpii::setup/run for Application = FiveMoment (warpii.cc:126-196, five_moment.cc:22-52, five_moment.h:99-243)
+ * on HyperRectangle grids: the same entries, defaults and patterns, parsed by an independent reader
+ * (warpii_b200/host/parameter_file.hpp) and expression evaluator (expression.hpp).  create needs no GPU; setup and run do.
+ * The frame callback stands where the reference writes solution_<n>.vtu (frame 0 fires in setup). */
+typedef struct warpii_app warpii_app;
+typedef void (*warpii_frame_fn)(unsigned frame, double t, void* user);
+int warpii_app_create(const char* input_text, int rank, int n_ranks, int device, warpii_app** out);
+int warpii_app_destroy(warpii_app* app);
+/* the app's solver, valid until warpii_app_destroy (state access, node coordinates, communicator attachment ...) */
+warpii_box_solver* warpii_app_solver(warpii_app* app);
+/* parsed parameters: ints = {n_dims, n_species, n_boundaries, fe_degree, fields_enabled, write_output,
+ * n_writeout_frames, nx[3], periodic[3]}, dbls = {gas_gamma, t_end, left[3], right[3]} */
+int warpii_app_describe(const warpii_app* app, int32_t ints[16], double dbls[16]);
+int warpii_app_species(const warpii_app* app, int species, char name[16], double* charge, double* mass,
+                       int32_t* bc_kinds /* [n_boundaries] */);
+/* evaluate a parsed SpeciesFunc on the host: boundary_id < 0 = the initial condition, else that boundary's inflow
+ * function.  xyz[n][n_dims] -> q5_out[n][5] conserved (species_func.cc:9-30). */
+int warpii_app_eval_function(const warpii_app* app, int species, int boundary_id, int64_t n, const double* xyz,
+                             double t, double* q5_out, int32_t* time_dependent_out);
+/* with write_output, frames go to <dir>/solution_<frame>.f64 (raw doubles, device order) + frames.txt; "" = no files */
+int warpii_app_set_output_dir(warpii_app* app, const char* dir);
+/* WorkDir format of the input (%A__%I by default) expanded as format_workdir does (warpii.cc:205-219) */
+int warpii_app_format_workdir(const warpii_app* app, const char* input_name, char* out, int out_len);
+/* 0: drive every stage from the host like the reference's solve(); 1 (default): device-resident loop when no inflow
+ * function depends on t */
+int warpii_app_set_device_loop(warpii_app* app, int on);
+int warpii_app_setup(warpii_app* app);
+int warpii_app_run(warpii_app* app, warpii_frame_fn cb, void* user, int64_t* steps_out);
 
 /* the time loop alone (timestepper.cc:6-56) with C callbacks, for the reference's TimestepperTest cases */
 typedef int (*warpii_step_fn)(double t, double dt, void* user);

@@ -15,6 +15,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libwarpii_ref.so")
 
 BC_WALL, BC_OUTFLOW, BC_INFLOW = 0, 1, 2
+INFLOW_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_void_p)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -91,6 +92,7 @@ def lib():
         L.orc_n_boundaries.argtypes = [C.c_void_p]
         L.orc_node_coords.argtypes = [C.c_void_p, _dp]
         L.orc_set_inflow.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+        L.orc_set_inflow_function.argtypes = [C.c_void_p, C.c_int, C.c_int, INFLOW_FN, C.c_void_p]
         L.orc_rhs.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp]
         L.orc_alpha.argtypes = [C.c_void_p, _dp, _dp]
         L.orc_cell_residual.argtypes = [C.c_void_p, _dp, C.c_double, _dp]
@@ -280,6 +282,22 @@ class Oracle:
 
     def set_inflow(self, species, boundary_id, q):
         lib().orc_set_inflow(self.h, species, boundary_id, _ptr(_f64(q)))
+
+    def set_inflow_function(self, species, boundary_id, fn):
+        """fn(x: ndarray[dim], t: float) -> 5 conserved values, evaluated at every boundary quadrature point with the
+        stage time, like the Function<dim> of EulerBCMap::get_inflow (fluid_flux_es_dgsem_operator.h:139-144, 381-384)."""
+        dim = self.dim
+
+        def thunk(x, t, q5, _user):
+            q = fn(np.array([x[d] for d in range(dim)]), t)
+            for k in range(5):
+                q5[k] = float(q[k])
+
+        cb = INFLOW_FN(thunk)
+        if not hasattr(self, "_inflow_cbs"):
+            self._inflow_cbs = {}
+        self._inflow_cbs[(species, boundary_id)] = cb   # keep the thunk alive
+        lib().orc_set_inflow_function(self.h, species, boundary_id, cb, None)
 
     def project(self, prim_fn, species=0, u=None, conserved=False):
         """Nodal interpolation of an IC given as fn(xyz[...,dim]) -> [...,5] (dg_solution_helper.cc:24-48)."""

@@ -341,6 +341,13 @@ struct Ctx {
     Basis B;
     std::vector<int> bc_kind;     // [nsp][2*dim]
     std::vector<double> inflow;   // [nsp][2*dim][5]
+    // space/time-dependent inflow: the Function<dim> of EulerBCMap::get_inflow, evaluated at the boundary quadrature
+    // points with the stage time (fluid_flux_es_dgsem_operator.h:139-144, 381-384)
+    struct InflowFn { orc_inflow_fn fn = nullptr; void* user = nullptr; };
+    std::vector<InflowFn> inflow_fn;            // [nsp][2*dim]
+    std::vector<int64_t> bface_of;              // [nelem][2*dim] -> boundary face number or -1
+    int64_t n_bfaces = 0;
+    mutable std::vector<double> inflow_vals;    // [nsp][n_bfaces][nG][5], refreshed at the start of every RHS
     // Cartesian geometry, formed the way the reference forms it from inverse_jacobian(q)
     double Jinv[3] = {1, 1, 1};   // diagonal of J^{-T}
     double Jdet = 1;              // jacobian_utils.h:12-18: 1/det(Jinv)
@@ -656,7 +663,12 @@ void face_residual(const Ctx& c, const double* u, int64_t e, int sp, double* R, 
                 for (int a = 1; a < dim; a++) rho_u_dot_n += wm[1 + a] * n[a];
                 double wp[5];
                 if (kind == ORC_BC_INFLOW) {
-                    for (int k = 0; k < 5; k++) wp[k] = c.inflow[((size_t)sp * 2 * dim + bid) * 5 + k];
+                    if (c.inflow_fn[(size_t)sp * 2 * dim + bid].fn) {
+                        const int64_t bfn = c.bface_of[(size_t)e * 2 * dim + f];
+                        for (int k = 0; k < 5; k++) wp[k] = c.inflow_vals[(((size_t)sp * c.n_bfaces + bfn) * nG + g) * 5 + k];
+                    } else {
+                        for (int k = 0; k < 5; k++) wp[k] = c.inflow[((size_t)sp * 2 * dim + bid) * 5 + k];
+                    }
                 } else if (kind == ORC_BC_OUTFLOW) {
                     for (int k = 0; k < 5; k++) wp[k] = wm[k];
                 } else {  // wall (:394-405)
@@ -691,10 +703,45 @@ void face_residual(const Ctx& c, const double* u, int64_t e, int sp, double* R, 
     }
 }
 
+// Evaluate the inflow functions at every boundary quadrature point for stage time t (serially: the callbacks may be
+// Python).  Point of Gauss index g on face f of element e: the face's coordinate in d, Gauss abscissae in the others.
+template <int dim>
+void refresh_inflow(const Ctx& c, double t) {
+    bool any = false;
+    for (const auto& f : c.inflow_fn) any = any || f.fn;
+    if (!any) return;
+    const int Ng = c.B.Ng, nG = c.nfaceG;
+    c.inflow_vals.assign((size_t)c.nsp * c.n_bfaces * nG * 5, 0.0);
+    for (int64_t e = 0; e < c.nelem; e++) {
+        int idx[3];
+        c.elem_coords(e, idx);
+        for (int f = 0; f < 2 * dim; f++) {
+            const int64_t bfn = c.bface_of[(size_t)e * 2 * dim + f];
+            if (bfn < 0) continue;
+            const int d = f / 2, side = f % 2;
+            for (int sp = 0; sp < c.nsp; sp++) {
+                const auto& fn = c.inflow_fn[(size_t)sp * 2 * dim + f];
+                if (!fn.fn || c.bc_kind[(size_t)sp * 2 * dim + f] != ORC_BC_INFLOW) continue;
+                for (int g = 0; g < nG; g++) {
+                    int gi[2] = {g % Ng, (g / Ng) % Ng};
+                    double x[3] = {0, 0, 0};
+                    int k = 0;
+                    for (int a = 0; a < dim; a++) {
+                        if (a == d) x[a] = c.left[a] + (idx[a] + side) * c.h[a];
+                        else x[a] = c.left[a] + (idx[a] + c.B.xg[gi[k++]]) * c.h[a];
+                    }
+                    fn.fn(x, t, &c.inflow_vals[(((size_t)sp * c.n_bfaces + bfn) * nG + g) * 5], fn.user);
+                }
+            }
+        }
+    }
+}
+
 // dudt = M^-1 R(u):  mf.loop + inverse mass (fluid_flux_es_dgsem_operator.h:183-240)
 template <int dim>
-void rhs_impl(const Ctx& c, const double* u, double /*t*/, double* dudt, double* bif_rate, double* alpha_out) {
+void rhs_impl(const Ctx& c, const double* u, double t, double* dudt, double* bif_rate, double* alpha_out) {
     const int NN = c.NN, nb5 = 5 * 2 * dim;
+    refresh_inflow<dim>(c, t);
     const int nthreads = std::max(1, c.nthreads);
     std::vector<std::vector<double>> bif_local(nthreads, std::vector<double>(nb5, 0.0));
 #pragma omp parallel for num_threads(nthreads) schedule(static)
@@ -984,6 +1031,11 @@ void* orc_create(int dim, int fe_degree, int n_species, int fields_enabled, doub
     c->bc_kind.assign((size_t)n_species * 2 * dim, ORC_BC_WALL);   // species.cc:17 default "Wall"
     if (bc_kinds) for (size_t i = 0; i < c->bc_kind.size(); i++) c->bc_kind[i] = bc_kinds[i];
     c->inflow.assign((size_t)n_species * 2 * dim * 5, 0.0);
+    c->inflow_fn.assign((size_t)n_species * 2 * dim, Ctx::InflowFn());
+    c->bface_of.assign((size_t)c->nelem * 2 * dim, -1);
+    for (int64_t e = 0; e < c->nelem; e++)
+        for (int f = 0; f < 2 * dim; f++)
+            if (c->neighbor(e, f) < 0) c->bface_of[(size_t)e * 2 * dim + f] = c->n_bfaces++;
     return c;
 }
 void orc_destroy(void* h) { delete (Ctx*)h; }
@@ -1010,6 +1062,11 @@ void orc_node_coords(void* h, double* xyz) {
 void orc_set_inflow(void* h, int species, int boundary_id, const double q[5]) {
     Ctx& c = *(Ctx*)h;
     for (int k = 0; k < 5; k++) c.inflow[((size_t)species * 2 * c.dim + boundary_id) * 5 + k] = q[k];
+}
+void orc_set_inflow_function(void* h, int species, int boundary_id, orc_inflow_fn fn, void* user) {
+    Ctx& c = *(Ctx*)h;
+    c.inflow_fn[(size_t)species * 2 * c.dim + boundary_id].fn = fn;
+    c.inflow_fn[(size_t)species * 2 * c.dim + boundary_id].user = user;
 }
 void orc_rhs(void* h, const double* u, double t, double* dudt, double* bif_rate) {
     Ctx& c = *(Ctx*)h;

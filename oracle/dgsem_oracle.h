@@ -87,6 +87,11 @@ int orc_n_boundaries(void* h);    // 2*dim
 void orc_node_coords(void* h, double* xyz);
 // Constant conserved inflow state for (species, boundary id).
 void orc_set_inflow(void* h, int species, int boundary_id, const double q[5]);
+// Space/time-dependent conserved inflow state q5 = fn(x[dim], t): the Function<dim> the reference evaluates at every
+// boundary quadrature point after set_time(t) with the stage time (fluid_flux_es_dgsem_operator.h:139-144, 381-384).
+// NULL restores the constant state.
+typedef void (*orc_inflow_fn)(const double* x, double t, double* q5, void* user);
+void orc_set_inflow_function(void* h, int species, int boundary_id, orc_inflow_fn fn, void* user);
 // dudt = M^-1 R(u) (fluid comps only; field comps 0); bif_rate[5*n_boundaries] per species summed as the reference does.
 void orc_rhs(void* h, const double* u, double t, double* dudt, double* bif_rate);
 // Integrated cell residual (volume + subcell FV, value*JxW as integrate_scatter leaves it) of ONE cell/species with a

@@ -5,6 +5,8 @@ import os
 import numpy as np
 
 BC_WALL, BC_OUTFLOW, BC_INFLOW = 0, 1, 2
+INFLOW_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_void_p)
+FRAME_FN = C.CFUNCTYPE(None, C.c_uint, C.c_double, C.c_void_p)
 FUSE_CFL = 1
 NCCL_ID_BYTES = 128
 
@@ -84,6 +86,24 @@ def lib():
     L.warpii_box_solver_get_state.argtypes = [vp, _dp]
     L.warpii_box_solver_set_inflow.argtypes = [vp, C.c_int, C.c_int, _dp]
     L.warpii_box_solver_attach_comm.argtypes = [vp, C.c_char_p]
+    L.warpii_box_solver_set_inflow_function.argtypes = [vp, C.c_int, C.c_int, INFLOW_FN, vp, C.c_int]
+    L.warpii_box_solver_n_boundary_faces.restype = C.c_int64
+    L.warpii_box_solver_n_boundary_faces.argtypes = [vp]
+    L.warpii_box_solver_boundary_points.argtypes = [vp, _dp, _i32p]
+    L.warpii_gpu_n_boundary_points.argtypes = [vp, _i64p, _i32p]
+    L.warpii_gpu_set_inflow_table.argtypes = [vp, C.c_int, _dp]
+    L.warpii_app_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.warpii_app_destroy.argtypes = [vp]
+    L.warpii_app_solver.restype = vp
+    L.warpii_app_solver.argtypes = [vp]
+    L.warpii_app_describe.argtypes = [vp, _i32p, _dp]
+    L.warpii_app_species.argtypes = [vp, C.c_int, C.c_char_p, _dp, _dp, _i32p]
+    L.warpii_app_eval_function.argtypes = [vp, C.c_int, C.c_int, C.c_int64, _dp, C.c_double, _dp, _i32p]
+    L.warpii_app_set_output_dir.argtypes = [vp, C.c_char_p]
+    L.warpii_app_format_workdir.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int]
+    L.warpii_app_set_device_loop.argtypes = [vp, C.c_int]
+    L.warpii_app_setup.argtypes = [vp]
+    L.warpii_app_run.argtypes = [vp, FRAME_FN, vp, _i64p]
     L.warpii_box_solver_solve.argtypes = [vp, C.c_double, C.c_double, C.c_double, vp, vp, _i64p]
     L.warpii_box_solver_step.argtypes = [vp, C.c_double, C.c_double]
     L.warpii_box_solver_recommend_dt.argtypes = [vp, _dp]
@@ -193,6 +213,20 @@ class BoxSolver:
         _check(L.warpii_box_solver_create(dim, fe_degree, n_species, int(fields_enabled), gamma, nx_a.ctypes.data_as(_i32p),
                                           _ptr(l_a), _ptr(r_a), per_a.ctypes.data_as(_i32p), n_boundaries, bc_p, rank, n_ranks,
                                           device, C.byref(h)), host=True)
+        self._owned = True
+        self._bind(h)
+
+    @classmethod
+    def _view(cls, h, dim, fe_degree, gamma, n_species, n_boundaries):
+        """A BoxSolver over a handle owned by something else (App.solver)."""
+        self = cls.__new__(cls)
+        self.dim, self.p, self.gamma, self.nsp, self.n_boundaries = dim, fe_degree, gamma, n_species, n_boundaries
+        self._owned = False
+        self._bind(h)
+        return self
+
+    def _bind(self, h):
+        L = lib()
         self.h = h
         self.ctx = C.c_void_p(L.warpii_box_solver_ctx(h))
         self.n_elems = L.warpii_box_solver_n_local_elems(h)
@@ -233,7 +267,8 @@ class BoxSolver:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().warpii_box_solver_destroy(self.h)
+            if self._owned:
+                lib().warpii_box_solver_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -263,6 +298,34 @@ class BoxSolver:
     def set_inflow(self, species, boundary_id, q):
         q = np.ascontiguousarray(q, dtype=np.float64)
         _check(lib().warpii_box_solver_set_inflow(self.h, species, boundary_id, _ptr(q)), host=True)
+
+    def set_inflow_function(self, species, boundary_id, fn, time_dependent=True):
+        """fn(x: ndarray[dim], t) -> 5 conserved values (EulerBCMap::set_inflow_boundary, bc_helper.h:52-64)."""
+        dim = self.dim
+
+        def thunk(x, t, q5, _user):
+            q = fn(np.array([x[d] for d in range(dim)]), t)
+            for k in range(5):
+                q5[k] = float(q[k])
+
+        cb = INFLOW_FN(thunk)
+        if not hasattr(self, "_inflow_cbs"):
+            self._inflow_cbs = []
+        self._inflow_cbs.append(cb)   # keep the thunk alive as long as the solver
+        _check(lib().warpii_box_solver_set_inflow_function(self.h, species, boundary_id, cb, None, int(time_dependent)), host=True)
+
+    def boundary_points(self):
+        """(xyz[face][point][dim], boundary id per face) of this rank's boundary quadrature points."""
+        nf = lib().warpii_box_solver_n_boundary_faces(self.h)
+        nq = (self.p + 2) ** (self.dim - 1)
+        xyz = np.zeros((nf, nq, self.dim))
+        ids = np.zeros(nf, dtype=np.int32)
+        _check(lib().warpii_box_solver_boundary_points(self.h, _ptr(xyz), ids.ctypes.data_as(_i32p)), host=True)
+        return xyz, ids
+
+    def set_inflow_table(self, species, table):
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        _check(lib().warpii_gpu_set_inflow_table(self.ctx, species, _ptr(table)))
 
     def attach_comm(self, nccl_id):
         _check(lib().warpii_box_solver_attach_comm(self.h, nccl_id), host=True)
@@ -358,6 +421,88 @@ class BoxSolver:
         p = C.c_void_p()
         _check(lib().warpii_gpu_stream(self.ctx, C.byref(p)))
         return p.value
+
+
+class App:
+    """The FiveMoment application from a WarpII input file (include/warpii_host.h, warpii_app_*): the GPU-path stand-in
+    for `Warpii::create_from_cli / setup / run` (warpii.cc:61-196) with Application = FiveMoment."""
+
+    def __init__(self, input_text, rank=0, n_ranks=1, device=0):
+        h = C.c_void_p()
+        _check(lib().warpii_app_create(input_text.encode(), rank, n_ranks, device, C.byref(h)), host=True)
+        self.h = h
+        ints = np.zeros(16, dtype=np.int32)
+        dbls = np.zeros(16)
+        _check(lib().warpii_app_describe(h, ints.ctypes.data_as(_i32p), _ptr(dbls)), host=True)
+        (self.n_dims, self.n_species, self.n_boundaries, self.fe_degree) = (int(v) for v in ints[:4])
+        self.fields_enabled, self.write_output = bool(ints[4]), bool(ints[5])
+        self.n_writeout_frames = int(ints[6])
+        d = self.n_dims
+        self.nx = [int(v) for v in ints[7:7 + d]]
+        self.periodic = [bool(v) for v in ints[10:10 + d]]
+        self.gas_gamma, self.t_end = float(dbls[0]), float(dbls[1])
+        self.left = [float(v) for v in dbls[2:2 + d]]
+        self.right = [float(v) for v in dbls[5:5 + d]]
+        self.solver = None
+        self.frames = []
+
+    def species(self, i):
+        name = C.create_string_buffer(16)
+        charge, mass = C.c_double(), C.c_double()
+        kinds = np.zeros(max(self.n_boundaries, 1), dtype=np.int32)
+        _check(lib().warpii_app_species(self.h, i, name, C.byref(charge), C.byref(mass), kinds.ctypes.data_as(_i32p)), host=True)
+        return dict(name=name.value.decode(), charge=charge.value, mass=mass.value, bc_kinds=[int(k) for k in kinds[:self.n_boundaries]])
+
+    def eval_function(self, species, xyz, t=0.0, boundary_id=-1):
+        """Conserved values of the parsed initial condition (boundary_id < 0) or inflow function at xyz[n][n_dims]."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, self.n_dims)
+        out = np.zeros((xyz.shape[0], 5))
+        td = np.zeros(1, dtype=np.int32)
+        _check(lib().warpii_app_eval_function(self.h, species, boundary_id, xyz.shape[0], _ptr(xyz), t, _ptr(out),
+                                              td.ctypes.data_as(_i32p)), host=True)
+        return out, bool(td[0])
+
+    def format_workdir(self, input_name):
+        buf = C.create_string_buffer(512)
+        _check(lib().warpii_app_format_workdir(self.h, input_name.encode(), buf, 512), host=True)
+        return buf.value.decode()
+
+    def set_output_dir(self, path):
+        _check(lib().warpii_app_set_output_dir(self.h, (path or "").encode()), host=True)
+
+    def set_device_loop(self, on):
+        _check(lib().warpii_app_set_device_loop(self.h, int(on)), host=True)
+
+    def setup(self):
+        _check(lib().warpii_app_setup(self.h), host=True)
+        self.solver = BoxSolver._view(C.c_void_p(lib().warpii_app_solver(self.h)), self.n_dims, self.fe_degree, self.gas_gamma,
+                                      self.n_species, self.n_boundaries)
+        return self
+
+    def run(self, frame_callback=None):
+        """Returns the number of SSPRK2 steps; frame times end up in self.frames (frame 0 fires in setup)."""
+        def on_frame(frame, t, _user):
+            self.frames.append((int(frame), float(t)))
+            if frame_callback:
+                frame_callback(int(frame), float(t))
+
+        cb = FRAME_FN(on_frame)
+        steps = C.c_int64(0)
+        _check(lib().warpii_app_run(self.h, cb, None, C.byref(steps)), host=True)
+        if self.solver is None:
+            self.solver = BoxSolver._view(C.c_void_p(lib().warpii_app_solver(self.h)), self.n_dims, self.fe_degree,
+                                          self.gas_gamma, self.n_species, self.n_boundaries)
+        return steps.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            if self.solver is not None:
+                self.solver.close()
+            lib().warpii_app_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 def point_fluxes(qa, qb, d, gamma, device=0):

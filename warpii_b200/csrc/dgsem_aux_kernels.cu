@@ -53,7 +53,12 @@ __global__ void boundary_kernel(const BoundaryParams P) {
         }
         double wp[5];
         if (kind == 2) {   // inflow: prescribed conserved state
-            for (int c = 0; c < 5; c++) wp[c] = P.inflow[((size_t)sp * P.n_boundaries + bid) * 5 + c];
+            if (P.inflow_table) {
+                const double* tab = P.inflow_table + (((size_t)sp * P.n_bfaces + bf) * NG + g) * 5;
+                for (int c = 0; c < 5; c++) wp[c] = tab[c];
+            } else {
+                for (int c = 0; c < 5; c++) wp[c] = P.inflow[((size_t)sp * P.n_boundaries + bid) * 5 + c];
+            }
         } else if (kind == 1) {   // (supersonic) outflow
             for (int c = 0; c < 5; c++) wp[c] = wm[c];
         } else {   // wall: reflect the normal momentum over the first dim components, zero the rest

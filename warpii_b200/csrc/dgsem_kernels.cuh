@@ -61,6 +61,7 @@ struct BoundaryParams {
     const int32_t* bf_id;
     const int32_t* bc_kind;       // [nsp][n_boundaries]
     const double* inflow;         // [nsp][n_boundaries][5]
+    const double* inflow_table;   // nullable: [nsp][n_bfaces][NG][5], state at every boundary quadrature point
     int64_t n_bfaces;
     int32_t nc, nsp, n_boundaries;
     double gamma;

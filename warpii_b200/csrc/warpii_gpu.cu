@@ -99,7 +99,10 @@ struct warpii_gpu_ctx {
     double h[3] = {1, 1, 1}, inv_h[3] = {1, 1, 1}, inv_hw[3] = {1, 1, 1}, Jdet = 1, max_eig = 1;
     ElemTables T;
     BoundaryParams B;
-    std::vector<int32_t> h_bc_kind;
+    std::vector<int32_t> h_bc_kind, h_bf_id;
+    std::vector<double> h_inflow;           // mirror of d_inflow
+    std::vector<double> h_inflow_table;     // mirror of d_inflow_table (empty until warpii_gpu_set_inflow_table)
+    double* d_inflow_table = nullptr;
     int32_t *d_nbr = nullptr, *d_bf_elem = nullptr, *d_bf_side = nullptr, *d_bf_id = nullptr, *d_bc_kind = nullptr;
     double *d_inflow = nullptr, *d_w = nullptr, *d_bres = nullptr, *d_bflux = nullptr, *d_ghost = nullptr,
            *d_sendbuf = nullptr, *d_partial = nullptr, *d_out5 = nullptr, *d_alpha = nullptr;
@@ -390,6 +393,8 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
     rc |= upload(&c->d_bf_id, m->boundary_face_id, (size_t)c->n_bfaces);
     rc |= upload(&c->d_bc_kind, c->h_bc_kind.data(), c->h_bc_kind.size());
     rc |= upload<double>(&c->d_inflow, nullptr, (size_t)c->nsp * (c->n_boundaries > 0 ? c->n_boundaries : 1) * 5);
+    c->h_inflow.assign((size_t)c->nsp * (c->n_boundaries > 0 ? c->n_boundaries : 1) * 5, 0.0);
+    if (c->n_bfaces > 0) c->h_bf_id.assign(m->boundary_face_id, m->boundary_face_id + c->n_bfaces);
     rc |= upload(&c->d_w, re.w.data(), (size_t)c->Np);
     rc |= upload<double>(&c->d_bres, nullptr, (size_t)c->n_bfaces * c->nsp * 5 * c->NF);
     rc |= upload<double>(&c->d_bflux, nullptr, (size_t)c->n_bfaces * c->nsp * 5);
@@ -458,7 +463,7 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     for (double* v : c->vec) cudaFree(v);
     for (double* v : c->bif) cudaFree(v);
     cudaFree(c->d_nbr); cudaFree(c->d_bf_elem); cudaFree(c->d_bf_side); cudaFree(c->d_bf_id); cudaFree(c->d_bc_kind);
-    cudaFree(c->d_inflow); cudaFree(c->d_w); cudaFree(c->d_bres); cudaFree(c->d_bflux); cudaFree(c->d_ghost);
+    cudaFree(c->d_inflow); cudaFree(c->d_inflow_table); cudaFree(c->d_w); cudaFree(c->d_bres); cudaFree(c->d_bflux); cudaFree(c->d_ghost);
     cudaFree(c->d_sendbuf); cudaFree(c->d_partial); cudaFree(c->d_out5); cudaFree(c->d_alpha); cudaFree(c->d_vmax);
     cudaFree(c->d_send_elem); cudaFree(c->d_send_side);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -545,15 +550,69 @@ int warpii_gpu_device_ptr(warpii_gpu_ctx* c, int vec, void** out) {
     return 0;
 }
 
+namespace {
+// (re)upload one species' slice of the inflow table
+int push_inflow_table(warpii_gpu_ctx* c, int species) {
+    const size_t per_species = (size_t)c->n_bfaces * ipow(c->Np + 1, c->dim - 1) * 5;
+    if (per_species == 0) return 0;
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaMemcpy(c->d_inflow_table + per_species * species, c->h_inflow_table.data() + per_species * species,
+                       per_species * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+}  // namespace
+
 int warpii_gpu_set_inflow(warpii_gpu_ctx* c, int species, int boundary_id, const double q[5]) {
     if (!c) return fail("null context");
     if (species < 0 || species >= c->nsp) return fail("set_inflow: species %d out of range", species);
     if (boundary_id < 0 || boundary_id >= c->n_boundaries) return fail("set_inflow: boundary id %d out of range", boundary_id);
-    for (int k = 0; k < 5; k++) c->h_small[8 + k] = q[k];
+    for (int k = 0; k < 5; k++) c->h_small[8 + k] = c->h_inflow[((size_t)species * c->n_boundaries + boundary_id) * 5 + k] = q[k];
     CUDA_OK(cudaMemcpyAsync(c->d_inflow + ((size_t)species * c->n_boundaries + boundary_id) * 5, c->h_small + 8,
                             5 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (!c->h_inflow_table.empty()) {   // a table is active: the constant state replaces this boundary's rows
+        const int NG = ipow(c->Np + 1, c->dim - 1);
+        for (int64_t bf = 0; bf < c->n_bfaces; bf++) {
+            if (c->h_bf_id[bf] != boundary_id) continue;
+            for (int g = 0; g < NG; g++)
+                for (int k = 0; k < 5; k++) c->h_inflow_table[(((size_t)species * c->n_bfaces + bf) * NG + g) * 5 + k] = q[k];
+        }
+        return push_inflow_table(c, species);
+    }
     return 0;
+}
+
+int warpii_gpu_n_boundary_points(const warpii_gpu_ctx* c, int64_t* n_faces_out, int* points_per_face_out) {
+    if (!c) return fail("null context");
+    if (n_faces_out) *n_faces_out = c->n_bfaces;
+    if (points_per_face_out) *points_per_face_out = ipow(c->Np + 1, c->dim - 1);
+    return 0;
+}
+
+int warpii_gpu_set_inflow_table(warpii_gpu_ctx* c, int species, const double* table) {
+    if (!c) return fail("null context");
+    if (species < 0 || species >= c->nsp) return fail("set_inflow_table: species %d out of range", species);
+    if (!table) return fail("set_inflow_table: null table");
+    const int NG = ipow(c->Np + 1, c->dim - 1);
+    const size_t per_species = (size_t)c->n_bfaces * NG * 5;
+    if (per_species == 0) return 0;   // this rank owns no boundary faces
+    if (c->h_inflow_table.empty()) {
+        // first use: every species starts from its constant states, then the kernel reads the table only
+        c->h_inflow_table.resize(per_species * c->nsp);
+        for (int sp = 0; sp < c->nsp; sp++)
+            for (int64_t bf = 0; bf < c->n_bfaces; bf++)
+                for (int g = 0; g < NG; g++)
+                    for (int k = 0; k < 5; k++)
+                        c->h_inflow_table[(((size_t)sp * c->n_bfaces + bf) * NG + g) * 5 + k] =
+                            c->h_inflow[((size_t)sp * c->n_boundaries + c->h_bf_id[bf]) * 5 + k];
+        CUDA_OK(cudaSetDevice(c->device));
+        CUDA_OK(cudaMalloc((void**)&c->d_inflow_table, per_species * c->nsp * sizeof(double)));
+        for (int sp = 0; sp < c->nsp; sp++)
+            if (sp != species && push_inflow_table(c, sp)) return 1;
+        c->B.inflow_table = c->d_inflow_table;
+    }
+    std::memcpy(c->h_inflow_table.data() + per_species * species, table, per_species * sizeof(double));
+    return push_inflow_table(c, species);
 }
 
 int warpii_gpu_forward_euler_step_ex(warpii_gpu_ctx* c, int dst, int u, double dt, double /*t*/, double alpha,

@@ -16,6 +16,10 @@ namespace warpii_b200 {
 struct SpeciesBC {
     std::vector<int32_t> kind;                     // per boundary id: WARPII_BC_*
     std::vector<std::array<double, 5>> inflow;     // conserved inflow state per boundary id
+    // optional: a function of (x, t) per boundary id instead of the constant state (species.cc:51-57); an empty
+    // function means "use the constant".  time_dependent[b] = false tabulates it once.
+    std::vector<InflowFunction> inflow_function;
+    std::vector<bool> time_dependent;
 };
 
 class FiveMomentGpuSolver {
@@ -46,9 +50,44 @@ class FiveMomentGpuSolver {
         op_ = std::make_unique<GpuFluidFluxESDGSEMOperator>(ctx_);
         integrator_ = std::make_unique<Integrator>();
         integrator_->reinit(*solution_, 3);
+        op_->set_boundary_points(boundary_quadrature_points(), tables_.boundary_face_id(), tables_.box().dim, n_species_);
         for (int s = 0; s < n_species_ && s < (int)bcs_.size(); s++)
-            for (int b = 0; b < n_boundaries_ && b < (int)bcs_[s].inflow.size(); b++)
-                if (bcs_[s].kind[b] == WARPII_BC_INFLOW) op_->set_inflow(s, b, bcs_[s].inflow[b].data());
+            for (int b = 0; b < n_boundaries_ && b < (int)bcs_[s].kind.size(); b++) {
+                if (bcs_[s].kind[b] != WARPII_BC_INFLOW) continue;
+                if (b < (int)bcs_[s].inflow_function.size() && bcs_[s].inflow_function[b])
+                    op_->set_inflow_function(s, b, bcs_[s].inflow_function[b],
+                                             b < (int)bcs_[s].time_dependent.size() ? (bool)bcs_[s].time_dependent[b] : true);
+                else if (b < (int)bcs_[s].inflow.size())
+                    op_->set_inflow(s, b, bcs_[s].inflow[b].data());
+            }
+    }
+
+    // xyz[face][point][dim] of the boundary quadrature points of this rank: Gauss(fe_degree+2) abscissae in the
+    // tangential dimensions (lower dimension fastest), the face's coordinate in the normal one.  Faces in the order of
+    // the mesh tables.  These are the phi.quadrature_point(q) of fluid_flux_es_dgsem_operator.h:381-384.
+    std::vector<double> boundary_quadrature_points() const {
+        const BoxDescription& box = tables_.box();
+        const int dim = box.dim, Ng = element_.Ng;
+        int nq = 1;
+        for (int d = 1; d < dim; d++) nq *= Ng;
+        const auto& bf_elem = tables_.boundary_face_elem();
+        const auto& bf_side = tables_.boundary_face_side();
+        std::vector<double> xyz(bf_elem.size() * nq * dim);
+        for (size_t f = 0; f < bf_elem.size(); f++) {
+            int idx[3];
+            tables_.elem_multi_index(tables_.local_to_global()[bf_elem[f]], idx);
+            const int d = bf_side[f] / 2, side = bf_side[f] % 2;
+            for (int q = 0; q < nq; q++) {
+                int t = q;
+                for (int a = 0; a < dim; a++) {
+                    double x;
+                    if (a == d) x = box.left[a] + (idx[a] + side) * tables_.h(a);
+                    else { x = box.left[a] + (idx[a] + element_.xg[t % Ng]) * tables_.h(a); t /= Ng; }
+                    xyz[(f * nq + q) * dim + a] = x;
+                }
+            }
+        }
+        return xyz;
     }
 
     // Node coordinates of the owned elements in device order, xyz[elem][node][dim].
@@ -95,9 +134,24 @@ class FiveMomentGpuSolver {
         solution_->upload(host_.data());
     }
 
-    // dg_solver.cc:23-38
+    // dg_solver.cc:23-38.  Without time-dependent inflow the inner loop of advance() runs resident on the device side
+    // of the ABI (warpii_gpu_advance_to: same dt sequence, no host round trip per step); otherwise every stage goes
+    // through the operator so that the inflow tables can follow the stage time.
     void solve(TimestepCallback writeout_callback) {
         steps_ = 0;
+        std::vector<TimestepCallback> cbs = {writeout_callback};
+        if (device_loop_ && !op_->has_time_dependent_inflow()) {
+            op_->refresh_inflow(0.0);
+            advance_segments(
+                [&](double t, double stop) {
+                    int64_t n = 0;
+                    check(warpii_gpu_advance_to(ctx_->get(), solution_->id(), f1_id(), &t, stop, fixed_dt_, 0, &n));
+                    steps_ += n;
+                    return t;
+                },
+                t_end_, cbs);
+            return;
+        }
         auto step = [&](double t, double dt) -> bool {
             integrator_->evolve_one_time_step(*op_, *solution_, dt, t);
             steps_++;
@@ -115,6 +169,8 @@ class FiveMomentGpuSolver {
     int64_t steps_taken() const { return steps_; }
     void set_t_end(double t) { t_end_ = t; }
     void set_fixed_dt(double dt) { fixed_dt_ = dt; }
+    void set_device_loop(bool on) { device_loop_ = on; }
+    int f1_id() const { return integrator_->stage_vector().id(); }
     int n_components() const { return nc_; }
     int nodes_per_elem() const { return nn_; }
 
@@ -136,6 +192,7 @@ class FiveMomentGpuSolver {
     std::vector<double> host_;
     int64_t steps_ = 0;
     double fixed_dt_ = 0.0;
+    bool device_loop_ = true;
 };
 
 }  // namespace warpii_b200

@@ -9,6 +9,7 @@
 // message, as AssertThrow does in the reference), so a caller written against the reference compiles against
 // these with the type names swapped.  The state never leaves HBM between calls.
 #pragma once
+#include <array>
 #include <cmath>
 #include <functional>
 #include <memory>
@@ -91,6 +92,9 @@ class GpuSolutionVec {
     int id_ = -1;
 };
 
+// q5 = f(x[dim], t): conserved inflow state, the Function<dim> handed to EulerBCMap::set_inflow_boundary (bc_helper.h:52-64)
+using InflowFunction = std::function<void(const double* x, double t, double* q5)>;
+
 class GpuFluidFluxESDGSEMOperator {
    public:
     explicit GpuFluidFluxESDGSEMOperator(std::shared_ptr<GpuContext> ctx) : ctx_(std::move(ctx)) {}
@@ -101,6 +105,7 @@ class GpuFluidFluxESDGSEMOperator {
     void perform_forward_euler_step(GpuSolutionVec& dst, const GpuSolutionVec& u, std::vector<GpuSolutionVec>& /*sol_registers*/,
                                     const double dt, const double t, const double alpha = 1.0, const double beta = 0.0,
                                     const ZeroOutPolicy /*zero_out_policy*/ = DO_NOT_ZERO_DST_VECTOR) {
+        refresh_inflow(t);   // set_time(t) on every inflow function, :139-144
         // the second SSPRK2 stage is the one whose result recommend_dt is asked about next: fuse the CFL sweep there
         const int flags = (beta != 0.0) ? WARPII_FUSE_CFL : 0;
         check(warpii_gpu_forward_euler_step_ex(ctx_->get(), dst.id(), u.id(), dt, t, alpha, beta, flags));
@@ -113,10 +118,86 @@ class GpuFluidFluxESDGSEMOperator {
         return dt;
     }
 
-    void set_inflow(int species, int boundary_id, const double q[5]) { check(warpii_gpu_set_inflow(ctx_->get(), species, boundary_id, q)); }
+    void set_inflow(int species, int boundary_id, const double q[5]) {
+        check(warpii_gpu_set_inflow(ctx_->get(), species, boundary_id, q));
+        constants_.push_back({species, boundary_id, {{q[0], q[1], q[2], q[3], q[4]}}});
+        if (species >= 0 && species < (int)tables_.size() && !tables_[species].empty()) fill_constant(tables_[species], constants_.back());
+    }
+
+    // Where the inflow functions are evaluated: xyz[face][point][dim] of this rank's boundary quadrature points and the
+    // boundary id of every face, both in the order of warpii_gpu_mesh.boundary_face_* (the solver provides them).
+    void set_boundary_points(std::vector<double> xyz, std::vector<int32_t> face_boundary_id, int dim, int n_species) {
+        bxyz_ = std::move(xyz);
+        bid_ = std::move(face_boundary_id);
+        dim_ = dim;
+        tables_.assign(n_species, {});
+    }
+    // Space/time-dependent inflow (EulerBCMap::set_inflow_boundary).  time_dependent = false tabulates the function
+    // once, at the first stage; true re-tabulates it at every stage time and rules out the device-resident time loop.
+    void set_inflow_function(int species, int boundary_id, InflowFunction f, bool time_dependent = true) {
+        if (species < 0 || species >= (int)tables_.size()) throw std::invalid_argument("set_inflow_function: species out of range");
+        inflow_.push_back({species, boundary_id, std::move(f), time_dependent});
+        stale_ = true;
+    }
+    bool has_time_dependent_inflow() const {
+        for (const auto& e : inflow_)
+            if (e.time_dependent) return true;
+        return false;
+    }
+    // Tabulate the inflow functions at time t and upload (no-op without functions, or when nothing changed).
+    void refresh_inflow(double t) {
+        if (inflow_.empty()) return;
+        if (!stale_ && (!has_time_dependent_inflow() || t == table_time_)) return;
+        const size_t n_faces = bid_.size();
+        if (n_faces == 0) { stale_ = false; table_time_ = t; return; }
+        const size_t nq = bxyz_.size() / (n_faces * dim_);
+        std::vector<bool> touched(tables_.size(), false);
+        for (const auto& e : inflow_) {
+            if (!stale_ && !e.time_dependent) continue;
+            std::vector<double>& tab = tables_[e.species];
+            if (tab.empty()) {
+                tab.assign(n_faces * nq * 5, 0.0);
+                for (const auto& k : constants_)
+                    if (k.species == e.species) fill_constant(tab, k);
+            }
+            for (size_t f = 0; f < n_faces; f++) {
+                if (bid_[f] != e.boundary_id) continue;
+                for (size_t q = 0; q < nq; q++) e.f(&bxyz_[(f * nq + q) * dim_], t, &tab[(f * nq + q) * 5]);
+            }
+            touched[e.species] = true;
+        }
+        for (size_t s = 0; s < tables_.size(); s++)
+            if (touched[s]) check(warpii_gpu_set_inflow_table(ctx_->get(), (int)s, tables_[s].data()));
+        stale_ = false;
+        table_time_ = t;
+    }
 
    private:
+    struct InflowEntry {
+        int species, boundary_id;
+        InflowFunction f;
+        bool time_dependent;
+    };
+    struct InflowConstant {
+        int species, boundary_id;
+        std::array<double, 5> q;
+    };
+    void fill_constant(std::vector<double>& tab, const InflowConstant& k) const {
+        const size_t n_faces = bid_.size(), nq = n_faces ? tab.size() / (n_faces * 5) : 0;
+        for (size_t f = 0; f < n_faces; f++)
+            if (bid_[f] == k.boundary_id)
+                for (size_t q = 0; q < nq; q++)
+                    for (int c = 0; c < 5; c++) tab[(f * nq + q) * 5 + c] = k.q[c];
+    }
     std::shared_ptr<GpuContext> ctx_;
+    std::vector<InflowEntry> inflow_;
+    std::vector<InflowConstant> constants_;
+    std::vector<double> bxyz_;
+    std::vector<int32_t> bid_;
+    std::vector<std::vector<double>> tables_;   // per species [face][point][5]
+    int dim_ = 1;
+    bool stale_ = false;
+    double table_time_ = 0.0;
 };
 
 // rk.h:79-117
@@ -133,6 +214,7 @@ class SSPRK2Integrator {
     // The GPU operator needs no scratch registers, so sol_register_count device vectors are NOT allocated:
     // at C4 size each would cost 10.5 GB of HBM for nothing.
     void reinit(const SolutionVec& sol, int /*sol_register_count*/) { f_1.reinit(sol); }
+    const SolutionVec& stage_vector() const { return f_1; }
 
    private:
     SolutionVec f_1;
@@ -149,9 +231,10 @@ struct TimestepCallback {
     bool perform_final;    // fire at t_end even if not scheduled
 };
 
-// timestepper.cc:6-56: adaptive dt clipped to the next callback / end time, 1e-12 of slack against stutter steps
-inline void advance(std::function<bool(double t, double dt)> step, double t_end, std::function<double()> recommend_dt,
-                    std::vector<TimestepCallback>& callbacks) {
+// The outer structure of advance() (timestepper.cc:6-56): run to the next due callback or t_end, fire, repeat.
+// run_to(t, stop) advances the state from t to stop (within 1e-12) and returns the time it reached.
+inline void advance_segments(const std::function<double(double t, double stop)>& run_to, double t_end,
+                             std::vector<TimestepCallback>& callbacks) {
     const double slack = 1e-12;
     double t = 0.0;
     std::vector<double> due(callbacks.size());
@@ -166,10 +249,7 @@ inline void advance(std::function<bool(double t, double dt)> step, double t_end,
         const double next_due = callbacks.empty() ? t_end : due[next];
         const bool fire = next_due < t_end && std::fabs(next_due - t_end) > slack;
         const double stop = std::fmin(next_due, t_end);
-        while (t < stop - slack) {
-            const double dt = std::fmin(recommend_dt(), stop - t);
-            if (step(t, dt)) t += dt;
-        }
+        t = run_to(t, stop);
         if (fire) {
             callbacks[next].callback(t);
             due[next] = t + callbacks[next].interval;
@@ -177,6 +257,21 @@ inline void advance(std::function<bool(double t, double dt)> step, double t_end,
     }
     for (size_t i = 0; i < callbacks.size(); i++)
         if (std::fabs(t_end - due[i]) < slack || callbacks[i].perform_final) callbacks[i].callback(t_end);
+}
+
+// timestepper.cc:6-56: adaptive dt clipped to the next callback / end time, 1e-12 of slack against stutter steps
+inline void advance(std::function<bool(double t, double dt)> step, double t_end, std::function<double()> recommend_dt,
+                    std::vector<TimestepCallback>& callbacks) {
+    const double slack = 1e-12;
+    advance_segments(
+        [&](double t, double stop) {
+            while (t < stop - slack) {
+                const double dt = std::fmin(recommend_dt(), stop - t);
+                if (step(t, dt)) t += dt;
+            }
+            return t;
+        },
+        t_end, callbacks);
 }
 
 }  // namespace warpii_b200

@@ -6,12 +6,18 @@
 #include <string>
 
 #include "dg_solver.hpp"
+#include "five_moment_app.hpp"
 
 using namespace warpii_b200;
 
 struct warpii_box_solver {
-    std::unique_ptr<FiveMomentGpuSolver> solver;
+    std::shared_ptr<FiveMomentGpuSolver> solver;
     int rank = 0, n_ranks = 1;
+};
+
+struct warpii_app {
+    std::unique_ptr<FiveMomentGpuApp> app;
+    warpii_box_solver solver_view;   // the app's solver behind the warpii_box_solver_* accessors
 };
 
 namespace {
@@ -63,7 +69,7 @@ int warpii_box_solver_create(int dim, int fe_degree, int n_species, int fields_e
         s->rank = rank;
         s->n_ranks = n_ranks;
         try {
-            s->solver = std::make_unique<FiveMomentGpuSolver>(box, fe_degree, n_species, fields_enabled != 0, gas_gamma, 0.0,
+            s->solver = std::make_shared<FiveMomentGpuSolver>(box, fe_degree, n_species, fields_enabled != 0, gas_gamma, 0.0,
                                                               n_boundaries, bcs, rank, n_ranks, device);
             s->solver->reinit();
         } catch (...) {
@@ -106,6 +112,24 @@ int warpii_box_solver_set_inflow(warpii_box_solver* s, int species, int boundary
     GUARD({ s->solver->get_fluid_flux_operator().set_inflow(species, boundary_id, q); })
 }
 
+int warpii_box_solver_set_inflow_function(warpii_box_solver* s, int species, int boundary_id, warpii_inflow_fn fn, void* user,
+                                          int time_dependent) {
+    GUARD({
+        if (!fn) throw std::invalid_argument("set_inflow_function: null function");
+        s->solver->get_fluid_flux_operator().set_inflow_function(
+            species, boundary_id, [=](const double* x, double t, double* q5) { fn(x, t, q5, user); }, time_dependent != 0);
+    })
+}
+int64_t warpii_box_solver_n_boundary_faces(const warpii_box_solver* s) { return (int64_t)s->solver->tables().boundary_face_elem().size(); }
+int warpii_box_solver_boundary_points(const warpii_box_solver* s, double* xyz, int32_t* face_boundary_id) {
+    GUARD({
+        const std::vector<double> v = s->solver->boundary_quadrature_points();
+        if (xyz && !v.empty()) std::memcpy(xyz, v.data(), v.size() * sizeof(double));
+        const auto& ids = s->solver->tables().boundary_face_id();
+        if (face_boundary_id && !ids.empty()) std::memcpy(face_boundary_id, ids.data(), ids.size() * sizeof(int32_t));
+    })
+}
+
 int warpii_box_solver_attach_comm(warpii_box_solver* s, const char id[WARPII_GPU_NCCL_ID_BYTES]) {
     GUARD({
         warpii_gpu_halo halo;
@@ -137,6 +161,79 @@ int warpii_box_solver_step(warpii_box_solver* s, double dt, double t) {
 
 int warpii_box_solver_recommend_dt(warpii_box_solver* s, double* dt_out) {
     GUARD({ *dt_out = s->solver->get_fluid_flux_operator().recommend_dt(s->solver->get_solution()); })
+}
+
+// ---- the FiveMoment application from an input file --------------------------------------------------------------
+int warpii_app_create(const char* input_text, int rank, int n_ranks, int device, warpii_app** out) {
+    GUARD({
+        if (!input_text || !out) throw std::invalid_argument("warpii_app_create: null argument");
+        auto* a = new warpii_app();
+        try {
+            a->app = FiveMomentGpuApp::create_from_input(input_text, rank, n_ranks, device);
+        } catch (...) {
+            delete a;
+            throw;
+        }
+        a->solver_view.solver = a->app->solver_ptr();
+        a->solver_view.rank = rank;
+        a->solver_view.n_ranks = n_ranks;
+        *out = a;
+    })
+}
+int warpii_app_destroy(warpii_app* a) {
+    delete a;
+    return 0;
+}
+warpii_box_solver* warpii_app_solver(warpii_app* a) { return a ? &a->solver_view : nullptr; }
+int warpii_app_describe(const warpii_app* a, int32_t ints[16], double dbls[16]) {
+    GUARD({
+        const FiveMomentGpuApp& app = *a->app;
+        for (int i = 0; i < 16; i++) { ints[i] = 0; dbls[i] = 0.0; }
+        ints[0] = app.n_dims();
+        ints[1] = app.n_species();
+        ints[2] = app.n_boundaries();
+        ints[3] = app.fe_degree();
+        ints[4] = app.fields_enabled();
+        ints[5] = app.write_output();
+        ints[6] = app.n_writeout_frames();
+        for (int d = 0; d < 3; d++) { ints[7 + d] = app.box().nx[d]; ints[10 + d] = app.box().periodic[d]; }
+        dbls[0] = app.gas_gamma();
+        dbls[1] = app.t_end();
+        for (int d = 0; d < 3; d++) { dbls[2 + d] = app.box().left[d]; dbls[5 + d] = app.box().right[d]; }
+    })
+}
+int warpii_app_species(const warpii_app* a, int species, char name[16], double* charge, double* mass, int32_t* bc_kinds) {
+    GUARD({
+        const SpeciesDescription& sp = a->app->species().at(species);
+        std::snprintf(name, 16, "%s", sp.name.c_str());
+        *charge = sp.charge;
+        *mass = sp.mass;
+        for (size_t b = 0; b < sp.bc_kind.size(); b++) bc_kinds[b] = sp.bc_kind[b];
+    })
+}
+int warpii_app_eval_function(const warpii_app* a, int species, int boundary_id, int64_t n, const double* xyz, double t, double* q5_out,
+                             int32_t* time_dependent_out) {
+    GUARD({
+        const SpeciesDescription& sp = a->app->species().at(species);
+        const SpeciesFunc* f = boundary_id < 0 ? sp.initial_condition.get() : sp.inflow.at(boundary_id).get();
+        if (!f) throw std::invalid_argument("boundary " + std::to_string(boundary_id) + " has no inflow function");
+        const int dim = a->app->n_dims();
+        for (int64_t i = 0; i < n; i++) f->conserved(xyz + i * dim, t, q5_out + i * 5);
+        if (time_dependent_out) *time_dependent_out = f->time_dependent();
+    })
+}
+int warpii_app_set_output_dir(warpii_app* a, const char* dir) { GUARD({ a->app->set_output_dir(dir ? dir : ""); }) }
+int warpii_app_format_workdir(const warpii_app* a, const char* input_name, char* out, int out_len) {
+    GUARD({ std::snprintf(out, out_len, "%s", a->app->format_workdir(input_name).c_str()); })
+}
+int warpii_app_set_device_loop(warpii_app* a, int on) { GUARD({ a->app->get_solver().set_device_loop(on != 0); }) }
+int warpii_app_setup(warpii_app* a) { GUARD({ a->app->setup(); }) }
+int warpii_app_run(warpii_app* a, warpii_frame_fn cb, void* user, int64_t* steps_out) {
+    GUARD({
+        if (cb) a->app->set_frame_callback([=](unsigned frame, double t) { cb(frame, t, user); });
+        a->app->run();
+        if (steps_out) *steps_out = a->app->get_solver().steps_taken();
+    })
 }
 
 int warpii_host_advance(warpii_step_fn step, double t_end, warpii_dt_fn recommend_dt, int n_callbacks, const double* intervals,
