@@ -86,8 +86,9 @@ typedef struct warpii_gpu_halo {
 const char* warpii_gpu_last_error(void);
 int warpii_gpu_abi_version(void);
 /* Number of consecutive elements one thread block of the stage kernel works on.  Purely a performance hint for
- * the host's element ordering: faces between two elements of the same group of this many consecutive elements
- * are evaluated once, so compact patches (e.g. 4x4 in 2D) should be numbered consecutively.  Any ordering is correct. */
+ * the host's element ordering: a face neighbour inside the same group of this many consecutive elements is read
+ * from the block's shared memory instead of L2/HBM, so compact patches (e.g. 4x2 in 2D p=3) should be numbered
+ * consecutively.  Any ordering is correct. */
 int warpii_gpu_elems_per_block(int dim, int fe_degree);
 
 /* -- lifetime -------------------------------------------------------------- */
