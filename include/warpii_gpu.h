@@ -182,6 +182,14 @@ int warpii_gpu_stream(warpii_gpu_ctx* ctx, void** stream_out);
 int warpii_gpu_point_fluxes(int device, int n, const double* qa, const double* qb, int d, double gamma,
                             double* ec_out, double* es_out, double* prim_out);
 
+/* Self-check of the kernels' branch-free correctly rounded division (csrc/det_log.cuh, div_rn_fast) against the IEEE
+ * division on n pseudo-random operand pairs: mode 0 general operands, 1 the f/(2+f) of the logarithm, 2 quotients
+ * close to 1, 3 short numerators (exact quotients and ties).  *mismatches_out counts results that differ in any bit;
+ * first_bad_out (nullable) = {a, b, got, want} of one of them.  The bit-for-bit parity of beta and of the logarithm
+ * with the CPU path rests on this being 0.  Needs no context. */
+int warpii_gpu_check_division(int device, int64_t n, uint64_t seed, int mode, int64_t* mismatches_out,
+                              double first_bad_out[4]);
+
 #ifdef __cplusplus
 }
 #endif

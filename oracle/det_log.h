@@ -7,7 +7,8 @@
 // in the last bit for ~0.5 % of arguments, so the reference's own RHS is only reproducible to ~1e-10 across
 // platforms on BASELINE-sized meshes (tests/test_oracle_golden.py::test_libm_sensitivity measures it).
 // To compare the CUDA path with the CPU restatement at the 1e-12 level both sides therefore use THIS logarithm:
-// a fixed sequence of IEEE-754 binary64 operations (no contraction, one correctly rounded division), hence
+// a fixed sequence of IEEE-754 binary64 operations (explicit fused multiply-adds, no other contraction, one correctly
+// rounded division), hence
 // bit-identical on x86-64 and on sm_100a (warpii_b200/csrc/det_log.cuh is the same sequence).
 //
 // Algorithm: the classical argument reduction x = 2^k m, m in [sqrt(2)/2, sqrt(2)), s = f/(2+f) with f = m - 1, and
@@ -42,11 +43,15 @@ inline double det_log(double x) {
     const double s = f / (2.0 + f);
     const double z = s * s;
     const double w = z * z;
-    const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
-    const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    // std::fma is the IEEE fused multiply-add (one rounding): vfmadd on x86-64-v3, FMA on sm_100a
+    const double t1 = w * std::fma(w, std::fma(w, Lg6, Lg4), Lg2);
+    const double t2 = z * std::fma(w, std::fma(w, std::fma(w, Lg7, Lg5), Lg3), Lg1);
     const double R = t2 + t1;
     const double dk = (double)k;
-    return (((s * (hfsq + R) + dk * ln2_lo) - hfsq) + f) + dk * ln2_hi;
+    double r = std::fma(s, hfsq + R, dk * ln2_lo);
+    r = r - hfsq;
+    r = r + f;
+    return std::fma(dk, ln2_hi, r);
 }
 
 }  // namespace detlog

@@ -105,3 +105,36 @@ def test_device_es_flux_is_entropy_dissipative():
         qL, qR = oracle.entropy_flux(1, qa[i], g)[0], oracle.entropy_flux(1, qb[i], g)[0]
         psiL, psiR = wL @ fL - qL, wR @ fR - qR
         assert (wR - wL) @ es[i] - (psiR - psiL) <= 1e-9 * (abs(qL) + abs(qR))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_branch_free_division_is_the_ieee_division(mode):
+    """div_rn_fast (csrc/det_log.cuh) == __ddiv_rn bit for bit: 2^27 operand pairs per distribution and seed."""
+    from warpii_b200.capi import check_division
+    for seed in (1, 20261017):
+        bad, first = check_division(1 << 27, seed=seed, mode=mode)
+        assert bad == 0, f"{bad} mismatches, e.g. a={first[0]!r} b={first[1]!r} got={first[2]!r} want={first[3]!r}"
+
+
+def test_device_logarithm_is_the_oracle_logarithm_bit_for_bit():
+    """200k densities over 12 decades: log rho and log beta of the device == oracle.det_log of the same doubles."""
+    rng = np.random.default_rng(5)
+    n = 200000
+    g = 1.4
+    rho = np.exp(rng.uniform(-14, 14, n))
+    u = rng.normal(size=(n, 3))
+    p = np.exp(rng.uniform(-10, 10, n))
+    q = np.zeros((n, 5))
+    q[:, 0] = rho
+    q[:, 1:4] = rho[:, None] * u
+    q[:, 4] = 0.5 * rho * (u ** 2).sum(axis=1) + p / (g - 1)
+    _, _, prim = point_fluxes(q, q, 0, g)
+    want_rho = np.array([oracle.det_log(x) for x in q[:, 0]])
+    want_beta = np.array([oracle.det_log(x) for x in prim[:, 4]])
+    assert np.array_equal(prim[:, 5], want_rho)
+    assert np.array_equal(prim[:, 6], want_beta)
+    pr = np.array([oracle.pressure(x, g) for x in q])
+    assert np.array_equal(prim[:, 8], pr) and np.array_equal(prim[:, 4], q[:, 0] / (2.0 * pr))
+    # and it is a logarithm: < 1 ulp from the correctly rounded value
+    ref = np.log(q[:, 0].astype(np.longdouble)).astype(np.float64)
+    assert (np.abs(want_rho - ref) <= np.spacing(np.abs(ref))).all()

@@ -505,6 +505,16 @@ class App:
         self.close()
 
 
+def check_division(n, seed=1, mode=0, device=0):
+    """(mismatches, [a, b, got, want]) of div_rn_fast vs the IEEE division on n operand pairs (warpii_gpu_check_division)."""
+    L = lib()
+    L.warpii_gpu_check_division.argtypes = [C.c_int, C.c_int64, C.c_uint64, C.c_int, _i64p, _dp]
+    count = C.c_int64(0)
+    bad = np.zeros(4)
+    _check(L.warpii_gpu_check_division(device, n, seed, mode, C.byref(count), _ptr(bad)))
+    return count.value, bad
+
+
 def point_fluxes(qa, qb, d, gamma, device=0):
     """Device evaluation of the EC flux (direction d) and the ES flux (normal +e_d) for state pairs; see warpii_gpu.h."""
     qa = np.ascontiguousarray(qa, dtype=np.float64).reshape(-1, 5)

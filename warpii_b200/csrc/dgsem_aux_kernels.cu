@@ -316,3 +316,57 @@ void launch_point_flux(int n, const double* qa, const double* qb, int d, double 
     if (n > 0) point_flux_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, qa, qb, d, gamma, ec, es, prim);
 }
 }  // namespace wgpu
+
+// ---- self-check of div_rn_fast against the IEEE division, bit for bit ------------------------------------------
+namespace wgpu {
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& x) {
+    unsigned long long z = (x += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+// mode 0: random significands, exponents in [-60, 60], random signs; mode 1: f / (2 + f) with f = m - 1,
+// m in [sqrt(2)/2, sqrt(2)) (the division of det_log); mode 2: ratios close to 1 (b within a few thousand ulp of a);
+// mode 3: numerators with few significant bits (exact and nearly exact quotients, ties).
+__global__ void division_check_kernel(long long n, unsigned long long seed, int mode, unsigned long long* mismatches,
+                                      double* first_bad) {
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (long long i = i0; i < n; i += stride) {
+        unsigned long long st = seed + 0x632be59bd9b4e019ull * (unsigned long long)(i + 1);
+        const unsigned long long r0 = splitmix64(st), r1 = splitmix64(st), r2 = splitmix64(st);
+        double a, b;
+        if (mode == 1) {
+            const double u = (double)(r0 >> 11) * 0x1.0p-53;
+            const double m = 0.70710678118654752 + u * (1.41421356237309505 - 0.70710678118654752);
+            a = m - 1.0;
+            b = 2.0 + a;
+        } else if (mode == 2) {
+            a = __longlong_as_double((long long)((r0 & 0x000fffffffffffffull) | 0x3ff0000000000000ull));
+            b = __longlong_as_double(__double_as_longlong(a) + (long long)(r1 % 8192) - 4096);
+            a = ldexp(a, (int)(r2 % 41) - 20);
+        } else {
+            const int ea = (int)(r2 % 121) - 60, eb = (int)((r2 >> 16) % 121) - 60;
+            unsigned long long ma = r0 & 0x000fffffffffffffull;
+            if (mode == 3) ma &= 0x000ff00000000000ull << (r2 >> 40) % 8;
+            a = ldexp(__longlong_as_double((long long)(ma | 0x3ff0000000000000ull)), ea);
+            b = ldexp(__longlong_as_double((long long)((r1 & 0x000fffffffffffffull) | 0x3ff0000000000000ull)), eb);
+            if (r2 >> 63) a = -a;
+            if ((r2 >> 62) & 1) b = -b;
+        }
+        const double want = __ddiv_rn(a, b);
+        const double got = div_rn_fast(a, b);
+        if (__double_as_longlong(want) != __double_as_longlong(got)) {
+            if (atomicAdd(mismatches, 1ull) == 0ull) { first_bad[0] = a; first_bad[1] = b; first_bad[2] = got; first_bad[3] = want; }
+            bad++;
+        }
+    }
+    (void)bad;
+}
+void launch_division_check(long long n, unsigned long long seed, int mode, unsigned long long* mismatches, double* first_bad,
+                           cudaStream_t s) {
+    division_check_kernel<<<148 * 8, 256, 0, s>>>(n, seed, mode, mismatches, first_bad);
+}
+}  // namespace wgpu
+

@@ -22,6 +22,10 @@
 #include "dgsem_common.cuh"
 #include "dgsem_physics.cuh"
 
+#ifndef WGPU_PAIR_CHUNK
+#define WGPU_PAIR_CHUNK 3
+#endif
+
 namespace wgpu {
 
 constexpr int kPS = 14;   // doubles per node in the shared primitive table (12 used; 14 keeps 16-byte loads conflict-free)
@@ -111,6 +115,14 @@ __device__ __forceinline__ void load_flux(const double* rec, double F[5]) {
     F[0] = a.x; F[1] = a.y; F[2] = b.x; F[3] = b.y; F[4] = rec[4];
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): the data of a later phase travels while this thread computes
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int GROUP, int NODES>
 __device__ __forceinline__ void group_sync(const int tid) {
     if (GROUP == 32) __syncwarp();
@@ -190,6 +202,30 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
         if (active) {
 #pragma unroll
             for (int c = 0; c < 5; c++) q[c] = P.u[off + (size_t)c * NN];
+            // Prefetch what this thread's face tasks will need from outside the patch (neighbour traces, ghost traces,
+            // boundary contributions) straight into the task's own result record: the copies are in flight during the
+            // node, indicator and pair phases instead of stalling the face phase.
+            for (int ft = j; ft < NFACE * NF; ft += NN) {
+                const int f = ft / NF, t = ft - f * NF;
+                const int v = P.nbr[(size_t)e * NFACE + f];
+                if (v >= e0 && v < e_hi) continue;
+                double* const rec = sFace + ((le * NFACE + f) * NF + t) * kFS;
+                const double* src;
+                size_t stride;
+                if (v < 0) {
+                    src = P.bres + (((size_t)(-1 - v) * P.nsp + sp) * 5) * NF + t;
+                    stride = NF;
+                } else if (v < P.n_elems) {
+                    src = P.u + ((size_t)v * nc + 5 * sp) * NN + node_of_face_node<DIM, NP>(f >> 1, 1 - (f & 1), t);
+                    stride = NN;
+                } else {
+                    src = P.ghost + ((size_t)(v - P.n_elems) * (5 * P.nsp) + 5 * sp) * NF + t;
+                    stride = NF;
+                }
+#pragma unroll
+                for (int c = 0; c < 5; c++) cp_async8(rec + c, src + (size_t)c * stride);
+            }
+            cp_async_commit();
         }
         {
             const Prim me = make_prim(q[0], q[1], q[2], q[3], q[4], gamma);
@@ -241,53 +277,51 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
 
         // ---- task phase ---------------------------------------------------------------------------------------
         // (a) unordered node pairs of the pencils of this thread's element: symmetric two-point flux, once
+        // The rounds of a chunk are evaluated into registers and stored afterwards: a shared-memory store between two
+        // evaluations would pin their order (the compiler cannot prove that sPair and sP do not alias), and
+        // independent flux evaluations in flight are what hides the FP64 latency at 4 warps per scheduler.
+        constexpr int CHUNK = WGPU_PAIR_CHUNK;
 #pragma unroll
-        for (int r = 0; r < ROUNDS; r++) {
-            const int p = r * NN + j;
-            if (PPE % NN == 0 || p < PPE) {
-                const int d = p / (NF * NPAIR);
-                const int rem = p - d * (NF * NPAIR);
-                const int pe = rem / NPAIR, pid = rem - pe * NPAIR;
-                const int jl = sPairJL[pid];
-                const int st = stride_of(NP, d);
-                const int n0 = le * NN + pencil_first_node<DIM, NP>(d, pe);
-                const Prim a = load_prim_ec(sP, n0 + (jl & 255) * st);
-                const Prim b = load_prim_ec(sP, n0 + (jl >> 8) * st);
-                double F[5], ibl;
-                ec_flux_d(d, a, b, hig, F, ibl);
-                store_flux(sPair + (le * PPE + p) * kFS, F);
+        for (int r0 = 0; r0 < ROUNDS; r0 += CHUNK) {
+            double F[CHUNK][5];
+#pragma unroll
+            for (int rr = 0; rr < CHUNK; rr++) {
+                const int p = (r0 + rr) * NN + j;
+                if (r0 + rr < ROUNDS && (PPE % NN == 0 || p < PPE)) {
+                    const int d = p / (NF * NPAIR);
+                    const int rem = p - d * (NF * NPAIR);
+                    const int pe = rem / NPAIR, pid = rem - pe * NPAIR;
+                    const int jl = sPairJL[pid];
+                    const int st = stride_of(NP, d);
+                    const int n0 = le * NN + pencil_first_node<DIM, NP>(d, pe);
+                    const Prim a = load_prim_ec(sP, n0 + (jl & 255) * st);
+                    const Prim b = load_prim_ec(sP, n0 + (jl >> 8) * st);
+                    double ibl;
+                    ec_flux_d(d, a, b, hig, F[rr], ibl);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < CHUNK; rr++) {
+                const int p = (r0 + rr) * NN + j;
+                if (r0 + rr < ROUNDS && (PPE % NN == 0 || p < PPE)) store_flux(sPair + (le * PPE + p) * kFS, F[rr]);
             }
         }
         // (b) the element's face nodes: its own side of every face (gather form, no atomics)
+        cp_async_wait_all();   // this thread's prefetched records (each task reads only what its own thread fetched)
         for (int ft = j; ft < NFACE * NF; ft += NN) {
             const int f = ft / NF, t = ft - f * NF;
             const int d = f >> 1, side = f & 1;
             double* const rec = sFace + ((le * NFACE + f) * NF + t) * kFS;
             const int v = active ? P.nbr[(size_t)e * NFACE + f] : (int)e0;
-            if (v < 0) {   // domain boundary: rate contribution prepared by boundary_kernel
-                const size_t offb = (((size_t)(-1 - v) * P.nsp + sp) * 5) * NF + t;
-                double Fb[5];
-#pragma unroll
-                for (int c = 0; c < 5; c++) Fb[c] = P.bres[offb + (size_t)c * NF];
-                store_flux(rec, Fb);
-                continue;
-            }
+            if (v < 0) continue;   // domain boundary: the rate contribution prepared by boundary_kernel is already in rec
             const Prim a = load_prim(sP, le * NN + node_of_face_node<DIM, NP>(d, side, t));
             const int nn = node_of_face_node<DIM, NP>(d, 1 - side, t);
             Prim b;
             if (v >= e0 && v < e_hi) {   // neighbour inside the patch: its primitives are in shared memory
                 b = load_prim(sP, (int)(v - e0) * NN + nn);
-            } else {
+            } else {   // owned element outside the patch or ghost trace: conserved values prefetched into rec
                 double qn[5];
-                if (v < P.n_elems) {
-                    const size_t offn = ((size_t)v * nc + 5 * sp) * NN + nn;
-#pragma unroll
-                    for (int c = 0; c < 5; c++) qn[c] = P.u[offn + (size_t)c * NN];
-                } else {
-                    const size_t offg = ((size_t)(v - P.n_elems) * (5 * P.nsp) + 5 * sp) * NF + t;
-#pragma unroll
-                    for (int c = 0; c < 5; c++) qn[c] = P.ghost[offg + (size_t)c * NF];
-                }
+                load_flux(rec, qn);
                 b = make_prim(qn[0], qn[1], qn[2], qn[3], qn[4], gamma);
             }
             const double sgn = side ? 1.0 : -1.0;

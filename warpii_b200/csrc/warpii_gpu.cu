@@ -857,6 +857,34 @@ extern "C" int warpii_gpu_point_fluxes(int device, int n, const double* qa, cons
     return 0;
 }
 
+namespace wgpu {
+void launch_division_check(long long n, unsigned long long seed, int mode, unsigned long long* mismatches, double* first_bad,
+                           cudaStream_t s);
+}
+
+extern "C" int warpii_gpu_check_division(int device, int64_t n, uint64_t seed, int mode, int64_t* mismatches_out,
+                                         double first_bad_out[4]) {
+    if (!mismatches_out) return fail("null argument");
+    if (mode < 0 || mode > 3) return fail("check_division: mode %d out of range", mode);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail("no CUDA device available");
+    CUDA_OK(cudaSetDevice(device));
+    unsigned long long* d_count = nullptr;
+    double* d_bad = nullptr;
+    if (upload<unsigned long long>(&d_count, nullptr, 1) || upload<double>(&d_bad, nullptr, 4)) return 1;
+    wgpu::launch_division_check((long long)n, (unsigned long long)seed, mode, d_count, d_bad, nullptr);
+    CUDA_OK(cudaDeviceSynchronize());
+    unsigned long long count = 0;
+    double bad[4] = {0, 0, 0, 0};
+    CUDA_OK(cudaMemcpy(&count, d_count, sizeof count, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+    cudaFree(d_count);
+    cudaFree(d_bad);
+    *mismatches_out = (int64_t)count;
+    if (first_bad_out) for (int i = 0; i < 4; i++) first_bad_out[i] = bad[i];
+    return 0;
+}
+
 extern "C" int warpii_gpu_sm_clock_probes(warpii_gpu_ctx* c, double* mhz_out, int max_out, int* n_out) {
     if (!c || !n_out) return fail("null argument");
     CUDA_OK(cudaStreamSynchronize(c->stream));
