@@ -159,7 +159,10 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
     double* const sAlpha = smem + GEO::OFF_ALPHA;
     double* const sRed = smem + GEO::OFF_RED;
 
-    if (P.skip_dev && *P.skip_dev) return;   // uniform: the device-resident time loop has finished
+    // device-resident time loop: "finished" flag and dt live in global memory.  The loads are issued here, the flag is
+    // tested only after this thread's state and neighbour-table loads are in flight, so that the block pays one
+    // memory latency at its start instead of two.
+    const int skip = P.skip_dev ? *P.skip_dev : 0;
     const double dt = P.dt_dev ? *P.dt_dev : P.dt;
 
     const int tid = threadIdx.x;
@@ -172,30 +175,13 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
     const bool active = e < P.elem_end;
     const int64_t e_hi = (e0 + G < P.elem_end) ? e0 + G : P.elem_end;   // elements [e0, e_hi) have primitives in shared memory
 
-    for (int i = tid; i < NP * NP; i += NODES) { sD[i] = P.T.D[i]; sV[i] = P.T.V[i]; }
-    for (int i = tid; i < NP; i += NODES) sW[i] = P.T.w[i];
-    // pair numbering of a pencil: ids 0..NP-2 are the adjacent pairs (j, j+1), the rest follow in (j, l) order
-    for (int i = tid; i < NP * NP; i += NODES) {
-        const int a = i / NP, b = i % NP;
-        const int lo = a < b ? a : b, hi = a < b ? b : a;
-        int id = 0;
-        if (hi == lo + 1) id = lo;
-        else if (hi > lo + 1) {
-            id = NP - 1;
-            for (int jj = 0; jj < lo; jj++) id += (NP - 2 - jj) > 0 ? (NP - 2 - jj) : 0;
-            id += hi - lo - 2;
-        }
-        sPairId[i] = id;
-        if (a < b) sPairJL[id] = a | (b << 8);
-    }
-
     const double gamma = P.gamma, gm1 = P.gamma - 1.0;
     const double hig = P.hig;   // 1 / (2 (gamma - 1)), formed on the host
     const int nc = P.nc;
     double vmax_local = 0.0;
 
     for (int sp = 0; sp < P.nsp; sp++) {
-        __syncthreads();   // shared-memory reuse across species (and the table fill above)
+        if (sp > 0) __syncthreads();   // shared-memory reuse across species
         // ---- node phase: load, primitives, logs, wave speed ----------------------------------------------
         const size_t off = ((size_t)e * nc + 5 * sp) * NN + j;
         double q[5] = {1.0, 0.0, 0.0, 0.0, 1.0};
@@ -226,6 +212,29 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 for (int c = 0; c < 5; c++) cp_async8(rec + c, src + (size_t)c * stride);
             }
             cp_async_commit();
+        }
+        if (sp == 0) {
+            if (skip) {   // uniform: the device-resident time loop has finished
+                cp_async_wait_all();
+                return;
+            }
+            // small tables, filled while the loads above are in flight (visible after the barrier below)
+            for (int i = tid; i < NP * NP; i += NODES) { sD[i] = P.T.D[i]; sV[i] = P.T.V[i]; }
+            for (int i = tid; i < NP; i += NODES) sW[i] = P.T.w[i];
+            // pair numbering of a pencil: ids 0..NP-2 are the adjacent pairs (j, j+1), the rest follow in (j, l) order
+            for (int i = tid; i < NP * NP; i += NODES) {
+                const int a = i / NP, b = i % NP;
+                const int lo = a < b ? a : b, hi = a < b ? b : a;
+                int id = 0;
+                if (hi == lo + 1) id = lo;
+                else if (hi > lo + 1) {
+                    id = NP - 1;
+                    for (int jj = 0; jj < lo; jj++) id += (NP - 2 - jj) > 0 ? (NP - 2 - jj) : 0;
+                    id += hi - lo - 2;
+                }
+                sPairId[i] = id;
+                if (a < b) sPairJL[id] = a | (b << 8);
+            }
         }
         {
             const Prim me = make_prim(q[0], q[1], q[2], q[3], q[4], gamma);
@@ -336,6 +345,22 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             for (int c = 0; c < 5; c++) R[c] = cf * (sgn * (Fm[c] - Fe[c]) + Dv[c]);
             store_flux(rec, R);
         }
+        // The differentiation weights and pair-record offsets of this node's rows depend only on its position: fetch them
+        // before the barrier so that the flux records can be read back to back after it.  Row l runs over the other
+        // NP-1 nodes of the pencil in rotated order, l = (j_d + k) mod NP (no wasted slot, no divergence).
+        double dw[DIM][NP - 1];
+        int poff[DIM][NP - 1];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            const int jd = idx[d];
+#pragma unroll
+            for (int k = 1; k < NP; k++) {
+                int l = jd + k;
+                if (l >= NP) l -= NP;
+                dw[d][k - 1] = sD[jd * NP + l];
+                poff[d][k - 1] = sPairId[jd * NP + l] * kFS;
+            }
+        }
         group_sync<GROUP, NODES>(tid);
 
         // ---- node phase 2: assemble the rate of this node ----------------------------------------------------
@@ -357,13 +382,11 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 for (int c = 0; c < 5; c++) acc[c] = djj * Fp[c];
             }
 #pragma unroll
-            for (int l = 0; l < NP; l++) {
-                // branch-free: the l == j_d slot re-reads pair 0 with weight 0 (its term was added above)
-                const double djl = (l == jd) ? 0.0 : sD[jd * NP + l];
+            for (int k = 0; k < NP - 1; k++) {
                 double F[5];
-                load_flux(prec + sPairId[jd * NP + l] * kFS, F);
+                load_flux(prec + poff[d][k], F);
 #pragma unroll
-                for (int c = 0; c < 5; c++) acc[c] = fma(djl, F[c], acc[c]);
+                for (int c = 0; c < 5; c++) acc[c] = fma(dw[d][k], F[c], acc[c]);
             }
             const double s = -2.0 * P.inv_h[d];
 #pragma unroll
