@@ -14,21 +14,36 @@
 //                named barrier for Np^dim a multiple of 32, the block barrier otherwise) and warps never wait for
 //                the slowest warp of the block;
 //   indicator    sum-factorised Legendre analysis of p*rho, alpha per element;
-//   task phase   the element's own threads share (a) every UNORDERED node pair (j,l) of its pencils once (the
-//                two-point flux is symmetric) and (b) its face nodes; a neighbour inside the patch is read from the
-//                shared primitive table, others are gathered from L2/HBM (or the NCCL ghost buffer);
+//   task phase   (a) every UNORDERED node pair of a pencil once (the two-point flux is symmetric), grouped by cyclic
+//                distance: each thread evaluates the pairs (own node, own node + c) and parks the flux in its own slot
+//                of a component-plane table, so stores and the later gathers are bank-conflict free and only the
+//                partner's record is loaded; (b) the element's face nodes; a neighbour inside the patch is read from
+//                the shared primitive table, others were prefetched from L2/HBM (or the NCCL ghost buffer) by cp.async;
 //   node phase 2 gather D-weighted pair fluxes, FV differences (only where alpha > 0) and face terms, update,
 //                store, CFL.
 #include "dgsem_common.cuh"
 #include "dgsem_physics.cuh"
 
-#ifndef WGPU_PAIR_CHUNK
-#define WGPU_PAIR_CHUNK 3
+#ifndef WGPU_RESIDENT_THREADS
+#define WGPU_RESIDENT_THREADS 512   // threads the register budget is sized for: 4 blocks of 128 per SM
 #endif
 
 namespace wgpu {
 
 constexpr int kPS = 14;   // doubles per node in the shared primitive table (12 used; 14 keeps 16-byte loads conflict-free)
+
+// Offset (in doubles) of node n's record in the shared primitive table.  Records are 7 sixteen-byte units apart, so the
+// 8 lanes of a quarter-warp reading 8 consecutive nodes (or two x-rows of another y/z position, which is what the pair
+// and face phases do) hit 8 different bank groups.  With an even NP two xy-planes are a multiple of 8 units apart; one
+// unit of padding per plane separates them (3D: 2x fewer wavefronts on the pair loads, measured and modelled).
+template <int NP>
+__device__ __forceinline__ constexpr int prim_off(const int n) {
+    return (NP % 2 == 0) ? n * kPS + 2 * (n / (NP * NP)) : n * kPS;
+}
+template <int NP>
+constexpr int prim_table_doubles(const int nodes) {
+    return (NP % 2 == 0) ? nodes * kPS + 2 * (nodes / (NP * NP) + 1) : nodes * kPS;
+}
 constexpr int kFS = 6;    // doubles per flux record (5 used)
 
 template <int DIM, int NP>
@@ -39,23 +54,28 @@ struct Geo {
     static constexpr int NODES = NN * G;                // nodes (= threads) per block
     static constexpr int NFACE = 2 * DIM;
     static constexpr int NSLOT = G * NFACE * NF;        // face-node result slots per block
-    static constexpr int NPAIR = NP * (NP - 1) / 2;     // unordered node pairs per pencil; ids 0..NP-2 are (j, j+1)
-    static constexpr int PPE = DIM * NF * NPAIR;        // pair tasks per element
-    static constexpr int ROUNDS = (PPE + NN - 1) / NN;  // pair tasks per thread (last round may be partial)
+    // Node pairs of a pencil are grouped by cyclic distance c = 1..NP/2: class c holds the pairs (j, (j+c) mod NP).  A full
+    // class has one pair per node (its "first" endpoint j), the half class c = NP/2 of an even NP one per node with
+    // j < NP/2.  One pair-flux slot per (direction, class, first-endpoint node).
+    static constexpr int NFULL = (NP - 1) / 2;          // full classes per direction
+    static constexpr int HALF = (NP % 2 == 0) ? 1 : 0;  // is there a half class
+    static constexpr int NCL = NFULL + HALF;            // classes per direction
+    static constexpr int HTASKS = HALF * DIM * (NN / 2);            // half-class pair tasks per element
+    static constexpr int HROUNDS = (HTASKS + NN - 1) / NN;          // ... per thread (last round may be partial)
+    static constexpr int PLANE = G * DIM * NCL * NN;    // pair-flux slots per block = doubles per component plane
     static constexpr int THREADS = NODES;
     // threads that synchronise among themselves after the node phase: whole warps holding whole elements
     static constexpr int GROUP = (32 % NN == 0 && NODES % 32 == 0) ? 32 : ((NN % 32 == 0 && NODES / NN <= 15) ? NN : NODES);
-    static constexpr int MIN_BLOCKS = (512 / THREADS) > 0 ? (512 / THREADS) : 1;
+    static constexpr int MIN_BLOCKS = (WGPU_RESIDENT_THREADS / THREADS) > 0 ? (WGPU_RESIDENT_THREADS / THREADS) : 1;
     // dynamic shared memory, in doubles (every offset even => 16-byte aligned)
     static constexpr int even(int x) { return (x + 1) & ~1; }
     static constexpr int OFF_D = 0;
     static constexpr int OFF_V = even(OFF_D + NP * NP);
     static constexpr int OFF_W = even(OFF_V + NP * NP);
-    static constexpr int OFF_TAB = OFF_W + 8;                               // int tables: pair -> (j,l), (j,l) -> pair
-    static constexpr int OFF_P = even(OFF_TAB + (NPAIR + NP * NP + 1) / 2 + 1);   // [NODES][kPS]
-    static constexpr int OFF_A = OFF_P + kPS * NODES;                       // [2][NODES] indicator scratch
-    static constexpr int OFF_PAIR = OFF_A + 2 * NODES;                      // [G*PPE][kFS]
-    static constexpr int OFF_FACE = OFF_PAIR + kFS * G * PPE;               // [NSLOT][kFS]
+    static constexpr int OFF_P = OFF_W + 8;                                 // primitive records of the block's nodes
+    static constexpr int OFF_A = even(OFF_P + prim_table_doubles<NP>(NODES));                      // [2][NODES] indicator scratch
+    static constexpr int OFF_PAIR = OFF_A + 2 * NODES;                      // [5][PLANE] pair fluxes, component planes
+    static constexpr int OFF_FACE = even(OFF_PAIR + 5 * PLANE);             // [NSLOT][kFS]
     static constexpr int OFF_ALPHA = OFF_FACE + kFS * NSLOT;                // [G]
     static constexpr int OFF_RED = even(OFF_ALPHA + G);                     // [32]
     static constexpr int SMEM_DOUBLES = OFF_RED + 32;
@@ -77,8 +97,9 @@ __device__ __forceinline__ double blending_from_energies(const double g0, const 
 }
 
 // node record: [rho u0 | u1 u2 | beta lrho | lbeta q2 | p H | lam ib | - -]
+template <int NP>
 __device__ __forceinline__ void store_prim(double* sP, const int n, const Prim& P) {
-    double2* r = reinterpret_cast<double2*>(sP + n * kPS);
+    double2* r = reinterpret_cast<double2*>(sP + prim_off<NP>(n));
     r[0] = make_double2(P.rho, P.u0);
     r[1] = make_double2(P.u1, P.u2);
     r[2] = make_double2(P.beta, P.lrho);
@@ -87,16 +108,18 @@ __device__ __forceinline__ void store_prim(double* sP, const int n, const Prim& 
     r[5] = make_double2(P.lam, P.ib);
 }
 // the 8 fields the entropy-conserving flux needs
+template <int NP>
 __device__ __forceinline__ Prim load_prim_ec(const double* sP, const int n) {
-    const double2* r = reinterpret_cast<const double2*>(sP + n * kPS);
+    const double2* r = reinterpret_cast<const double2*>(sP + prim_off<NP>(n));
     const double2 a = r[0], b = r[1], c = r[2], d = r[3];
     Prim o;
     o.rho = a.x; o.u0 = a.y; o.u1 = b.x; o.u2 = b.y; o.beta = c.x; o.lrho = c.y; o.lbeta = d.x; o.q2 = d.y;
     o.p = 0.0; o.H = 0.0; o.lam = 0.0; o.ib = 0.0;
     return o;
 }
+template <int NP>
 __device__ __forceinline__ Prim load_prim(const double* sP, const int n) {
-    const double2* r = reinterpret_cast<const double2*>(sP + n * kPS);
+    const double2* r = reinterpret_cast<const double2*>(sP + prim_off<NP>(n));
     const double2 a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5];
     Prim o;
     o.rho = a.x; o.u0 = a.y; o.u1 = b.x; o.u2 = b.y; o.beta = c.x; o.lrho = c.y; o.lbeta = d.x; o.q2 = d.y;
@@ -143,14 +166,12 @@ template <int DIM, int NP>
 __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCKS) stage_kernel(const StageParams P) {
     using GEO = Geo<DIM, NP>;
     constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G, NODES = GEO::NODES, NFACE = GEO::NFACE;
-    constexpr int NPAIR = GEO::NPAIR, PPE = GEO::PPE, ROUNDS = GEO::ROUNDS, GROUP = GEO::GROUP;
+    constexpr int NFULL = GEO::NFULL, HALF = GEO::HALF, NCL = GEO::NCL, PLANE = GEO::PLANE, GROUP = GEO::GROUP;
 
     extern __shared__ __align__(16) double smem[];
     double* const sD = smem + GEO::OFF_D;
     double* const sV = smem + GEO::OFF_V;
     double* const sW = smem + GEO::OFF_W;
-    int* const sPairJL = reinterpret_cast<int*>(smem + GEO::OFF_TAB);   // [NPAIR]: j | l << 8
-    int* const sPairId = sPairJL + NPAIR;                               // [NP*NP]: pair id of (a, b), a != b
     double* const sP = smem + GEO::OFF_P;
     double* const sPair = smem + GEO::OFF_PAIR;
     double* const sA = smem + GEO::OFF_A;   // indicator scratch; only the owning group touches its nodes' slots
@@ -221,24 +242,10 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             // small tables, filled while the loads above are in flight (visible after the barrier below)
             for (int i = tid; i < NP * NP; i += NODES) { sD[i] = P.T.D[i]; sV[i] = P.T.V[i]; }
             for (int i = tid; i < NP; i += NODES) sW[i] = P.T.w[i];
-            // pair numbering of a pencil: ids 0..NP-2 are the adjacent pairs (j, j+1), the rest follow in (j, l) order
-            for (int i = tid; i < NP * NP; i += NODES) {
-                const int a = i / NP, b = i % NP;
-                const int lo = a < b ? a : b, hi = a < b ? b : a;
-                int id = 0;
-                if (hi == lo + 1) id = lo;
-                else if (hi > lo + 1) {
-                    id = NP - 1;
-                    for (int jj = 0; jj < lo; jj++) id += (NP - 2 - jj) > 0 ? (NP - 2 - jj) : 0;
-                    id += hi - lo - 2;
-                }
-                sPairId[i] = id;
-                if (a < b) sPairJL[id] = a | (b << 8);
-            }
         }
         {
             const Prim me = make_prim(q[0], q[1], q[2], q[3], q[4], gamma);
-            store_prim(sP, tid, me);
+            store_prim<NP>(sP, tid, me);
             sA[tid] = me.p * me.rho;   // indicator variable, fluid_flux_es_dgsem_operator.h:286-290
         }
         __syncthreads();
@@ -286,33 +293,53 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
 
         // ---- task phase ---------------------------------------------------------------------------------------
         // (a) unordered node pairs of the pencils of this thread's element: symmetric two-point flux, once
-        // The rounds of a chunk are evaluated into registers and stored afterwards: a shared-memory store between two
-        // evaluations would pin their order (the compiler cannot prove that sPair and sP do not alias), and
-        // independent flux evaluations in flight are what hides the FP64 latency at 4 warps per scheduler.
-        constexpr int CHUNK = WGPU_PAIR_CHUNK;
+        // Full classes: this thread's own node is the first endpoint, so only the partner's record is loaded; the five
+        // components go to this node's slot of the class (component planes: consecutive lanes, consecutive words).
+        {
+            const Prim mine = load_prim_ec<NP>(sP, tid);
+            double* const slot = sPair + (le * DIM * NCL) * NN + j;
 #pragma unroll
-        for (int r0 = 0; r0 < ROUNDS; r0 += CHUNK) {
-            double F[CHUNK][5];
+            for (int d = 0; d < DIM; d++) {
+                const int st = stride_of(NP, d);
 #pragma unroll
-            for (int rr = 0; rr < CHUNK; rr++) {
-                const int p = (r0 + rr) * NN + j;
-                if (r0 + rr < ROUNDS && (PPE % NN == 0 || p < PPE)) {
-                    const int d = p / (NF * NPAIR);
-                    const int rem = p - d * (NF * NPAIR);
-                    const int pe = rem / NPAIR, pid = rem - pe * NPAIR;
-                    const int jl = sPairJL[pid];
-                    const int st = stride_of(NP, d);
-                    const int n0 = le * NN + pencil_first_node<DIM, NP>(d, pe);
-                    const Prim a = load_prim_ec(sP, n0 + (jl & 255) * st);
-                    const Prim b = load_prim_ec(sP, n0 + (jl >> 8) * st);
-                    double ibl;
-                    ec_flux_d(d, a, b, hig, F[rr], ibl);
+                for (int c = 1; c <= NFULL; c++) {
+                    int l = idx[d] + c;
+                    if (l >= NP) l -= NP;
+                    const Prim other = load_prim_ec<NP>(sP, tid + (l - idx[d]) * st);
+                    double F[5], ibl;
+                    ec_flux_d(d, mine, other, hig, F, ibl);
+                    double* const o = slot + (d * NCL + (c - 1)) * NN;
+#pragma unroll
+                    for (int q = 0; q < 5; q++) o[q * PLANE] = F[q];
                 }
             }
+        }
+        // Half class of an even NP (cyclic distance NP/2): one pair per node in the lower half of its pencil, DIM * NN/2
+        // tasks per element spread over all threads; the direction is a run-time value (branch-free in ec_flux_d).
+        if (HALF) {
 #pragma unroll
-            for (int rr = 0; rr < CHUNK; rr++) {
-                const int p = (r0 + rr) * NN + j;
-                if (r0 + rr < ROUNDS && (PPE % NN == 0 || p < PPE)) store_flux(sPair + (le * PPE + p) * kFS, F[rr]);
+            for (int r = 0; r < GEO::HROUNDS; r++) {
+                const int p = r * NN + j;
+                if (GEO::HTASKS % NN == 0 || p < GEO::HTASKS) {
+                    const int d = p / (NN / 2);
+                    int q = p - d * (NN / 2);
+                    int n = 0, mul = 1;   // node whose coordinate along d is below NP/2
+#pragma unroll
+                    for (int a = 0; a < DIM; a++) {
+                        const int ext = (a == d) ? NP / 2 : NP;
+                        n += (q % ext) * mul;
+                        q /= ext;
+                        mul *= NP;
+                    }
+                    const int st = stride_of(NP, d);
+                    const Prim a = load_prim_ec<NP>(sP, le * NN + n);
+                    const Prim b = load_prim_ec<NP>(sP, le * NN + n + (NP / 2) * st);
+                    double F[5], ibl;
+                    ec_flux_d(d, a, b, hig, F, ibl);
+                    double* const o = sPair + ((le * DIM + d) * NCL + NFULL) * NN + n;
+#pragma unroll
+                    for (int c = 0; c < 5; c++) o[c * PLANE] = F[c];
+                }
             }
         }
         // (b) the element's face nodes: its own side of every face (gather form, no atomics)
@@ -323,11 +350,11 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             double* const rec = sFace + ((le * NFACE + f) * NF + t) * kFS;
             const int v = active ? P.nbr[(size_t)e * NFACE + f] : (int)e0;
             if (v < 0) continue;   // domain boundary: the rate contribution prepared by boundary_kernel is already in rec
-            const Prim a = load_prim(sP, le * NN + node_of_face_node<DIM, NP>(d, side, t));
+            const Prim a = load_prim<NP>(sP, le * NN + node_of_face_node<DIM, NP>(d, side, t));
             const int nn = node_of_face_node<DIM, NP>(d, 1 - side, t);
             Prim b;
             if (v >= e0 && v < e_hi) {   // neighbour inside the patch: its primitives are in shared memory
-                b = load_prim(sP, (int)(v - e0) * NN + nn);
+                b = load_prim<NP>(sP, (int)(v - e0) * NN + nn);
             } else {   // owned element outside the patch or ghost trace: conserved values prefetched into rec
                 double qn[5];
                 load_flux(rec, qn);
@@ -353,26 +380,28 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
             const int jd = idx[d];
+            const int st = stride_of(NP, d);
 #pragma unroll
             for (int k = 1; k < NP; k++) {
                 int l = jd + k;
                 if (l >= NP) l -= NP;
                 dw[d][k - 1] = sD[jd * NP + l];
-                poff[d][k - 1] = sPairId[jd * NP + l] * kFS;
+                // pair (jd, l) has cyclic distance c = min(k, NP - k); its slot belongs to its first endpoint
+                const int c = (k < NP - k) ? k : NP - k;
+                const bool own_first = (2 * k < NP) || (2 * k == NP && jd < NP / 2);
+                poff[d][k - 1] = ((le * DIM + d) * NCL + (c - 1)) * NN + (own_first ? j : j + (l - jd) * st);
             }
         }
         group_sync<GROUP, NODES>(tid);
 
         // ---- node phase 2: assemble the rate of this node ----------------------------------------------------
         const double alpha = sAlpha[le];
-        const Prim me = load_prim(sP, tid);
+        const Prim me = load_prim<NP>(sP, tid);
         double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         // split-form volume term: (1-alpha) * sum_d (-2/h_d) sum_l D[j_d][l] F#_d(u_j,u_l)   (split_form_volume_flux.h:68-98)
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
             const int jd = idx[d];
-            const int pe = face_node_index<DIM, NP>(d, i0, i1, i2);
-            const double* const prec = sPair + (le * PPE + d * (NF * NPAIR) + pe * NPAIR) * kFS;
             double acc[5];
             {   // F#(u,u) = f(u); its weight D[j][j] vanishes except at the two end nodes
                 const double djj = sD[jd * NP + jd];
@@ -383,10 +412,8 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             }
 #pragma unroll
             for (int k = 0; k < NP - 1; k++) {
-                double F[5];
-                load_flux(prec + poff[d][k], F);
 #pragma unroll
-                for (int c = 0; c < 5; c++) acc[c] = fma(dw[d][k], F[c], acc[c]);
+                for (int c = 0; c < 5; c++) acc[c] = fma(dw[d][k], sPair[c * PLANE + poff[d][k]], acc[c]);
             }
             const double s = -2.0 * P.inv_h[d];
 #pragma unroll
@@ -403,29 +430,27 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             for (int d = 0; d < DIM; d++) {
                 const int jd = idx[d];
                 const int st = stride_of(NP, d);
-                const int pe = face_node_index<DIM, NP>(d, i0, i1, i2);
-                const double* const prec = sPair + (le * PPE + d * (NF * NPAIR) + pe * NPAIR) * kFS;
+                // adjacent pairs (a, a+1) have cyclic distance 1: class 0, slot of node a
+                const double* const cls0 = sPair + ((le * DIM + d) * NCL) * NN + j;
                 double Fp[5], left[5], right[5];
                 phys_flux_d(d, me, Fp);
 #pragma unroll
                 for (int c = 0; c < 5; c++) { left[c] = Fp[c]; right[c] = Fp[c]; }
                 if (jd > 0) {
-                    const Prim o = load_prim(sP, tid - st);
+                    const Prim o = load_prim<NP>(sP, tid - st);
                     double Fd[5], Dv[5], ibl;
                     ec_flux_d(d, o, me, hig, Fd, ibl);   // only for 1/beta_ln; the flux itself comes from the table
                     es_dissipation(o, me, ibl, hig, Dv);
-                    load_flux(prec + (jd - 1) * kFS, Fd);
 #pragma unroll
-                    for (int c = 0; c < 5; c++) left[c] = Fd[c] - Dv[c];
+                    for (int c = 0; c < 5; c++) left[c] = cls0[c * PLANE - st] - Dv[c];
                 }
                 if (jd < NP - 1) {
-                    const Prim o = load_prim(sP, tid + st);
+                    const Prim o = load_prim<NP>(sP, tid + st);
                     double Fd[5], Dv[5], ibl;
                     ec_flux_d(d, me, o, hig, Fd, ibl);
                     es_dissipation(me, o, ibl, hig, Dv);
-                    load_flux(prec + jd * kFS, Fd);
 #pragma unroll
-                    for (int c = 0; c < 5; c++) right[c] = Fd[c] - Dv[c];
+                    for (int c = 0; c < 5; c++) right[c] = cls0[c * PLANE] - Dv[c];
                 }
                 const double cf = alpha * P.inv_h[d] / sW[jd];
 #pragma unroll
