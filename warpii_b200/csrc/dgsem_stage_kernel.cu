@@ -25,7 +25,7 @@
 #include "dgsem_physics.cuh"
 
 #ifndef WGPU_RESIDENT_THREADS
-#define WGPU_RESIDENT_THREADS 512   // threads the register budget is sized for: 4 blocks of 128 per SM
+#define WGPU_RESIDENT_THREADS 0     // 0: 640 threads per SM in 1D/2D (5 blocks of 128, 96 registers), 512 in 3D (4 blocks, 128 registers)
 #endif
 
 namespace wgpu {
@@ -44,7 +44,6 @@ template <int NP>
 constexpr int prim_table_doubles(const int nodes) {
     return (NP % 2 == 0) ? nodes * kPS + 2 * (nodes / (NP * NP) + 1) : nodes * kPS;
 }
-constexpr int kFS = 6;    // doubles per flux record (5 used)
 
 template <int DIM, int NP>
 struct Geo {
@@ -66,7 +65,9 @@ struct Geo {
     static constexpr int THREADS = NODES;
     // threads that synchronise among themselves after the node phase: whole warps holding whole elements
     static constexpr int GROUP = (32 % NN == 0 && NODES % 32 == 0) ? 32 : ((NN % 32 == 0 && NODES / NN <= 15) ? NN : NODES);
-    static constexpr int MIN_BLOCKS = (WGPU_RESIDENT_THREADS / THREADS) > 0 ? (WGPU_RESIDENT_THREADS / THREADS) : 1;
+    // measured: 2D p=3 gains 6 % from the fifth block per SM despite 56 bytes of spills; 3D p=3 loses 9 %
+    static constexpr int RESIDENT = WGPU_RESIDENT_THREADS > 0 ? WGPU_RESIDENT_THREADS : (DIM <= 2 ? 640 : 512);
+    static constexpr int MIN_BLOCKS = (RESIDENT / THREADS) > 0 ? (RESIDENT / THREADS) : 1;
     // dynamic shared memory, in doubles (every offset even => 16-byte aligned)
     static constexpr int even(int x) { return (x + 1) & ~1; }
     static constexpr int OFF_D = 0;
@@ -75,8 +76,8 @@ struct Geo {
     static constexpr int OFF_P = OFF_W + 8;                                 // primitive records of the block's nodes
     static constexpr int OFF_A = even(OFF_P + prim_table_doubles<NP>(NODES));                      // [2][NODES] indicator scratch
     static constexpr int OFF_PAIR = OFF_A + 2 * NODES;                      // [5][PLANE] pair fluxes, component planes
-    static constexpr int OFF_FACE = even(OFF_PAIR + 5 * PLANE);             // [NSLOT][kFS]
-    static constexpr int OFF_ALPHA = OFF_FACE + kFS * NSLOT;                // [G]
+    static constexpr int OFF_FACE = even(OFF_PAIR + 5 * PLANE);             // [5][NSLOT] face-node records, component planes
+    static constexpr int OFF_ALPHA = even(OFF_FACE + 5 * NSLOT);            // [G]
     static constexpr int OFF_RED = even(OFF_ALPHA + G);                     // [32]
     static constexpr int SMEM_DOUBLES = OFF_RED + 32;
 };
@@ -117,6 +118,16 @@ __device__ __forceinline__ Prim load_prim_ec(const double* sP, const int n) {
     o.p = 0.0; o.H = 0.0; o.lam = 0.0; o.ib = 0.0;
     return o;
 }
+// the 6 fields the physical flux needs
+template <int NP>
+__device__ __forceinline__ Prim load_prim_phys(const double* sP, const int n) {
+    const double2* r = reinterpret_cast<const double2*>(sP + prim_off<NP>(n));
+    const double2 a = r[0], b = r[1], e = r[4];
+    Prim o;
+    o.rho = a.x; o.u0 = a.y; o.u1 = b.x; o.u2 = b.y; o.p = e.x; o.H = e.y;
+    o.beta = 0.0; o.lrho = 0.0; o.lbeta = 0.0; o.q2 = 0.0; o.lam = 0.0; o.ib = 0.0;
+    return o;
+}
 template <int NP>
 __device__ __forceinline__ Prim load_prim(const double* sP, const int n) {
     const double2* r = reinterpret_cast<const double2*>(sP + prim_off<NP>(n));
@@ -126,18 +137,6 @@ __device__ __forceinline__ Prim load_prim(const double* sP, const int n) {
     o.p = e.x; o.H = e.y; o.lam = f.x; o.ib = f.y;
     return o;
 }
-__device__ __forceinline__ void store_flux(double* rec, const double F[5]) {
-    double2* r = reinterpret_cast<double2*>(rec);
-    r[0] = make_double2(F[0], F[1]);
-    r[1] = make_double2(F[2], F[3]);
-    rec[4] = F[4];
-}
-__device__ __forceinline__ void load_flux(const double* rec, double F[5]) {
-    const double2* r = reinterpret_cast<const double2*>(rec);
-    const double2 a = r[0], b = r[1];
-    F[0] = a.x; F[1] = a.y; F[2] = b.x; F[3] = b.y; F[4] = rec[4];
-}
-
 // 8-byte asynchronous global -> shared copy (LDGSTS): the data of a later phase travels while this thread computes
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -165,7 +164,7 @@ __device__ __forceinline__ int pencil_first_node(const int d, const int pe) {
 template <int DIM, int NP>
 __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCKS) stage_kernel(const StageParams P) {
     using GEO = Geo<DIM, NP>;
-    constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G, NODES = GEO::NODES, NFACE = GEO::NFACE;
+    constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G, NODES = GEO::NODES, NFACE = GEO::NFACE, NSLOT = GEO::NSLOT;
     constexpr int NFULL = GEO::NFULL, HALF = GEO::HALF, NCL = GEO::NCL, PLANE = GEO::PLANE, GROUP = GEO::GROUP;
 
     extern __shared__ __align__(16) double smem[];
@@ -216,7 +215,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 const int f = ft / NF, t = ft - f * NF;
                 const int v = P.nbr[(size_t)e * NFACE + f];
                 if (v >= e0 && v < e_hi) continue;
-                double* const rec = sFace + ((le * NFACE + f) * NF + t) * kFS;
+                double* const rec = sFace + (le * NFACE + f) * NF + t;   // component c at rec[c * NSLOT]
                 const double* src;
                 size_t stride;
                 if (v < 0) {
@@ -230,7 +229,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                     stride = NF;
                 }
 #pragma unroll
-                for (int c = 0; c < 5; c++) cp_async8(rec + c, src + (size_t)c * stride);
+                for (int c = 0; c < 5; c++) cp_async8(rec + c * NSLOT, src + (size_t)c * stride);
             }
             cp_async_commit();
         }
@@ -243,12 +242,36 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             for (int i = tid; i < NP * NP; i += NODES) { sD[i] = P.T.D[i]; sV[i] = P.T.V[i]; }
             for (int i = tid; i < NP; i += NODES) sW[i] = P.T.w[i];
         }
+        Prim mine;   // this node's record stays in registers for the pair rounds that follow the barrier
         {
             const Prim me = make_prim(q[0], q[1], q[2], q[3], q[4], gamma);
             store_prim<NP>(sP, tid, me);
             sA[tid] = me.p * me.rho;   // indicator variable, fluid_flux_es_dgsem_operator.h:286-290
+            mine = me;
         }
         __syncthreads();
+
+        // ---- task phase (a), full classes: unordered node pairs of the pencils, symmetric two-point flux, once ------
+        // Full classes: this thread's own node is the first endpoint, so only the partner's record is loaded; the five
+        // components go to this node's slot of the class (component planes: consecutive lanes, consecutive words).
+        {
+            double* const slot = sPair + (le * DIM * NCL) * NN + j;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                const int st = stride_of(NP, d);
+#pragma unroll
+                for (int c = 1; c <= NFULL; c++) {
+                    int l = idx[d] + c;
+                    if (l >= NP) l -= NP;
+                    const Prim other = load_prim_ec<NP>(sP, tid + (l - idx[d]) * st);
+                    double F[5], ibl;
+                    ec_flux_d(d, mine, other, hig, F, ibl);
+                    double* const o = slot + (d * NCL + (c - 1)) * NN;
+#pragma unroll
+                    for (int q = 0; q < 5; q++) o[q * PLANE] = F[q];
+                }
+            }
+        }
 
         // ---- shock indicator: sum-factorised Legendre analysis of p*rho (group-local from here on) ------------
         {
@@ -293,27 +316,6 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
 
         // ---- task phase ---------------------------------------------------------------------------------------
         // (a) unordered node pairs of the pencils of this thread's element: symmetric two-point flux, once
-        // Full classes: this thread's own node is the first endpoint, so only the partner's record is loaded; the five
-        // components go to this node's slot of the class (component planes: consecutive lanes, consecutive words).
-        {
-            const Prim mine = load_prim_ec<NP>(sP, tid);
-            double* const slot = sPair + (le * DIM * NCL) * NN + j;
-#pragma unroll
-            for (int d = 0; d < DIM; d++) {
-                const int st = stride_of(NP, d);
-#pragma unroll
-                for (int c = 1; c <= NFULL; c++) {
-                    int l = idx[d] + c;
-                    if (l >= NP) l -= NP;
-                    const Prim other = load_prim_ec<NP>(sP, tid + (l - idx[d]) * st);
-                    double F[5], ibl;
-                    ec_flux_d(d, mine, other, hig, F, ibl);
-                    double* const o = slot + (d * NCL + (c - 1)) * NN;
-#pragma unroll
-                    for (int q = 0; q < 5; q++) o[q * PLANE] = F[q];
-                }
-            }
-        }
         // Half class of an even NP (cyclic distance NP/2): one pair per node in the lower half of its pencil, DIM * NN/2
         // tasks per element spread over all threads; the direction is a run-time value (branch-free in ec_flux_d).
         if (HALF) {
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
         for (int ft = j; ft < NFACE * NF; ft += NN) {
             const int f = ft / NF, t = ft - f * NF;
             const int d = f >> 1, side = f & 1;
-            double* const rec = sFace + ((le * NFACE + f) * NF + t) * kFS;
+            double* const rec = sFace + (le * NFACE + f) * NF + t;
             const int v = active ? P.nbr[(size_t)e * NFACE + f] : (int)e0;
             if (v < 0) continue;   // domain boundary: the rate contribution prepared by boundary_kernel is already in rec
             const Prim a = load_prim<NP>(sP, le * NN + node_of_face_node<DIM, NP>(d, side, t));
@@ -357,7 +359,8 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                 b = load_prim<NP>(sP, (int)(v - e0) * NN + nn);
             } else {   // owned element outside the patch or ghost trace: conserved values prefetched into rec
                 double qn[5];
-                load_flux(rec, qn);
+#pragma unroll
+                for (int c = 0; c < 5; c++) qn[c] = rec[c * NSLOT];
                 b = make_prim(qn[0], qn[1], qn[2], qn[3], qn[4], gamma);
             }
             const double sgn = side ? 1.0 : -1.0;
@@ -367,10 +370,8 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             es_dissipation(a, b, ibl, hig, Dv);
             phys_flux_d(d, a, Fm);
             // (f(u_m).n - f*) / (h_d w_0) with f* = sgn F# - D   (fluid_flux_es_dgsem_operator.h:318-333)
-            double R[5];
 #pragma unroll
-            for (int c = 0; c < 5; c++) R[c] = cf * (sgn * (Fm[c] - Fe[c]) + Dv[c]);
-            store_flux(rec, R);
+            for (int c = 0; c < 5; c++) rec[c * NSLOT] = cf * (sgn * (Fm[c] - Fe[c]) + Dv[c]);
         }
         // The differentiation weights and pair-record offsets of this node's rows depend only on its position: fetch them
         // before the barrier so that the flux records can be read back to back after it.  Row l runs over the other
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
 
         // ---- node phase 2: assemble the rate of this node ----------------------------------------------------
         const double alpha = sAlpha[le];
-        const Prim me = load_prim<NP>(sP, tid);
+        const Prim me = load_prim_phys<NP>(sP, tid);
         double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         // split-form volume term: (1-alpha) * sum_d (-2/h_d) sum_l D[j_d][l] F#_d(u_j,u_l)   (split_form_volume_flux.h:68-98)
 #pragma unroll
@@ -420,6 +421,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             for (int c = 0; c < 5; c++) r[c] = fma(s, acc[c], r[c]);
         }
         if (alpha > 0.0) {
+            const Prim me = load_prim<NP>(sP, tid);   // the dissipation needs the whole record
             const double oma = 1.0 - alpha;
 #pragma unroll
             for (int c = 0; c < 5; c++) r[c] *= oma;
@@ -463,10 +465,9 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             const int t = face_node_index<DIM, NP>(d, i0, i1, i2);
             if (idx[d] == 0 || idx[d] == NP - 1) {   // NP >= 2: a node is on at most one face per direction
                 const int f = 2 * d + (idx[d] == 0 ? 0 : 1);
-                double F[5];
-                load_flux(sFace + ((le * NFACE + f) * NF + t) * kFS, F);
+                const double* const rec = sFace + (le * NFACE + f) * NF + t;
 #pragma unroll
-                for (int c = 0; c < 5; c++) r[c] += F[c];
+                for (int c = 0; c < 5; c++) r[c] += rec[c * NSLOT];
             }
         }
 
