@@ -122,6 +122,15 @@ int warpii_gpu_set_inflow(warpii_gpu_ctx* ctx, int species, int boundary_id, con
 int warpii_gpu_n_boundary_points(const warpii_gpu_ctx* ctx, int64_t* n_faces_out, int* points_per_face_out);
 int warpii_gpu_set_inflow_table(warpii_gpu_ctx* ctx, int species, const double* table);
 
+/* -- two-fluid source terms (north_star kernel 4) ------------------------------------------------------
+ * NOT part of the reference operator, which carries the 8 field components [Ex,Ey,Ez,Bx,By,Bz,phi,psi]
+ * (five_moment.h:131-137) through unchanged; off by default so that the drop-in stays one.  When enabled (requires
+ * fields_enabled), every stage adds, per node: (q/m)_s (rho_s E + m_s x B) to the momentum and (q/m)_s m_s.E to the
+ * energy of species s, -J/epsilon0 to E and chi rho_c/epsilon0 to phi, with J = sum_s (q/m)_s m_s and
+ * rho_c = sum_s (q/m)_s rho_s (Species::charge / Species::mass, species.h:43-44).  The curl and divergence-cleaning
+ * fluxes of Maxwell's equations are not evolved.  recommend_dt does not know about the plasma frequency. */
+int warpii_gpu_set_sources(warpii_gpu_ctx* ctx, int enabled, double epsilon0, double chi, const double* charge_over_mass);
+
 /* -- the operator ----------------------------------------------------------------------------------
  * dst = beta*dst + alpha*(u + dt * M^-1 R(u)), and the same for the boundary-integrated fluxes
  * (replaces perform_forward_euler_step, fluid_flux_es_dgsem_operator.h:127-214). dst != u. */

@@ -58,6 +58,9 @@ int warpii_box_solver_set_inflow(warpii_box_solver* s, int species, int boundary
 typedef void (*warpii_inflow_fn)(const double* x, double t, double* q5, void* user);
 int warpii_box_solver_set_inflow_function(warpii_box_solver* s, int species, int boundary_id, warpii_inflow_fn fn,
                                           void* user, int time_dependent);
+/* two-fluid source terms on/off (warpii_gpu_set_sources); charge_over_mass[n_species] */
+int warpii_box_solver_set_sources(warpii_box_solver* s, int enabled, double epsilon0, double chi,
+                                  const double* charge_over_mass);
 /* this rank's boundary faces: xyz[face][point][dim] of the quadrature points (Gauss(fe_degree+2)^(dim-1) per face) and
  * the boundary id of every face, in the order of the inflow table; either output may be NULL */
 int64_t warpii_box_solver_n_boundary_faces(const warpii_box_solver* s);

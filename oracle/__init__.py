@@ -283,6 +283,13 @@ class Oracle:
     def set_inflow(self, species, boundary_id, q):
         lib().orc_set_inflow(self.h, species, boundary_id, _ptr(_f64(q)))
 
+    def set_sources(self, enabled, epsilon0=1.0, chi=0.0, charge_over_mass=None):
+        """Two-fluid source terms (new physics, not in the reference): see dgsem_oracle.cc::add_sources."""
+        qm = _f64(charge_over_mass if charge_over_mass is not None else np.zeros(self.nsp))
+        L = lib()
+        L.orc_set_sources.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _dp]
+        L.orc_set_sources(self.h, int(enabled), epsilon0, chi, _ptr(qm))
+
     def set_inflow_function(self, species, boundary_id, fn):
         """fn(x: ndarray[dim], t: float) -> 5 conserved values, evaluated at every boundary quadrature point with the
         stage time, like the Function<dim> of EulerBCMap::get_inflow (fluid_flux_es_dgsem_operator.h:139-144, 381-384)."""

@@ -348,6 +348,10 @@ struct Ctx {
     std::vector<int64_t> bface_of;              // [nelem][2*dim] -> boundary face number or -1
     int64_t n_bfaces = 0;
     mutable std::vector<double> inflow_vals;    // [nsp][n_bfaces][nG][5], refreshed at the start of every RHS
+    // two-fluid source terms (off by default: the reference has none)
+    bool sources_on = false;
+    double epsilon0 = 1.0, chi = 0.0;
+    std::vector<double> charge_over_mass;       // [nsp]
     // Cartesian geometry, formed the way the reference forms it from inverse_jacobian(q)
     double Jinv[3] = {1, 1, 1};   // diagonal of J^{-T}
     double Jdet = 1;              // jacobian_utils.h:12-18: 1/det(Jinv)
@@ -703,6 +707,40 @@ void face_residual(const Ctx& c, const double* u, int64_t e, int sp, double* R, 
     }
 }
 
+// Two-fluid source terms of the five-moment system (north_star kernel 4; NOT in the reference, which carries the field
+// components through unchanged -- SURVEY 8(c) "new-physics note"; parity unpinned by construction, switched off by
+// default).  Per node, with the 8 field components [Ex,Ey,Ez,Bx,By,Bz,phi,psi] of five_moment.h:131-137:
+//   d(m_s)/dt  += (q/m)_s (rho_s E + m_s x B)          Lorentz force on species s
+//   d(E_s)/dt  += (q/m)_s m_s . E                      work done by the electric field
+//   dE/dt      += -J / eps0,   J     = sum_s (q/m)_s m_s
+//   dphi/dt    += chi rho_c / eps0,  rho_c = sum_s (q/m)_s rho_s      (perfectly hyperbolic Maxwell correction source)
+// The curl / divergence-cleaning fluxes of Maxwell's equations are not part of this operator.
+inline void add_sources(const Ctx& c, const double* u, int64_t e, double* dudt) {
+    const int NN = c.NN;
+    const double* uf = u + ((size_t)e * c.nc + 5 * c.nsp) * NN;
+    double* df = dudt + ((size_t)e * c.nc + 5 * c.nsp) * NN;
+    for (int j = 0; j < NN; j++) {
+        const double Ex = uf[0 * NN + j], Ey = uf[1 * NN + j], Ez = uf[2 * NN + j];
+        const double Bx = uf[3 * NN + j], By = uf[4 * NN + j], Bz = uf[5 * NN + j];
+        double Jx = 0, Jy = 0, Jz = 0, rc = 0;
+        for (int sp = 0; sp < c.nsp; sp++) {
+            const double qm = c.charge_over_mass[sp];
+            const double* us = u + ((size_t)e * c.nc + 5 * sp) * NN;
+            double* ds = dudt + ((size_t)e * c.nc + 5 * sp) * NN;
+            const double rho = us[0 * NN + j], mx = us[1 * NN + j], my = us[2 * NN + j], mz = us[3 * NN + j];
+            ds[1 * NN + j] += qm * (rho * Ex + (my * Bz - mz * By));
+            ds[2 * NN + j] += qm * (rho * Ey + (mz * Bx - mx * Bz));
+            ds[3 * NN + j] += qm * (rho * Ez + (mx * By - my * Bx));
+            ds[4 * NN + j] += qm * (mx * Ex + my * Ey + mz * Ez);
+            Jx += qm * mx; Jy += qm * my; Jz += qm * mz; rc += qm * rho;
+        }
+        df[0 * NN + j] = -Jx / c.epsilon0;
+        df[1 * NN + j] = -Jy / c.epsilon0;
+        df[2 * NN + j] = -Jz / c.epsilon0;
+        df[6 * NN + j] = c.chi * rc / c.epsilon0;
+    }
+}
+
 // Evaluate the inflow functions at every boundary quadrature point for stage time t (serially: the callbacks may be
 // Python).  Point of Gauss index g on face f of element e: the face's coordinate in d, Gauss abscissae in the others.
 template <int dim>
@@ -764,9 +802,11 @@ void rhs_impl(const Ctx& c, const double* u, double t, double* dudt, double* bif
                     for (int j = 0; j < NN; j++) de[k * NN + j] = R[k * NN + j] / (c.Jdet * c.wN[j]);   // :216-240 (diagonal mass)
             }
         }
-        if (dudt)
+        if (dudt) {
             for (int k = 5 * c.nsp; k < c.nc; k++)
                 for (int j = 0; j < NN; j++) dudt[((size_t)e * c.nc + k) * NN + j] = 0.0;
+            if (c.sources_on && c.nc >= 5 * c.nsp + 8) add_sources(c, u, e, dudt);
+        }
     }
     if (bif_rate) {
         for (int i = 0; i < nb5; i++) {
@@ -799,7 +839,7 @@ void forward_euler(const Ctx& c, double* dst, const double* u, double dt, double
         // the reference's post-loop lambda (:195-205) runs over every DoF, fields included (dudt = 0 there)
         for (size_t i = 0; i < blockN; i++) {
             const size_t g = (size_t)e * blockN + i;
-            const double dudt_i = (i < fluidN) ? dudt[g] : 0.0;
+            const double dudt_i = (i < fluidN || c.sources_on) ? dudt[g] : 0.0;
             dst[g] = beta * dst[g] + a * (u[g] + dt * dudt_i);
         }
     }
@@ -1062,6 +1102,14 @@ void orc_node_coords(void* h, double* xyz) {
 void orc_set_inflow(void* h, int species, int boundary_id, const double q[5]) {
     Ctx& c = *(Ctx*)h;
     for (int k = 0; k < 5; k++) c.inflow[((size_t)species * 2 * c.dim + boundary_id) * 5 + k] = q[k];
+}
+void orc_set_sources(void* h, int enabled, double epsilon0, double chi, const double* charge_over_mass) {
+    Ctx& c = *(Ctx*)h;
+    c.sources_on = enabled != 0;
+    c.epsilon0 = epsilon0;
+    c.chi = chi;
+    c.charge_over_mass.assign(c.nsp, 0.0);
+    if (charge_over_mass) for (int s = 0; s < c.nsp; s++) c.charge_over_mass[s] = charge_over_mass[s];
 }
 void orc_set_inflow_function(void* h, int species, int boundary_id, orc_inflow_fn fn, void* user) {
     Ctx& c = *(Ctx*)h;

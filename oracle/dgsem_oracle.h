@@ -90,6 +90,10 @@ void orc_set_inflow(void* h, int species, int boundary_id, const double q[5]);
 // Space/time-dependent conserved inflow state q5 = fn(x[dim], t): the Function<dim> the reference evaluates at every
 // boundary quadrature point after set_time(t) with the stage time (fluid_flux_es_dgsem_operator.h:139-144, 381-384).
 // NULL restores the constant state.
+// Two-fluid source terms (Lorentz force, E.J work, -J/eps0 on E, chi rho_c/eps0 on phi): north_star kernel 4.  The
+// reference has no such terms (field components are carried through unchanged), so this is new physics defined in
+// dgsem_oracle.cc::add_sources; off unless enabled here.  charge_over_mass[n_species].
+void orc_set_sources(void* h, int enabled, double epsilon0, double chi, const double* charge_over_mass);
 typedef void (*orc_inflow_fn)(const double* x, double t, double* q5, void* user);
 void orc_set_inflow_function(void* h, int species, int boundary_id, orc_inflow_fn fn, void* user);
 // dudt = M^-1 R(u) (fluid comps only; field comps 0); bif_rate[5*n_boundaries] per species summed as the reference does.

@@ -87,6 +87,7 @@ def lib():
     L.warpii_box_solver_set_inflow.argtypes = [vp, C.c_int, C.c_int, _dp]
     L.warpii_box_solver_attach_comm.argtypes = [vp, C.c_char_p]
     L.warpii_box_solver_set_inflow_function.argtypes = [vp, C.c_int, C.c_int, INFLOW_FN, vp, C.c_int]
+    L.warpii_box_solver_set_sources.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp]
     L.warpii_box_solver_n_boundary_faces.restype = C.c_int64
     L.warpii_box_solver_n_boundary_faces.argtypes = [vp]
     L.warpii_box_solver_boundary_points.argtypes = [vp, _dp, _i32p]
@@ -313,6 +314,11 @@ class BoxSolver:
             self._inflow_cbs = []
         self._inflow_cbs.append(cb)   # keep the thunk alive as long as the solver
         _check(lib().warpii_box_solver_set_inflow_function(self.h, species, boundary_id, cb, None, int(time_dependent)), host=True)
+
+    def set_sources(self, enabled, epsilon0=1.0, chi=0.0, charge_over_mass=None):
+        """Two-fluid source terms (north_star kernel 4; not in the reference operator): warpii_gpu_set_sources."""
+        qm = np.ascontiguousarray(charge_over_mass if charge_over_mass is not None else np.zeros(self.nsp), dtype=np.float64)
+        _check(lib().warpii_box_solver_set_sources(self.h, int(enabled), epsilon0, chi, _ptr(qm)), host=True)
 
     def boundary_points(self):
         """(xyz[face][point][dim], boundary id per face) of this rank's boundary quadrature points."""

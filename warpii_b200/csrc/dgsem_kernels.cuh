@@ -49,6 +49,11 @@ struct StageParams {
     double inv_hw[3];             // 1/(h_d * w_0): face lifting factor (face JxW / cell JxW on a Cartesian cell)
     double max_eig;               // sqrt(lambda_max(J^-T J^-1)), :487-502 of the reference operator
     double ind_T, ind_sT;         // shock-indicator threshold T(Np) and gain s/T (persson_peraire_shock_indicator.h:110-112)
+    // two-fluid source terms (north_star kernel 4; not in the reference, off by default): Lorentz force and E.J work on
+    // the species, -J/eps0 on E and chi rho_c/eps0 on phi, fused into the stage update
+    int32_t src_on;
+    double inv_eps0, chi;
+    const double* qm;             // [nsp] charge / mass
     ElemTables T;
 };
 

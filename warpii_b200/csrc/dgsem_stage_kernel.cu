@@ -471,6 +471,18 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             }
         }
 
+        // ---- two-fluid sources on this species: (q/m)(rho E + m x B) and (q/m) m.E  (uniform branch) ----------
+        if (P.src_on && active) {
+            const size_t fo = ((size_t)e * nc + 5 * P.nsp) * NN + j;
+            const double Ex = P.u[fo], Ey = P.u[fo + NN], Ez = P.u[fo + 2 * (size_t)NN];
+            const double Bx = P.u[fo + 3 * (size_t)NN], By = P.u[fo + 4 * (size_t)NN], Bz = P.u[fo + 5 * (size_t)NN];
+            const double qm = P.qm[sp];
+            r[1] += qm * (q[0] * Ex + (q[2] * Bz - q[3] * By));
+            r[2] += qm * (q[0] * Ey + (q[3] * Bx - q[1] * Bz));
+            r[3] += qm * (q[0] * Ez + (q[1] * By - q[2] * Bx));
+            r[4] += qm * (q[1] * Ex + q[2] * Ey + q[3] * Ez);
+        }
+
         // ---- inverse mass is folded into the factors above; stage update ------------------------------------
         if (active) {
             double qn[5];
@@ -504,14 +516,34 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
         }
     }
 
-    // ---- field components are carried through unchanged by this operator -----------------
+    // ---- field components: carried through unchanged by the reference's operator; with the two-fluid
+    // sources switched on, E gets -J/eps0 and phi gets chi rho_c/eps0 (J, rho_c summed over the species of this node)
     if (active && nc > 5 * P.nsp) {
-        for (int c = 5 * P.nsp; c < nc; c++) {
-            const size_t off = ((size_t)e * nc + c) * NN + j;
+        double S[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (P.src_on) {
+            double Jx = 0.0, Jy = 0.0, Jz = 0.0, rc = 0.0;
+            for (int sp = 0; sp < P.nsp; sp++) {
+                const size_t so = ((size_t)e * nc + 5 * sp) * NN + j;
+                const double qm = P.qm[sp];
+                rc += qm * P.u[so];
+                Jx += qm * P.u[so + NN];
+                Jy += qm * P.u[so + 2 * (size_t)NN];
+                Jz += qm * P.u[so + 3 * (size_t)NN];
+            }
+            S[0] = -Jx * P.inv_eps0;
+            S[1] = -Jy * P.inv_eps0;
+            S[2] = -Jz * P.inv_eps0;
+            S[6] = P.chi * rc * P.inv_eps0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {   // fields_enabled means exactly these 8 components (five_moment.h:123-138)
+            if (5 * P.nsp + k >= nc) break;
+            const size_t off = ((size_t)e * nc + 5 * P.nsp + k) * NN + j;
+            const double rate = S[k];
             double v;
-            if (P.mode == 1) v = 0.0;
-            else if (P.beta == 0.0) v = P.a * P.u[off];
-            else v = P.beta * P.dst[off] + P.a * P.u[off];
+            if (P.mode == 1) v = rate;
+            else if (P.beta == 0.0) v = P.a * (P.u[off] + dt * rate);
+            else v = P.beta * P.dst[off] + P.a * (P.u[off] + dt * rate);
             P.dst[off] = v;
         }
     }

@@ -100,6 +100,9 @@ struct warpii_gpu_ctx {
     ElemTables T;
     BoundaryParams B;
     std::vector<int32_t> h_bc_kind, h_bf_id;
+    bool src_on = false;                    // two-fluid source terms (warpii_gpu_set_sources)
+    double inv_eps0 = 1.0, chi = 0.0;
+    double* d_qm = nullptr;                 // [nsp] charge / mass
     std::vector<double> h_inflow;           // mirror of d_inflow
     std::vector<double> h_inflow_table;     // mirror of d_inflow_table (empty until warpii_gpu_set_inflow_table)
     double* d_inflow_table = nullptr;
@@ -186,6 +189,10 @@ StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a,
     P.beta = beta;
     for (int d = 0; d < 3; d++) { P.inv_h[d] = c->inv_h[d]; P.inv_hw[d] = c->inv_hw[d]; }
     P.max_eig = c->max_eig;
+    P.src_on = c->src_on ? 1 : 0;
+    P.inv_eps0 = c->inv_eps0;
+    P.chi = c->chi;
+    P.qm = c->d_qm;
     P.T = c->T;
     return P;
 }
@@ -463,7 +470,7 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     for (double* v : c->vec) cudaFree(v);
     for (double* v : c->bif) cudaFree(v);
     cudaFree(c->d_nbr); cudaFree(c->d_bf_elem); cudaFree(c->d_bf_side); cudaFree(c->d_bf_id); cudaFree(c->d_bc_kind);
-    cudaFree(c->d_inflow); cudaFree(c->d_inflow_table); cudaFree(c->d_w); cudaFree(c->d_bres); cudaFree(c->d_bflux); cudaFree(c->d_ghost);
+    cudaFree(c->d_inflow); cudaFree(c->d_inflow_table); cudaFree(c->d_qm); cudaFree(c->d_w); cudaFree(c->d_bres); cudaFree(c->d_bflux); cudaFree(c->d_ghost);
     cudaFree(c->d_sendbuf); cudaFree(c->d_partial); cudaFree(c->d_out5); cudaFree(c->d_alpha); cudaFree(c->d_vmax);
     cudaFree(c->d_send_elem); cudaFree(c->d_send_side);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -579,6 +586,25 @@ int warpii_gpu_set_inflow(warpii_gpu_ctx* c, int species, int boundary_id, const
         }
         return push_inflow_table(c, species);
     }
+    return 0;
+}
+
+int warpii_gpu_set_sources(warpii_gpu_ctx* c, int enabled, double epsilon0, double chi, const double* charge_over_mass) {
+    if (!c) return fail("null context");
+    if (!enabled) {
+        c->src_on = false;
+        return 0;
+    }
+    if (c->nc < 5 * c->nsp + 8) return fail("set_sources: the source terms need the 8 field components (fields_enabled)");
+    if (!(epsilon0 > 0.0)) return fail("set_sources: epsilon0 must be positive");
+    if (!charge_over_mass) return fail("set_sources: null charge_over_mass");
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!c->d_qm) CUDA_OK(cudaMalloc((void**)&c->d_qm, (size_t)c->nsp * sizeof(double)));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaMemcpy(c->d_qm, charge_over_mass, (size_t)c->nsp * sizeof(double), cudaMemcpyHostToDevice));
+    c->inv_eps0 = 1.0 / epsilon0;
+    c->chi = chi;
+    c->src_on = true;
     return 0;
 }
 

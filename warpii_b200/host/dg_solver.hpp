@@ -172,6 +172,7 @@ class FiveMomentGpuSolver {
     void set_device_loop(bool on) { device_loop_ = on; }
     int f1_id() const { return integrator_->stage_vector().id(); }
     int n_components() const { return nc_; }
+    int n_species() const { return n_species_; }
     int nodes_per_elem() const { return nn_; }
 
    private:

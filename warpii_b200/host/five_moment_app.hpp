@@ -143,6 +143,11 @@ class FiveMomentGpuApp {
         prm.declare_entry("t_end", "0.0", Pat::Double(0.0));
         prm.declare_entry("write_output", "true", Pat::Bool());
         prm.declare_entry("n_writeout_frames", "10", Pat::Integer(0));
+        // Extension of the input format (no counterpart in the reference, whose operator leaves the fields untouched):
+        // the two-fluid source terms of north_star kernel 4, see include/warpii_gpu.h, warpii_gpu_set_sources.
+        prm.declare_entry("five_moment_sources", "false", Pat::Bool());
+        prm.declare_entry("epsilon0", "1.0", Pat::Double(1e-300));
+        prm.declare_entry("phm_chi", "0.0", Pat::Double(0.0));
         prm.parse_input_from_string(input, false);
 
         // FiveMomentApp<dim>::create_from_parameters (five_moment.h:149-198)
@@ -184,6 +189,11 @@ class FiveMomentGpuApp {
         app->write_output_ = prm.get_bool("write_output");
         app->n_writeout_frames_ = (int)prm.get_integer("n_writeout_frames");
         app->workdir_format_ = prm.get("WorkDir");
+        app->sources_ = prm.get_bool("five_moment_sources");
+        app->epsilon0_ = prm.get_double("epsilon0");
+        app->chi_ = prm.get_double("phm_chi");
+        if (app->sources_ && !app->fields_enabled_)
+            throw std::invalid_argument("five_moment_sources = true needs the field components (fields_enabled)");
         app->rank_ = rank;
         app->n_ranks_ = n_ranks;
 
@@ -209,6 +219,11 @@ class FiveMomentGpuApp {
     // FiveMomentApp::setup (five_moment.h:221-231): grid + solver reinit, initial condition, frame 0
     void setup() {
         solver_->reinit();
+        if (sources_) {
+            std::vector<double> qm;
+            for (const SpeciesDescription& sp : species_) qm.push_back(sp.charge / sp.mass);
+            solver_->get_fluid_flux_operator().set_sources(true, epsilon0_, chi_, qm);
+        }
         for (int s = 0; s < n_species_; s++) {
             std::shared_ptr<SpeciesFunc> ic = species_[s].initial_condition;
             solver_->project_initial_condition(s, [ic](const double* x, double* q5) { ic->conserved(x, 0.0, q5); }, false);
@@ -256,6 +271,8 @@ class FiveMomentGpuApp {
     double gas_gamma() const { return gas_gamma_; }
     double t_end() const { return t_end_; }
     bool write_output() const { return write_output_; }
+    bool sources_enabled() const { return sources_; }
+    double epsilon0() const { return epsilon0_; }
     int n_writeout_frames() const { return n_writeout_frames_; }
     unsigned frames_written() const { return frames_written_; }
 
@@ -328,8 +345,8 @@ class FiveMomentGpuApp {
     }
 
     int dim_ = 1, n_species_ = 1, n_boundaries_ = 0, fe_degree_ = 2, n_writeout_frames_ = 10, rank_ = 0, n_ranks_ = 1;
-    bool fields_enabled_ = false, write_output_ = true, setup_done_ = false;
-    double gas_gamma_ = 5.0 / 3.0, t_end_ = 0.0;
+    bool fields_enabled_ = false, write_output_ = true, setup_done_ = false, sources_ = false;
+    double gas_gamma_ = 5.0 / 3.0, t_end_ = 0.0, epsilon0_ = 1.0, chi_ = 0.0;
     BoxDescription box_;
     std::vector<SpeciesDescription> species_;
     std::shared_ptr<FiveMomentGpuSolver> solver_;

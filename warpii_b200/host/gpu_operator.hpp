@@ -124,6 +124,11 @@ class GpuFluidFluxESDGSEMOperator {
         if (species >= 0 && species < (int)tables_.size() && !tables_[species].empty()) fill_constant(tables_[species], constants_.back());
     }
 
+    // Two-fluid source terms (north_star kernel 4; not in the reference operator, off by default): see warpii_gpu_set_sources.
+    void set_sources(bool enabled, double epsilon0, double chi, const std::vector<double>& charge_over_mass) {
+        check(warpii_gpu_set_sources(ctx_->get(), enabled ? 1 : 0, epsilon0, chi, charge_over_mass.data()));
+    }
+
     // Where the inflow functions are evaluated: xyz[face][point][dim] of this rank's boundary quadrature points and the
     // boundary id of every face, both in the order of warpii_gpu_mesh.boundary_face_* (the solver provides them).
     void set_boundary_points(std::vector<double> xyz, std::vector<int32_t> face_boundary_id, int dim, int n_species) {

@@ -120,6 +120,14 @@ int warpii_box_solver_set_inflow_function(warpii_box_solver* s, int species, int
             species, boundary_id, [=](const double* x, double t, double* q5) { fn(x, t, q5, user); }, time_dependent != 0);
     })
 }
+int warpii_box_solver_set_sources(warpii_box_solver* s, int enabled, double epsilon0, double chi, const double* charge_over_mass) {
+    GUARD({
+        const int n = s->solver->n_species();
+        std::vector<double> qm(n, 0.0);
+        if (charge_over_mass) qm.assign(charge_over_mass, charge_over_mass + n);
+        s->solver->get_fluid_flux_operator().set_sources(enabled != 0, epsilon0, chi, qm);
+    })
+}
 int64_t warpii_box_solver_n_boundary_faces(const warpii_box_solver* s) { return (int64_t)s->solver->tables().boundary_face_elem().size(); }
 int warpii_box_solver_boundary_points(const warpii_box_solver* s, double* xyz, int32_t* face_boundary_id) {
     GUARD({
