@@ -38,6 +38,10 @@ WORKLOADS = {
                 label="2D Euler periodic vortex, degree 3, 1024x1024 elements (C3 size, doubly periodic)"),
     "V3D3": dict(dim=3, p=3, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[10.0, 5.0, 5.0], gamma=1.4, ic="vortex",
                  label="3D Euler periodic vortex, degree 3, 64^3 elements"),
+    "C5s": dict(dim=2, p=3, nx=[1024, 512], left=[0.0, -5.0], right=[20.0, 5.0], gamma=5.0 / 3.0, ic="two_fluid", n_species=2,
+                fields=True, sources=dict(epsilon0=1.0, chi=1.0, charge_over_mass=[1.0 / 25.0, -1.0]),
+                label="C5 shape: 2D two-species five-moment + 8 field components with Lorentz/current sources "
+                      "(no Maxwell curl fluxes), degree 3, 1024x512 elements"),
     "C4s": dict(dim=3, p=4, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[10.0, 5.0, 5.0], gamma=1.4, ic="vortex",
                 label="3D Euler periodic vortex, degree 4, 64^3 elements per GPU (C4 shape)"),
 }
@@ -115,7 +119,25 @@ class ClockSampler:
 def build_ic(w, xyz):
     if w["ic"] == "vortex":
         return cases.to_state(cases.isentropic_vortex(w["gamma"])(xyz), w["gamma"])
+    if w["ic"] == "two_fluid":
+        # smooth two-fluid wave: ion (mass 25) and electron fluids, non-zero B so that the Lorentz term is active
+        s = np.sin(2 * np.pi * xyz[..., 0] / 20.0) * np.cos(2 * np.pi * xyz[..., 1] / 10.0)
+        u = np.zeros((xyz.shape[0], 18, xyz.shape[1]))
+        for sp, (rho0, vel, p0) in enumerate([(25.0, (0.05, -0.02, 0.01), 1.0), (1.0, (-0.2, 0.1, 0.05), 1.0)]):
+            prim = np.zeros(xyz.shape[:-1] + (5,))
+            prim[..., 0] = rho0 * (1 + 0.1 * s)
+            for d in range(3):
+                prim[..., 1 + d] = vel[d] * (1 + 0.2 * s)
+            prim[..., 4] = p0 * (1 + 0.05 * s)
+            cases.to_state(prim, w["gamma"], nc=18, species=sp, u=u)
+        for c, amp in enumerate([0.01, -0.02, 0.015, 0.1, -0.05, 0.2, 0.0, 0.0]):
+            u[:, 10 + c, :] = amp * (1 + 0.3 * s)
+        return u
     raise ValueError(w["ic"])
+
+
+def species_kwargs(w):
+    return dict(n_species=w.get("n_species", 1), fields_enabled=w.get("fields", False))
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -133,7 +155,9 @@ def cpu_run(w, steps, warmup, threads, budget_s, rows=None):
         nxp = nx[:-1] + [probe]
         right = list(w["right"])
         right[-1] = w["left"][-1] + (w["right"][-1] - w["left"][-1]) * probe / full_last
-        o = Oracle(dim, w["p"], nxp, w["left"], right, gamma=w["gamma"], threads=threads)
+        o = Oracle(dim, w["p"], nxp, w["left"], right, gamma=w["gamma"], threads=threads, **species_kwargs(w))
+        if w.get("sources"):
+            o.set_sources(True, **w["sources"])
         u = build_ic(w, o.node_coords())
         dt = o.recommend_dt(u)
         t0 = time.perf_counter()
@@ -143,7 +167,9 @@ def cpu_run(w, steps, warmup, threads, budget_s, rows=None):
     nxs = nx[:-1] + [rows]
     right = list(w["right"])
     right[-1] = w["left"][-1] + (w["right"][-1] - w["left"][-1]) * rows / full_last
-    o = Oracle(dim, w["p"], nxs, w["left"], right, gamma=w["gamma"], threads=threads)
+    o = Oracle(dim, w["p"], nxs, w["left"], right, gamma=w["gamma"], threads=threads, **species_kwargs(w))
+    if w.get("sources"):
+        o.set_sources(True, **w["sources"])
     u = build_ic(w, o.node_coords())
     t = 0.0
     for _ in range(warmup):
@@ -204,7 +230,9 @@ def run_ours(args, w):
     # weak scaling: one workload-sized slab per GPU along the last dimension
     nx[-1] *= world
     right[-1] = left[-1] + (right[-1] - left[-1]) * world
-    g = BoxSolver(dim, p, nx, left, right, gamma=gamma, rank=rank, n_ranks=world, device=local_rank)
+    g = BoxSolver(dim, p, nx, left, right, gamma=gamma, rank=rank, n_ranks=world, device=local_rank, **species_kwargs(w))
+    if w.get("sources"):
+        g.set_sources(True, **w["sources"])
     if world > 1:
         if rank == 0:
             uid = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
