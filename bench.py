@@ -38,6 +38,13 @@ WORKLOADS = {
                 label="2D Euler periodic vortex, degree 3, 1024x1024 elements (C3 size, doubly periodic)"),
     "V3D3": dict(dim=3, p=3, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[10.0, 5.0, 5.0], gamma=1.4, ic="vortex",
                  label="3D Euler periodic vortex, degree 3, 64^3 elements"),
+    "C3": dict(dim=2, p=3, nx=[1024, 1024], left=[-0.5, 0.0], right=[0.5, 2 * np.pi / (1.2 * np.pi)], gamma=5.0 / 3.0, ic="kh",
+               periodic=[0, 1], bc=[[0, 0, 0, 0]],
+               label="C3: 2D Euler Kelvin-Helmholtz, walls in x, periodic in y, degree 3, 1024x1024 elements"),
+    "C3s": dict(dim=2, p=3, nx=[1024, 1024], left=[-0.5, 0.0], right=[0.5, 2 * np.pi / (1.2 * np.pi)], gamma=5.0 / 3.0, ic="kh_steep",
+                periodic=[0, 1], bc=[[0, 0, 0, 0]],
+                label="C3 with an under-resolved interface (tanh width = one element): subcell-FV blend active, walls in x, "
+                      "degree 3, 1024x1024 elements"),
     "C5s": dict(dim=2, p=3, nx=[1024, 512], left=[0.0, -5.0], right=[20.0, 5.0], gamma=5.0 / 3.0, ic="two_fluid", n_species=2,
                 fields=True, sources=dict(epsilon0=1.0, chi=1.0, charge_over_mass=[1.0 / 25.0, -1.0]),
                 label="C5 shape: 2D two-species five-moment + 8 field components with Lorentz/current sources "
@@ -119,6 +126,17 @@ class ClockSampler:
 def build_ic(w, xyz):
     if w["ic"] == "vortex":
         return cases.to_state(cases.isentropic_vortex(w["gamma"])(xyz), w["gamma"])
+    if w["ic"] in ("kh", "kh_steep"):
+        k = 1.2 * np.pi
+        if w["ic"] == "kh":
+            return cases.to_state(cases.kelvin_helmholtz(k)(xyz), w["gamma"])
+        x, y = xyz[..., 0], xyz[..., 1]
+        steep = 4.0 * w["nx"][0] / (w["right"][0] - w["left"][0])      # transition over about one element
+        prim = np.zeros(x.shape + (5,))
+        prim[..., 0] = 0.65 + 0.35 * np.tanh(-(x - 0.003 * np.sin(k * y)) * steep)
+        prim[..., 2] = 0.1 * np.tanh(-x * steep)
+        prim[..., 4] = 1.0
+        return cases.to_state(prim, w["gamma"])
     if w["ic"] == "two_fluid":
         # smooth two-fluid wave: ion (mass 25) and electron fluids, non-zero B so that the Lorentz term is active
         s = np.sin(2 * np.pi * xyz[..., 0] / 20.0) * np.cos(2 * np.pi * xyz[..., 1] / 10.0)
@@ -137,7 +155,10 @@ def build_ic(w, xyz):
 
 
 def species_kwargs(w):
-    return dict(n_species=w.get("n_species", 1), fields_enabled=w.get("fields", False))
+    kw = dict(n_species=w.get("n_species", 1), fields_enabled=w.get("fields", False))
+    if w.get("periodic") is not None:
+        kw.update(periodic=w["periodic"], bc_kinds=w.get("bc"))
+    return kw
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -317,6 +338,7 @@ def run_ours(args, w):
     e2e_ms = max(e2e_ms, e2e_wall)   # the host-side copies are synchronous: count whichever clock saw more
     e2e_value = 2.0 * n_dofs_total * e2e_steps / (e2e_ms * 1e-3)
     assert np.isfinite(host_np).all()
+    fv_frac = float((g.shock_indicator(0) > 0.0).mean())   # elements (x species) whose subcell-FV blend is active now
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -330,7 +352,8 @@ def run_ours(args, w):
             "config": {"workload": w["label"] + (f" per GPU ({nx[-1]} rows in total, slab-sharded)" if world > 1 else ""),
                        "n_dofs": int(n_dofs_total), "state_bytes": int(8 * n_dofs_local),
                        "l2_policy": "state (2 x %.0f MB per GPU) exceeds the 126 MB L2; no flush" % (8e-6 * n_dofs_local),
-                       "parallelism": f"elements sharded over {world} GPU(s), NCCL send/recv halo + allreduce(max) dt"},
+                       "parallelism": f"elements sharded over {world} GPU(s), NCCL send/recv halo + allreduce(max) dt",
+                       "fv_blend_active_fraction_rank0": fv_frac},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_dofs_local),
                     "d2h_bytes_per_step": int(8 * n_dofs_local), "steps": e2e_steps,
                     "note": "per step: pinned host state -> HBM, recommend_dt + SSPRK2 step through the C ABI, HBM -> host"},
