@@ -82,7 +82,7 @@ int warpii_box_solver_recommend_dt(warpii_box_solver* s, double* dt_out);
  * Replaces Warpii::setup/run for Application = FiveMoment (warpii.cc:126-196, five_moment.cc:22-52, five_moment.h:99-243)
  * on HyperRectangle grids: the same entries, defaults and patterns, parsed by an independent reader
  * (warpii_b200/host/parameter_file.hpp) and expression evaluator (expression.hpp).  create needs no GPU; setup and run do.
- * The frame callback stands where the reference writes solution_<n>.vtu (frame 0 fires in setup). */
+ * The frame callback fires where the reference writes solution_<n>.vtu (frame 0 in setup). */
 typedef struct warpii_app warpii_app;
 typedef void (*warpii_frame_fn)(unsigned frame, double t, void* user);
 int warpii_app_create(const char* input_text, int rank, int n_ranks, int device, warpii_app** out);
@@ -98,7 +98,8 @@ int warpii_app_species(const warpii_app* app, int species, char name[16], double
  * function.  xyz[n][n_dims] -> q5_out[n][5] conserved (species_func.cc:9-30). */
 int warpii_app_eval_function(const warpii_app* app, int species, int boundary_id, int64_t n, const double* xyz,
                              double t, double* q5_out, int32_t* time_dependent_out);
-/* with write_output, frames go to <dir>/solution_<frame>.f64 (raw doubles, device order) + frames.txt; "" = no files */
+/* with write_output, frames go to <dir>/solution_<frame>.vtu (the fields of five_moment.h:245-315 and of the
+ * post-processor, postprocessor.h:33-62) + a frames.txt index; "" = no files */
 int warpii_app_set_output_dir(warpii_app* app, const char* dir);
 /* WorkDir format of the input (%A__%I by default) expanded as format_workdir does (warpii.cc:205-219) */
 int warpii_app_format_workdir(const warpii_app* app, const char* input_name, char* out, int out_len);
@@ -107,6 +108,12 @@ int warpii_app_format_workdir(const warpii_app* app, const char* input_name, cha
 int warpii_app_set_device_loop(warpii_app* app, int on);
 int warpii_app_setup(warpii_app* app);
 int warpii_app_run(warpii_app* app, warpii_frame_fn cb, void* user, int64_t* steps_out);
+
+/* the frame writer alone (warpii_b200/host/vtu_writer.hpp; stands in for FiveMomentApp::output_results + DataOut,
+ * five_moment.h:245-315): state[elem][comp][node], xyz[elem][node][dim], species_names comma-separated */
+int warpii_host_write_vtu(const char* path, int dim, int fe_degree, int64_t n_elems, int nc, int n_species,
+                          const char* species_names, int fields_enabled, double gas_gamma, int owner_rank,
+                          const double* state, const double* xyz);
 
 /* the time loop alone (timestepper.cc:6-56) with C callbacks, for the reference's TimestepperTest cases */
 typedef int (*warpii_step_fn)(double t, double dt, void* user);

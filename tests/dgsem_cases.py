@@ -144,3 +144,22 @@ def rel_l2_guarded(got, want, scale, kappa=1e-2):
         den = max(np.linalg.norm(want[:, c, :]), kappa * scale[c])
         out.append(num / den if den > 0 else num)
     return np.array(out)
+
+
+def read_vtu(path):
+    """Minimal reader of the raw-appended VTK XML files the product writes: {array name: ndarray} plus counts."""
+    import re
+    raw = open(path, "rb").read()
+    head, _, tail = raw.partition(b'<AppendedData encoding="raw">')
+    blob = tail[tail.index(b"_") + 1:]
+    text = head.decode()
+    n_points = int(re.search(r'NumberOfPoints="(\d+)"', text).group(1))
+    n_cells = int(re.search(r'NumberOfCells="(\d+)"', text).group(1))
+    out = {"n_points": n_points, "n_cells": n_cells}
+    dtypes = {"Float64": np.float64, "Int64": np.int64, "UInt8": np.uint8}
+    for m in re.finditer(r'<DataArray type="(\w+)" Name="([^"]+)" NumberOfComponents="(\d+)" format="appended" offset="(\d+)"/>', text):
+        typ, name, ncomp, off = m.group(1), m.group(2), int(m.group(3)), int(m.group(4))
+        nbytes = int(np.frombuffer(blob[off:off + 8], dtype=np.uint64)[0])
+        a = np.frombuffer(blob[off + 8:off + 8 + nbytes], dtype=dtypes[typ])
+        out[name] = a.reshape(-1, ncomp) if ncomp > 1 else a
+    return out

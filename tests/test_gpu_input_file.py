@@ -249,9 +249,28 @@ def test_inflow_channel_input_with_pulsing_jet(tmp_path):
     assert [f for f, _ in app.frames] == [1, 2, 3, 4]
     assert np.allclose([t for _, t in app.frames], [0.005, 0.01, 0.015, 0.02], rtol=0, atol=1e-12)
     names = sorted(os.listdir(tmp_path))
-    assert names == ["frames.txt"] + [f"solution_{i:03d}.f64" for i in range(5)]
-    last = np.fromfile(tmp_path / "solution_004.f64").reshape(app.solver.shape)
-    assert np.array_equal(last, app.solver.get_state())
+    assert names == ["frames.txt"] + [f"solution_{i:03d}.vtu" for i in range(5)]
+    # the last frame holds the final state: names of five_moment.h:259-300, derived fields of postprocessor.h:33-62
+    vtu = cases.read_vtu(tmp_path / "solution_004.vtu")
+    state = app.solver.get_state()                                    # device order, like the file
+    n_el, NN = state.shape[0], state.shape[2]
+    assert vtu["n_points"] == n_el * NN and vtu["n_cells"] == n_el * 9 and (vtu["types"] == 9).all()
+    assert np.array_equal(vtu["neutral_density"], state[:, 0].reshape(-1))
+    assert np.array_equal(vtu["neutral_x_momentum"], state[:, 1].reshape(-1))
+    assert np.array_equal(vtu["neutral_energy"], state[:, 4].reshape(-1))
+    rho, mx, my, E = (state[:, c].reshape(-1) for c in (0, 1, 2, 4))
+    p = (app.gas_gamma - 1) * (E - (mx ** 2 + my ** 2) / (2 * rho))
+    np.testing.assert_allclose(vtu["pressure"], p, rtol=1e-13)
+    np.testing.assert_allclose(vtu["x_velocity"], mx / rho, rtol=1e-15)
+    np.testing.assert_allclose(vtu["specific_entropy"], np.log(p) - app.gas_gamma * np.log(rho), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(vtu["speed_of_sound"], np.sqrt(app.gas_gamma * p / rho), rtol=1e-13)
+    assert np.array_equal(vtu["Points"][:, :2], app.solver.node_coords().reshape(-1, 2)) and (vtu["owner"] == 0).all()
+    # sub-cells are counter-clockwise quads of neighbouring GLL nodes of ONE element
+    quad = vtu["connectivity"].reshape(-1, 4)
+    assert (quad // NN == (quad[:, :1] // NN)).all() and (vtu["offsets"] == 4 * np.arange(1, len(quad) + 1)).all()
+    xy = vtu["Points"][quad][:, :, :2]
+    area2 = ((xy[:, 1, 0] - xy[:, 0, 0]) * (xy[:, 2, 1] - xy[:, 0, 1]) - (xy[:, 2, 0] - xy[:, 0, 0]) * (xy[:, 1, 1] - xy[:, 0, 1]))
+    assert (area2 > 0).all() and abs(area2.sum() - 1.5 * 1.0) < 1e-12               # the sub-cells tile the 1.5 x 1 box
     lines = (tmp_path / "frames.txt").read_text().splitlines()
     assert len(lines) == 5 and lines[0].split()[0] == "0" and abs(float(lines[-1].split()[1]) - 0.02) < 1e-12
     app.close()
@@ -267,11 +286,11 @@ def test_cli_runs_an_input_file(tmp_path):
     r = subprocess.run([exe, "fs1d.inp"], capture_output=True, text=True, cwd=tmp_path, timeout=300)
     assert r.returncode == 0, r.stderr
     out_dir = tmp_path / "FiveMoment__fs1d"                                   # WorkDir = %A__%I, warpii.cc:139-149
-    assert sorted(os.listdir(out_dir)) == ["frames.txt", "solution_000.f64", "solution_001.f64", "solution_002.f64"]
+    assert sorted(os.listdir(out_dir)) == ["frames.txt", "solution_000.vtu", "solution_001.vtu", "solution_002.vtu"]
     app = App(inp.read_text())
     app.setup()
     app.run()
-    assert np.array_equal(np.fromfile(out_dir / "solution_002.f64").reshape(app.solver.shape), app.solver.get_state())
+    assert np.array_equal(cases.read_vtu(out_dir / "solution_002.vtu")["neutral_density"], app.solver.get_state()[:, 0].reshape(-1))
     app.close()
     r = subprocess.run([exe, "--setup-only", "fs1d.inp"], capture_output=True, text=True, cwd=tmp_path, timeout=300)
     assert r.returncode == 0 and "steps =" not in r.stdout

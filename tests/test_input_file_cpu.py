@@ -207,3 +207,52 @@ def test_cli_reports_usage_and_input_errors(tmp_path):
     bad.write_text("set n_dims = 9\n")
     r = subprocess.run([exe, str(bad)], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 1 and "outside the allowed range" in r.stderr
+
+
+@pytest.mark.parametrize("dim,p", [(1, 2), (2, 3), (3, 2)])
+def test_vtu_frames(tmp_path, dim, p):
+    """The frame writer (stand-in for output_results + DataOut, five_moment.h:245-315): names, derived fields, sub-cells."""
+    import oracle
+    from oracle import Oracle
+    import dgsem_cases as cases
+    from warpii_b200.capi import write_vtu
+    nx = [3, 2, 2][:dim]
+    o = Oracle(dim, p, nx, [0.0] * dim, [1.0, 2.0, 0.5][:dim], gamma=1.4, n_species=2, fields_enabled=True)
+    rng = np.random.default_rng(dim)
+    u = np.zeros(o.shape)
+    for s in range(2):
+        prim = np.concatenate([rng.uniform(0.5, 2.0, o.shape[:1] + (o.NN, 1)), rng.normal(size=o.shape[:1] + (o.NN, 3)),
+                               rng.uniform(0.5, 2.0, o.shape[:1] + (o.NN, 1))], axis=-1)
+        cases.to_state(prim, 1.4, nc=18, species=s, u=u)
+    u[:, 10:] = rng.normal(size=(o.n_elems, 8, o.NN))
+    path = tmp_path / "solution_000.vtu"
+    write_vtu(path, dim, p, u, o.node_coords(), ["ion", "electron"], fields_enabled=True, gas_gamma=1.4, owner_rank=3)
+    v = cases.read_vtu(path)
+    nsub, verts = p ** dim, 2 ** dim
+    assert v["n_points"] == o.n_elems * o.NN and v["n_cells"] == o.n_elems * nsub
+    assert (v["types"] == {1: 3, 2: 9, 3: 12}[dim]).all() and (v["owner"] == 3).all() and len(v["owner"]) == v["n_cells"]
+    pts = v["Points"]
+    assert np.array_equal(pts[:, :dim], o.node_coords().reshape(-1, dim)) and (pts[:, dim:] == 0).all()
+    for s, name in enumerate(["ion", "electron"]):
+        for k, comp in enumerate(["density", "x_momentum", "y_momentum", "z_momentum", "energy"]):
+            assert np.array_equal(v[f"{name}_{comp}"], u[:, 5 * s + k].reshape(-1))
+        q = u[:, 5 * s:5 * s + 5].transpose(0, 2, 1).reshape(-1, 5)
+        pr = np.array([oracle.pressure(x, 1.4) for x in q])
+        np.testing.assert_allclose(v[f"{name}_pressure"], pr, rtol=1e-14)
+        np.testing.assert_allclose(v[f"{name}_y_velocity"], q[:, 2] / q[:, 0], rtol=1e-15)
+        np.testing.assert_allclose(v[f"{name}_specific_entropy"], np.log(pr) - 1.4 * np.log(q[:, 0]), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(v[f"{name}_speed_of_sound"], np.sqrt(1.4 * pr / q[:, 0]), rtol=1e-14)
+    for k, name in enumerate(["E_field_x", "E_field_y", "E_field_z", "B_field_x", "B_field_y", "B_field_z",
+                              "ph_maxwell_gauss_error", "ph_maxwell_monopole_error"]):
+        assert np.array_equal(v[name], u[:, 10 + k].reshape(-1))
+    cells = v["connectivity"].reshape(-1, verts)
+    assert (v["offsets"] == verts * np.arange(1, len(cells) + 1)).all()
+    assert (cells // o.NN == cells[:, :1] // o.NN).all()                      # a sub-cell never spans two elements
+    # the sub-cells tile the box: their measures (from the first vertex and the far corner) add up to its volume
+    lo, hi = pts[cells].min(axis=1)[:, :dim], pts[cells].max(axis=1)[:, :dim]
+    assert np.isclose(np.prod(hi - lo, axis=1).sum(), np.prod([1.0, 2.0, 0.5][:dim]), rtol=1e-13)
+    if dim >= 2:                                                               # counter-clockwise bottom face
+        a, b, c = pts[cells[:, 0]], pts[cells[:, 1]], pts[cells[:, 2]]
+        assert (((b - a)[:, 0] * (c - a)[:, 1] - (c - a)[:, 0] * (b - a)[:, 1]) > 0).all()
+    if dim == 3:
+        assert (pts[cells[:, 4], 2] > pts[cells[:, 0], 2]).all()

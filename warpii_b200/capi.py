@@ -511,6 +511,18 @@ class App:
         self.close()
 
 
+def write_vtu(path, dim, fe_degree, state, xyz, species_names, fields_enabled=False, gas_gamma=5.0 / 3.0, owner_rank=0):
+    """The product's frame writer on host arrays: state[elem][comp][node], xyz[elem][node][dim]."""
+    L = lib()
+    L.warpii_host_write_vtu.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_double,
+                                        C.c_int, _dp, _dp]
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    _check(L.warpii_host_write_vtu(str(path).encode(), dim, fe_degree, state.shape[0], state.shape[1], len(species_names),
+                                   ",".join(species_names).encode(), int(fields_enabled), gas_gamma, owner_rank, _ptr(state),
+                                   _ptr(xyz)), host=True)
+
+
 def check_division(n, seed=1, mode=0, device=0):
     """(mismatches, [a, b, got, want]) of div_rn_fast vs the IEEE division on n operand pairs (warpii_gpu_check_division)."""
     L = lib()

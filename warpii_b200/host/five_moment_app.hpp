@@ -4,7 +4,7 @@
 // (five_moment.cc:13-52, five_moment.h:99-243), Species / SpeciesFunc (species.cc:9-66, species_func.cc:9-51) and the
 // HyperRectangle grid description (grid_descriptions.cc:27-49): same entries, defaults, patterns and two-pass parsing.
 // Differences, all stated where they occur: only GridType = HyperRectangle is supported; n_dims = 3 is accepted (the
-// reference's case 3 is commented out); VTU output is replaced by raw frames (the post-processor is out of scope).
+// reference's case 3 is commented out); the VTU frames come from an own writer (vtu_writer.hpp) instead of DataOut.
 #pragma once
 #include <cstdio>
 #include <fstream>
@@ -15,6 +15,7 @@
 #include "dg_solver.hpp"
 #include "expression.hpp"
 #include "parameter_file.hpp"
+#include "vtu_writer.hpp"
 
 namespace warpii_b200 {
 
@@ -242,8 +243,8 @@ class FiveMomentGpuApp {
         solver_->solve(writeout_callback);
     }
 
-    // frame_callback replaces the VTU writer for library users; with write_output the raw state also goes to
-    // <output_dir>/solution_<frame>.f64 ([local elem][comp][node] doubles, device order; see local_to_global()).
+    // frame_callback is the hook for library users; with write_output every frame also goes to
+    // <output_dir>/solution_<frame>.vtu, like the reference's output_results.
     void set_frame_callback(std::function<void(unsigned frame, double t)> cb) { frame_callback_ = std::move(cb); }
     void set_output_dir(const std::string& dir) { output_dir_ = dir; }
 
@@ -324,24 +325,26 @@ class FiveMomentGpuApp {
         return sp;
     }
 
-    // FiveMomentApp::output_results (five_moment.h:245-): the reference writes solution_<n>.vtu through DataOut; here the
-    // frame callback fires and, with write_output, the raw state is written.
+    // FiveMomentApp::output_results (five_moment.h:245-315): the frame callback fires and, with write_output, the state is
+    // downloaded (the only device -> host traffic of a run) and written as solution_<n>.vtu (vtu_writer.hpp).
     void output_results(unsigned frame, double t) {
         frames_written_++;
         if (frame_callback_) frame_callback_(frame, t);
         if (!write_output_ || output_dir_.empty()) return;
         std::vector<double> host((size_t)solver_->context()->n_dofs());
         solver_->get_solution().download(host.data());
+        if (node_xyz_.empty()) node_xyz_ = solver_->node_coords();
         char name[64];
-        if (n_ranks_ > 1) std::snprintf(name, sizeof name, "/solution_%03u.rank%d.f64", frame, rank_);
-        else std::snprintf(name, sizeof name, "/solution_%03u.f64", frame);
-        std::ofstream out(output_dir_ + name, std::ios::binary);
-        if (!out) throw std::runtime_error("cannot write " + output_dir_ + name);
-        out.write(reinterpret_cast<const char*>(host.data()), (std::streamsize)(host.size() * sizeof(double)));
+        if (n_ranks_ > 1) std::snprintf(name, sizeof name, "solution_%03u.rank%d.vtu", frame, rank_);
+        else std::snprintf(name, sizeof name, "solution_%03u.vtu", frame);
+        std::vector<VtuSpecies> names;
+        for (const SpeciesDescription& sp : species_) names.push_back({sp.name});
+        VtuWriter::write(output_dir_ + "/" + name, dim_, fe_degree_, solver_->tables().n_local(), solver_->n_components(), names,
+                         fields_enabled_, gas_gamma_, rank_, host.data(), node_xyz_.data());
         std::ofstream index(output_dir_ + (n_ranks_ > 1 ? "/frames.rank" + std::to_string(rank_) + ".txt" : std::string("/frames.txt")),
                             frame == 0 ? std::ios::trunc : std::ios::app);
         index.precision(17);
-        index << frame << " " << t << " " << (name + 1) << "\n";
+        index << frame << " " << t << " " << name << "\n";
     }
 
     int dim_ = 1, n_species_ = 1, n_boundaries_ = 0, fe_degree_ = 2, n_writeout_frames_ = 10, rank_ = 0, n_ranks_ = 1;
@@ -351,6 +354,7 @@ class FiveMomentGpuApp {
     std::vector<SpeciesDescription> species_;
     std::shared_ptr<FiveMomentGpuSolver> solver_;
     std::function<void(unsigned, double)> frame_callback_;
+    std::vector<double> node_xyz_;
     std::string output_dir_, workdir_format_ = "%A__%I";
     unsigned frames_written_ = 0;
 };

@@ -5,7 +5,7 @@
 //
 // Options: --setup-only (stop after setup), --enable-fpe (trap host floating point exceptions while the input is
 // evaluated; on the device an unphysical state stops the run with an error instead), --device N.
-// The working directory follows the input's WorkDir format (%A__%I) and receives the raw frames when write_output is set.
+// The working directory follows the input's WorkDir format (%A__%I) and receives the solution_<n>.vtu frames when write_output is set.
 #include <fenv.h>
 #include <sys/stat.h>
 

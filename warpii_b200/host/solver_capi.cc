@@ -244,6 +244,16 @@ int warpii_app_run(warpii_app* a, warpii_frame_fn cb, void* user, int64_t* steps
     })
 }
 
+int warpii_host_write_vtu(const char* path, int dim, int fe_degree, int64_t n_elems, int nc, int n_species, const char* species_names,
+                          int fields_enabled, double gas_gamma, int owner_rank, const double* state, const double* xyz) {
+    GUARD({
+        std::vector<VtuSpecies> names;
+        for (const std::string& n : ParameterFile::split(species_names ? species_names : "", ',')) names.push_back({ParameterFile::trim(n)});
+        if ((int)names.size() != n_species) throw std::invalid_argument("write_vtu: need one name per species");
+        VtuWriter::write(path, dim, fe_degree, n_elems, nc, names, fields_enabled != 0, gas_gamma, owner_rank, state, xyz);
+    })
+}
+
 int warpii_host_advance(warpii_step_fn step, double t_end, warpii_dt_fn recommend_dt, int n_callbacks, const double* intervals,
                         const int32_t* perform_zeroth, const int32_t* perform_final, warpii_cb_index_fn cb, void* user) {
     GUARD({
