@@ -54,6 +54,15 @@ WORKLOADS = {
 }
 
 
+def measured_traffic(workload):
+    """DRAM bytes per stage-kernel launch from the committed ncu capture of this workload (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return int(json.load(f)[workload]["bytes"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -360,7 +369,8 @@ def run_ours(args, w):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": f"wgpu::stage_kernel<{dim},{p + 1}>", "peak_source": peak_src,
+                         "traffic": measured_traffic(args.workload) if world == 1 else None,
+                         "kernel": f"wgpu::stage_kernel<{dim},{p + 1}>", "peak_source": peak_src,
                          "avg_launch_ms": avg_stage_ms, "launches_timed": int(stage_n),
                          "algorithmic_bytes_per_launch": BYTES_PER_DOF_UPDATE * n_dofs_local},
         }
