@@ -29,7 +29,7 @@ class FiveMomentGpuSolver {
     FiveMomentGpuSolver(const BoxDescription& box, int fe_degree, int n_species, bool fields_enabled, double gas_gamma,
                         double t_end, int n_boundaries, std::vector<SpeciesBC> bcs, int rank, int n_ranks, int device)
         : t_end_(t_end), fe_degree_(fe_degree), n_species_(n_species), fields_enabled_(fields_enabled), gas_gamma_(gas_gamma),
-          n_boundaries_(n_boundaries), bcs_(std::move(bcs)), device_(device),
+          n_boundaries_(n_boundaries), bcs_(std::move(bcs)), device_(device), rank_(rank), n_ranks_(n_ranks),
           tables_(box, rank, n_ranks, warpii_gpu_elems_per_block(box.dim, fe_degree)), element_(fe_degree) {
         nc_ = 5 * n_species + (fields_enabled ? 8 : 0);
         nn_ = 1;
@@ -162,6 +162,13 @@ class FiveMomentGpuSolver {
         advance(step, t_end_, recommend_dt, callbacks);
     }
 
+    // One process per GPU: hand the halo lists of this rank's slab and the communicator id to the context
+    void attach_comm(const char id[WARPII_GPU_NCCL_ID_BYTES]) {
+        warpii_gpu_halo halo;
+        tables_.fill(halo);
+        check(warpii_gpu_attach_comm(ctx_->get(), id, rank_, n_ranks_, &halo));
+    }
+
     GpuSolutionVec& get_solution() { return *solution_; }
     GpuFluidFluxESDGSEMOperator& get_fluid_flux_operator() { return *op_; }
     const BoxMeshTables& tables() const { return tables_; }
@@ -182,7 +189,7 @@ class FiveMomentGpuSolver {
     double gas_gamma_;
     int n_boundaries_;
     std::vector<SpeciesBC> bcs_;
-    int device_;
+    int device_, rank_ = 0, n_ranks_ = 1;
     BoxMeshTables tables_;
     ReferenceElement element_;
     int nc_ = 5, nn_ = 1;

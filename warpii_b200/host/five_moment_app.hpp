@@ -259,6 +259,9 @@ class FiveMomentGpuApp {
         return out;
     }
 
+    // sharded runs: attach the NCCL communicator (after setup(), before run()); id from warpii_gpu_nccl_unique_id on rank 0
+    void attach_comm(const char id[WARPII_GPU_NCCL_ID_BYTES]) { solver_->attach_comm(id); }
+
     FiveMomentGpuSolver& get_solver() { return *solver_; }
     std::shared_ptr<FiveMomentGpuSolver> solver_ptr() const { return solver_; }
     GpuSolutionVec& get_solution() { return solver_->get_solution(); }
@@ -341,6 +344,17 @@ class FiveMomentGpuApp {
         for (const SpeciesDescription& sp : species_) names.push_back({sp.name});
         VtuWriter::write(output_dir_ + "/" + name, dim_, fe_degree_, solver_->tables().n_local(), solver_->n_components(), names,
                          fields_enabled_, gas_gamma_, rank_, host.data(), node_xyz_.data());
+        if (n_ranks_ > 1 && rank_ == 0) {
+            std::vector<std::string> pieces;
+            for (int r = 0; r < n_ranks_; r++) {
+                char piece[64];
+                std::snprintf(piece, sizeof piece, "solution_%03u.rank%d.vtu", frame, r);
+                pieces.push_back(piece);
+            }
+            char index_name[64];
+            std::snprintf(index_name, sizeof index_name, "/solution_%03u.pvtu", frame);
+            VtuWriter::write_pvtu(output_dir_ + index_name, names, fields_enabled_, pieces);
+        }
         std::ofstream index(output_dir_ + (n_ranks_ > 1 ? "/frames.rank" + std::to_string(rank_) + ".txt" : std::string("/frames.txt")),
                             frame == 0 ? std::ios::trunc : std::ios::app);
         index.precision(17);

@@ -139,6 +139,38 @@ class VtuWriter {
         if (!out) throw std::runtime_error("error while writing " + path);
     }
 
+    // Names of the point-data arrays in file order (solution components, fields, derived fields).
+    static std::vector<std::string> point_data_names(const std::vector<VtuSpecies>& species, bool fields_enabled) {
+        std::vector<std::string> out;
+        const int n_species = (int)species.size();
+        for (const VtuSpecies& sp : species)
+            for (const char* c : {"_density", "_x_momentum", "_y_momentum", "_z_momentum", "_energy"}) out.push_back(sp.name + c);
+        if (fields_enabled)
+            for (const char* c : {"E_field_x", "E_field_y", "E_field_z", "B_field_x", "B_field_y", "B_field_z", "ph_maxwell_gauss_error",
+                                  "ph_maxwell_monopole_error"})
+                out.push_back(c);
+        for (const VtuSpecies& sp : species)
+            for (const char* c : {"x_velocity", "y_velocity", "z_velocity", "pressure", "specific_entropy", "speed_of_sound"})
+                out.push_back((n_species > 1 ? sp.name + "_" : std::string()) + c);
+        return out;
+    }
+
+    // solution_<n>.pvtu: the index a sharded run's rank 0 writes next to the per-rank pieces (what DataOut's
+    // write_vtu_in_parallel / write_pvtu_record provide in the reference, five_moment.h:312-314).
+    static void write_pvtu(const std::string& path, const std::vector<VtuSpecies>& species, bool fields_enabled,
+                           const std::vector<std::string>& piece_files) {
+        std::ofstream out(path);
+        if (!out) throw std::runtime_error("cannot write " + path);
+        out << "<?xml version=\"1.0\"?>\n<VTKFile type=\"PUnstructuredGrid\" version=\"1.0\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n"
+            << "  <PUnstructuredGrid GhostLevel=\"0\">\n    <PPoints>\n      <PDataArray type=\"Float64\" Name=\"Points\" NumberOfComponents=\"3\"/>\n"
+            << "    </PPoints>\n    <PPointData>\n";
+        for (const std::string& n : point_data_names(species, fields_enabled))
+            out << "      <PDataArray type=\"Float64\" Name=\"" << n << "\" NumberOfComponents=\"1\"/>\n";
+        out << "    </PPointData>\n    <PCellData>\n      <PDataArray type=\"Float64\" Name=\"owner\" NumberOfComponents=\"1\"/>\n    </PCellData>\n";
+        for (const std::string& f : piece_files) out << "    <Piece Source=\"" << f << "\"/>\n";
+        out << "  </PUnstructuredGrid>\n</VTKFile>\n";
+    }
+
    private:
     struct Array {
         Array() = default;
