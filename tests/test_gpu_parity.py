@@ -347,3 +347,34 @@ def test_full_size_c2_properties():
     r = g.download(1)
     assert np.abs(r).max() < 1e-9   # |D| / h ~ 3e2, flux ~ 1, eps ~ 1e-16
     g.close()
+
+
+def test_graph_replay_of_the_time_loop_is_bitwise_identical(monkeypatch):
+    """Full batches of the device-resident loop are replayed from a CUDA graph; a context created with
+    WARPII_GPU_NO_GRAPH=1 launches the same kernels one by one.  Same numbers, and a captured batch is dropped when a
+    setter changes kernel arguments (here: the inflow state between two runs)."""
+    gamma = 1.4
+    bc = [[BC_INFLOW, BC_OUTFLOW]]
+    q_a = oracle.primitive_to_conserved([1.0, 0.8, 0.0, 0.0, 1.0], gamma)
+    q_b = oracle.primitive_to_conserved([1.3, 0.9, 0.0, 0.0, 1.2], gamma)
+    results = []
+    for no_graph in ("0", "1"):
+        monkeypatch.setenv("WARPII_GPU_NO_GRAPH", no_graph)
+        o, g = make_pair(1, 3, [24], [0.0], [1.0], periodic=[0], gamma=gamma, bc=bc)
+        g.set_inflow(0, 0, q_a)
+        u = o.project(cases.sine_wave(amp=0.2, vel=(0.8, 0.0, 0.0)))
+        g.set_state_global(u)
+        t, n1 = g.advance_to(0.0, 1e30, max_steps=40)          # 5 full batches
+        g.set_inflow(0, 0, q_b)                                # must invalidate the captured batch
+        t, n2 = g.advance_to(t, 1e30, max_steps=21)            # 2 full batches + 5 single steps
+        results.append((t, n1 + n2, g.get_state_global(), g.boundary_fluxes(0), g.launch_count()))
+        if no_graph == "1":
+            o.set_inflow(0, 0, q_a)
+            o.solve(u, 1e30, max_steps=40)
+            o.set_inflow(0, 0, q_b)
+            o.solve(u, 1e30, max_steps=21)
+            assert (cases.rel_l2_per_component(results[-1][2], u)[[0, 1, 4]] < STEPS_TOL).all()
+        g.close()
+    (ta, na, ua, ba, la), (tb, nb, ub, bb, lb) = results
+    assert ta == tb and na == nb == 61 and la == lb
+    assert np.array_equal(ua, ub) and np.array_equal(ba, bb)

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -100,6 +101,12 @@ struct warpii_gpu_ctx {
     ElemTables T;
     BoundaryParams B;
     std::vector<int32_t> h_bc_kind, h_bf_id;
+    // CUDA graph of one full batch of the device-resident time loop (single GPU, timing off): the launch sequence and all
+    // kernel arguments are the same for every batch because dt, t and the stop flag live in device memory
+    cudaGraphExec_t batch_graph = nullptr;
+    int batch_graph_solution = -1, batch_graph_f1 = -1;
+    int64_t batch_graph_launches = 0;
+    bool use_graphs = true;
     bool src_on = false;                    // two-fluid source terms (warpii_gpu_set_sources)
     double inv_eps0 = 1.0, chi = 0.0;
     double* d_qm = nullptr;                 // [nsp] charge / mass
@@ -427,6 +434,7 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
         return 1;
     }
 
+    if (const char* env = std::getenv("WARPII_GPU_NO_GRAPH")) c->use_graphs = !(env[0] == '1');
     // persson_peraire_shock_indicator.h:110-112
     c->ind_T = 0.5 * std::pow(10.0, -1.8 * std::pow((double)c->Np, 0.25));
     c->ind_sT = 9.21024 / c->ind_T;
@@ -470,6 +478,7 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     for (double* v : c->vec) cudaFree(v);
     for (double* v : c->bif) cudaFree(v);
     cudaFree(c->d_nbr); cudaFree(c->d_bf_elem); cudaFree(c->d_bf_side); cudaFree(c->d_bf_id); cudaFree(c->d_bc_kind);
+    if (c->batch_graph) cudaGraphExecDestroy(c->batch_graph);
     cudaFree(c->d_inflow); cudaFree(c->d_inflow_table); cudaFree(c->d_qm); cudaFree(c->d_w); cudaFree(c->d_bres); cudaFree(c->d_bflux); cudaFree(c->d_ghost);
     cudaFree(c->d_sendbuf); cudaFree(c->d_partial); cudaFree(c->d_out5); cudaFree(c->d_alpha); cudaFree(c->d_vmax);
     cudaFree(c->d_send_elem); cudaFree(c->d_send_side);
@@ -558,6 +567,13 @@ int warpii_gpu_device_ptr(warpii_gpu_ctx* c, int vec, void** out) {
 }
 
 namespace {
+// anything that changes kernel arguments (pointers, flags) makes the captured batch stale
+void drop_batch_graph(warpii_gpu_ctx* c) {
+    if (c->batch_graph) cudaGraphExecDestroy(c->batch_graph);
+    c->batch_graph = nullptr;
+    c->batch_graph_solution = c->batch_graph_f1 = -1;
+}
+
 // (re)upload one species' slice of the inflow table
 int push_inflow_table(warpii_gpu_ctx* c, int species) {
     const size_t per_species = (size_t)c->n_bfaces * ipow(c->Np + 1, c->dim - 1) * 5;
@@ -577,6 +593,7 @@ int warpii_gpu_set_inflow(warpii_gpu_ctx* c, int species, int boundary_id, const
     CUDA_OK(cudaMemcpyAsync(c->d_inflow + ((size_t)species * c->n_boundaries + boundary_id) * 5, c->h_small + 8,
                             5 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    drop_batch_graph(c);
     if (!c->h_inflow_table.empty()) {   // a table is active: the constant state replaces this boundary's rows
         const int NG = ipow(c->Np + 1, c->dim - 1);
         for (int64_t bf = 0; bf < c->n_bfaces; bf++) {
@@ -591,6 +608,7 @@ int warpii_gpu_set_inflow(warpii_gpu_ctx* c, int species, int boundary_id, const
 
 int warpii_gpu_set_sources(warpii_gpu_ctx* c, int enabled, double epsilon0, double chi, const double* charge_over_mass) {
     if (!c) return fail("null context");
+    drop_batch_graph(c);
     if (!enabled) {
         c->src_on = false;
         return 0;
@@ -636,6 +654,7 @@ int warpii_gpu_set_inflow_table(warpii_gpu_ctx* c, int species, const double* ta
         for (int sp = 0; sp < c->nsp; sp++)
             if (sp != species && push_inflow_table(c, sp)) return 1;
         c->B.inflow_table = c->d_inflow_table;
+        drop_batch_graph(c);
     }
     std::memcpy(c->h_inflow_table.data() + per_species * species, table, per_species * sizeof(double));
     return push_inflow_table(c, species);
@@ -705,16 +724,51 @@ int warpii_gpu_advance_to(warpii_gpu_ctx* c, int solution, int f1, double* t_ino
     for (;;) {
         int n = batch;
         if (max_steps > 0 && max_steps - known_steps < n) n = (int)(max_steps - known_steps);
-        for (int i = 0; i < n; i++) {
-            launch_clock(c->d_clock, c->d_vmax + solution, 0, c->stream);
-            if (run_stage(c, f1, solution, 0.0, 1.0, 0.0, 0, false, true)) return 1;        // rk.h:102-103
-            if (run_stage(c, solution, f1, 0.0, 0.5, 0.5, 0, true, true)) return 1;         // rk.h:104-105
-            if (c->comm && c->n_ranks > 1)
-                NCCL_OK(g_nccl.AllReduce(c->d_vmax + solution, c->d_vmax + solution, 1, ncclDouble, ncclMax, c->comm, c->stream));
+        // A full batch on one GPU with timing off is replayed from a CUDA graph (captured on first use): same kernels, same
+        // arguments, one launch call instead of ~30, which is what small meshes are bound by.
+        const bool graphable = c->use_graphs && !c->comm && !c->timing && n == batch;
+        if (graphable && c->batch_graph && c->batch_graph_solution == solution && c->batch_graph_f1 == f1) {
+            CUDA_OK(cudaGraphLaunch(c->batch_graph, c->stream));
+            c->launches += c->batch_graph_launches;
+        } else {
+            const bool capture = graphable;
+            const int64_t launches_before = c->launches;
+            if (capture) {
+                drop_batch_graph(c);
+                CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            }
+            int rc = 0;
+            for (int i = 0; i < n && !rc; i++) {
+                launch_clock(c->d_clock, c->d_vmax + solution, 0, c->stream);
+                rc = run_stage(c, f1, solution, 0.0, 1.0, 0.0, 0, false, true);                 // rk.h:102-103
+                if (!rc) rc = run_stage(c, solution, f1, 0.0, 0.5, 0.5, 0, true, true);         // rk.h:104-105
+                if (!rc && c->comm && c->n_ranks > 1)
+                    NCCL_OK(g_nccl.AllReduce(c->d_vmax + solution, c->d_vmax + solution, 1, ncclDouble, ncclMax, c->comm, c->stream));
+            }
+            if (!rc) launch_clock(c->d_clock, c->d_vmax + solution, 1, c->stream);   // book the last step of the batch, test for the end
+            c->launches += n + 1;
+            if (capture) {
+                cudaGraph_t graph = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+                if (rc || ce != cudaSuccess) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return rc ? 1 : fail("advance_to: graph capture failed: %s", cudaGetErrorString(ce));
+                }
+                const cudaError_t ci = cudaGraphInstantiate(&c->batch_graph, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ci != cudaSuccess) {
+                    c->batch_graph = nullptr;
+                    return fail("advance_to: graph instantiation failed: %s", cudaGetErrorString(ci));
+                }
+                c->batch_graph_solution = solution;
+                c->batch_graph_f1 = f1;
+                c->batch_graph_launches = c->launches - launches_before;
+                CUDA_OK(cudaGraphLaunch(c->batch_graph, c->stream));   // the captured work has not run yet
+            } else if (rc) {
+                return 1;
+            }
+            if (c->timing && c->n_probes < 64) launch_sm_clock_probe(c->d_probe + c->n_probes++, c->stream);
         }
-        launch_clock(c->d_clock, c->d_vmax + solution, 1, c->stream);   // book the last step of the batch, test for the end
-        if (c->timing && c->n_probes < 64) launch_sm_clock_probe(c->d_probe + c->n_probes++, c->stream);
-        c->launches += n + 1;
         CUDA_OK(cudaMemcpyAsync(hc, c->d_clock, sizeof(DevClock), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
         known_steps = hc->steps;
