@@ -190,7 +190,8 @@ def test_reference_freestream_1d_from_the_input_file():
 
 
 def test_reference_sod_and_pseudo_2d_inputs_run():
-    """InputTest.SodShocktube / FreeStreamPseudo2D (test/input_test.cc:68-135): the reference only asks them to run."""
+    """InputTest.SodShocktube / FreeStreamPseudo2D / FreeStream2DDiagonal (test/input_test.cc:68-168): the reference only asks
+    them to run; here they also have to follow the oracle."""
     app = App(read_input("sod_shocktube.inp"))
     app.setup()
     o = oracle_for(app)
@@ -204,17 +205,18 @@ def test_reference_sod_and_pseudo_2d_inputs_run():
     assert err[0] < 1e-8 and err[1] < 1e-8 and err[4] < 1e-8, err      # shock run: alpha switches are chaotic in the last bits
     app.close()
 
-    app = App(read_input("freestream_pseudo_2d.inp"))
-    app.setup()
-    ic = app.solver.global_integral(0)
-    steps = app.run()
-    assert steps > 10
-    assert np.allclose(app.solver.global_integral(0), ic, rtol=0, atol=1e-13)
-    o = oracle_for(app)
-    u = oracle_initial_state(app, o)
-    assert oracle_run(app, o, u) == steps
-    assert (cases.rel_l2_per_component(app.solver.get_state_global(), u)[[0, 1, 4]] < STEPS_TOL).all()
-    app.close()
+    for name, comps in (("freestream_pseudo_2d.inp", [0, 1, 4]), ("freestream_2d_diagonal_test.inp", [0, 1, 2, 4])):
+        app = App(read_input(name))
+        app.setup()
+        ic = app.solver.global_integral(0)
+        steps = app.run()
+        assert steps > 10
+        assert np.allclose(app.solver.global_integral(0), ic, rtol=0, atol=1e-13)
+        o = oracle_for(app)
+        u = oracle_initial_state(app, o)
+        assert oracle_run(app, o, u) == steps
+        assert (cases.rel_l2_per_component(app.solver.get_state_global(), u)[comps] < STEPS_TOL).all()
+        app.close()
 
 
 def test_device_loop_equals_host_driven_loop():

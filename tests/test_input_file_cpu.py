@@ -186,6 +186,9 @@ def test_comments_defaults_and_workdir():
     assert (a.n_dims, a.fe_degree, a.t_end, a.write_output, a.nx, a.left, a.right) == (1, 2, 1.5, True, [1], [0.0], [1.0])
     assert a.format_workdir("sod_shocktube") == "FiveMoment__sod_shocktube"           # WorkDir default %A__%I, warpii.cc:139-149
     assert App("set WorkDir = runs/%I-%A-%I").format_workdir("STDIN") == "runs/STDIN-FiveMoment-STDIN"
+    # UtilitiesTests.RemoveFileExtensionTest (test/utilities_test.cc:4-8): directories and the last extension go
+    for name, stem in [("foo.inp", "foo"), ("baz.foo.inp", "baz.foo"), ("../examples/foo.inp", "foo"), ("plain", "plain")]:
+        assert a.format_workdir(name) == "FiveMoment__" + stem
     # later `set` lines and repeated subsections override earlier ones
     b = App("set fe_degree = 3\nsubsection geometry\n set nx = 5\nend\nset fe_degree = 4\nsubsection geometry\n set nx = 9\nend")
     assert (b.fe_degree, b.nx) == (4, [9])

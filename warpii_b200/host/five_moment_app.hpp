@@ -248,6 +248,15 @@ class FiveMomentGpuApp {
     void set_frame_callback(std::function<void(unsigned frame, double t)> cb) { frame_callback_ = std::move(cb); }
     void set_output_dir(const std::string& dir) { output_dir_ = dir; }
 
+    // remove_file_extension (utilities.cc:67-88; UtilitiesTests.RemoveFileExtensionTest): the file name without its
+    // directories and without its last extension
+    static std::string remove_file_extension(const std::string& filename) {
+        const size_t slash = filename.find_last_of('/');
+        const std::string file_part = slash == std::string::npos ? filename : filename.substr(slash + 1);
+        const size_t dot = file_part.find_last_of('.');
+        return dot == std::string::npos ? file_part : file_part.substr(0, dot);
+    }
+
     // format_workdir (warpii.cc:205-219): %A -> application name, %I -> input name without extension ("STDIN" for stdin)
     std::string format_workdir(const std::string& input_name) const {
         std::string out = workdir_format_;

@@ -114,12 +114,7 @@ int main(int argc, char** argv) {
         // parse once in the launcher (no device involved): input errors surface before anything is forked
         auto probe = warpii_b200::FiveMomentGpuApp::create_from_input(text.str(), 0, gpus, device);
         // remove_file_extension + format_workdir (warpii.cc:198-219)
-        std::string stem = input_name == "-" ? "STDIN" : input_name;
-        if (input_name != "-") {
-            const size_t slash = stem.find_last_of('/');
-            const size_t dot = stem.find_last_of('.');
-            if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) stem.erase(dot);
-        }
+        const std::string stem = input_name == "-" ? "STDIN" : warpii_b200::FiveMomentGpuApp::remove_file_extension(input_name);
         workdir = probe->format_workdir(stem);
     } catch (const std::exception& e) {
         std::cerr << "Error: " << e.what() << std::endl;

@@ -232,7 +232,12 @@ int warpii_app_eval_function(const warpii_app* a, int species, int boundary_id, 
 }
 int warpii_app_set_output_dir(warpii_app* a, const char* dir) { GUARD({ a->app->set_output_dir(dir ? dir : ""); }) }
 int warpii_app_format_workdir(const warpii_app* a, const char* input_name, char* out, int out_len) {
-    GUARD({ std::snprintf(out, out_len, "%s", a->app->format_workdir(input_name).c_str()); })
+    GUARD({
+        // the name of an input FILE goes through remove_file_extension first, like format_workdir's caller (warpii.cc:209-210)
+        const std::string name = input_name ? input_name : "";
+        const std::string stem = name == "STDIN" ? name : FiveMomentGpuApp::remove_file_extension(name);
+        std::snprintf(out, out_len, "%s", a->app->format_workdir(stem).c_str());
+    })
 }
 int warpii_app_set_device_loop(warpii_app* a, int on) { GUARD({ a->app->get_solver().set_device_loop(on != 0); }) }
 int warpii_app_setup(warpii_app* a) { GUARD({ a->app->setup(); }) }
