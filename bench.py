@@ -49,6 +49,9 @@ WORKLOADS = {
                 fields=True, sources=dict(epsilon0=1.0, chi=1.0, charge_over_mass=[1.0 / 25.0, -1.0]),
                 label="C5 shape: 2D two-species five-moment + 8 field components with Lorentz/current sources "
                       "(no Maxwell curl fluxes), degree 3, 1024x512 elements"),
+    "N3D": dict(dim=3, p=3, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[20.0, 5.0, 5.0], gamma=5.0 / 3.0, ic="two_fluid", n_species=2,
+                fields=True, sources=dict(epsilon0=1.0, chi=1.0, charge_over_mass=[1.0 / 25.0, -1.0]),
+                label="north-star shape: 3D two-species five-moment + 8 field components with sources, degree 3, 64^3 elements"),
     "C4s": dict(dim=3, p=4, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[10.0, 5.0, 5.0], gamma=1.4, ic="vortex",
                 label="3D Euler periodic vortex, degree 4, 64^3 elements per GPU (C4 shape)"),
 }
