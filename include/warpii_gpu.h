@@ -97,6 +97,29 @@ int warpii_gpu_destroy(warpii_gpu_ctx* ctx);
 int64_t warpii_gpu_n_dofs(const warpii_gpu_ctx* ctx);            /* n_elems * n_components * Np^dim */
 int warpii_gpu_synchronize(warpii_gpu_ctx* ctx);
 
+/* -- general geometry ----------------------------------------------------------
+ * Curved or non-rectangular elements and arbitrary conforming face pairing: what the reference obtains from
+ * MappingQ(fe_degree) + MatrixFree (nodal_dg_discretization.h:80, nodal_dg_discretization.cc:15-28) and reads per
+ * quadrature point.  The adapter copies these out of MatrixFree once; warpii_b200/host/mapped_mesh.hpp builds them
+ * from the elements' Gauss-Lobatto support points when deal.II is not there.  Call once, after create and before
+ * the first step; from then on every entry point runs the general-geometry kernels (warpii_gpu_mesh.h is ignored).
+ * Host pointers, copied during the call. */
+typedef struct warpii_gpu_geometry {
+    const double* inverse_jacobian;   /* [n_elems][Np^dim][dim][dim]: J^{-T} at the GLL nodes, FEEvaluation::inverse_jacobian(q)
+                                         (jacobian_utils.h:14,36; fluid_flux_es_dgsem_operator.h:476) */
+    const double* face_normal;        /* [n_elems][2*dim][Np^(dim-1)][dim]: unit OUTWARD normal at the face GLL nodes,
+                                         FEFaceEvaluation::normal_vector(q) of quadrature 1 (:317); the two sides of an
+                                         interior face must hold exactly opposite vectors */
+    const double* face_jacobian;      /* [n_elems][2*dim][Np^(dim-1)]: surface Jacobian = face JxW / tensor GLL weight */
+    const int32_t* neighbor_face;     /* [n_elems][2*dim] or NULL: local face of the neighbour that matches this face, + 8 if
+                                         its face nodes run in the opposite tangential order (2D).  NULL = the opposite
+                                         face, same order (structured meshes) */
+    const double* boundary_normal;    /* [n_boundary_faces][(fe_degree+2)^(dim-1)][dim]: unit outward normal at the
+                                         Gauss(p+2) points of the boundary faces (quadrature 0, :355-361) */
+    const double* boundary_jacobian;  /* [n_boundary_faces][(fe_degree+2)^(dim-1)]: surface Jacobian there */
+} warpii_gpu_geometry;
+int warpii_gpu_set_geometry(warpii_gpu_ctx* ctx, const warpii_gpu_geometry* geometry);
+
 /* -- state transfer (FiveMSolutionVec::mesh_sol <-> HBM; solution_vec.h:45-51) ----------------------
  * dof_index == NULL: host array is already in device layout.  Otherwise host[dof_index[i]] <-> device[i]
  * (build it once from cell->get_dof_indices()). */

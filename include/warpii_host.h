@@ -123,6 +123,15 @@ int warpii_host_advance(warpii_step_fn step, double t_end, warpii_dt_fn recommen
                         const double* intervals, const int32_t* perform_zeroth, const int32_t* perform_final,
                         warpii_cb_index_fn cb, void* user);
 
+/* metric terms of a mesh of curved quadrilaterals / hexahedra from the elements' Gauss-Lobatto support points
+ * xyz[n_elems][Np^dim][dim] (warpii_b200/host/mapped_mesh.hpp; stands in for MappingQ(fe_degree) + MatrixFree's mapping
+ * info): fills the tables of warpii_gpu_geometry, plus the physical coordinates of the boundary Gauss points
+ * (boundary_points, may be NULL).  No GPU needed. */
+int warpii_host_mapped_metrics(int dim, int fe_degree, int64_t n_elems, const double* xyz, const int32_t* face_neighbor,
+                               const int32_t* neighbor_face, int64_t n_boundary_faces, const int32_t* bf_elem,
+                               const int32_t* bf_side, double* inverse_jacobian, double* face_normal, double* face_jacobian,
+                               double* boundary_normal, double* boundary_jacobian, double* boundary_points);
+
 /* mesh-table builder alone (no GPU): fills caller-provided arrays for tests of the partitioning logic.
  * Pass NULL output pointers to query sizes through the counts array:
  * counts = {n_local, n_interface, n_ghost_faces, n_boundary_faces, n_peers, n_send}. */

@@ -369,3 +369,62 @@ class Oracle:
         out = np.zeros(5)
         lib().orc_global_integral(self.h, _ptr(_f64(u)), species, _ptr(out))
         return out
+
+
+class GeneralOracle(Oracle):
+    """The same operator on an arbitrary conforming mesh of (curved) quadrilaterals / hexahedra: orc_create_general.
+
+    mesh: dict with face_neighbor [n_elems][2*dim] (neighbour or -1 - boundary face number), optional neighbor_face,
+    bf_id [n_bfaces]; geometry: dict with inverse_jacobian, face_normal, face_jacobian, boundary_normal,
+    boundary_jacobian (the tables of include/warpii_gpu.h::warpii_gpu_geometry).  PARITY UNPINNED (see dgsem_oracle.h).
+    """
+
+    def __init__(self, dim, fe_degree, mesh, geometry, n_boundaries=0, bc_kinds=None, gamma=1.6666666666667, n_species=1,
+                 fields_enabled=False, threads=1):
+        L = lib()
+        i64p, i32p = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+        L.orc_create_general.restype = C.c_void_p
+        L.orc_create_general.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int, i64p, i32p,
+                                         C.c_int64, i32p, _ip, _dp, _dp, _dp, _dp, _dp]
+        self.dim, self.p, self.gamma, self.nsp = dim, fe_degree, gamma, n_species
+        nbr = np.ascontiguousarray(mesh["face_neighbor"], dtype=np.int64)
+        n_elems = nbr.shape[0]
+        nbrf = mesh.get("neighbor_face")
+        nbrf = None if nbrf is None else np.ascontiguousarray(nbrf, dtype=np.int32)
+        bf_id = np.ascontiguousarray(mesh.get("bf_id", np.zeros(0)), dtype=np.int32)
+        bc_a = None
+        if bc_kinds is not None and n_boundaries > 0:
+            flat = np.asarray(bc_kinds, dtype=np.int32).reshape(-1)
+            assert flat.size == n_species * n_boundaries
+            bc_a = (C.c_int * flat.size)(*[int(v) for v in flat])
+        g = {k: _f64(v) for k, v in geometry.items() if v is not None}
+        opt = lambda k: _ptr(g[k]) if k in g and g[k].size else None
+        self.h = L.orc_create_general(dim, fe_degree, n_species, int(fields_enabled), gamma, n_elems, n_boundaries,
+                                      nbr.ctypes.data_as(i64p), nbrf.ctypes.data_as(i32p) if nbrf is not None else None,
+                                      bf_id.size, bf_id.ctypes.data_as(i32p), bc_a, _ptr(g["inverse_jacobian"]),
+                                      _ptr(g["face_normal"]), _ptr(g["face_jacobian"]), opt("boundary_normal"),
+                                      opt("boundary_jacobian"))
+        if not self.h:
+            raise ValueError("orc_create_general failed (bad arguments or unknown boundary id)")
+        self.n_elems = L.orc_n_elems(self.h)
+        self.nc = L.orc_n_components(self.h)
+        self.NN = L.orc_nodes_per_elem(self.h)
+        self.n_dofs = L.orc_n_dofs(self.h)
+        self.n_boundaries = L.orc_n_boundaries(self.h)
+        self.shape = (self.n_elems, self.nc, self.NN)
+        if threads != 1:
+            L.orc_set_threads(self.h, threads)
+
+    def node_coords(self):
+        raise NotImplementedError("a general mesh has no box coordinates; the caller holds xyz")
+
+    def set_inflow_function(self, *a, **k):
+        raise NotImplementedError("inflow functions are a box-grid service of the oracle")
+
+    def project_xyz(self, xyz, prim_fn, species=0, u=None, conserved=False):
+        if u is None:
+            u = np.zeros(self.shape)
+        vals = _f64(prim_fn(xyz))
+        cons = vals if conserved else primitive_to_conserved(vals, self.gamma)
+        u[:, 5 * species:5 * species + 5, :] = np.transpose(cons, (0, 2, 1))
+        return u

@@ -363,6 +363,43 @@ struct Ctx {
     std::vector<double> Lfull;    // tensor Legendre analysis matrix [NN][NN] (mode k, node q)
     std::vector<int> shell;       // per mode: 1 if max_d k_d == Np-1
     double max_eig = 1;           // power-iteration result of :487-502 (constant on a Cartesian box)
+    int nbnd = 2;                 // number of boundary ids (2*dim on a box: grid_descriptions.cc:55-57 colorize)
+    // ---- general geometry (curved / unstructured elements: what MappingQ(p) + MatrixFree hand to the operator) -------
+    // Supplied per node / per face point by orc_create_general; the operator code below reads geometry only through
+    // jdet() / Jai() / jinv_mat(), which on a box return the constants above (bit-identical to the Cartesian path).
+    bool general = false;
+    std::vector<double> gJinv;    // [nelem][NN][dim][dim]  J^{-T} = FEEvaluation::inverse_jacobian(q)
+    std::vector<double> gJdet;    // [nelem][NN]            jacobian_utils.h:12-18
+    std::vector<double> geig;     // [nelem][NN]            power-iteration value of :487-502 (depends on geometry only)
+    std::vector<int64_t> gnbr;    // [nelem][2*dim]         neighbour element, or -1 - (boundary face number)
+    std::vector<int> gnbrf;       // [nelem][2*dim]         neighbour's local face + 8 * (tangential order reversed)
+    std::vector<int> gbf_id;      // [n_bfaces]             boundary id of every boundary face
+    std::vector<double> gfn;      // [nelem][2*dim][nF][dim] unit outward normal, FEFaceEvaluation::normal_vector(q), quadrature 1
+    std::vector<double> gfJ;      // [nelem][2*dim][nF]      surface Jacobian: face JxW = gfJ * (tensor GLL weight)
+    std::vector<double> gbn;      // [n_bfaces][nG][dim]     unit outward normal at the Gauss(p+2) points of boundary faces
+    std::vector<double> gbJ;      // [n_bfaces][nG]          surface Jacobian there
+
+    double jdet(int64_t e, int q) const { return general ? gJdet[(size_t)e * NN + q] : Jdet; }
+    // J^{-T} at node q as a full matrix K[r][c]
+    void jinv_mat(int64_t e, int q, double K[3][3]) const {
+        for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) K[r][cc] = 0.0;
+        if (general) {
+            const double* g = &gJinv[((size_t)e * NN + q) * dim * dim];
+            for (int r = 0; r < dim; r++) for (int cc = 0; cc < dim; cc++) K[r][cc] = g[r * dim + cc];
+        } else {
+            for (int d = 0; d < dim; d++) K[d][d] = Jinv[d];
+        }
+    }
+    // scaled contravariant basis vector Ja^d = Jdet * column d of J^{-T}  (jacobian_utils.h:32-40)
+    void Jai(int64_t e, int q, int d, double* out) const {
+        if (general) {
+            const double* g = &gJinv[((size_t)e * NN + q) * dim * dim];
+            const double J = gJdet[(size_t)e * NN + q];
+            for (int r = 0; r < dim; r++) out[r] = J * g[r * dim + d];
+        } else {
+            for (int r = 0; r < dim; r++) out[r] = (r == d) ? Ja[d] : 0.0;
+        }
+    }
 
     int64_t elem_index(const int* idx) const {
         int64_t e = 0;
@@ -375,6 +412,7 @@ struct Ctx {
     }
     // neighbour across face f = 2*d+side; returns -1 - boundary_id on a non-periodic boundary
     int64_t neighbor(int64_t e, int f) const {
+        if (general) return gnbr[(size_t)e * 2 * dim + f];
         int idx[3];
         elem_coords(e, idx);
         int d = f / 2, side = f % 2;
@@ -519,7 +557,7 @@ double cell_alpha(const Ctx& c, const double* ue /* [5][NN] of one species */) {
 // R[5][NN] receives the INTEGRATED residual (value * JxW), as integrate_scatter does.
 // ---------------------------------------------------------------------------
 template <int dim>
-void cell_residual(const Ctx& c, const double* ue, double alpha, double* R) {
+void cell_residual(const Ctx& c, int64_t e_geo, const double* ue, double alpha, double* R) {
     const int Np = c.Np, NN = c.NN;
     const double gamma = c.gamma;
     const double* D = c.B.D.data();
@@ -531,9 +569,9 @@ void cell_residual(const Ctx& c, const double* ue, double alpha, double* R) {
     for (int d = 0; d < dim; d++) {
         const int st = c.stride(d);
         for (int qj = 0; qj < NN; qj++) {
-            const double Jdet_j = c.Jdet;
+            const double Jdet_j = c.jdet(e_geo, qj);
             double Jai_j[dim];
-            for (int e = 0; e < dim; e++) Jai_j[e] = (e == d) ? c.Ja[d] : 0.0;
+            c.Jai(e_geo, qj, d, Jai_j);
             const int j = (qj / st) % Np;
             const int base = qj - j * st;
             double uj[5];
@@ -541,11 +579,9 @@ void cell_residual(const Ctx& c, const double* ue, double alpha, double* R) {
             double flux_j[5] = {0, 0, 0, 0, 0};
             for (int l = 0; l < Np; l++) {
                 const int ql = base + st * l;
-                double Jai_avg[dim];
-                for (int e = 0; e < dim; e++) {
-                    const double Jai_l = (e == d) ? c.Ja[d] : 0.0;
-                    Jai_avg[e] = 0.5 * (Jai_j[e] + Jai_l);
-                }
+                double Jai_avg[dim], Jai_l[dim];
+                c.Jai(e_geo, ql, d, Jai_l);
+                for (int e = 0; e < dim; e++) Jai_avg[e] = 0.5 * (Jai_j[e] + Jai_l[e]);
                 double ul[5];
                 state(ql, ul);
                 const double d_jl = D[j * Np + l];
@@ -558,7 +594,7 @@ void cell_residual(const Ctx& c, const double* ue, double alpha, double* R) {
                     flux_j[k] -= acc;
                 }
             }
-            const double JxW = c.Jdet * c.wN[qj];
+            const double JxW = c.jdet(e_geo, qj) * c.wN[qj];
             for (int k = 0; k < 5; k++) R[k * NN + qj] += ((1.0 - alpha) * flux_j[k] / Jdet_j) * JxW;
         }
     }
@@ -570,18 +606,21 @@ void cell_residual(const Ctx& c, const double* ue, double alpha, double* R) {
         for (int ps = 0; ps < NN; ps++) {
             if ((ps / st) % Np != 0) continue;   // pencil starts: nodes whose d-index is 0 (dof_utils.cc:77-96)
             std::fill(fd.begin(), fd.end(), 0.0);
-            double n[dim];
-            for (int e = 0; e < dim; e++) n[e] = (e == d) ? c.Ja[d] : 0.0;
-            const double Jdet = c.Jdet;
+            double n[dim], Jad_m[dim];
+            c.Jai(e_geo, ps, d, n);
+            const double Jdet_0 = c.jdet(e_geo, ps);
             double s0[5], F0[5][dim], f0[5];
             state(ps, s0);
             euler_flux<dim>(s0, gamma, F0);
             flux_dot<dim>(F0, n, f0);
-            for (int k = 0; k < 5; k++) fd[0 * 5 + k] += alpha * f0[k] / w1[0] / Jdet;
+            for (int k = 0; k < 5; k++) fd[0 * 5 + k] += alpha * f0[k] / w1[0] / Jdet_0;
             for (int i = 0; i < Np - 1; i++) {
                 const int qi = ps + st * i;
-                for (int m = 0; m < Np; m++)
-                    for (int e = 0; e < dim; e++) n[e] += Q[i * Np + m] * ((e == d) ? c.Ja[d] : 0.0);
+                for (int m = 0; m < Np; m++) {
+                    c.Jai(e_geo, ps + st * m, d, Jad_m);
+                    for (int e = 0; e < dim; e++) n[e] += Q[i * Np + m] * Jad_m[e];
+                }
+                const double Jdet_i = c.jdet(e_geo, qi), Jdet_i_plus_1 = c.jdet(e_geo, qi + st);
                 double nsq = 0;
                 for (int e = 0; e < dim; e++) nsq += n[e] * n[e];
                 const double nn = std::sqrt(nsq);
@@ -593,21 +632,24 @@ void cell_residual(const Ctx& c, const double* ue, double alpha, double* R) {
                 es_flux<dim>(sl, sr, nhat, gamma, fl);
                 for (int k = 0; k < 5; k++) {
                     const double fdn = fl[k] * nn;
-                    fd[i * 5 + k] += (-alpha * fdn / w1[i] / Jdet);
-                    fd[(i + 1) * 5 + k] += alpha * fdn / w1[i + 1] / Jdet;
+                    fd[i * 5 + k] += (-alpha * fdn / w1[i] / Jdet_i);
+                    fd[(i + 1) * 5 + k] += alpha * fdn / w1[i + 1] / Jdet_i_plus_1;
                 }
             }
-            for (int m = 0; m < Np; m++)
-                for (int e = 0; e < dim; e++) n[e] += Q[(Np - 1) * Np + m] * ((e == d) ? c.Ja[d] : 0.0);
+            for (int m = 0; m < Np; m++) {
+                c.Jai(e_geo, ps + st * m, d, Jad_m);
+                for (int e = 0; e < dim; e++) n[e] += Q[(Np - 1) * Np + m] * Jad_m[e];
+            }
             const int qN = ps + st * (Np - 1);
+            const double Jdet_Np = c.jdet(e_geo, qN);
             double sN[5], FN[5][dim], fN[5];
             state(qN, sN);
             euler_flux<dim>(sN, gamma, FN);
             flux_dot<dim>(FN, n, fN);
-            for (int k = 0; k < 5; k++) fd[(Np - 1) * 5 + k] += (-alpha * fN[k] / w1[Np - 1] / Jdet);
+            for (int k = 0; k < 5; k++) fd[(Np - 1) * 5 + k] += (-alpha * fN[k] / w1[Np - 1] / Jdet_Np);
             for (int i = 0; i < Np; i++) {
                 const int q = ps + st * i;
-                const double JxW = c.Jdet * c.wN[q];
+                const double JxW = c.jdet(e_geo, q) * c.wN[q];
                 for (int k = 0; k < 5; k++) R[k * NN + q] += fd[i * 5 + k] * JxW;
             }
         }
@@ -633,22 +675,30 @@ void face_residual(const Ctx& c, const double* u, int64_t e, int sp, double* R, 
         const int64_t nb = c.neighbor(e, f);
         if (nb >= 0) {
             const double* un = u + ((size_t)nb * c.nc + 5 * sp) * NN;
+            // the neighbour's matching face: the opposite one on a box; on a general mesh any of its faces, possibly
+            // traversed in the opposite tangential order (2D)
+            const int nf_code = c.general ? c.gnbrf[(size_t)e * 2 * dim + f] : (f ^ 1);
+            const int nfa = nf_code & 7, flip = nf_code >> 3;
             for (int t = 0; t < nF; t++) {
                 const int qm = c.face_node(d, side, t);
-                const int qp = c.face_node(d, 1 - side, t);
+                const int qp = c.face_node(nfa / 2, nfa % 2, flip ? nF - 1 - t : t);
+                if (c.general)
+                    for (int k = 0; k < dim; k++) n[k] = c.gfn[(((size_t)e * 2 * dim + f) * nF + t) * dim + k];
                 double sm[5], spl[5];
                 for (int k = 0; k < 5; k++) { sm[k] = ue[k * NN + qm]; spl[k] = un[k * NN + qp]; }
                 double Fm[5][dim], fm[5], fs[5];
                 euler_flux<dim>(sm, gamma, Fm);
                 flux_dot<dim>(Fm, n, fm);
                 es_flux<dim>(sm, spl, n, gamma, fs);
-                const double JxW = c.face_area[d] * c.wF[t];
+                const double JxW = (c.general ? c.gfJ[((size_t)e * 2 * dim + f) * nF + t] : c.face_area[d]) * c.wF[t];
                 for (int k = 0; k < 5; k++) R[k * NN + qm] += (fm[k] - fs[k]) * JxW;
             }
         } else {
             // boundary face, Gauss(p+2) quadrature (quad_no 0, :355-358)
-            const int bid = f;
-            const int kind = c.bc_kind[(size_t)sp * 2 * dim + bid];
+            const int64_t bface = c.general ? -1 - nb : c.bface_of[(size_t)e * 2 * dim + f];
+            const int bid = c.general ? c.gbf_id[bface] : f;
+            // (an unknown id, fluid_flux_es_dgsem_operator.h:406-411, is rejected by orc_create_general)
+            const int kind = c.bc_kind[(size_t)sp * c.nbnd + bid];
             const int Ng = c.B.Ng, nG = c.nfaceG;
             std::vector<double> val((size_t)nG * 5);   // submitted values at Gauss points
             double bsum[5] = {0, 0, 0, 0, 0};
@@ -663,15 +713,17 @@ void face_residual(const Ctx& c, const double* u, int64_t e, int sp, double* R, 
                     const int qm = c.face_node(d, side, t);
                     for (int k = 0; k < 5; k++) wm[k] += phi * ue[k * NN + qm];
                 }
+                if (c.general)
+                    for (int k = 0; k < dim; k++) n[k] = c.gbn[((size_t)bface * nG + g) * dim + k];
                 double rho_u_dot_n = wm[1] * n[0];
                 for (int a = 1; a < dim; a++) rho_u_dot_n += wm[1 + a] * n[a];
                 double wp[5];
                 if (kind == ORC_BC_INFLOW) {
-                    if (c.inflow_fn[(size_t)sp * 2 * dim + bid].fn) {
-                        const int64_t bfn = c.bface_of[(size_t)e * 2 * dim + f];
+                    if (!c.general && c.inflow_fn[(size_t)sp * c.nbnd + bid].fn) {
+                        const int64_t bfn = bface;
                         for (int k = 0; k < 5; k++) wp[k] = c.inflow_vals[(((size_t)sp * c.n_bfaces + bfn) * nG + g) * 5 + k];
                     } else {
-                        for (int k = 0; k < 5; k++) wp[k] = c.inflow[((size_t)sp * 2 * dim + bid) * 5 + k];
+                        for (int k = 0; k < 5; k++) wp[k] = c.inflow[((size_t)sp * c.nbnd + bid) * 5 + k];
                     }
                 } else if (kind == ORC_BC_OUTFLOW) {
                     for (int k = 0; k < 5; k++) wp[k] = wm[k];
@@ -685,7 +737,7 @@ void face_residual(const Ctx& c, const double* u, int64_t e, int sp, double* R, 
                 euler_flux<dim>(wm, gamma, Fm);
                 flux_dot<dim>(Fm, n, fm);
                 lf_flux<dim>(wm, wp, n, gamma, fs);
-                const double JxW = c.face_area[d] * c.wG[g];
+                const double JxW = (c.general ? c.gbJ[(size_t)bface * nG + g] : c.face_area[d]) * c.wG[g];
                 for (int k = 0; k < 5; k++) {
                     val[(size_t)g * 5 + k] = (fm[k] - fs[k]) * JxW;
                     bsum[k] += fs[k] * JxW;
@@ -778,8 +830,8 @@ void refresh_inflow(const Ctx& c, double t) {
 // dudt = M^-1 R(u):  mf.loop + inverse mass (fluid_flux_es_dgsem_operator.h:183-240)
 template <int dim>
 void rhs_impl(const Ctx& c, const double* u, double t, double* dudt, double* bif_rate, double* alpha_out) {
-    const int NN = c.NN, nb5 = 5 * 2 * dim;
-    refresh_inflow<dim>(c, t);
+    const int NN = c.NN, nb5 = 5 * c.nbnd;
+    if (!c.general) refresh_inflow<dim>(c, t);
     const int nthreads = std::max(1, c.nthreads);
     std::vector<std::vector<double>> bif_local(nthreads, std::vector<double>(nb5, 0.0));
 #pragma omp parallel for num_threads(nthreads) schedule(static)
@@ -795,11 +847,11 @@ void rhs_impl(const Ctx& c, const double* u, double t, double* dudt, double* bif
             const double alpha = cell_alpha<dim>(c, ue);
             if (alpha_out) alpha_out[(size_t)e * c.nsp + sp] = alpha;
             if (dudt) {
-                cell_residual<dim>(c, ue, alpha, R.data());
+                cell_residual<dim>(c, e, ue, alpha, R.data());
                 face_residual<dim>(c, u, e, sp, R.data(), bif_rate ? bif_local[tid].data() : nullptr);
                 double* de = dudt + ((size_t)e * c.nc + 5 * sp) * NN;
                 for (int k = 0; k < 5; k++)
-                    for (int j = 0; j < NN; j++) de[k * NN + j] = R[k * NN + j] / (c.Jdet * c.wN[j]);   // :216-240 (diagonal mass)
+                    for (int j = 0; j < NN; j++) de[k * NN + j] = R[k * NN + j] / (c.jdet(e, j) * c.wN[j]);   // :216-240 (diagonal mass)
             }
         }
         if (dudt) {
@@ -828,7 +880,7 @@ void forward_euler(const Ctx& c, double* dst, const double* u, double dt, double
                    double* bif_dst, const double* bif_u) {
     const size_t N = (size_t)c.nelem * c.nc * c.NN;
     std::vector<double> dudt(N);
-    const int nb5 = 5 * 2 * c.dim;
+    const int nb5 = 5 * c.nbnd;
     std::vector<double> rate(nb5, 0.0);
     rhs_dispatch(c, u, t, dudt.data(), rate.data(), nullptr);
     const int nthreads = std::max(1, c.nthreads);
@@ -866,10 +918,22 @@ double max_transport_speed(const Ctx& c, const double* u) {
                 for (int k = 0; k < 5; k++) q[k] = ue[k * NN + j];
                 const double inv = 1. / q[0];
                 const double pr = pressure(q, c.gamma);
-                double conv = 0;
-                for (int d = 0; d < dim; d++) conv = std::max(conv, std::fabs(c.Jinv[d] * (q[d + 1] * inv)));
+                double conv = 0, eig = c.max_eig;
+                if (c.general) {
+                    // convective_speed = inverse_jacobian * velocity (:476-481), with the full matrix
+                    double K[3][3];
+                    c.jinv_mat(e, j, K);
+                    for (int r = 0; r < dim; r++) {
+                        double s = 0;
+                        for (int cc = 0; cc < dim; cc++) s += K[r][cc] * (q[cc + 1] * inv);
+                        conv = std::max(conv, std::fabs(s));
+                    }
+                    eig = c.geig[(size_t)e * NN + j];
+                } else {
+                    for (int d = 0; d < dim; d++) conv = std::max(conv, std::fabs(c.Jinv[d] * (q[d + 1] * inv)));
+                }
                 const double cs = std::sqrt(c.gamma * pr * (1. / q[0]));
-                m = std::max(m, c.max_eig * cs + conv);
+                m = std::max(m, eig * cs + conv);
             }
         }
         max_transport = std::max(max_transport, m);
@@ -881,7 +945,7 @@ void ssprk2(const Ctx& c, double* u, double* f1, double dt, double t, double* bi
     // rk.h:97-106.  f_1's previous contents are multiplied by beta = 0.
     const size_t N = (size_t)c.nelem * c.nc * c.NN;
     std::fill(f1, f1 + N, 0.0);
-    if (bif_f1) std::fill(bif_f1, bif_f1 + 5 * 2 * c.dim, 0.0);
+    if (bif_f1) std::fill(bif_f1, bif_f1 + 5 * c.nbnd, 0.0);
     forward_euler(c, f1, u, dt, t, 1.0, 0.0, bif_f1, bif);
     forward_euler(c, u, f1, dt, t + dt, 0.5, 0.5, bif, bif_f1);
 }
@@ -1067,6 +1131,7 @@ void* orc_create(int dim, int fe_degree, int n_species, int fields_enabled, doub
         c->nelem *= nx[d];
     }
     c->B.init(c->Np);
+    c->nbnd = 2 * dim;
     setup_geometry(*c);
     c->bc_kind.assign((size_t)n_species * 2 * dim, ORC_BC_WALL);   // species.cc:17 default "Wall"
     if (bc_kinds) for (size_t i = 0; i < c->bc_kind.size(); i++) c->bc_kind[i] = bc_kinds[i];
@@ -1078,13 +1143,87 @@ void* orc_create(int dim, int fe_degree, int n_species, int fields_enabled, doub
             if (c->neighbor(e, f) < 0) c->bface_of[(size_t)e * 2 * dim + f] = c->n_bfaces++;
     return c;
 }
+// General geometry: the operator on an arbitrary conforming mesh of (curved) quadrilaterals / hexahedra, fed with what
+// the reference reads from deal.II per quadrature point: inverse_jacobian(q) (fluid_flux_es_dgsem_operator.h:476,
+// jacobian_utils.h:14,36), normal_vector(q) and the face JxW (:317-339, :361-437).  Box-only services (node_coords,
+// inflow functions) are not available on such a context.
+void* orc_create_general(int dim, int fe_degree, int n_species, int fields_enabled, double gamma, int64_t n_elems,
+                         int n_boundaries, const int64_t* face_neighbor, const int32_t* neighbor_face, int64_t n_bfaces,
+                         const int32_t* bf_id, const int* bc_kinds, const double* inverse_jacobian,
+                         const double* face_normal, const double* face_jacobian, const double* boundary_normal,
+                         const double* boundary_jacobian) {
+    if (dim < 1 || dim > 3 || fe_degree < 1 || n_species < 1 || n_elems < 0 || !face_neighbor || !inverse_jacobian ||
+        !face_normal || !face_jacobian)
+        return nullptr;
+    for (int64_t b = 0; b < n_bfaces; b++)
+        if (bf_id[b] < 0 || bf_id[b] >= n_boundaries) return nullptr;   // "Unknown boundary id" (:406-411)
+    Ctx* c = new Ctx();
+    c->dim = dim;
+    c->p = fe_degree;
+    c->Np = fe_degree + 1;
+    c->NN = ipow(c->Np, dim);
+    c->nsp = n_species;
+    c->nc = 5 * n_species + (fields_enabled ? 8 : 0);
+    c->gamma = gamma;
+    c->nelem = n_elems;
+    for (int d = 0; d < dim; d++) { c->nx[d] = 1; c->left[d] = 0; c->right[d] = 1; c->periodic[d] = 0; }
+    c->B.init(c->Np);
+    setup_geometry(*c);   // reference-element tables (weights, Legendre analysis); the box constants are not used
+    c->general = true;
+    c->nbnd = n_boundaries;
+    c->n_bfaces = n_bfaces;
+    const int nf = 2 * dim, NN = c->NN, nF = c->nfaceN, nG = c->nfaceG;
+    c->gnbr.assign(face_neighbor, face_neighbor + (size_t)n_elems * nf);
+    c->gnbrf.resize((size_t)n_elems * nf);
+    for (size_t i = 0; i < c->gnbrf.size(); i++) c->gnbrf[i] = neighbor_face ? neighbor_face[i] : (int)((i % nf) ^ 1);
+    c->gbf_id.assign(bf_id, bf_id + n_bfaces);
+    c->gJinv.assign(inverse_jacobian, inverse_jacobian + (size_t)n_elems * NN * dim * dim);
+    c->gfn.assign(face_normal, face_normal + (size_t)n_elems * nf * nF * dim);
+    c->gfJ.assign(face_jacobian, face_jacobian + (size_t)n_elems * nf * nF);
+    if (n_bfaces > 0) {
+        c->gbn.assign(boundary_normal, boundary_normal + (size_t)n_bfaces * nG * dim);
+        c->gbJ.assign(boundary_jacobian, boundary_jacobian + (size_t)n_bfaces * nG);
+    }
+    c->gJdet.resize((size_t)n_elems * NN);
+    c->geig.resize((size_t)n_elems * NN);
+    for (int64_t e = 0; e < n_elems; e++)
+        for (int q = 0; q < NN; q++) {
+            double K[3][3];
+            c->jinv_mat(e, q, K);
+            // tensor_utils.h:70-82 (1x1, 2x2); the 3x3 cofactor expansion is the extension the reference lacks
+            double det;
+            if (dim == 1) det = K[0][0];
+            else if (dim == 2) det = K[0][0] * K[1][1] - K[0][1] * K[1][0];
+            else det = K[0][0] * (K[1][1] * K[2][2] - K[1][2] * K[2][1]) - K[0][1] * (K[1][0] * K[2][2] - K[1][2] * K[2][0]) +
+                       K[0][2] * (K[1][0] * K[2][1] - K[1][1] * K[2][0]);
+            c->gJdet[(size_t)e * NN + q] = 1.0 / det;   // jacobian_utils.h:15-16
+            // fluid_flux_es_dgsem_operator.h:487-502: 5 power iterations on K^T K from (1,...,1)
+            double ev[3] = {1, 1, 1};
+            for (int it = 0; it < 5; it++) {
+                double Kv[3] = {0, 0, 0}, w[3] = {0, 0, 0}, nrm = 0;
+                for (int r = 0; r < dim; r++) for (int cc = 0; cc < dim; cc++) Kv[r] += K[r][cc] * ev[cc];
+                for (int r = 0; r < dim; r++) for (int cc = 0; cc < dim; cc++) w[r] += K[cc][r] * Kv[cc];
+                for (int r = 0; r < dim; r++) nrm = std::max(nrm, std::fabs(w[r]));
+                for (int r = 0; r < dim; r++) ev[r] = w[r] / nrm;
+            }
+            double Kv[3] = {0, 0, 0}, num = 0, den = 0;
+            for (int r = 0; r < dim; r++) for (int cc = 0; cc < dim; cc++) Kv[r] += K[r][cc] * ev[cc];
+            for (int r = 0; r < dim; r++) { num += Kv[r] * Kv[r]; den += ev[r] * ev[r]; }
+            c->geig[(size_t)e * NN + q] = std::sqrt(num / den);
+        }
+    c->bc_kind.assign((size_t)n_species * std::max(1, n_boundaries), ORC_BC_WALL);
+    if (bc_kinds) for (size_t i = 0; i < (size_t)n_species * n_boundaries; i++) c->bc_kind[i] = bc_kinds[i];
+    c->inflow.assign((size_t)n_species * std::max(1, n_boundaries) * 5, 0.0);
+    c->inflow_fn.assign((size_t)n_species * std::max(1, n_boundaries), Ctx::InflowFn());
+    return c;
+}
 void orc_destroy(void* h) { delete (Ctx*)h; }
 void orc_set_threads(void* h, int n) { ((Ctx*)h)->nthreads = std::max(1, n); }
 int64_t orc_n_elems(void* h) { return ((Ctx*)h)->nelem; }
 int64_t orc_n_dofs(void* h) { Ctx* c = (Ctx*)h; return c->nelem * c->nc * c->NN; }
 int orc_n_components(void* h) { return ((Ctx*)h)->nc; }
 int orc_nodes_per_elem(void* h) { return ((Ctx*)h)->NN; }
-int orc_n_boundaries(void* h) { return 2 * ((Ctx*)h)->dim; }
+int orc_n_boundaries(void* h) { return ((Ctx*)h)->nbnd; }
 void orc_node_coords(void* h, double* xyz) {
     Ctx& c = *(Ctx*)h;
     for (int64_t e = 0; e < c.nelem; e++) {
@@ -1101,7 +1240,7 @@ void orc_node_coords(void* h, double* xyz) {
 }
 void orc_set_inflow(void* h, int species, int boundary_id, const double q[5]) {
     Ctx& c = *(Ctx*)h;
-    for (int k = 0; k < 5; k++) c.inflow[((size_t)species * 2 * c.dim + boundary_id) * 5 + k] = q[k];
+    for (int k = 0; k < 5; k++) c.inflow[((size_t)species * c.nbnd + boundary_id) * 5 + k] = q[k];
 }
 void orc_set_sources(void* h, int enabled, double epsilon0, double chi, const double* charge_over_mass) {
     Ctx& c = *(Ctx*)h;
@@ -1118,15 +1257,15 @@ void orc_set_inflow_function(void* h, int species, int boundary_id, orc_inflow_f
 }
 void orc_rhs(void* h, const double* u, double t, double* dudt, double* bif_rate) {
     Ctx& c = *(Ctx*)h;
-    if (bif_rate) std::fill(bif_rate, bif_rate + 5 * 2 * c.dim, 0.0);
+    if (bif_rate) std::fill(bif_rate, bif_rate + 5 * c.nbnd, 0.0);
     rhs_dispatch(c, u, t, dudt, bif_rate, nullptr);
 }
 void orc_cell_residual(void* h, const double* ue, double alpha, double* R) {
     Ctx& c = *(Ctx*)h;
     std::fill(R, R + 5 * c.NN, 0.0);
-    if (c.dim == 1) cell_residual<1>(c, ue, alpha, R);
-    else if (c.dim == 2) cell_residual<2>(c, ue, alpha, R);
-    else cell_residual<3>(c, ue, alpha, R);
+    if (c.dim == 1) cell_residual<1>(c, 0, ue, alpha, R);
+    else if (c.dim == 2) cell_residual<2>(c, 0, ue, alpha, R);
+    else cell_residual<3>(c, 0, ue, alpha, R);
 }
 double orc_shock_indicator(void* h, const double* v) { return shock_indicator(*(Ctx*)h, v); }
 void orc_alpha(void* h, const double* u, double* alpha) { rhs_dispatch(*(Ctx*)h, u, 0.0, nullptr, nullptr, alpha); }
@@ -1147,7 +1286,7 @@ int64_t orc_solve(void* h, double* u, double t_end, double* bif, int64_t max_ste
     // five_moment/dg_solver.cc:23-38: step = SSPRK2, recommend_dt every step, no callbacks
     Ctx& c = *(Ctx*)h;
     const size_t N = (size_t)c.nelem * c.nc * c.NN;
-    std::vector<double> f1(N, 0.0), bif_f1(5 * 2 * c.dim, 0.0);
+    std::vector<double> f1(N, 0.0), bif_f1(5 * c.nbnd, 0.0);
     int64_t steps = 0;
     std::vector<Callback> cbs;
     bool stop = false;
@@ -1170,7 +1309,7 @@ void orc_global_integral(void* h, const double* u, int species, double out[5]) {
         const double* ue = u + ((size_t)e * c.nc + 5 * species) * c.NN;
         double cell[5] = {0, 0, 0, 0, 0};
         for (int j = 0; j < c.NN; j++)
-            for (int k = 0; k < 5; k++) cell[k] += ue[k * c.NN + j] * (c.Jdet * c.wN[j]);
+            for (int k = 0; k < 5; k++) cell[k] += ue[k * c.NN + j] * (c.jdet(e, j) * c.wN[j]);
         for (int k = 0; k < 5; k++) out[k] += cell[k];
     }
 }

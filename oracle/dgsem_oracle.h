@@ -76,6 +76,21 @@ enum { ORC_BC_WALL = 0, ORC_BC_OUTFLOW = 1, ORC_BC_INFLOW = 2 };
 void* orc_create(int dim, int fe_degree, int n_species, int fields_enabled, double gamma,
                  const int* nx, const double* left, const double* right, const int* periodic,
                  const int* bc_kinds);
+// The same operator on an arbitrary conforming mesh of (curved) quadrilaterals / hexahedra: the
+// caller supplies what the reference reads from deal.II's MappingQ(p) + MatrixFree per point.
+//   face_neighbor[n_elems][2*dim]   neighbour element, or -1 - (boundary face number)
+//   neighbor_face[n_elems][2*dim]   local face of the neighbour + 8 * (tangential order reversed, 2D); NULL = opposite face
+//   bf_id[n_bfaces]                 boundary id per boundary face; bc_kinds[n_species][n_boundaries]
+//   inverse_jacobian[n_elems][NN][dim][dim]   J^{-T} at the GLL nodes (FEEvaluation::inverse_jacobian)
+//   face_normal[n_elems][2*dim][nF][dim], face_jacobian[n_elems][2*dim][nF]   unit outward normal and surface Jacobian
+//       at the face GLL nodes (FEFaceEvaluation::normal_vector, JxW / weight), identical on both sides up to sign
+//   boundary_normal[n_bfaces][nG][dim], boundary_jacobian[n_bfaces][nG]   the same at the Gauss(p+2) points of boundary faces
+// PARITY UNPINNED: the reference's tests never leave Cartesian meshes, and deal.II is not available here.
+void* orc_create_general(int dim, int fe_degree, int n_species, int fields_enabled, double gamma, int64_t n_elems,
+                         int n_boundaries, const int64_t* face_neighbor, const int32_t* neighbor_face, int64_t n_bfaces,
+                         const int32_t* bf_id, const int* bc_kinds, const double* inverse_jacobian,
+                         const double* face_normal, const double* face_jacobian, const double* boundary_normal,
+                         const double* boundary_jacobian);
 void orc_destroy(void* h);
 void orc_set_threads(void* h, int n);   // OpenMP threads for the cell/face loops (default 1, like the reference)
 int64_t orc_n_elems(void* h);

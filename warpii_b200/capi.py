@@ -429,6 +429,104 @@ class BoxSolver:
         return p.value
 
 
+class _Mesh(C.Structure):   # warpii_gpu_mesh
+    _fields_ = [("dim", C.c_int32), ("fe_degree", C.c_int32), ("n_species", C.c_int32), ("fields_enabled", C.c_int32),
+                ("gas_gamma", C.c_double), ("n_elems", C.c_int64), ("n_ghost_faces", C.c_int64),
+                ("n_boundary_faces", C.c_int64), ("n_boundaries", C.c_int32), ("h", C.c_double * 3),
+                ("face_neighbor", _i32p), ("boundary_face_elem", _i32p), ("boundary_face_side", _i32p),
+                ("boundary_face_id", _i32p), ("bc_kind", _i32p), ("n_vectors", C.c_int32)]
+
+
+class _Geometry(C.Structure):   # warpii_gpu_geometry
+    _fields_ = [("inverse_jacobian", _dp), ("face_normal", _dp), ("face_jacobian", _dp), ("neighbor_face", _i32p),
+                ("boundary_normal", _dp), ("boundary_jacobian", _dp)]
+
+
+def mapped_metrics(dim, fe_degree, xyz, face_neighbor, neighbor_face=None, bf_elem=None, bf_side=None):
+    """warpii_host_mapped_metrics (warpii_b200/host/mapped_mesh.hpp): the tables of warpii_gpu_geometry from the elements'
+    Gauss-Lobatto support points xyz[n_elems][Np^dim][dim].  No GPU needed."""
+    L = lib()
+    L.warpii_host_mapped_metrics.argtypes = [C.c_int, C.c_int, C.c_int64, _dp, _i32p, _i32p, C.c_int64, _i32p, _i32p, _dp, _dp,
+                                             _dp, _dp, _dp, _dp]
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    n_elems, NN = xyz.shape[0], xyz.shape[1]
+    Np = fe_degree + 1
+    NF, NG = Np ** (dim - 1), (Np + 1) ** (dim - 1)
+    nbr = _arr32(face_neighbor)
+    nbf = None if neighbor_face is None else _arr32(neighbor_face)
+    bfe = _arr32(bf_elem if bf_elem is not None else [])
+    bfs = _arr32(bf_side if bf_side is not None else [])
+    nb = bfe.size
+    g = {"inverse_jacobian": np.zeros((n_elems, NN, dim, dim)), "face_normal": np.zeros((n_elems, 2 * dim, NF, dim)),
+         "face_jacobian": np.zeros((n_elems, 2 * dim, NF)), "boundary_normal": np.zeros((nb, NG, dim)),
+         "boundary_jacobian": np.zeros((nb, NG)), "boundary_points": np.zeros((nb, NG, dim))}
+    _check(L.warpii_host_mapped_metrics(dim, fe_degree, n_elems, _ptr(xyz), nbr.ctypes.data_as(_i32p),
+                                        nbf.ctypes.data_as(_i32p) if nbf is not None else None, nb,
+                                        bfe.ctypes.data_as(_i32p), bfs.ctypes.data_as(_i32p), _ptr(g["inverse_jacobian"]),
+                                        _ptr(g["face_normal"]), _ptr(g["face_jacobian"]), _ptr(g["boundary_normal"]),
+                                        _ptr(g["boundary_jacobian"]), _ptr(g["boundary_points"])), host=True)
+    return g
+
+
+class MeshSolver(BoxSolver):
+    """The operator ABI (include/warpii_gpu.h) on caller-supplied mesh tables and general geometry: warpii_gpu_create +
+    warpii_gpu_set_geometry.  Elements are in the caller's order; vector 0 = solution, 1 = f_1."""
+
+    def __init__(self, dim, fe_degree, mesh, geometry, n_boundaries=0, bc_kinds=None, gamma=1.6666666666667, n_species=1,
+                 fields_enabled=False, device=0, n_vectors=2):
+        L = lib()
+        L.warpii_gpu_create.argtypes = [C.POINTER(_Mesh), C.c_int, C.POINTER(C.c_void_p)]
+        L.warpii_gpu_set_geometry.argtypes = [C.c_void_p, C.POINTER(_Geometry)]
+        self.dim, self.p, self.gamma, self.nsp, self.n_boundaries = dim, fe_degree, gamma, n_species, n_boundaries
+        keep = self._keep = {}
+        keep["nbr"] = _arr32(mesh["face_neighbor"])
+        keep["bfe"], keep["bfs"], keep["bfi"] = (_arr32(mesh.get(k, [])) for k in ("bf_elem", "bf_side", "bf_id"))
+        keep["bc"] = _arr32(np.asarray(bc_kinds if bc_kinds is not None else np.zeros(n_species * max(n_boundaries, 1))).reshape(-1))
+        m = _Mesh()
+        m.dim, m.fe_degree, m.n_species, m.fields_enabled, m.gas_gamma = dim, fe_degree, n_species, int(fields_enabled), gamma
+        m.n_elems, m.n_ghost_faces, m.n_boundary_faces, m.n_boundaries = keep["nbr"].shape[0], 0, keep["bfe"].size, n_boundaries
+        m.h[0] = m.h[1] = m.h[2] = 1.0   # unused once the geometry is set
+        p32 = lambda a: a.ctypes.data_as(_i32p)
+        m.face_neighbor, m.boundary_face_elem, m.boundary_face_side = p32(keep["nbr"]), p32(keep["bfe"]), p32(keep["bfs"])
+        m.boundary_face_id, m.bc_kind, m.n_vectors = p32(keep["bfi"]), p32(keep["bc"]), n_vectors
+        ctx = C.c_void_p()
+        _check(L.warpii_gpu_create(C.byref(m), device, C.byref(ctx)))
+        self.ctx, self.h, self._owned = ctx, None, True
+        g = _Geometry()
+        for k in ("inverse_jacobian", "face_normal", "face_jacobian", "boundary_normal", "boundary_jacobian"):
+            keep[k] = np.ascontiguousarray(geometry[k], dtype=np.float64)
+            setattr(g, k, _ptr(keep[k]) if keep[k].size else None)
+        nbf = mesh.get("neighbor_face")
+        if nbf is not None:
+            keep["nbf"] = _arr32(nbf)
+            g.neighbor_face = p32(keep["nbf"])
+        _check(L.warpii_gpu_set_geometry(self.ctx, C.byref(g)))
+        self.n_elems = int(m.n_elems)
+        self.nc = 5 * n_species + (8 if fields_enabled else 0)
+        self.NN = (fe_degree + 1) ** dim
+        self.shape = (self.n_elems, self.nc, self.NN)
+        self.n_dofs = self.n_elems * self.nc * self.NN
+        self.l2g = np.arange(self.n_elems, dtype=np.int64)
+
+    def set_inflow(self, species, boundary_id, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        _check(lib().warpii_gpu_set_inflow(self.ctx, species, boundary_id, _ptr(q)))
+
+    def set_sources(self, enabled, epsilon0=1.0, chi=0.0, charge_over_mass=None):
+        L = lib()
+        L.warpii_gpu_set_sources.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _dp]
+        qm = np.ascontiguousarray(charge_over_mass if charge_over_mass is not None else np.zeros(self.nsp), dtype=np.float64)
+        _check(L.warpii_gpu_set_sources(self.ctx, int(enabled), epsilon0, chi, _ptr(qm)))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            lib().warpii_gpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        self.close()
+
+
 class App:
     """The FiveMoment application from a WarpII input file (include/warpii_host.h, warpii_app_*): the GPU-path stand-in
     for `Warpii::create_from_cli / setup / run` (warpii.cc:61-196) with Application = FiveMoment."""

@@ -77,6 +77,22 @@ struct BoundaryParams {
     double Ig[(kMaxNp + 1) * kMaxNp];   // Ig[q*Np+i] = l_i(xg_q)
 };
 
+// General geometry (curved / non-rectangular elements, arbitrary conforming connectivity): per-node and per-face metric
+// tables derived on the host from warpii_gpu_geometry (warpii_gpu_set_geometry), read by stage_kernel_general and the
+// *_general auxiliary kernels.  K = dim*dim below.
+struct GeneralParams {
+    const double* gnode;      // [n_elems][K+2][NN]: plane d*dim+r = component r of Ja^d = Jdet * column d of J^-T
+                              //   (jacobian_utils.h:32-40), plane K = 1/Jdet, plane K+1 = power-iteration value of :487-502
+    const double* gsub;       // [n_elems][K][NN]: plane d*dim+r = component r of the subcell-face normal to the RIGHT of the
+                              //   node along d, n_i = Ja^d_0 + sum_{k<=i} sum_m Q(k,m) Ja^d_m (subcell_finite_volume_flux.h:101-106,
+                              //   :140-145); read only where alpha > 0
+    const double* gface;      // [n_elems][2*dim][dim+1][NF]: unit outward normal, then face Jacobian / (Jdet * w_0) at the node
+    const int32_t* nbrf;      // [n_elems][2*dim]: neighbour's local face + 8 * (tangential order reversed)
+    const double* jdet;       // [n_elems][NN]: Jdet at the nodes (global integrals)
+    const double* bgeo;       // [n_bfaces][NG][dim+1]: unit outward normal and surface Jacobian at the boundary Gauss points
+    const double* bmass;      // [n_bfaces][NF]: 1 / (Jdet * tensor GLL weight) of the face nodes
+};
+
 // Device-resident clock of warpii_gpu_advance_to: the inner loop of advance() (timestepper.cc:34-42) without a host
 // round trip per step.
 struct DevClock {
@@ -106,6 +122,15 @@ void launch_cfl(int dim, int Np, const double* u, int64_t n_elems, int nc, int n
 int integral_blocks(int64_t n_elems);
 void launch_integral(int dim, int Np, const double* u, int64_t n_elems, int nc, int species, double Jdet,
                      const double* w, double* partial, double* out, cudaStream_t s);
+// general-geometry counterparts (dgsem_general_kernel.cu)
+int stage_general_smem_bytes(int dim, int Np);
+int prepare_general_kernels(int dim, int Np);
+void launch_stage_general(int dim, int Np, const StageParams& P, const GeneralParams& GP, cudaStream_t s);
+void launch_boundary_general(int dim, int Np, const BoundaryParams& P, const GeneralParams& GP, cudaStream_t s);
+void launch_cfl_general(int dim, int Np, const double* u, int64_t n_elems, int nc, int nsp, double gamma,
+                        const GeneralParams& GP, unsigned long long* vmax, cudaStream_t s);
+void launch_integral_general(int dim, int Np, const double* u, int64_t n_elems, int nc, int species, const GeneralParams& GP,
+                             const double* w, double* partial, double* out, cudaStream_t s);
 // halo: sendbuf[i][5*nsp][nF] = trace of (send_elem[i], send_side[i])
 void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, const int32_t* send_side,
                  int64_t n_send, int nc, int nsp, double* sendbuf, cudaStream_t s);

@@ -127,6 +127,12 @@ struct warpii_gpu_ctx {
     DevClock* h_clock = nullptr;            // pinned mirror
     double* d_probe = nullptr;              // SM clock probes (MHz), ring of 64
     int n_probes = 0;
+    // general geometry (warpii_gpu_set_geometry)
+    bool general = false;
+    GeneralParams GP{};
+    double *d_gnode = nullptr, *d_gsub = nullptr, *d_gface = nullptr, *d_jdet = nullptr, *d_bgeo = nullptr, *d_bmass = nullptr;
+    int32_t* d_nbrf = nullptr;
+    std::vector<int32_t> h_bf_elem, h_bf_side;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, n_ranks = 1;
@@ -168,6 +174,20 @@ int get_events(warpii_gpu_ctx* c, cudaEvent_t* a, cudaEvent_t* b) {
     *a = c->ev_pool[c->ev_used++];
     *b = c->ev_pool[c->ev_used++];
     return 0;
+}
+
+// the Cartesian kernels or their general-geometry counterparts
+void do_launch_stage(warpii_gpu_ctx* c, const StageParams& P, cudaStream_t s) {
+    if (c->general) launch_stage_general(c->dim, c->Np, P, c->GP, s);
+    else launch_stage(c->dim, c->Np, P, s);
+}
+void do_launch_boundary(warpii_gpu_ctx* c, const BoundaryParams& B, cudaStream_t s) {
+    if (c->general) launch_boundary_general(c->dim, c->Np, B, c->GP, s);
+    else launch_boundary(c->dim, c->Np, B, s);
+}
+void do_launch_cfl(warpii_gpu_ctx* c, int vec) {
+    if (c->general) launch_cfl_general(c->dim, c->Np, c->vec[vec], c->n_elems, c->nc, c->nsp, c->gamma, c->GP, c->d_vmax + vec, c->stream);
+    else launch_cfl(c->dim, c->Np, c->vec[vec], c->n_elems, c->nc, c->nsp, c->gamma, c->inv_h, c->max_eig, c->d_vmax + vec, c->stream);
 }
 
 StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double beta, int mode, bool fuse_cfl) {
@@ -234,7 +254,7 @@ int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double bet
     if (c->n_bfaces > 0) {
         BoundaryParams B = c->B;
         B.u = c->vec[u];
-        launch_boundary(c->dim, c->Np, B, c->stream);
+        do_launch_boundary(c, B, c->stream);
         c->launches++;
     }
     if (c->n_boundaries > 0) {
@@ -261,16 +281,16 @@ int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double bet
         StageParams Pi = P;
         Pi.elem_begin = 0;
         Pi.elem_end = c->n_interface;
-        launch_stage(c->dim, c->Np, Pi, c->comm_stream);
+        do_launch_stage(c, Pi, c->comm_stream);
         if (Pi.elem_end > Pi.elem_begin) c->launches++;
         CUDA_OK(cudaEventRecord(c->ev_recv, c->comm_stream));
         P.elem_begin = c->n_interface;
         P.elem_end = c->n_elems;
-        launch_stage(c->dim, c->Np, P, c->stream);
+        do_launch_stage(c, P, c->stream);
         if (P.elem_end > P.elem_begin) c->launches++;
         CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_recv, 0));
     } else {
-        launch_stage(c->dim, c->Np, P, c->stream);
+        do_launch_stage(c, P, c->stream);
         c->launches++;
     }
     if (c->timing) CUDA_OK(cudaEventRecord(e1, c->stream));
@@ -282,7 +302,7 @@ int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double bet
 int max_speed(warpii_gpu_ctx* c, int vec, double* out) {
     if (!c->vmax_valid[vec]) {
         CUDA_OK(cudaMemsetAsync(c->d_vmax + vec, 0, sizeof(unsigned long long), c->stream));
-        launch_cfl(c->dim, c->Np, c->vec[vec], c->n_elems, c->nc, c->nsp, c->gamma, c->inv_h, c->max_eig, c->d_vmax + vec, c->stream);
+        do_launch_cfl(c, vec);
         c->launches++;
         c->vmax_valid[vec] = 1;
     }
@@ -408,7 +428,11 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
     rc |= upload(&c->d_bc_kind, c->h_bc_kind.data(), c->h_bc_kind.size());
     rc |= upload<double>(&c->d_inflow, nullptr, (size_t)c->nsp * (c->n_boundaries > 0 ? c->n_boundaries : 1) * 5);
     c->h_inflow.assign((size_t)c->nsp * (c->n_boundaries > 0 ? c->n_boundaries : 1) * 5, 0.0);
-    if (c->n_bfaces > 0) c->h_bf_id.assign(m->boundary_face_id, m->boundary_face_id + c->n_bfaces);
+    if (c->n_bfaces > 0) {
+        c->h_bf_id.assign(m->boundary_face_id, m->boundary_face_id + c->n_bfaces);
+        c->h_bf_elem.assign(m->boundary_face_elem, m->boundary_face_elem + c->n_bfaces);
+        c->h_bf_side.assign(m->boundary_face_side, m->boundary_face_side + c->n_bfaces);
+    }
     rc |= upload(&c->d_w, re.w.data(), (size_t)c->Np);
     rc |= upload<double>(&c->d_bres, nullptr, (size_t)c->n_bfaces * c->nsp * 5 * c->NF);
     rc |= upload<double>(&c->d_bflux, nullptr, (size_t)c->n_bfaces * c->nsp * 5);
@@ -482,6 +506,8 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     cudaFree(c->d_inflow); cudaFree(c->d_inflow_table); cudaFree(c->d_qm); cudaFree(c->d_w); cudaFree(c->d_bres); cudaFree(c->d_bflux); cudaFree(c->d_ghost);
     cudaFree(c->d_sendbuf); cudaFree(c->d_partial); cudaFree(c->d_out5); cudaFree(c->d_alpha); cudaFree(c->d_vmax);
     cudaFree(c->d_send_elem); cudaFree(c->d_send_side);
+    cudaFree(c->d_gnode); cudaFree(c->d_gsub); cudaFree(c->d_gface); cudaFree(c->d_jdet); cudaFree(c->d_bgeo); cudaFree(c->d_bmass);
+    cudaFree(c->d_nbrf);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h_clock) cudaFreeHost(c->h_clock);
@@ -626,6 +652,126 @@ int warpii_gpu_set_sources(warpii_gpu_ctx* c, int enabled, double epsilon0, doub
     return 0;
 }
 
+int warpii_gpu_set_geometry(warpii_gpu_ctx* c, const warpii_gpu_geometry* g) {
+    if (!c) return fail("null context");
+    if (!g || !g->inverse_jacobian || !g->face_normal || !g->face_jacobian) return fail("set_geometry: null table");
+    if (c->n_bfaces > 0 && (!g->boundary_normal || !g->boundary_jacobian)) return fail("set_geometry: boundary tables missing");
+    if (c->general) return fail("set_geometry: geometry already set");
+    CUDA_OK(cudaSetDevice(c->device));
+    const int dim = c->dim, Np = c->Np, NN = c->NN, NF = c->NF, K = dim * dim, nf = 2 * dim;
+    const int NG = ipow(Np + 1, dim - 1);
+    const int64_t ne = c->n_elems;
+    warpii_b200::ReferenceElement re(c->p);
+    std::vector<double> gnode((size_t)ne * (K + 2) * NN), gsub((size_t)ne * K * NN), jdet((size_t)ne * NN);
+    auto stride = [&](int d) { return d == 0 ? 1 : (d == 1 ? Np : Np * Np); };
+    for (int64_t e = 0; e < ne; e++) {
+        double* ge = &gnode[(size_t)e * (K + 2) * NN];
+        for (int q = 0; q < NN; q++) {
+            const double* Kq = g->inverse_jacobian + ((size_t)e * NN + q) * K;
+            double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            for (int r = 0; r < dim; r++) for (int cc = 0; cc < dim; cc++) M[r][cc] = Kq[r * dim + cc];
+            double det;   // tensor_utils.h:70-82; 3x3 by cofactors
+            if (dim == 1) det = M[0][0];
+            else if (dim == 2) det = M[0][0] * M[1][1] - M[0][1] * M[1][0];
+            else det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                       M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+            if (!(det > 0.0) || !std::isfinite(det))
+                return fail("set_geometry: element %lld node %d has a non-positive Jacobian", (long long)e, q);
+            const double J = 1.0 / det;   // jacobian_utils.h:15-16
+            jdet[(size_t)e * NN + q] = J;
+            for (int d = 0; d < dim; d++)
+                for (int r = 0; r < dim; r++) ge[(size_t)(d * dim + r) * NN + q] = J * M[r][d];   // jacobian_utils.h:36-39
+            ge[(size_t)K * NN + q] = det;
+            // fluid_flux_es_dgsem_operator.h:487-502: 5 power iterations on K^T K from (1,...,1)
+            double ev[3] = {1, 1, 1};
+            for (int it = 0; it < 5; it++) {
+                double Kv[3] = {0, 0, 0}, w[3] = {0, 0, 0}, nrm = 0;
+                for (int r = 0; r < dim; r++) for (int cc = 0; cc < dim; cc++) Kv[r] += M[r][cc] * ev[cc];
+                for (int r = 0; r < dim; r++) for (int cc = 0; cc < dim; cc++) w[r] += M[cc][r] * Kv[cc];
+                for (int r = 0; r < dim; r++) nrm = std::fmax(nrm, std::fabs(w[r]));
+                for (int r = 0; r < dim; r++) ev[r] = w[r] / nrm;
+            }
+            double Kv[3] = {0, 0, 0}, num = 0, den = 0;
+            for (int r = 0; r < dim; r++) for (int cc = 0; cc < dim; cc++) Kv[r] += M[r][cc] * ev[cc];
+            for (int r = 0; r < dim; r++) { num += Kv[r] * Kv[r]; den += ev[r] * ev[r]; }
+            ge[(size_t)(K + 1) * NN + q] = std::sqrt(num / den);
+        }
+        // subcell-face normals along every pencil (subcell_finite_volume_flux.h:101-106, 140-145), Q = diag(w) D
+        double* se = &gsub[(size_t)e * K * NN];
+        for (int d = 0; d < dim; d++) {
+            const int st = stride(d);
+            for (int ps = 0; ps < NN; ps++) {
+                if ((ps / st) % Np != 0) continue;
+                double n[3] = {0, 0, 0};
+                for (int r = 0; r < dim; r++) n[r] = ge[(size_t)(d * dim + r) * NN + ps];
+                for (int i = 0; i < Np; i++) {
+                    for (int m = 0; m < Np; m++) {
+                        const double Qim = re.w[i] * re.D[i * Np + m];
+                        for (int r = 0; r < dim; r++) n[r] += Qim * ge[(size_t)(d * dim + r) * NN + ps + st * m];
+                    }
+                    for (int r = 0; r < dim; r++) se[(size_t)(d * dim + r) * NN + ps + st * i] = n[r];
+                }
+            }
+        }
+    }
+    // faces: unit normal + (face Jacobian) / (Jdet * w_0) = face JxW / cell JxW at the node
+    auto face_node = [&](int d, int side, int t) {
+        int idx[3] = {0, 0, 0};
+        for (int a = 0; a < dim; a++) { if (a == d) continue; idx[a] = t % Np; t /= Np; }
+        idx[d] = side ? Np - 1 : 0;
+        return idx[0] + Np * (idx[1] + Np * idx[2]);
+    };
+    std::vector<double> gface((size_t)ne * nf * (dim + 1) * NF);
+    for (int64_t e = 0; e < ne; e++)
+        for (int f = 0; f < nf; f++)
+            for (int t = 0; t < NF; t++) {
+                const int q = face_node(f / 2, f % 2, t);
+                double* o = &gface[((size_t)(e * nf + f) * (dim + 1)) * NF + t];
+                for (int r = 0; r < dim; r++) o[(size_t)r * NF] = g->face_normal[(((size_t)e * nf + f) * NF + t) * dim + r];
+                o[(size_t)dim * NF] = g->face_jacobian[((size_t)e * nf + f) * NF + t] / (jdet[(size_t)e * NN + q] * re.w[0]);
+            }
+    std::vector<int32_t> nbrf((size_t)ne * nf);
+    for (size_t i = 0; i < nbrf.size(); i++) {
+        nbrf[i] = g->neighbor_face ? g->neighbor_face[i] : (int32_t)((i % nf) ^ 1);
+        if (nbrf[i] < 0 || nbrf[i] >= 16 || (nbrf[i] & 7) >= nf || ((nbrf[i] >> 3) && dim != 2))
+            return fail("set_geometry: neighbor_face[%lld] = %d is not a (face, orientation) code of this dimension", (long long)i, nbrf[i]);
+    }
+    std::vector<double> bgeo((size_t)c->n_bfaces * NG * (dim + 1)), bmass((size_t)c->n_bfaces * NF);
+    for (int64_t b = 0; b < c->n_bfaces; b++) {
+        for (int gq = 0; gq < NG; gq++) {
+            for (int r = 0; r < dim; r++) bgeo[((size_t)b * NG + gq) * (dim + 1) + r] = g->boundary_normal[((size_t)b * NG + gq) * dim + r];
+            bgeo[((size_t)b * NG + gq) * (dim + 1) + dim] = g->boundary_jacobian[(size_t)b * NG + gq];
+        }
+        const int e = c->h_bf_elem[b], f = c->h_bf_side[b];
+        for (int t = 0; t < NF; t++) {
+            const int q = face_node(f / 2, f % 2, t);
+            double wF = 1.0;
+            int tt = t;
+            for (int a = 0; a < dim - 1; a++) { wF *= re.w[tt % Np]; tt /= Np; }
+            bmass[(size_t)b * NF + t] = 1.0 / (jdet[(size_t)e * NN + q] * re.w[0] * wF);
+        }
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (upload(&c->d_gnode, gnode.data(), gnode.size()) || upload(&c->d_gsub, gsub.data(), gsub.size()) ||
+        upload(&c->d_gface, gface.data(), gface.size()) || upload(&c->d_jdet, jdet.data(), jdet.size()) ||
+        upload(&c->d_nbrf, nbrf.data(), nbrf.size()) || upload(&c->d_bgeo, bgeo.data(), bgeo.size()) ||
+        upload(&c->d_bmass, bmass.data(), bmass.size()))
+        return 1;
+    if (prepare_general_kernels(c->dim, c->Np))
+        return fail("set_geometry: kernel preparation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    c->GP.gnode = c->d_gnode;
+    c->GP.gsub = c->d_gsub;
+    c->GP.gface = c->d_gface;
+    c->GP.nbrf = c->d_nbrf;
+    c->GP.jdet = c->d_jdet;
+    c->GP.bgeo = c->d_bgeo;
+    c->GP.bmass = c->d_bmass;
+    c->general = true;
+    std::fill(c->vmax_valid.begin(), c->vmax_valid.end(), 0);
+    drop_batch_graph(c);
+    return 0;
+}
+
 int warpii_gpu_n_boundary_points(const warpii_gpu_ctx* c, int64_t* n_faces_out, int* points_per_face_out) {
     if (!c) return fail("null context");
     if (n_faces_out) *n_faces_out = c->n_bfaces;
@@ -710,7 +856,7 @@ int warpii_gpu_advance_to(warpii_gpu_ctx* c, int solution, int f1, double* t_ino
     // batches and the host looks at the clock once per batch, so there is no host round trip (and no launch gap) per step.
     if (!c->vmax_valid[solution]) {
         CUDA_OK(cudaMemsetAsync(c->d_vmax + solution, 0, sizeof(unsigned long long), c->stream));
-        launch_cfl(c->dim, c->Np, c->vec[solution], c->n_elems, c->nc, c->nsp, c->gamma, c->inv_h, c->max_eig, c->d_vmax + solution, c->stream);
+        do_launch_cfl(c, solution);
         c->launches++;
         c->vmax_valid[solution] = 1;
     }
@@ -803,7 +949,8 @@ int warpii_gpu_global_integral(warpii_gpu_ctx* c, int vec, int species, double o
     if (check_vec(c, vec, "global_integral")) return 1;
     if (species < 0 || species >= c->nsp) return fail("global_integral: species %d out of range", species);
     CUDA_OK(cudaSetDevice(c->device));
-    launch_integral(c->dim, c->Np, c->vec[vec], c->n_elems, c->nc, species, c->Jdet, c->d_w, c->d_partial, c->d_out5, c->stream);
+    if (c->general) launch_integral_general(c->dim, c->Np, c->vec[vec], c->n_elems, c->nc, species, c->GP, c->d_w, c->d_partial, c->d_out5, c->stream);
+    else launch_integral(c->dim, c->Np, c->vec[vec], c->n_elems, c->nc, species, c->Jdet, c->d_w, c->d_partial, c->d_out5, c->stream);
     c->launches += 2;
     if (c->comm && c->n_ranks > 1)   // replaces Utilities::MPI::sum, dg_solution_helper.cc:96
         NCCL_OK(g_nccl.AllReduce(c->d_out5, c->d_out5, 5, ncclDouble, ncclSum, c->comm, c->stream));
@@ -827,7 +974,7 @@ int warpii_gpu_shock_indicator(warpii_gpu_ctx* c, int vec, double* alpha_out) {
     if (c->n_bfaces > 0) {
         BoundaryParams B = c->B;
         B.u = c->vec[vec];
-        launch_boundary(c->dim, c->Np, B, c->stream);
+        do_launch_boundary(c, B, c->stream);
     }
     if (c->comm && !c->peer_rank.empty()) {
         if (start_exchange(c, vec)) { cudaFree(scratch); return 1; }
@@ -835,10 +982,10 @@ int warpii_gpu_shock_indicator(warpii_gpu_ctx* c, int vec, double* alpha_out) {
     }
     if (c->n_interface > 0) {
         P.elem_begin = 0; P.elem_end = c->n_interface;
-        launch_stage(c->dim, c->Np, P, c->stream);
+        do_launch_stage(c, P, c->stream);
         P.elem_begin = c->n_interface; P.elem_end = c->n_elems;
     }
-    launch_stage(c->dim, c->Np, P, c->stream);
+    do_launch_stage(c, P, c->stream);
     c->launches++;
     CUDA_OK(cudaMemcpyAsync(alpha_out, c->d_alpha, (size_t)c->n_elems * c->nsp * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));

@@ -7,6 +7,7 @@
 
 #include "dg_solver.hpp"
 #include "five_moment_app.hpp"
+#include "mapped_mesh.hpp"
 
 using namespace warpii_b200;
 
@@ -267,6 +268,25 @@ int warpii_host_advance(warpii_step_fn step, double t_end, warpii_dt_fn recommen
             cbs.emplace_back(intervals[i], [=](double t) { cb(t, i, user); }, perform_zeroth[i] != 0, perform_final[i] != 0);
         advance([&](double t, double dt) { return step(t, dt, user) != 0; }, t_end, [&]() { return recommend_dt(user); }, cbs);
     })
+}
+
+int warpii_host_mapped_metrics(int dim, int fe_degree, int64_t n_elems, const double* xyz, const int32_t* face_neighbor,
+                               const int32_t* neighbor_face, int64_t n_boundary_faces, const int32_t* bf_elem,
+                               const int32_t* bf_side, double* inverse_jacobian, double* face_normal, double* face_jacobian,
+                               double* boundary_normal, double* boundary_jacobian, double* boundary_points) {
+    GUARD({
+        if (!xyz || !face_neighbor || !inverse_jacobian || !face_normal || !face_jacobian)
+            throw std::invalid_argument("warpii_host_mapped_metrics: null argument");
+        if (fe_degree < 1 || fe_degree > 6) throw std::invalid_argument("fe_degree must be in [1,6]");
+        const MappedMeshMetrics M = build_mapped_metrics(dim, fe_degree, n_elems, xyz, face_neighbor, neighbor_face,
+                                                         n_boundary_faces, bf_elem, bf_side);
+        std::memcpy(inverse_jacobian, M.inverse_jacobian.data(), M.inverse_jacobian.size() * sizeof(double));
+        std::memcpy(face_normal, M.face_normal.data(), M.face_normal.size() * sizeof(double));
+        std::memcpy(face_jacobian, M.face_jacobian.data(), M.face_jacobian.size() * sizeof(double));
+        if (boundary_normal) std::memcpy(boundary_normal, M.boundary_normal.data(), M.boundary_normal.size() * sizeof(double));
+        if (boundary_jacobian) std::memcpy(boundary_jacobian, M.boundary_jacobian.data(), M.boundary_jacobian.size() * sizeof(double));
+        if (boundary_points) std::memcpy(boundary_points, M.boundary_points.data(), M.boundary_points.size() * sizeof(double));
+    });
 }
 
 int warpii_host_box_tables(int dim, const int32_t* nx, const int32_t* periodic, int rank, int n_ranks, int elems_per_block, int64_t counts[6],
