@@ -164,6 +164,16 @@ int warpii_gpu_forward_euler_step_ex(warpii_gpu_ctx* ctx, int dst, int u, double
 /* dt = 0.5 / (vmax * (p+1)^2), vmax reduced over nodes, elements, species and ranks
  * (replaces recommend_dt + compute_cell_transport_speed, :442-514; MPI::max -> ncclAllReduce(max)). */
 int warpii_gpu_recommend_dt(warpii_gpu_ctx* ctx, int vec, double* dt_out);
+/* One stage of a low-storage Runge-Kutta scheme: what LowStorageRungeKuttaIntegrator::perform_time_step asks of
+ * pde_operator.perform_stage(t, b_i*dt, a_i*dt, current_ri, vec_ki, solution, next_ri) (rk.h:53-71, deal.II step-67):
+ *   k = M^-1 R(r_in);   sol_out = sol_in + factor_solution * k;   r_out = sol_in + factor_ai * k
+ * (tutorial-67.cc:880-899: both from the OLD solution; r_out is left untouched when factor_ai == 0, the last stage)
+ * fused into one launch (k is never stored).  r_in is read at neighbouring nodes while the stage writes, so sol_out and
+ * r_out must differ from r_in; sol_out may be sol_in (in place) when sol_in != r_in.  Three vectors suffice for a step:
+ * first stage (S, S) -> (K, R), later stages alternate r between R and S with the solution in place in K
+ * (warpii_b200/host/gpu_operator.hpp::LowStorageRungeKuttaIntegrator does the bookkeeping).  Needs n_vectors >= 3. */
+int warpii_gpu_lsrk_stage(warpii_gpu_ctx* ctx, int sol_out, int r_out, int sol_in, int r_in, double factor_solution,
+                          double factor_ai, double t);
 int warpii_gpu_max_transport_speed(warpii_gpu_ctx* ctx, int vec, double* vmax_out);
 /* One SSPRK2 step (replaces SSPRK2Integrator::evolve_one_time_step, rk.h:97-106): two stages, the second with
  * the fused CFL reduction. */

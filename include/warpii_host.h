@@ -77,6 +77,10 @@ int warpii_box_solver_solve(warpii_box_solver* s, double t_end, double fixed_dt,
 /* SSPRK2Integrator::evolve_one_time_step / operator.recommend_dt on the solver's own solution vector */
 int warpii_box_solver_step(warpii_box_solver* s, double dt, double t);
 int warpii_box_solver_recommend_dt(warpii_box_solver* s, double* dt_out);
+/* LowStorageRungeKuttaIntegrator(scheme).perform_time_step on the solver's solution vector (rk.h:10-77);
+ * scheme: 0 = stage_3_order_3, 1 = stage_5_order_4 (2, 3: ExcNotImplemented, see gpu_operator.hpp).
+ * coefficients (may be NULL) receives b[n], a[n-1], c[n] back to back; n_stages_out the stage count. */
+int warpii_box_solver_lsrk_step(warpii_box_solver* s, int scheme, double dt, double t, double* coefficients, int* n_stages_out);
 
 /* ---- the FiveMoment application driven by a WarpII input file ------------------------------------------------------
  * Replaces Warpii::setup/run for Application = FiveMoment (warpii.cc:126-196, five_moment.cc:22-52, five_moment.h:99-243)

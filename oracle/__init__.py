@@ -346,6 +346,21 @@ class Oracle:
                                      _ptr(bif_u) if bif_u is not None else None)
         return dst
 
+    def lsrk_stage(self, sol, r_out, r_in, factor_solution, factor_ai, t=0.0):
+        """k = M^-1 R(r_in); r_out = sol + factor_ai k; sol += factor_solution k (rk.h:53-71); r_out may be r_in."""
+        L = lib()
+        L.orc_lsrk_stage.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double]
+        assert sol.flags.c_contiguous and r_out.flags.c_contiguous and r_in.flags.c_contiguous
+        L.orc_lsrk_stage(self.h, _ptr(sol), _ptr(r_out), _ptr(r_in), factor_solution, factor_ai, t)
+
+    def lsrk_step(self, u, b, a, c, dt, t=0.0):
+        """LowStorageRungeKuttaIntegrator::perform_time_step (rk.h:53-71) with coefficients (b, a, c)."""
+        ri = np.zeros_like(u)
+        self.lsrk_stage(u, ri, u.copy(), b[0] * dt, a[0] * dt, t)
+        for s in range(1, len(b)):
+            self.lsrk_stage(u, ri, ri.copy(), b[s] * dt, 0.0 if s == len(b) - 1 else a[s] * dt, t + c[s] * dt)
+        return u
+
     def max_transport_speed(self, u):
         return lib().orc_max_transport_speed(self.h, _ptr(_f64(u)))
 

@@ -1273,6 +1273,22 @@ void orc_forward_euler_step(void* h, double* dst, const double* u, double dt, do
                             double* bif_dst, const double* bif_u) {
     forward_euler(*(Ctx*)h, dst, u, dt, t, a, beta, bif_dst, bif_u);
 }
+// One low-storage Runge-Kutta stage as LowStorageRungeKuttaIntegrator::perform_time_step asks of the operator (rk.h:53-71;
+// tutorial-67.cc:880-899): k = M^-1 R(r_in); with s = sol: sol = s + factor_solution * k; r_out = s + factor_ai * k
+// (r_out not written when factor_ai == 0).  r_out may alias r_in (k is formed first), as in the reference's calls.
+void orc_lsrk_stage(void* h, double* sol, double* r_out, const double* r_in, double factor_solution, double factor_ai, double t) {
+    Ctx& c = *(Ctx*)h;
+    const size_t N = (size_t)c.nelem * c.nc * c.NN;
+    std::vector<double> k(N, 0.0);
+    rhs_dispatch(c, r_in, t, k.data(), nullptr, nullptr);
+    const size_t blockN = (size_t)c.nc * c.NN, fluidN = (size_t)5 * c.nsp * c.NN;
+    for (size_t g = 0; g < N; g++) {
+        const double k_i = ((g % blockN) < fluidN || c.sources_on) ? k[g] : 0.0;
+        const double sol_i = sol[g];
+        sol[g] = sol_i + factor_solution * k_i;
+        if (factor_ai != 0.0) r_out[g] = sol_i + factor_ai * k_i;
+    }
+}
 double orc_max_transport_speed(void* h, const double* u) { return max_transport_speed(*(Ctx*)h, u); }
 double orc_recommend_dt(void* h, const double* u) {
     Ctx& c = *(Ctx*)h;   // fluid_flux_es_dgsem_operator.h:442-448

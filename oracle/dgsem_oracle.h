@@ -123,6 +123,8 @@ void orc_alpha(void* h, const double* u, double* alpha);
 // dst = beta*dst + a*(u + dt*M^-1 R(u)); bif likewise (fluid_flux_es_dgsem_operator.h:127-214).
 void orc_forward_euler_step(void* h, double* dst, const double* u, double dt, double t, double a,
                             double beta, double* bif_dst, const double* bif_u);
+// one low-storage RK stage (rk.h:53-71, tutorial-67.cc:880-899): k = M^-1 R(r_in); r_out = sol + factor_ai k; sol += factor_solution k
+void orc_lsrk_stage(void* h, double* sol, double* r_out, const double* r_in, double factor_solution, double factor_ai, double t);
 double orc_max_transport_speed(void* h, const double* u);    // :450-514
 double orc_recommend_dt(void* h, const double* u);           // :442-448
 // One SSPRK2 step (rk.h:97-106). f1/bif_f1 are scratch of the same size as u/bif.

@@ -108,6 +108,7 @@ def lib():
     L.warpii_box_solver_solve.argtypes = [vp, C.c_double, C.c_double, C.c_double, vp, vp, _i64p]
     L.warpii_box_solver_step.argtypes = [vp, C.c_double, C.c_double]
     L.warpii_box_solver_recommend_dt.argtypes = [vp, _dp]
+    L.warpii_box_solver_lsrk_step.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp, C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -153,6 +154,17 @@ def host_advance(step, t_end, recommend_dt, callbacks):
     d = DT_FN(lambda _u: recommend_dt())
     cb = CBI_FN(lambda t, i, _u: callbacks[i][1](t))
     _check(L.warpii_host_advance(s, t_end, d, n, _ptr(iv), pz.ctypes.data_as(_i32p), pf.ctypes.data_as(_i32p), cb, None), host=True)
+
+
+def lsrk_coefficients(scheme):
+    """(b, a, c) of the host layer's LowStorageRungeKuttaIntegrator (no GPU needed)."""
+    L = lib()
+    L.warpii_box_solver_lsrk_step.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _dp, C.POINTER(C.c_int)]
+    buf = np.zeros(32)
+    n = C.c_int(0)
+    _check(L.warpii_box_solver_lsrk_step(None, scheme, 0.0, 0.0, _ptr(buf), C.byref(n)), host=True)
+    n = n.value
+    return buf[:n].copy(), buf[n:2 * n - 1].copy(), buf[2 * n - 1:3 * n - 1].copy()
 
 
 def elems_per_block(dim, fe_degree):
@@ -343,6 +355,11 @@ class BoxSolver:
                                              None, C.byref(steps)), host=True)
         return steps.value
 
+    def lsrk_step(self, scheme, dt, t=0.0):
+        """LowStorageRungeKuttaIntegrator(scheme).perform_time_step on the solver's solution (host layer); the solution may
+        live in another device vector afterwards: read it with get_state()."""
+        _check(lib().warpii_box_solver_lsrk_step(self.h, scheme, dt, t, None, None), host=True)
+
     # ---- operator ABI ---------------------------------------------------------------------------------
     def upload(self, vec, u):
         u = np.ascontiguousarray(u, dtype=np.float64)
@@ -371,6 +388,11 @@ class BoxSolver:
         steps = C.c_int64(0)
         _check(lib().warpii_gpu_advance_to(self.ctx, solution, f1, C.byref(tt), t_stop, fixed_dt, max_steps, C.byref(steps)))
         return tt.value, steps.value
+
+    def lsrk_stage(self, sol_out, r_out, sol_in, r_in, factor_solution, factor_ai, t=0.0):
+        L = lib()
+        L.warpii_gpu_lsrk_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        _check(L.warpii_gpu_lsrk_stage(self.ctx, sol_out, r_out, sol_in, r_in, factor_solution, factor_ai, t))
 
     def recommend_dt(self, vec=0):
         dt = C.c_double(0)

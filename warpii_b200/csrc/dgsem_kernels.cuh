@@ -40,7 +40,10 @@ struct StageParams {
     int64_t elem_begin, elem_end; // element range of this launch
     int64_t n_elems;
     int32_t nc, nsp;
-    int32_t mode;                 // 0: dst = beta*dst + a*(u + dt*rate); 1: dst = rate
+    int32_t mode;                 // 0: dst = beta*dst + a*(u + dt*rate); 1: dst = rate;
+                                  // 2: dst = sol_in + a*rate, dst2 = sol_in + beta*rate (low-storage RK stage, rk.h:53-71)
+    const double* sol_in;         // mode 2 only (may alias dst: every thread touches its own node only)
+    double* dst2;                 // mode 2 only; differs from u and dst
     double gamma, dt, a, beta;
     const double* dt_dev;         // if non-null the time step is read from device memory (device-resident time loop)
     const int* skip_dev;          // if non-null and *skip_dev != 0 the launch is a no-op (time loop already finished)

@@ -354,6 +354,14 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             if (P.mode == 1) {
 #pragma unroll
                 for (int c = 0; c < 5; c++) qn[c] = r[c];
+            } else if (P.mode == 2) {   // low-storage RK stage (rk.h:53-71; tutorial-67.cc:880-899): with s = old solution,
+                                        // solution = s + b_i dt k, next r = s + a_i dt k (not written when a_i = 0)
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    const double s0 = P.sol_in[off + (size_t)c * NN];
+                    qn[c] = fma(P.a, r[c], s0);
+                    if (P.beta != 0.0) P.dst2[off + (size_t)c * NN] = fma(P.beta, r[c], s0);
+                }
             } else if (P.beta == 0.0) {
 #pragma unroll
                 for (int c = 0; c < 5; c++) qn[c] = P.a * (q[c] + dt * r[c]);
@@ -407,6 +415,11 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             const double rate = S[k];
             double v;
             if (P.mode == 1) v = rate;
+            else if (P.mode == 2) {
+                const double s0 = P.sol_in[off];
+                v = fma(P.a, rate, s0);
+                if (P.beta != 0.0) P.dst2[off] = fma(P.beta, rate, s0);
+            }
             else if (P.beta == 0.0) v = P.a * (P.u[off] + dt * rate);
             else v = P.beta * P.dst[off] + P.a * (P.u[off] + dt * rate);
             P.dst[off] = v;

@@ -159,9 +159,15 @@ int upload(T** dptr, const T* host, size_t n) {
     return 0;
 }
 
-int check_vec(const warpii_gpu_ctx* c, int v, const char* what) {
+int check_vec(warpii_gpu_ctx* c, int v, const char* what) {
     if (!c) return fail("%s: null context", what);
     if (v < 0 || v >= (int)c->vec.size()) return fail("%s: vector id %d out of range [0,%d)", what, v, (int)c->vec.size());
+    if (!c->vec[v] && c->n_dofs > 0) {
+        // vectors beyond the first two (solution, f_1) take HBM only once somebody names them (low-storage RK registers)
+        CUDA_OK(cudaSetDevice(c->device));
+        if (upload<double>(&c->vec[v], nullptr, (size_t)c->n_dofs)) return 1;
+        if (upload<double>(&c->bif[v], nullptr, (size_t)5 * (c->n_boundaries > 0 ? c->n_boundaries : 1))) return 1;
+    }
     return 0;
 }
 
@@ -200,6 +206,8 @@ StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a,
     P.ghost = c->d_ghost;
     P.bres = c->d_bres;
     P.alpha_out = nullptr;
+    P.sol_in = nullptr;
+    P.dst2 = nullptr;
     P.vmax = fuse_cfl ? c->d_vmax + dst : nullptr;
     P.elem_begin = 0;
     P.elem_end = c->n_elems;
@@ -247,7 +255,7 @@ int start_exchange(warpii_gpu_ctx* c, int u) {
 }
 
 int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double beta, int mode, bool fuse_cfl,
-              bool device_clock = false) {
+              bool device_clock = false, int sol_in = -1, int dst2 = -1) {
     const double* dt_dev = device_clock ? &c->d_clock->dt : nullptr;
     const int* skip_dev = device_clock ? &c->d_clock->done : nullptr;
     // boundary faces first: their contributions are consumed by the stage kernel
@@ -258,8 +266,9 @@ int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double bet
         c->launches++;
     }
     if (c->n_boundaries > 0) {
+        // (a low-storage stage leaves the flux RATE in bif[dst]: the reference's perform_stage callers keep no such totals)
         launch_bif_update(c->d_bflux, c->d_bf_id, c->n_bfaces, c->nsp, c->n_boundaries, c->bif[dst], c->bif[u], dt, dt_dev,
-                          skip_dev, a, beta, mode, c->stream);
+                          skip_dev, a, beta, mode == 2 ? 1 : mode, c->stream);
         c->launches++;
     }
     // (with the device clock, clock_kernel clears the slot after it has read the previous maximum)
@@ -267,6 +276,10 @@ int run_stage(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double bet
     StageParams P = stage_params(c, dst, u, dt, a, beta, mode, fuse_cfl);
     P.dt_dev = dt_dev;
     P.skip_dev = skip_dev;
+    if (mode == 2) {
+        P.sol_in = c->vec[sol_in];
+        P.dst2 = c->vec[dst2];
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->timing) {
         if (get_events(c, &e0, &e1)) return 1;
@@ -443,7 +456,7 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
     c->vec.assign(c->n_vectors, nullptr);
     c->bif.assign(c->n_vectors, nullptr);
     c->vmax_valid.assign(c->n_vectors, 0);
-    for (int v = 0; v < c->n_vectors && !rc; v++) {
+    for (int v = 0; v < c->n_vectors && v < 2 && !rc; v++) {   // the others are allocated on first use (check_vec)
         rc |= upload<double>(&c->vec[v], nullptr, (size_t)c->n_dofs);
         rc |= upload<double>(&c->bif[v], nullptr, (size_t)5 * (c->n_boundaries > 0 ? c->n_boundaries : 1));
     }
@@ -823,6 +836,21 @@ int warpii_gpu_rhs(warpii_gpu_ctx* c, int dst, int u, double /*t*/) {
     if (dst == u) return fail("rhs: dst and u must be different vectors");
     CUDA_OK(cudaSetDevice(c->device));
     return run_stage(c, dst, u, 0.0, 1.0, 0.0, 1, false);
+}
+
+int warpii_gpu_lsrk_stage(warpii_gpu_ctx* c, int sol_out, int r_out, int sol_in, int r_in, double factor_solution,
+                          double factor_ai, double /*t*/) {
+    if (check_vec(c, sol_out, "lsrk_stage") || check_vec(c, r_out, "lsrk_stage") || check_vec(c, sol_in, "lsrk_stage") ||
+        check_vec(c, r_in, "lsrk_stage"))
+        return 1;
+    // the stage reads r_in at neighbouring nodes while it writes: nothing may be written into r_in
+    if (sol_out == r_in || r_out == r_in) return fail("lsrk_stage: sol_out and r_out must differ from r_in (use a third vector)");
+    if (sol_out == r_out) return fail("lsrk_stage: sol_out and r_out must be different vectors");
+    if (r_out == sol_in) return fail("lsrk_stage: r_out must differ from sol_in");
+    CUDA_OK(cudaSetDevice(c->device));
+    if (run_stage(c, sol_out, r_in, 0.0, factor_solution, factor_ai, 2, false, false, sol_in, r_out)) return 1;
+    c->vmax_valid[r_out] = 0;
+    return 0;
 }
 
 int warpii_gpu_max_transport_speed(warpii_gpu_ctx* c, int vec, double* vmax_out) {

@@ -15,6 +15,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "warpii_gpu.h"
@@ -79,6 +80,8 @@ class GpuSolutionVec {
         return out;
     }
     int id() const { return id_; }
+    // exchange the device storage of two vectors (what LinearAlgebra::distributed::Vector::swap does)
+    void swap(GpuSolutionVec& other) { std::swap(ctx_, other.ctx_); std::swap(id_, other.id_); }
     bool bound() const { return (bool)ctx_; }
     const std::shared_ptr<GpuContext>& context() const { return ctx_; }
 
@@ -109,6 +112,27 @@ class GpuFluidFluxESDGSEMOperator {
         // the second SSPRK2 stage is the one whose result recommend_dt is asked about next: fuse the CFL sweep there
         const int flags = (beta != 0.0) ? WARPII_FUSE_CFL : 0;
         check(warpii_gpu_forward_euler_step_ex(ctx_->get(), dst.id(), u.id(), dt, t, alpha, beta, flags));
+    }
+
+    // One low-storage Runge-Kutta stage, the interface LowStorageRungeKuttaIntegrator::perform_time_step drives (rk.h:53-71;
+    // deal.II step-67's EulerOperator::perform_stage, tutorial-67.cc:880-899):  k = M^-1 R(current_ri);
+    // next_ri = solution + factor_ai * k;  solution += factor_solution * k  (next_ri from the solution BEFORE its update).  vec_ki is the third register: the fused kernel never stores k, but it must not
+    // write into the vector whose neighbour traces it is reading, so the register is used to avoid exactly that and the
+    // vectors trade storage (swap) to end up where the caller expects them.
+    void perform_stage(const double current_time, const double factor_solution, const double factor_ai,
+                       GpuSolutionVec& current_ri, GpuSolutionVec& vec_ki, GpuSolutionVec& solution, GpuSolutionVec& next_ri) {
+        refresh_inflow(current_time);
+        warpii_gpu_ctx* c = ctx_->get();
+        if (&current_ri == &solution) {            // first stage: (solution, vec_ri, solution, vec_ri) -- vec_ki IS next_ri here
+            GpuSolutionVec& spare = (&vec_ki != &next_ri) ? vec_ki : lsrk_register(solution);
+            check(warpii_gpu_lsrk_stage(c, spare.id(), next_ri.id(), solution.id(), solution.id(), factor_solution, factor_ai, current_time));
+            solution.swap(spare);
+        } else if (&current_ri == &next_ri) {      // later stages: (vec_ri, vec_ki, solution, vec_ri)
+            check(warpii_gpu_lsrk_stage(c, solution.id(), vec_ki.id(), solution.id(), current_ri.id(), factor_solution, factor_ai, current_time));
+            next_ri.swap(vec_ki);
+        } else {
+            check(warpii_gpu_lsrk_stage(c, solution.id(), next_ri.id(), solution.id(), current_ri.id(), factor_solution, factor_ai, current_time));
+        }
     }
 
     // the reference also takes the MatrixFree object; its role is played by the context
@@ -178,6 +202,15 @@ class GpuFluidFluxESDGSEMOperator {
     }
 
    private:
+    // a register of the operator's own for the first low-storage stage (HBM is taken when it is first used)
+    GpuSolutionVec& lsrk_register(const GpuSolutionVec& like) {
+        if (!lsrk_register_) {
+            lsrk_register_ = std::make_unique<GpuSolutionVec>();
+            lsrk_register_->reinit(like);
+        }
+        return *lsrk_register_;
+    }
+    std::unique_ptr<GpuSolutionVec> lsrk_register_;
     struct InflowEntry {
         int species, boundary_id;
         InflowFunction f;
@@ -203,6 +236,65 @@ class GpuFluidFluxESDGSEMOperator {
     int dim_ = 1;
     bool stale_ = false;
     double table_time_ = 0.0;
+};
+
+// rk.h:10-77.  The reference takes the coefficients from deal.II's TimeStepping::LowStorageRungeKutta::get_coefficients;
+// deal.II is not available here, so the two schemes whose published coefficients (Kennedy, Carpenter & Lewis 2000) could
+// be restated AND verified against the order conditions are provided (tests/test_lsrk_cpu.py); the other two report
+// ExcNotImplemented, as the reference's default branch does.
+enum LowStorageRungeKuttaScheme {
+    stage_3_order_3, /* Kennedy, Carpenter, Lewis, 2000 */
+    stage_5_order_4, /* Kennedy, Carpenter, Lewis, 2000 */
+    stage_7_order_4, /* Tselios, Simos, 2007 */
+    stage_9_order_5, /* Kennedy, Carpenter, Lewis, 2000 */
+};
+
+class LowStorageRungeKuttaIntegrator {
+   public:
+    explicit LowStorageRungeKuttaIntegrator(const LowStorageRungeKuttaScheme scheme) {
+        switch (scheme) {
+            case stage_3_order_3:
+                bi = {0.245170287303492, 0.184896052186740, 0.569933660509768};
+                ai = {0.755726351946097, 0.386954477304099};
+                break;
+            case stage_5_order_4:
+                bi = {1153189308089. / 22510343858157., 1772645290293. / 4653164025191., -1672844663538. / 4480602732383.,
+                      2114624349019. / 3568978502595., 5198255086312. / 14908931495163.};
+                ai = {970286171893. / 4311952581923., 6584761158862. / 12103376702013., 2251764453980. / 15575788980749.,
+                      26877169314380. / 34165994151039.};
+                break;
+            default:
+                throw std::runtime_error("ExcNotImplemented: low-storage RK coefficients of this scheme are not available");
+        }
+        // c_i = row sums of the 2-register Butcher tableau: A[i][j] = b_j (j < i-1), A[i][i-1] = a_{i-1}
+        ci.assign(bi.size(), 0.0);
+        for (size_t i = 1; i < bi.size(); i++) {
+            double c = ai[i - 1];
+            for (size_t j = 0; j + 1 < i; j++) c += bi[j];
+            ci[i] = c;
+        }
+    }
+
+    unsigned int n_stages() const { return (unsigned int)bi.size(); }
+    const std::vector<double>& get_bi() const { return bi; }
+    const std::vector<double>& get_ai() const { return ai; }
+    const std::vector<double>& get_ci() const { return ci; }
+
+    template <typename VectorType, typename Operator>
+    void perform_time_step(Operator& pde_operator, const double current_time, const double time_step, VectorType& solution,
+                           VectorType& vec_ri, VectorType& vec_ki) const {
+        pde_operator.perform_stage(current_time, bi[0] * time_step, ai[0] * time_step, solution, vec_ri, solution, vec_ri);
+        for (unsigned int stage = 1; stage < bi.size(); ++stage) {
+            const double c_i = ci[stage];
+            pde_operator.perform_stage(current_time + c_i * time_step, bi[stage] * time_step,
+                                       (stage == bi.size() - 1 ? 0 : ai[stage] * time_step), vec_ri, vec_ki, solution, vec_ri);
+        }
+    }
+
+   private:
+    std::vector<double> bi;
+    std::vector<double> ai;
+    std::vector<double> ci;
 };
 
 // rk.h:79-117

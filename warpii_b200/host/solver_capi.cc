@@ -164,7 +164,27 @@ int warpii_box_solver_step(warpii_box_solver* s, double dt, double t) {
     GUARD({
         // one evolve_one_time_step through the same integrator solve() uses
         s->solver->set_t_end(0.0);
-        check(warpii_gpu_ssprk2_step(s->solver->context()->get(), 0, 1, dt, t));
+        check(warpii_gpu_ssprk2_step(s->solver->context()->get(), s->solver->get_solution().id(), s->solver->f1_id(), dt, t));
+    })
+}
+
+int warpii_box_solver_lsrk_step(warpii_box_solver* s, int scheme, double dt, double t, double* coefficients, int* n_stages_out) {
+    GUARD({
+        if (scheme < 0 || scheme > 3) throw std::invalid_argument("lsrk_step: scheme must be 0..3");
+        const LowStorageRungeKuttaIntegrator integrator((LowStorageRungeKuttaScheme)scheme);
+        if (n_stages_out) *n_stages_out = (int)integrator.n_stages();
+        if (coefficients) {
+            double* o = coefficients;
+            for (double v : integrator.get_bi()) *o++ = v;
+            for (double v : integrator.get_ai()) *o++ = v;
+            for (double v : integrator.get_ci()) *o++ = v;
+        }
+        if (dt > 0.0) {
+            GpuSolutionVec& sol = s->solver->get_solution();
+            GpuSolutionVec vec_ri(sol.context());
+            GpuSolutionVec vec_ki(sol.context());
+            integrator.perform_time_step(s->solver->get_fluid_flux_operator(), t, dt, sol, vec_ri, vec_ki);
+        }
     })
 }
 
