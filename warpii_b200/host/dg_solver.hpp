@@ -44,7 +44,7 @@ class FiveMomentGpuSolver {
         for (int s = 0; s < n_species_ && s < (int)bcs_.size(); s++)
             for (int b = 0; b < n_boundaries_ && b < (int)bcs_[s].kind.size(); b++) bc_kind[(size_t)s * n_boundaries_ + b] = bcs_[s].kind[b];
         warpii_gpu_mesh mesh;
-        tables_.fill(mesh, fe_degree_, n_species_, fields_enabled_, gas_gamma_, n_boundaries_, bc_kind, 4);   // ids; HBM is taken on first use
+        tables_.fill(mesh, fe_degree_, n_species_, fields_enabled_, gas_gamma_, n_boundaries_, bc_kind, 6);   // ids (solution, f_1, low-storage RK registers); HBM is taken on first use
         ctx_ = std::make_shared<GpuContext>(mesh, device_);
         solution_ = std::make_unique<GpuSolutionVec>(ctx_);
         op_ = std::make_unique<GpuFluidFluxESDGSEMOperator>(ctx_);
