@@ -66,13 +66,20 @@ __device__ __forceinline__ void ec_flux_n(const double* n, const Prim& a, const 
     F[4] = m * h_hat;
 }
 
+#ifndef WGPU_GENERAL_RESIDENT
+#define WGPU_GENERAL_RESIDENT 0     // 0: 512 threads per SM in 1D/2D (4 blocks of 128 at 128 registers, no spills), 384 in 3D
+#endif                              // measured on a 512^2 p=3 curved mesh: 384 -> 0.477 ms, 512 -> 0.393 ms, 640 -> 0.430 ms per stage
+
 template <int DIM, int NP>
 struct GeoG {
     using GEO = Geo<DIM, NP>;
     static constexpr int K = DIM * DIM;
     static constexpr int OFF_JA = GEO::SMEM_DOUBLES;                // [K][NODES] contravariant vectors of the block's nodes
-    static constexpr int SMEM_DOUBLES = OFF_JA + K * GEO::NODES;
-    static constexpr int MIN_BLOCKS = (384 / GEO::THREADS) > 0 ? (384 / GEO::THREADS) : 1;
+    static constexpr int OFF_GF = OFF_JA + K * GEO::NODES;          // [DIM+1][NSLOT] face normals and lifting factors
+    static constexpr int SMEM_DOUBLES = OFF_GF + (DIM + 1) * GEO::NSLOT;
+    static constexpr int RESIDENT = WGPU_GENERAL_RESIDENT > 0 ? WGPU_GENERAL_RESIDENT : (DIM <= 2 ? 512 : 384);
+    static constexpr int BLOCKS_BY_THREADS = (RESIDENT / GEO::THREADS) > 0 ? (RESIDENT / GEO::THREADS) : 1;
+    static constexpr int MIN_BLOCKS = BLOCKS_BY_THREADS > 4 ? 4 : BLOCKS_BY_THREADS;   // never below 128 registers per thread
 };
 
 template <int DIM, int NP>
@@ -95,6 +102,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
     double* const sAlpha = smem + GEO::OFF_ALPHA;
     double* const sRed = smem + GEO::OFF_RED;
     double* const sJa = smem + GeoG<DIM, NP>::OFF_JA;
+    double* const sGF = smem + GeoG<DIM, NP>::OFF_GF;
 
     const int skip = P.skip_dev ? *P.skip_dev : 0;
     const double dt = P.dt_dev ? *P.dt_dev : P.dt;
@@ -132,6 +140,17 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
     for (int d = 0; d < DIM; d++)
 #pragma unroll
         for (int r = 0; r < DIM; r++) sJa[(d * DIM + r) * NODES + tid] = Ja[d][r];
+    // the face tables of this thread's face tasks travel to shared memory while the node phase computes (they are the
+    // same for every species; the first species' cp.async group carries them)
+    if (active) {
+        for (int ft = j; ft < NFACE * NF; ft += NN) {
+            const int f = ft / NF, t = ft - f * NF;
+            const double* gf = GP.gface + ((size_t)(e * NFACE + f) * (DIM + 1)) * NF + t;
+            double* const dstg = sGF + (le * NFACE + f) * NF + t;
+#pragma unroll
+            for (int r = 0; r <= DIM; r++) cp_async8(dstg + r * NSLOT, gf + (size_t)r * NF);
+        }
+    }
 
     for (int sp = 0; sp < P.nsp; sp++) {
         if (sp > 0) __syncthreads();
@@ -293,10 +312,10 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
 #pragma unroll
             for (int r = 0; r < DIM; r++) n[r] = (r == d) ? 1.0 : 0.0;
             if (active) {
-                const double* gf = GP.gface + ((size_t)(e * NFACE + f) * (DIM + 1)) * NF + t;
+                const double* gf = sGF + (le * NFACE + f) * NF + t;
 #pragma unroll
-                for (int r = 0; r < DIM; r++) n[r] = gf[r * NF];
-                lift = gf[DIM * NF];
+                for (int r = 0; r < DIM; r++) n[r] = gf[r * NSLOT];
+                lift = gf[DIM * NSLOT];
             }
             const Prim a = load_prim<NP>(sP, le * NN + node_of_face_node<DIM, NP>(d, side, t));
             Prim b;
