@@ -90,6 +90,14 @@ int warpii_box_solver_lsrk_step(warpii_box_solver* s, int scheme, double dt, dou
 typedef struct warpii_app warpii_app;
 typedef void (*warpii_frame_fn)(unsigned frame, double t, void* user);
 int warpii_app_create(const char* input_text, int rank, int n_ranks, int device, warpii_app** out);
+/* GridType = Extension (src/extensions/extension.h:24-45; the reference passes a GridExtension object to
+ * Warpii::create_from_cli): the triangulation an extension would populate, as arrays.  vertices[n_vertices][2];
+ * cells[n_cells][4] in deal.II vertex order (v00, v10, v01, v11), counter-clockwise; face_boundary_ids[n_cells][4] (may be
+ * NULL): boundary id of each local face 0..3 = x-low, x-high, y-low, y-high, < 0 = leave the default (0), ignored on interior
+ * faces.  Elements are straight-sided (MappingQ without a manifold); one GPU.  C++ callers derive from
+ * warpii_b200::GridExtension instead (warpii_b200/host/general_mesh.hpp). */
+int warpii_app_create_with_triangulation(const char* input_text, int64_t n_vertices, const double* vertices, int64_t n_cells,
+                                         const int32_t* cells, const int32_t* face_boundary_ids, int device, warpii_app** out);
 int warpii_app_destroy(warpii_app* app);
 /* the app's solver, valid until warpii_app_destroy (state access, node coordinates, communicator attachment ...) */
 warpii_box_solver* warpii_app_solver(warpii_app* app);
@@ -135,6 +143,15 @@ int warpii_host_mapped_metrics(int dim, int fe_degree, int64_t n_elems, const do
                                const int32_t* neighbor_face, int64_t n_boundary_faces, const int32_t* bf_elem,
                                const int32_t* bf_side, double* inverse_jacobian, double* face_normal, double* face_jacobian,
                                double* boundary_normal, double* boundary_jacobian, double* boundary_points);
+
+/* connectivity builder alone (no GPU; warpii_b200/host/general_mesh.hpp::GeneralMesh::from_triangulation): the flat tables a
+ * triangulation of quadrilaterals turns into.  Outputs: face_neighbor[n_cells][4], neighbor_face[n_cells][4],
+ * xyz[n_cells][(fe_degree+1)^2][2]; boundary faces in bf_elem/bf_side/bf_id (each sized 4*n_cells by the caller), their
+ * number in *n_boundary_faces_out. */
+int warpii_host_triangulation_tables(int64_t n_vertices, const double* vertices, int64_t n_cells, const int32_t* cells,
+                                     const int32_t* face_boundary_ids, int fe_degree, int32_t* face_neighbor,
+                                     int32_t* neighbor_face, double* xyz, int32_t* bf_elem, int32_t* bf_side, int32_t* bf_id,
+                                     int64_t* n_boundary_faces_out);
 
 /* mesh-table builder alone (no GPU): fills caller-provided arrays for tests of the partitioning logic.
  * Pass NULL output pointers to query sizes through the counts array:

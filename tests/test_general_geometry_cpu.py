@@ -217,3 +217,50 @@ def test_convergence_on_curved_mesh():
         errs.append(abs(prod))
         assert prod <= 1e-14   # entropy stable: never produces mathematical entropy... (sign: dS/dt <= 0)
     assert errs[1] < errs[0] / 2 ** 4
+
+
+# ---- the host layer's connectivity builder (GridType = Extension) -----------------------------------------------------
+def triangulation_tables(verts, cells, ids, p):
+    import ctypes as C
+    L = capi.lib()
+    i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    L.warpii_host_triangulation_tables.argtypes = [C.c_int64, dp, C.c_int64, i32p, i32p, C.c_int, i32p, i32p, dp, i32p, i32p, i32p,
+                                                   C.POINTER(C.c_int64)]
+    v = np.ascontiguousarray(verts, dtype=np.float64)
+    c = np.ascontiguousarray(cells, dtype=np.int32)
+    fid = np.ascontiguousarray(ids, dtype=np.int32)
+    n = c.shape[0]
+    nbr, nbf = np.zeros((n, 4), dtype=np.int32), np.zeros((n, 4), dtype=np.int32)
+    xyz = np.zeros((n, (p + 1) ** 2, 2))
+    bfe, bfs, bfi = (np.zeros(4 * n, dtype=np.int32) for _ in range(3))
+    nb = C.c_int64(0)
+    p32 = lambda a: a.ctypes.data_as(i32p)
+    capi._check(L.warpii_host_triangulation_tables(v.shape[0], v.ctypes.data_as(dp), n, p32(c), p32(fid), p, p32(nbr), p32(nbf),
+                                                   xyz.ctypes.data_as(dp), p32(bfe), p32(bfs), p32(bfi), C.byref(nb)), host=True)
+    k = nb.value
+    return {"face_neighbor": nbr, "neighbor_face": nbf, "bf_elem": bfe[:k], "bf_side": bfs[:k], "bf_id": bfi[:k]}, xyz
+
+
+def hexagon_face_ids(verts, cells):
+    ids = -np.ones((len(cells), 4), dtype=np.int32)
+    for e, cell in enumerate(cells):
+        for f, (a, b) in enumerate(mc._FACE_VERTS):
+            ids[e, f] = mc.hexagon_boundary_id(0.5 * (verts[cell[a]] + verts[cell[b]]))
+    return ids
+
+
+def test_host_connectivity_builder_matches_the_test_mesh_builder():
+    p = 3
+    verts, cells = mc.hexagon_blocks(3)
+    want_mesh, want_xyz = mc.quad_mesh(verts, cells, p, mc.hexagon_boundary_id)
+    got_mesh, got_xyz = triangulation_tables(verts, cells, hexagon_face_ids(verts, cells), p)
+    for k in ("face_neighbor", "bf_elem", "bf_side", "bf_id"):
+        assert np.array_equal(got_mesh[k], want_mesh[k]), k
+    interior = want_mesh["face_neighbor"] >= 0
+    assert np.array_equal(got_mesh["neighbor_face"][interior], want_mesh["neighbor_face"][interior])
+    assert np.abs(got_xyz - want_xyz).max() <= 1e-15
+    # a clockwise cell is refused (negative Jacobian), like deal.II does
+    bad = cells.copy()
+    bad[0] = bad[0][[1, 0, 3, 2]]
+    with pytest.raises(capi.WarpiiGpuError, match="orientation"):
+        triangulation_tables(verts, bad, hexagon_face_ids(verts, bad), p)

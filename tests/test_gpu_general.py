@@ -289,3 +289,145 @@ def test_device_resident_loop_on_curved_mesh():
     o.solve(o_u, 1e9, max_steps=24)
     assert (rel_l2(a, o_u) <= STEPS_TOL).all()
     g.close()
+
+
+# ---- GridType = Extension through the application layer ---------------------------------------------------------------
+EXTENSION_INPUT = """
+set Application = FiveMoment
+set n_dims = 2
+set t_end = 0.02
+set fe_degree = 3
+set n_boundaries = 3
+set gas_gamma = 1.4
+set n_writeout_frames = 2
+subsection geometry
+    set GridType = Extension
+end
+subsection Species_1
+    subsection InitialCondition
+        set VariablesType = Primitive
+        set Function constants = pi=3.1415926535
+        set Function expression = 1.0 + 0.2*sin(1.3*x + 0.5*y); 0.4 + 0.1*cos(0.9*y); -0.2 + 0.1*sin(1.1*x); 0.1*cos(0.8*x - 0.6*y); 1.0 + 0.1*cos(0.7*x - 1.2*y)
+    end
+    subsection BoundaryConditions
+        set 0 = Wall
+        set 1 = Inflow
+        set 2 = Outflow
+        subsection 1_Inflow
+            set VariablesType = Primitive
+            set Function expression = 1.1; 0.3; 0.2; 0.0; 1.0
+        end
+    end
+end
+"""
+
+
+def test_extension_grid_through_the_application(tmp_path):
+    """An input file with GridType = Extension + the triangulation an extension would populate -> the same run as the
+    oracle started from the same initial condition on the same mesh; frames carry the real node coordinates."""
+    from test_general_geometry_cpu import hexagon_face_ids
+    from warpii_b200 import App
+    import dgsem_cases as cases
+    p = 3
+    verts, cells = mc.hexagon_blocks(3)
+    app = App.with_triangulation(EXTENSION_INPUT, verts, cells, hexagon_face_ids(verts, cells))
+    app.set_output_dir(str(tmp_path))
+    app.set_device_loop(False)
+    app.setup()
+    mesh, xyz = mc.quad_mesh(verts, cells, p, mc.hexagon_boundary_id)
+    assert np.abs(app.solver.node_coords() - xyz).max() <= 1e-15
+    bc = np.array([[BC_WALL, BC_INFLOW, BC_OUTFLOW]])
+    geo = metrics(2, p, mesh, xyz)
+    o = GeneralOracle(2, p, mesh, geo, n_boundaries=3, bc_kinds=bc, gamma=GAMMA, threads=4)
+    o.set_inflow(0, 1, mc.to_conserved(np.array([1.1, 0.3, 0.2, 0.0, 1.0]), GAMMA))
+    u = mc.state_from(mc.smooth_state(GAMMA, 2)(xyz), GAMMA)
+    assert (rel_l2(app.solver.get_state(), u) <= 1e-14).all()   # the parsed initial condition is the same function
+    steps = app.run()
+    # the oracle follows the same time loop: recommend_dt every step, stops at the two frame times
+    t, n = 0.0, 0
+    for stop in (0.01, 0.02):
+        while t < stop - 1e-12:
+            dt = min(o.recommend_dt(u), stop - t)
+            o.ssprk2_step(u, dt, t)
+            t += dt
+            n += 1
+    assert steps == n
+    assert (rel_l2(app.solver.get_state(), u) <= STEPS_TOL).all()
+    assert [f for f, _ in app.frames] == [1, 2]   # frame 0 was written by setup()
+    frame = cases.read_vtu(str(tmp_path / "solution_002.vtu"))
+    assert frame["n_points"] == xyz.shape[0] * xyz.shape[1]
+    app.close()
+
+
+def ffs_triangulation(rf=1):
+    """The mesh of examples/five-moment/forward_facing_step/main.cc: 15 x 5 channel (times rf) minus the step cells."""
+    Lx, Ly, nx, ny = 3.0, 1.0, 15 * rf, 5 * rf
+    dx, dy = Lx / 15, Ly / 5
+    hx, hy = Lx / nx, Ly / ny
+    vid, verts, cells = {}, [], []
+
+    def vertex(i, j):
+        if (i, j) not in vid:
+            vid[(i, j)] = len(verts)
+            verts.append([i * hx, j * hy])
+        return vid[(i, j)]
+
+    for j in range(ny):
+        for i in range(nx):
+            if (i + 0.5) * hx > 3 * dx and (j + 0.5) * hy < dy:
+                continue
+            cells.append([vertex(i, j), vertex(i + 1, j), vertex(i, j + 1), vertex(i + 1, j + 1)])
+    verts, cells = np.array(verts), np.array(cells)
+
+    def bid(mid):
+        tol = 1e-8
+        if abs(mid[0]) < tol: return 0
+        if abs(mid[1]) < tol: return 1
+        if abs(mid[0] - 3 * dx) < tol and mid[1] < dy: return 2
+        if abs(mid[1] - dy) < tol and mid[0] > 3 * dx: return 3
+        if abs(mid[0] - Lx) < tol: return 4
+        return 5
+    return verts, cells, bid
+
+
+def test_forward_facing_step_example(tmp_path):
+    """The reference's extension example on the GPU path: the executable runs from the example input; the same mesh and
+    input through the library match the oracle over the first steps of the Mach 3 start-up (shocks, alpha > 0)."""
+    import os
+    import subprocess
+    from warpii_b200 import App
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "examples", "five-moment", "forward_facing_step.inp")).read()
+    text = text.replace("set t_end = 3.000", "set t_end = 0.01").replace("set n_writeout_frames = 100", "set n_writeout_frames = 1")
+    text = text.replace("set RefinementFactor = 2", "set RefinementFactor = 1")
+    inp = tmp_path / "ffs.inp"
+    inp.write_text(text)
+    exe = os.path.join(root, "warpii_b200", "bin", "forward_facing_step")
+    out = subprocess.run([exe, str(inp)], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "frame 1  t = 0.01" in out.stdout and (tmp_path / "FiveMoment__ffs" / "solution_001.vtu").exists()
+    steps_exe = int(out.stdout.split("steps = ")[1].split()[0])
+
+    p = 4
+    verts, cells, bid = ffs_triangulation(1)
+    ids = np.array([[bid(0.5 * (verts[c[a]] + verts[c[b]])) for (a, b) in mc._FACE_VERTS] for c in cells], dtype=np.int32)
+    app = App.with_triangulation(text, verts, cells, ids)
+    app.set_device_loop(False)
+    app.setup()
+    mesh, xyz = mc.quad_mesh(verts, cells, p, bid)
+    bc = np.array([[BC_INFLOW, BC_WALL, BC_WALL, BC_WALL, BC_OUTFLOW, BC_WALL]])
+    o = GeneralOracle(2, p, mesh, metrics(2, p, mesh, xyz), n_boundaries=6, bc_kinds=bc, gamma=1.4, threads=8)
+    q_in = mc.to_conserved(np.array([1.4, 3.0, 0.0, 0.0, 1.0]), 1.4)
+    o.set_inflow(0, 0, q_in)
+    prim = np.zeros(xyz.shape[:-1] + (5,))
+    prim[...] = [1.4, 3.0, 0.0, 0.0, 1.0]
+    u = mc.state_from(prim, 1.4)
+    steps = app.run()
+    n = o.solve(u, 0.01)
+    assert steps == n == steps_exe
+    assert (o.alpha(u) > 0).any()
+    got = app.solver.get_state()
+    assert np.isfinite(got).all() and got[:, 0, :].min() > 0
+    err = rel_l2(got, u)
+    assert (err <= 1e-8).all(), err   # a shock run: alpha switches amplify round-off (same bar as the Sod run)
+    app.close()

@@ -157,7 +157,8 @@ def test_expression_language():
     ("set write_output = maybe", "is not a boolean"),
     ("set fields_enabled = sometimes", "is not one of true|false|auto"),
     ("set Application = Vlasov", "is not one of FiveMoment|FPETest"),
-    ("subsection geometry\n set GridType = Extension\nend", "not supported by the GPU path"),
+    ("subsection geometry\n set GridType = Extension\nend", "needs a grid extension"),
+    ("subsection geometry\n set GridType = ForwardFacingStep\nend", "not supported by the GPU path"),
     ("subsection geometry\n set nx = 3", "unbalanced"),
     ("end", "'end' without 'subsection'"),
     ("subsection Nowhere\nend", "no subsection 'Nowhere/'"),

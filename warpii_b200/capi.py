@@ -556,6 +556,9 @@ class App:
     def __init__(self, input_text, rank=0, n_ranks=1, device=0):
         h = C.c_void_p()
         _check(lib().warpii_app_create(input_text.encode(), rank, n_ranks, device, C.byref(h)), host=True)
+        self._adopt(h)
+
+    def _adopt(self, h):
         self.h = h
         ints = np.zeros(16, dtype=np.int32)
         dbls = np.zeros(16)
@@ -571,6 +574,23 @@ class App:
         self.right = [float(v) for v in dbls[5:5 + d]]
         self.solver = None
         self.frames = []
+
+    @classmethod
+    def with_triangulation(cls, input_text, vertices, cells, face_boundary_ids=None, device=0):
+        """GridType = Extension: the triangulation a GridExtension would populate, as arrays (warpii_host.h)."""
+        L = lib()
+        L.warpii_app_create_with_triangulation.argtypes = [C.c_char_p, C.c_int64, _dp, C.c_int64, _i32p, _i32p, C.c_int,
+                                                           C.POINTER(C.c_void_p)]
+        v = np.ascontiguousarray(vertices, dtype=np.float64)
+        c = _arr32(cells)
+        ids = None if face_boundary_ids is None else _arr32(face_boundary_ids)
+        h = C.c_void_p()
+        _check(L.warpii_app_create_with_triangulation(input_text.encode(), v.shape[0], _ptr(v), c.shape[0], c.ctypes.data_as(_i32p),
+                                                      ids.ctypes.data_as(_i32p) if ids is not None else None, device, C.byref(h)),
+               host=True)
+        self = cls.__new__(cls)
+        self._adopt(h)
+        return self
 
     def species(self, i):
         name = C.create_string_buffer(16)

@@ -8,7 +8,9 @@
 #include <vector>
 
 #include "box_mesh.hpp"
+#include "general_mesh.hpp"
 #include "gpu_operator.hpp"
+#include "mapped_mesh.hpp"
 #include "reference_element.hpp"
 
 namespace warpii_b200 {
@@ -38,6 +40,19 @@ class FiveMomentGpuSolver {
         // the reference throws "Unknown boundary id" from the face loop in that case, the ABI does so at create.
     }
 
+    // The same solver on a mesh that is not a Cartesian box (GridType = Extension, or a mapped box): tables and
+    // Gauss-Lobatto support points from GeneralMesh, metric terms from mapped_mesh.hpp, warpii_gpu_set_geometry.
+    // One rank (the reference does not shard either: serial Triangulation, src/grid.h:40).
+    FiveMomentGpuSolver(GeneralMesh mesh, int n_species, bool fields_enabled, double gas_gamma, double t_end, int n_boundaries,
+                        std::vector<SpeciesBC> bcs, int device)
+        : t_end_(t_end), fe_degree_(mesh.fe_degree), n_species_(n_species), fields_enabled_(fields_enabled), gas_gamma_(gas_gamma),
+          n_boundaries_(n_boundaries), bcs_(std::move(bcs)), device_(device), rank_(0), n_ranks_(1),
+          tables_(unit_box(mesh.dim), 0, 1, 1), element_(mesh.fe_degree), general_(std::make_unique<GeneralMesh>(std::move(mesh))) {
+        nc_ = 5 * n_species + (fields_enabled ? 8 : 0);
+        nn_ = 1;
+        for (int d = 0; d < general_->dim; d++) nn_ *= fe_degree_ + 1;
+    }
+
     // dg_solver.cc:7-12
     void reinit() {
         std::vector<int32_t> bc_kind((size_t)n_species_ * (n_boundaries_ > 0 ? n_boundaries_ : 0), WARPII_BC_WALL);
@@ -45,12 +60,37 @@ class FiveMomentGpuSolver {
             for (int b = 0; b < n_boundaries_ && b < (int)bcs_[s].kind.size(); b++) bc_kind[(size_t)s * n_boundaries_ + b] = bcs_[s].kind[b];
         warpii_gpu_mesh mesh;
         tables_.fill(mesh, fe_degree_, n_species_, fields_enabled_, gas_gamma_, n_boundaries_, bc_kind, 6);   // ids (solution, f_1, low-storage RK registers); HBM is taken on first use
+        if (general_) {
+            mesh.dim = general_->dim;
+            mesh.n_elems = general_->n_elems;
+            mesh.n_ghost_faces = 0;
+            mesh.n_boundary_faces = (int64_t)general_->bf_elem.size();
+            mesh.face_neighbor = general_->face_neighbor.data();
+            mesh.boundary_face_elem = general_->bf_elem.data();
+            mesh.boundary_face_side = general_->bf_side.data();
+            mesh.boundary_face_id = general_->bf_id.data();
+        }
         ctx_ = std::make_shared<GpuContext>(mesh, device_);
+        if (general_) {
+            metrics_ = build_mapped_metrics(general_->dim, fe_degree_, general_->n_elems, general_->xyz.data(),
+                                            general_->face_neighbor.data(),
+                                            general_->neighbor_face.empty() ? nullptr : general_->neighbor_face.data(),
+                                            (int64_t)general_->bf_elem.size(), general_->bf_elem.data(), general_->bf_side.data());
+            warpii_gpu_geometry g{};
+            g.inverse_jacobian = metrics_.inverse_jacobian.data();
+            g.face_normal = metrics_.face_normal.data();
+            g.face_jacobian = metrics_.face_jacobian.data();
+            g.neighbor_face = general_->neighbor_face.empty() ? nullptr : general_->neighbor_face.data();
+            g.boundary_normal = metrics_.boundary_normal.data();
+            g.boundary_jacobian = metrics_.boundary_jacobian.data();
+            check(warpii_gpu_set_geometry(ctx_->get(), &g));
+        }
         solution_ = std::make_unique<GpuSolutionVec>(ctx_);
         op_ = std::make_unique<GpuFluidFluxESDGSEMOperator>(ctx_);
         integrator_ = std::make_unique<Integrator>();
         integrator_->reinit(*solution_, 3);
-        op_->set_boundary_points(boundary_quadrature_points(), tables_.boundary_face_id(), tables_.box().dim, n_species_);
+        if (general_) op_->set_boundary_points(metrics_.boundary_points, general_->bf_id, general_->dim, n_species_);
+        else op_->set_boundary_points(boundary_quadrature_points(), tables_.boundary_face_id(), tables_.box().dim, n_species_);
         for (int s = 0; s < n_species_ && s < (int)bcs_.size(); s++)
             for (int b = 0; b < n_boundaries_ && b < (int)bcs_[s].kind.size(); b++) {
                 if (bcs_[s].kind[b] != WARPII_BC_INFLOW) continue;
@@ -92,6 +132,7 @@ class FiveMomentGpuSolver {
 
     // Node coordinates of the owned elements in device order, xyz[elem][node][dim].
     std::vector<double> node_coords() const {
+        if (general_) return general_->xyz;
         const BoxDescription& box = tables_.box();
         const int Np = fe_degree_ + 1;
         std::vector<double> xyz((size_t)tables_.n_local() * nn_ * box.dim);
@@ -115,8 +156,8 @@ class FiveMomentGpuSolver {
     void project_initial_condition(int species, const std::function<void(const double* x, double* out5)>& f, bool primitive = true) {
         if (host_.empty()) host_.assign((size_t)ctx_->n_dofs(), 0.0);
         const std::vector<double> xyz = node_coords();
-        const int dim = tables_.box().dim;
-        for (int64_t l = 0; l < tables_.n_local(); l++)
+        const int dim = n_dims();
+        for (int64_t l = 0; l < n_local_elems(); l++)
             for (int j = 0; j < nn_; j++) {
                 double v[5], q[5];
                 f(&xyz[((size_t)l * nn_ + j) * dim], v);
@@ -164,6 +205,7 @@ class FiveMomentGpuSolver {
 
     // One process per GPU: hand the halo lists of this rank's slab and the communicator id to the context
     void attach_comm(const char id[WARPII_GPU_NCCL_ID_BYTES]) {
+        if (general_) throw std::runtime_error("attach_comm: meshes from an extension run on one GPU (the reference's triangulation is serial too)");
         warpii_gpu_halo halo;
         tables_.fill(halo);
         check(warpii_gpu_attach_comm(ctx_->get(), id, rank_, n_ranks_, &halo));
@@ -178,6 +220,11 @@ class FiveMomentGpuSolver {
     void set_fixed_dt(double dt) { fixed_dt_ = dt; }
     void set_device_loop(bool on) { device_loop_ = on; }
     int f1_id() const { return integrator_->stage_vector().id(); }
+    bool general_geometry() const { return (bool)general_; }
+    int n_dims() const { return general_ ? general_->dim : tables_.box().dim; }
+    int64_t n_local_elems() const { return general_ ? general_->n_elems : tables_.n_local(); }
+    const GeneralMesh* general_mesh() const { return general_.get(); }
+    const MappedMeshMetrics& metrics() const { return metrics_; }
     int n_components() const { return nc_; }
     int n_species() const { return n_species_; }
     int nodes_per_elem() const { return nn_; }
@@ -198,6 +245,13 @@ class FiveMomentGpuSolver {
     std::unique_ptr<GpuFluidFluxESDGSEMOperator> op_;
     std::unique_ptr<Integrator> integrator_;
     std::vector<double> host_;
+    std::unique_ptr<GeneralMesh> general_;
+    MappedMeshMetrics metrics_;
+    static BoxDescription unit_box(int dim) {
+        BoxDescription b;
+        b.dim = dim;
+        return b;
+    }
     int64_t steps_ = 0;
     double fixed_dt_ = 0.0;
     bool device_loop_ = true;

@@ -94,7 +94,10 @@ struct SpeciesDescription {
 class FiveMomentGpuApp {
    public:
     // FiveMomentWrapper::declare_parameters + create_app (five_moment.cc:13-52)
-    static std::unique_ptr<FiveMomentGpuApp> create_from_input(const std::string& input, int rank = 0, int n_ranks = 1, int device = 0) {
+    // ext: the reference's `Warpii::create_from_cli(argc, argv, std::make_shared<MyExtension>())` (warpii.h; used by
+    // examples/five-moment/forward_facing_step/main.cc) -- needed when the input says GridType = Extension
+    static std::unique_ptr<FiveMomentGpuApp> create_from_input(const std::string& input, int rank = 0, int n_ranks = 1, int device = 0,
+                                                               std::shared_ptr<GridExtension> ext = nullptr) {
         using Pat = ParameterFile::Pattern;
         ParameterFile prm;
         prm.declare_entry("WorkDir", "%A__%I");                                          // warpii.cc:139-149
@@ -123,9 +126,16 @@ class FiveMomentGpuApp {
         }
         prm.enter_subsection("geometry");
         const std::string grid_type = prm.get("GridType");
-        if (grid_type != "HyperRectangle")
-            throw std::invalid_argument("GridType = " + grid_type + " is not supported by the GPU path (HyperRectangle only)");
-        {   // HyperRectangleDescription<dim>::declare_parameters (grid_descriptions.cc:27-33)
+        if (grid_type == "Extension") {
+            // grid.cc: the extension declares its own entries inside `geometry` and later fills the triangulation
+            if (!ext) throw std::invalid_argument("GridType = Extension needs a grid extension (create_from_input(..., ext))");
+            if (dim != 2) throw std::invalid_argument("GridType = Extension: extension grids are two-dimensional on the GPU path");
+            if (n_ranks != 1) throw std::invalid_argument("GridType = Extension runs on one GPU");
+            ext->declare_geometry_parameters(prm);
+        } else if (grid_type != "HyperRectangle") {
+            throw std::invalid_argument("GridType = " + grid_type + " is not supported by the GPU path (HyperRectangle or Extension)");
+        }
+        if (grid_type == "HyperRectangle") {   // HyperRectangleDescription<dim>::declare_parameters (grid_descriptions.cc:27-33)
             std::string zeros, ones, nx1;
             for (int d = 0; d < dim; d++) {
                 zeros += d ? ", 0" : "0";
@@ -165,7 +175,11 @@ class FiveMomentGpuApp {
         prm.enter_subsection("geometry");
         BoxDescription box;
         box.dim = dim;
-        {
+        Triangulation2D tria;
+        if (grid_type == "Extension") {
+            ext->populate_triangulation(tria, prm);
+            if (tria.cells.empty()) throw std::invalid_argument("GridType = Extension: the extension produced no cells");
+        } else {
             const std::vector<double> nx = ParameterFile::to_doubles(prm.get("nx"));
             const std::vector<double> left = ParameterFile::to_doubles(prm.get("left"));
             const std::vector<double> right = ParameterFile::to_doubles(prm.get("right"));
@@ -212,8 +226,13 @@ class FiveMomentGpuApp {
                 bcs[s].time_dependent[b] = f->time_dependent();
             }
         }
-        app->solver_ = std::make_shared<FiveMomentGpuSolver>(box, app->fe_degree_, n_species, app->fields_enabled_, app->gas_gamma_,
-                                                            app->t_end_, n_boundaries, bcs, rank, n_ranks, device);
+        if (grid_type == "Extension")
+            app->solver_ = std::make_shared<FiveMomentGpuSolver>(GeneralMesh::from_triangulation(tria, app->fe_degree_), n_species,
+                                                                app->fields_enabled_, app->gas_gamma_, app->t_end_, n_boundaries, bcs,
+                                                                device);
+        else
+            app->solver_ = std::make_shared<FiveMomentGpuSolver>(box, app->fe_degree_, n_species, app->fields_enabled_, app->gas_gamma_,
+                                                                app->t_end_, n_boundaries, bcs, rank, n_ranks, device);
         return app;
     }
 
@@ -351,7 +370,7 @@ class FiveMomentGpuApp {
         else std::snprintf(name, sizeof name, "solution_%03u.vtu", frame);
         std::vector<VtuSpecies> names;
         for (const SpeciesDescription& sp : species_) names.push_back({sp.name});
-        VtuWriter::write(output_dir_ + "/" + name, dim_, fe_degree_, solver_->tables().n_local(), solver_->n_components(), names,
+        VtuWriter::write(output_dir_ + "/" + name, dim_, fe_degree_, solver_->n_local_elems(), solver_->n_components(), names,
                          fields_enabled_, gas_gamma_, rank_, host.data(), node_xyz_.data());
         if (n_ranks_ > 1 && rank_ == 0) {
             std::vector<std::string> pieces;

@@ -37,9 +37,9 @@ extern "C" {
 
 const char* warpii_host_last_error(void) { return g_host_error.c_str(); }
 
-#define GUARD(body)                                   \
+#define GUARD(...)                                    \
     try {                                             \
-        body;                                         \
+        __VA_ARGS__;                                  \
         return 0;                                     \
     } catch (const std::exception& e) {               \
         return host_fail(e);                          \
@@ -87,7 +87,7 @@ int warpii_box_solver_destroy(warpii_box_solver* s) {
 }
 
 warpii_gpu_ctx* warpii_box_solver_ctx(warpii_box_solver* s) { return s ? s->solver->context()->get() : nullptr; }
-int64_t warpii_box_solver_n_local_elems(const warpii_box_solver* s) { return s->solver->tables().n_local(); }
+int64_t warpii_box_solver_n_local_elems(const warpii_box_solver* s) { return s->solver->n_local_elems(); }
 int64_t warpii_box_solver_n_interface_elems(const warpii_box_solver* s) { return s->solver->tables().n_interface(); }
 int64_t warpii_box_solver_n_ghost_faces(const warpii_box_solver* s) { return s->solver->tables().n_ghost_faces(); }
 int warpii_box_solver_n_components(const warpii_box_solver* s) { return s->solver->n_components(); }
@@ -95,6 +95,10 @@ int warpii_box_solver_nodes_per_elem(const warpii_box_solver* s) { return s->sol
 
 int warpii_box_solver_local_to_global(const warpii_box_solver* s, int64_t* out) {
     GUARD({
+        if (s->solver->general_geometry()) {   // an extension's cells keep their order
+            for (int64_t i = 0; i < s->solver->n_local_elems(); i++) out[i] = i;
+            return 0;
+        }
         const auto& v = s->solver->tables().local_to_global();
         std::memcpy(out, v.data(), v.size() * sizeof(int64_t));
     })
@@ -129,12 +133,16 @@ int warpii_box_solver_set_sources(warpii_box_solver* s, int enabled, double epsi
         s->solver->get_fluid_flux_operator().set_sources(enabled != 0, epsilon0, chi, qm);
     })
 }
-int64_t warpii_box_solver_n_boundary_faces(const warpii_box_solver* s) { return (int64_t)s->solver->tables().boundary_face_elem().size(); }
+int64_t warpii_box_solver_n_boundary_faces(const warpii_box_solver* s) {
+    return s->solver->general_geometry() ? (int64_t)s->solver->general_mesh()->bf_elem.size()
+                                         : (int64_t)s->solver->tables().boundary_face_elem().size();
+}
 int warpii_box_solver_boundary_points(const warpii_box_solver* s, double* xyz, int32_t* face_boundary_id) {
     GUARD({
-        const std::vector<double> v = s->solver->boundary_quadrature_points();
+        const bool general = s->solver->general_geometry();
+        const std::vector<double> v = general ? s->solver->metrics().boundary_points : s->solver->boundary_quadrature_points();
         if (xyz && !v.empty()) std::memcpy(xyz, v.data(), v.size() * sizeof(double));
-        const auto& ids = s->solver->tables().boundary_face_id();
+        const auto& ids = general ? s->solver->general_mesh()->bf_id : s->solver->tables().boundary_face_id();
         if (face_boundary_id && !ids.empty()) std::memcpy(face_boundary_id, ids.data(), ids.size() * sizeof(int32_t));
     })
 }
@@ -206,6 +214,63 @@ int warpii_app_create(const char* input_text, int rank, int n_ranks, int device,
         a->solver_view.solver = a->app->solver_ptr();
         a->solver_view.rank = rank;
         a->solver_view.n_ranks = n_ranks;
+        *out = a;
+    })
+}
+namespace {
+// an extension that hands over arrays (the C ABI cannot carry a C++ object)
+class TableExtension : public GridExtension {
+   public:
+    Triangulation2D tria;
+    void populate_triangulation(Triangulation2D& out, const ParameterFile&) override { out = tria; }
+};
+}  // namespace
+
+static void fill_triangulation(Triangulation2D& tria, int64_t n_vertices, const double* vertices, int64_t n_cells,
+                               const int32_t* cells, const int32_t* face_boundary_ids) {
+    for (int64_t v = 0; v < n_vertices; v++) tria.vertices.push_back({{vertices[2 * v], vertices[2 * v + 1]}});
+    for (int64_t c = 0; c < n_cells; c++) {
+        tria.cells.push_back({{cells[4 * c], cells[4 * c + 1], cells[4 * c + 2], cells[4 * c + 3]}});
+        for (int f = 0; f < 4 && face_boundary_ids; f++)
+            if (face_boundary_ids[4 * c + f] >= 0) tria.boundary_ids[{(int)c, f}] = face_boundary_ids[4 * c + f];
+    }
+}
+
+int warpii_host_triangulation_tables(int64_t n_vertices, const double* vertices, int64_t n_cells, const int32_t* cells,
+                                     const int32_t* face_boundary_ids, int fe_degree, int32_t* face_neighbor,
+                                     int32_t* neighbor_face, double* xyz, int32_t* bf_elem, int32_t* bf_side, int32_t* bf_id,
+                                     int64_t* n_boundary_faces_out) {
+    GUARD({
+        if (!vertices || !cells || !face_neighbor || !neighbor_face || !xyz) throw std::invalid_argument("triangulation_tables: null argument");
+        Triangulation2D tria;
+        fill_triangulation(tria, n_vertices, vertices, n_cells, cells, face_boundary_ids);
+        const GeneralMesh m = GeneralMesh::from_triangulation(tria, fe_degree);
+        std::memcpy(face_neighbor, m.face_neighbor.data(), m.face_neighbor.size() * sizeof(int32_t));
+        std::memcpy(neighbor_face, m.neighbor_face.data(), m.neighbor_face.size() * sizeof(int32_t));
+        std::memcpy(xyz, m.xyz.data(), m.xyz.size() * sizeof(double));
+        if (bf_elem) std::memcpy(bf_elem, m.bf_elem.data(), m.bf_elem.size() * sizeof(int32_t));
+        if (bf_side) std::memcpy(bf_side, m.bf_side.data(), m.bf_side.size() * sizeof(int32_t));
+        if (bf_id) std::memcpy(bf_id, m.bf_id.data(), m.bf_id.size() * sizeof(int32_t));
+        if (n_boundary_faces_out) *n_boundary_faces_out = (int64_t)m.bf_elem.size();
+    })
+}
+
+int warpii_app_create_with_triangulation(const char* input_text, int64_t n_vertices, const double* vertices, int64_t n_cells,
+                                         const int32_t* cells, const int32_t* face_boundary_ids, int device, warpii_app** out) {
+    GUARD({
+        if (!input_text || !out || !vertices || !cells) throw std::invalid_argument("warpii_app_create_with_triangulation: null argument");
+        auto ext = std::make_shared<TableExtension>();
+        fill_triangulation(ext->tria, n_vertices, vertices, n_cells, cells, face_boundary_ids);
+        auto* a = new warpii_app();
+        try {
+            a->app = FiveMomentGpuApp::create_from_input(input_text, 0, 1, device, ext);
+        } catch (...) {
+            delete a;
+            throw;
+        }
+        a->solver_view.solver = a->app->solver_ptr();
+        a->solver_view.rank = 0;
+        a->solver_view.n_ranks = 1;
         *out = a;
     })
 }
