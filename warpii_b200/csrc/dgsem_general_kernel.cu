@@ -123,7 +123,9 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
     double vmax_local = 0.0;
 
     // this node's metric terms: Ja[d][r] = component r of Ja^d, 1/Jdet (the same for every species)
-    double Ja[DIM][DIM], invJ = 1.0;
+    // (the loads are issued here; their first use - the shared-memory copy - comes after the state loads and the face
+    // prefetches of the first species have been issued, so that the block pays one memory latency at its start)
+    double Ja[DIM][DIM], invJ = 1.0, eig = 0.0;
 #pragma unroll
     for (int d = 0; d < DIM; d++)
 #pragma unroll
@@ -135,11 +137,8 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
 #pragma unroll
             for (int r = 0; r < DIM; r++) Ja[d][r] = g[(size_t)(d * DIM + r) * NN];
         invJ = g[(size_t)K * NN];
+        if (P.vmax && P.mode == 0) eig = g[(size_t)(K + 1) * NN];
     }
-#pragma unroll
-    for (int d = 0; d < DIM; d++)
-#pragma unroll
-        for (int r = 0; r < DIM; r++) sJa[(d * DIM + r) * NODES + tid] = Ja[d][r];
     // the face tables of this thread's face tasks travel to shared memory while the node phase computes (they are the
     // same for every species; the first species' cp.async group carries them)
     if (active) {
@@ -162,7 +161,8 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
             for (int c = 0; c < 5; c++) q[c] = P.u[off + (size_t)c * NN];
             for (int ft = j; ft < NFACE * NF; ft += NN) {
                 const int f = ft / NF, t = ft - f * NF;
-                const int v = P.nbr[(size_t)e * NFACE + f];
+                const int2 vc = GP.nbr2[(size_t)e * NFACE + f];   // (neighbour, its face + orientation): one load
+                const int v = vc.x;
                 if (v >= e0 && v < e_hi) continue;
                 double* const rec = sFace + (le * NFACE + f) * NF + t;
                 const double* src;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
                     src = P.bres + (((size_t)(-1 - v) * P.nsp + sp) * 5) * NF + t;
                     stride = NF;
                 } else {
-                    const int code = GP.nbrf[(size_t)e * NFACE + f];
+                    const int code = vc.y;
                     const int nfa = code & 7, tp = (code >> 3) ? NF - 1 - t : t;
                     if (v < P.n_elems) {
                         src = P.u + ((size_t)v * nc + 5 * sp) * NN + node_of_face_node<DIM, NP>(nfa >> 1, nfa & 1, tp);
@@ -191,6 +191,10 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
                 cp_async_wait_all();
                 return;
             }
+#pragma unroll
+            for (int d = 0; d < DIM; d++)
+#pragma unroll
+                for (int r = 0; r < DIM; r++) sJa[(d * DIM + r) * NODES + tid] = Ja[d][r];
             for (int i = tid; i < NP * NP; i += NODES) { sD[i] = P.T.D[i]; sV[i] = P.T.V[i]; }
             for (int i = tid; i < NP; i += NODES) sW[i] = P.T.w[i];
         }
@@ -304,9 +308,10 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
             const int f = ft / NF, t = ft - f * NF;
             const int d = f >> 1, side = f & 1;
             double* const rec = sFace + (le * NFACE + f) * NF + t;
-            const int v = active ? P.nbr[(size_t)e * NFACE + f] : (int)e0;
+            const int2 vc = active ? GP.nbr2[(size_t)e * NFACE + f] : make_int2((int)e0, f ^ 1);
+            const int v = vc.x;
             if (v < 0) continue;
-            const int code = active ? GP.nbrf[(size_t)e * NFACE + f] : (f ^ 1);
+            const int code = vc.y;
             const int nfa = code & 7, tp = (code >> 3) ? NF - 1 - t : t;
             double n[DIM], lift = 0.0;
 #pragma unroll
@@ -485,7 +490,6 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
                 }
                 const double c2 = gamma * pr * inv;
                 const double cs = (c2 > 0.0) ? sqrt_pos(c2) : sqrt(c2 - 1.0);
-                const double eig = GP.gnode[((size_t)e * (K + 2) + K + 1) * NN + j];
                 const double speed = eig * cs + conv;
                 vmax_local = (speed > vmax_local || speed != speed) ? speed : vmax_local;
             }

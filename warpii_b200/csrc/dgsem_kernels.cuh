@@ -90,7 +90,7 @@ struct GeneralParams {
                               //   node along d, n_i = Ja^d_0 + sum_{k<=i} sum_m Q(k,m) Ja^d_m (subcell_finite_volume_flux.h:101-106,
                               //   :140-145); read only where alpha > 0
     const double* gface;      // [n_elems][2*dim][dim+1][NF]: unit outward normal, then face Jacobian / (Jdet * w_0) at the node
-    const int32_t* nbrf;      // [n_elems][2*dim]: neighbour's local face + 8 * (tangential order reversed)
+    const int2* nbr2;         // [n_elems][2*dim]: (face_neighbor entry, neighbour's local face + 8 * (tangential order reversed))
     const double* jdet;       // [n_elems][NN]: Jdet at the nodes (global integrals)
     const double* bgeo;       // [n_bfaces][NG][dim+1]: unit outward normal and surface Jacobian at the boundary Gauss points
     const double* bmass;      // [n_bfaces][NF]: 1 / (Jdet * tensor GLL weight) of the face nodes

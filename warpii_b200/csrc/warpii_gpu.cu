@@ -131,7 +131,7 @@ struct warpii_gpu_ctx {
     bool general = false;
     GeneralParams GP{};
     double *d_gnode = nullptr, *d_gsub = nullptr, *d_gface = nullptr, *d_jdet = nullptr, *d_bgeo = nullptr, *d_bmass = nullptr;
-    int32_t* d_nbrf = nullptr;
+    int2* d_nbr2 = nullptr;
     std::vector<int32_t> h_bf_elem, h_bf_side;
     // multi-GPU
     ncclComm_t comm = nullptr;
@@ -520,7 +520,7 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     cudaFree(c->d_sendbuf); cudaFree(c->d_partial); cudaFree(c->d_out5); cudaFree(c->d_alpha); cudaFree(c->d_vmax);
     cudaFree(c->d_send_elem); cudaFree(c->d_send_side);
     cudaFree(c->d_gnode); cudaFree(c->d_gsub); cudaFree(c->d_gface); cudaFree(c->d_jdet); cudaFree(c->d_bgeo); cudaFree(c->d_bmass);
-    cudaFree(c->d_nbrf);
+    cudaFree(c->d_nbr2);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h_clock) cudaFreeHost(c->h_clock);
@@ -743,11 +743,14 @@ int warpii_gpu_set_geometry(warpii_gpu_ctx* c, const warpii_gpu_geometry* g) {
                 for (int r = 0; r < dim; r++) o[(size_t)r * NF] = g->face_normal[(((size_t)e * nf + f) * NF + t) * dim + r];
                 o[(size_t)dim * NF] = g->face_jacobian[((size_t)e * nf + f) * NF + t] / (jdet[(size_t)e * NN + q] * re.w[0]);
             }
-    std::vector<int32_t> nbrf((size_t)ne * nf);
-    for (size_t i = 0; i < nbrf.size(); i++) {
-        nbrf[i] = g->neighbor_face ? g->neighbor_face[i] : (int32_t)((i % nf) ^ 1);
-        if (nbrf[i] < 0 || nbrf[i] >= 16 || (nbrf[i] & 7) >= nf || ((nbrf[i] >> 3) && dim != 2))
-            return fail("set_geometry: neighbor_face[%lld] = %d is not a (face, orientation) code of this dimension", (long long)i, nbrf[i]);
+    std::vector<int32_t> h_nbr((size_t)ne * nf);
+    CUDA_OK(cudaMemcpy(h_nbr.data(), c->d_nbr, h_nbr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int2> nbr2((size_t)ne * nf);
+    for (size_t i = 0; i < nbr2.size(); i++) {
+        const int32_t code = g->neighbor_face ? g->neighbor_face[i] : (int32_t)((i % nf) ^ 1);
+        if (code < 0 || code >= 16 || (code & 7) >= nf || ((code >> 3) && dim != 2))
+            return fail("set_geometry: neighbor_face[%lld] = %d is not a (face, orientation) code of this dimension", (long long)i, code);
+        nbr2[i] = make_int2(h_nbr[i], code);
     }
     std::vector<double> bgeo((size_t)c->n_bfaces * NG * (dim + 1)), bmass((size_t)c->n_bfaces * NF);
     for (int64_t b = 0; b < c->n_bfaces; b++) {
@@ -767,7 +770,7 @@ int warpii_gpu_set_geometry(warpii_gpu_ctx* c, const warpii_gpu_geometry* g) {
     CUDA_OK(cudaStreamSynchronize(c->stream));
     if (upload(&c->d_gnode, gnode.data(), gnode.size()) || upload(&c->d_gsub, gsub.data(), gsub.size()) ||
         upload(&c->d_gface, gface.data(), gface.size()) || upload(&c->d_jdet, jdet.data(), jdet.size()) ||
-        upload(&c->d_nbrf, nbrf.data(), nbrf.size()) || upload(&c->d_bgeo, bgeo.data(), bgeo.size()) ||
+        upload(&c->d_nbr2, nbr2.data(), nbr2.size()) || upload(&c->d_bgeo, bgeo.data(), bgeo.size()) ||
         upload(&c->d_bmass, bmass.data(), bmass.size()))
         return 1;
     if (prepare_general_kernels(c->dim, c->Np))
@@ -775,7 +778,7 @@ int warpii_gpu_set_geometry(warpii_gpu_ctx* c, const warpii_gpu_geometry* g) {
     c->GP.gnode = c->d_gnode;
     c->GP.gsub = c->d_gsub;
     c->GP.gface = c->d_gface;
-    c->GP.nbrf = c->d_nbrf;
+    c->GP.nbr2 = c->d_nbr2;
     c->GP.jdet = c->d_jdet;
     c->GP.bgeo = c->d_bgeo;
     c->GP.bmass = c->d_bmass;
