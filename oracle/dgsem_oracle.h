@@ -15,7 +15,8 @@
 //     themselves against a minimal dealii::Tensor shim.
 //   * GLL quadrature / projection / D / Q / JxW / face lifting / inverse mass:
 //     pinned by the reference's integration tests restated in tests/.
-//   * shock indicator alpha, recommend_dt, every 3D result: PARITY UNPINNED
+//   * shock indicator alpha, recommend_dt, every 3D result, everything on general
+//     (curved / unstructured) geometry, low-storage RK stages: PARITY UNPINNED
 //     (deal.II is not available; no reference fixture exists).
 //
 // All arrays are C-contiguous doubles.  State layout (as deal.II FE_DGQ^nc
