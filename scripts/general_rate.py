@@ -52,5 +52,39 @@ for label, amp in (("general_identity", 0.0), ("general_curved", 0.02)):
     g.upload(0, cases.to_state(ic(box_xyz), gamma))
     run(g, label, g.n_dofs)
     g.close()
+
+# ---- 3D: 48^3 degree-3 elements, Cartesian kernel vs general kernel on the wavy box ------------------------------------
+n3 = int(sys.argv[3]) if len(sys.argv) > 3 else 48
+if n3 > 0:
+    dim, left, right = 3, [0.0, -5.0, -5.0], [10.0, 5.0, 5.0]
+    g = BoxSolver(dim, p, [n3] * 3, left, right, gamma=gamma)
+    g.set_state(cases.to_state(ic(g.node_coords()), gamma))
+    run(g, "cartesian_3d", g.n_dofs)
+    l2g = g.l2g.copy()
+    box_xyz = g.node_coords()
+    g.close()
+    t = box_tables(dim, [n3] * 3, [1, 1, 1], group=elems_per_block(dim, p))
+    assert np.array_equal(t["local_to_global"], l2g)
+    mesh = {"face_neighbor": t["face_neighbor"], "neighbor_face": None, "bf_elem": [], "bf_side": [], "bf_id": []}
+    geo = mapped_metrics(dim, p, mc.wavy(left, right, 0.01)(box_xyz), mesh["face_neighbor"])
+    g = MeshSolver(dim, p, mesh, geo, gamma=gamma)
+    del geo
+    g.upload(0, cases.to_state(ic(box_xyz), gamma))
+    run(g, "general_curved_3d", g.n_dofs)
+    g.close()
+
+# ---- low-storage RK: one fused stage (mode 2) on the C2 box -----------------------------------------------------------
+dim, left, right = 2, [0.0, -5.0], [10.0, 5.0]
+g = BoxSolver(dim, p, [n, n], left, right, gamma=gamma)
+g.set_state(cases.to_state(ic(g.node_coords()), gamma))
+dt = g.recommend_dt(0)
+g.lsrk_stage(2, 1, 0, 0, 0.2 * dt, 0.1 * dt)
+g.stage_timing(True)
+for k in range(10):
+    g.lsrk_stage(2, 3 if k % 2 == 0 else 1, 2, 1 if k % 2 == 0 else 3, 0.02 * dt, 0.01 * dt)
+ms, launches = g.stage_timing(False)
+out["lsrk_stage_cartesian"] = {"stage_ms": ms / launches, "launches": launches, "bytes_per_dof": 32}
+print("lsrk_stage_cartesian", out["lsrk_stage_cartesian"], flush=True)
+g.close()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "general_rate.json"), "w"), indent=1)
