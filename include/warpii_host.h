@@ -32,6 +32,14 @@ int warpii_box_solver_create(int dim, int fe_degree, int n_species, int fields_e
                              const int32_t* nx, const double* left, const double* right,
                              const int32_t* periodic, int n_boundaries, const int32_t* bc_kinds, int rank,
                              int n_ranks, int device, warpii_box_solver** out);
+/* The same solver on a MAPPED box: box connectivity (and slab sharding), element support points pushed through
+ * x' = mapping(x) (NULL = identity), i.e. curved elements on the general-geometry kernels (warpii_gpu_set_geometry).
+ * Every warpii_box_solver_* call works on the result; node_coords returns the mapped points. */
+typedef void (*warpii_mapping_fn)(const double* x, double* x_out, void* user);
+int warpii_mapped_box_solver_create(int dim, int fe_degree, int n_species, int fields_enabled, double gas_gamma,
+                                    const int32_t* nx, const double* left, const double* right, const int32_t* periodic,
+                                    int n_boundaries, const int32_t* bc_kinds, warpii_mapping_fn mapping, void* user, int rank,
+                                    int n_ranks, int device, warpii_box_solver** out);
 int warpii_box_solver_destroy(warpii_box_solver* s);
 /* the operator context underneath, for direct use of the warpii_gpu_* ABI (vector 0 = solution, 1 = f_1) */
 warpii_gpu_ctx* warpii_box_solver_ctx(warpii_box_solver* s);

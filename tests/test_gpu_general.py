@@ -432,3 +432,25 @@ def test_forward_facing_step_example(tmp_path):
     err = rel_l2(got, u)
     assert (err <= 1e-8).all(), err   # a shock run: alpha switches amplify round-off (same bar as the Sod run)
     app.close()
+
+
+def test_mapped_box_solver_of_the_host_layer():
+    """warpii_mapped_box_solver_create: the C++ host layer builds connectivity, support points and metric terms itself
+    (GeneralMesh::mapped_box + build_mapped_metrics) and runs the SSPRK2 loop on curved elements."""
+    dim, p, nx, left, right = 2, 3, [8, 6], [0.0, 0.0], [1.0, 1.2]
+    warp = mc.wavy(left, right, 0.04)
+    bc = [[BC_WALL, BC_OUTFLOW, BC_WALL, BC_WALL]]
+    g = BoxSolver.mapped(dim, p, nx, left, right, lambda x: warp(x[None, :])[0], periodic=[0, 1], gamma=GAMMA, n_boundaries=4,
+                         bc_kinds=bc)
+    mesh, xyz = mc.mapped_box(dim, p, nx, left, right, [0, 1], warp)
+    assert np.abs(g.node_coords() - xyz[g.l2g]).max() <= 1e-14
+    o = GeneralOracle(dim, p, mesh, metrics(dim, p, mesh, xyz), n_boundaries=4, bc_kinds=np.array(bc), gamma=GAMMA, threads=4)
+    prim = mc.periodic_state(GAMMA, left, right, dim)(mc.box_node_coords(dim, p, nx, left, right))
+    mc.add_kinks(prim)
+    u = mc.state_from(prim, GAMMA)
+    g.set_state_global(u)
+    steps = g.solve(0.01)
+    n = o.solve(u, 0.01)
+    assert steps == n and steps > 5
+    assert (rel_l2(g.get_state_global(), u) <= STEPS_TOL).all()
+    g.close()

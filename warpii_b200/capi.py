@@ -230,6 +230,41 @@ class BoxSolver:
         self._bind(h)
 
     @classmethod
+    def mapped(cls, dim, fe_degree, nx, left, right, mapping, periodic=None, gamma=1.6666666666667, n_species=1,
+               fields_enabled=False, n_boundaries=None, bc_kinds=None, rank=0, n_ranks=1, device=0):
+        """The solver on a mapped box (curved elements, general-geometry kernels): mapping(x: ndarray[dim]) -> ndarray[dim]
+        is applied to every Gauss-Lobatto support point (warpii_mapped_box_solver_create)."""
+        L = lib()
+        MAP_FN = C.CFUNCTYPE(None, _dp, _dp, C.c_void_p)
+        L.warpii_mapped_box_solver_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _i32p, _dp, _dp, _i32p, C.c_int,
+                                                      _i32p, MAP_FN, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        periodic = [1] * dim if periodic is None else [int(bool(p)) for p in periodic]
+        if n_boundaries is None:
+            n_boundaries = 0 if all(periodic) else 2 * dim
+
+        def thunk(x, y, _user):
+            out = mapping(np.array([x[d] for d in range(dim)]))
+            for d in range(dim):
+                y[d] = float(out[d])
+
+        self = cls.__new__(cls)
+        self.dim, self.p, self.gamma, self.nsp, self.n_boundaries = dim, fe_degree, gamma, n_species, n_boundaries
+        nx_a, per_a = _arr32(nx), _arr32(periodic)
+        l_a, r_a = np.ascontiguousarray(left, dtype=np.float64), np.ascontiguousarray(right, dtype=np.float64)
+        bc_p = C.cast(None, _i32p)
+        if bc_kinds is not None and n_boundaries > 0:
+            self._bc = _arr32(np.asarray(bc_kinds).reshape(n_species, n_boundaries))
+            bc_p = self._bc.ctypes.data_as(_i32p)
+        cb = MAP_FN(thunk)
+        h = C.c_void_p()
+        _check(L.warpii_mapped_box_solver_create(dim, fe_degree, n_species, int(fields_enabled), gamma, nx_a.ctypes.data_as(_i32p),
+                                                 _ptr(l_a), _ptr(r_a), per_a.ctypes.data_as(_i32p), n_boundaries, bc_p, cb, None,
+                                                 rank, n_ranks, device, C.byref(h)), host=True)
+        self._owned = True
+        self._bind(h)
+        return self
+
+    @classmethod
     def _view(cls, h, dim, fe_degree, gamma, n_species, n_boundaries):
         """A BoxSolver over a handle owned by something else (App.solver)."""
         self = cls.__new__(cls)

@@ -46,7 +46,7 @@ class FiveMomentGpuSolver {
     FiveMomentGpuSolver(GeneralMesh mesh, int n_species, bool fields_enabled, double gas_gamma, double t_end, int n_boundaries,
                         std::vector<SpeciesBC> bcs, int device)
         : t_end_(t_end), fe_degree_(mesh.fe_degree), n_species_(n_species), fields_enabled_(fields_enabled), gas_gamma_(gas_gamma),
-          n_boundaries_(n_boundaries), bcs_(std::move(bcs)), device_(device), rank_(0), n_ranks_(1),
+          n_boundaries_(n_boundaries), bcs_(std::move(bcs)), device_(device), rank_(mesh.rank), n_ranks_(mesh.n_ranks),
           tables_(unit_box(mesh.dim), 0, 1, 1), element_(mesh.fe_degree), general_(std::make_unique<GeneralMesh>(std::move(mesh))) {
         nc_ = 5 * n_species + (fields_enabled ? 8 : 0);
         nn_ = 1;
@@ -63,7 +63,7 @@ class FiveMomentGpuSolver {
         if (general_) {
             mesh.dim = general_->dim;
             mesh.n_elems = general_->n_elems;
-            mesh.n_ghost_faces = 0;
+            mesh.n_ghost_faces = general_->n_ghost_faces;
             mesh.n_boundary_faces = (int64_t)general_->bf_elem.size();
             mesh.face_neighbor = general_->face_neighbor.data();
             mesh.boundary_face_elem = general_->bf_elem.data();
@@ -205,9 +205,13 @@ class FiveMomentGpuSolver {
 
     // One process per GPU: hand the halo lists of this rank's slab and the communicator id to the context
     void attach_comm(const char id[WARPII_GPU_NCCL_ID_BYTES]) {
-        if (general_) throw std::runtime_error("attach_comm: meshes from an extension run on one GPU (the reference's triangulation is serial too)");
         warpii_gpu_halo halo;
-        tables_.fill(halo);
+        if (general_) {
+            if (general_->n_ranks <= 1) throw std::runtime_error("attach_comm: this mesh is not sharded (extension grids run on one GPU)");
+            general_->fill(halo);
+        } else {
+            tables_.fill(halo);
+        }
         check(warpii_gpu_attach_comm(ctx_->get(), id, rank_, n_ranks_, &halo));
     }
 

@@ -78,6 +78,21 @@ struct GeneralMesh {
     std::vector<int32_t> neighbor_face;   // [n_elems][2*dim]; empty = opposite face, same order
     std::vector<int32_t> bf_elem, bf_side, bf_id;
     std::vector<double> xyz;              // [n_elems][NN][dim]
+    // element-sharded mapped boxes only (empty / zero otherwise): ghost trace slots and the halo lists of this rank
+    int rank = 0, n_ranks = 1;
+    int64_t n_ghost_faces = 0, n_interface = 0;
+    std::vector<int64_t> local_to_global, send_offset, recv_offset;
+    std::vector<int32_t> peer_rank, send_elem, send_side;
+    void fill(warpii_gpu_halo& hl) const {
+        hl = warpii_gpu_halo{};
+        hl.n_peers = (int32_t)peer_rank.size();
+        hl.peer_rank = peer_rank.data();
+        hl.send_offset = send_offset.data();
+        hl.send_elem = send_elem.data();
+        hl.send_side = send_side.data();
+        hl.recv_offset = recv_offset.data();
+        hl.n_interface_elems = n_interface;
+    }
 
     // connectivity of a Triangulation2D + bilinear support points
     static GeneralMesh from_triangulation(const Triangulation2D& tria, int fe_degree) {
@@ -136,11 +151,25 @@ struct GeneralMesh {
         return m;
     }
 
-    // the connectivity of a box (one rank), support points pushed through x' = mapping(x): curved elements
+    // the connectivity of a box (this rank's slab of it), support points pushed through x' = mapping(x): curved elements.
+    // On a sharded run every rank evaluates the normals of its interface faces from its own element; the two sides agree
+    // to round-off (they are functions of the shared face nodes), so the run conserves to round-off like a single-GPU
+    // one, without being bit-identical to it.
     static GeneralMesh mapped_box(const BoxDescription& box, int fe_degree, int elems_per_block,
-                                  const std::function<void(const double* x, double* x_out)>& mapping) {
+                                  const std::function<void(const double* x, double* x_out)>& mapping, int rank = 0,
+                                  int n_ranks = 1) {
         GeneralMesh m;
-        const BoxMeshTables t(box, 0, 1, elems_per_block);
+        const BoxMeshTables t(box, rank, n_ranks, elems_per_block);
+        m.rank = rank;
+        m.n_ranks = n_ranks;
+        m.n_ghost_faces = t.n_ghost_faces();
+        m.n_interface = t.n_interface();
+        m.local_to_global = t.local_to_global();
+        m.peer_rank = t.peer_rank();
+        m.send_offset = t.send_offset();
+        m.recv_offset = t.recv_offset();
+        m.send_elem = t.send_elem();
+        m.send_side = t.send_side();
         m.dim = box.dim;
         m.fe_degree = fe_degree;
         m.n_elems = t.n_local();

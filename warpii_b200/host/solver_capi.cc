@@ -81,6 +81,45 @@ int warpii_box_solver_create(int dim, int fe_degree, int n_species, int fields_e
     })
 }
 
+int warpii_mapped_box_solver_create(int dim, int fe_degree, int n_species, int fields_enabled, double gas_gamma, const int32_t* nx,
+                                    const double* left, const double* right, const int32_t* periodic, int n_boundaries,
+                                    const int32_t* bc_kinds, warpii_mapping_fn mapping, void* user, int rank, int n_ranks,
+                                    int device, warpii_box_solver** out) {
+    GUARD({
+        if (!out || !nx || !left || !right) throw std::invalid_argument("warpii_mapped_box_solver_create: null argument");
+        if (dim < 1 || dim > 3) throw std::invalid_argument("n_dims must be 1, 2, or 3");
+        BoxDescription box;
+        box.dim = dim;
+        for (int d = 0; d < dim; d++) {
+            box.nx[d] = nx[d];
+            box.left[d] = left[d];
+            box.right[d] = right[d];
+            box.periodic[d] = periodic ? periodic[d] != 0 : true;
+        }
+        std::vector<SpeciesBC> bcs(n_species);
+        for (int sp = 0; sp < n_species; sp++) {
+            bcs[sp].kind.assign(n_boundaries, WARPII_BC_WALL);
+            bcs[sp].inflow.assign(n_boundaries, std::array<double, 5>{{0, 0, 0, 0, 0}});
+            for (int b = 0; b < n_boundaries && bc_kinds; b++) bcs[sp].kind[b] = bc_kinds[sp * n_boundaries + b];
+        }
+        std::function<void(const double*, double*)> map_fn;
+        if (mapping) map_fn = [=](const double* x, double* y) { mapping(x, y, user); };
+        GeneralMesh mesh = GeneralMesh::mapped_box(box, fe_degree, warpii_gpu_elems_per_block(dim, fe_degree), map_fn, rank, n_ranks);
+        auto* s = new warpii_box_solver();
+        try {
+            s->solver = std::make_shared<FiveMomentGpuSolver>(std::move(mesh), n_species, fields_enabled != 0, gas_gamma, 0.0,
+                                                             n_boundaries, bcs, device);
+            s->solver->reinit();
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        s->rank = rank;
+        s->n_ranks = n_ranks;
+        *out = s;
+    })
+}
+
 int warpii_box_solver_destroy(warpii_box_solver* s) {
     delete s;
     return 0;
@@ -88,15 +127,20 @@ int warpii_box_solver_destroy(warpii_box_solver* s) {
 
 warpii_gpu_ctx* warpii_box_solver_ctx(warpii_box_solver* s) { return s ? s->solver->context()->get() : nullptr; }
 int64_t warpii_box_solver_n_local_elems(const warpii_box_solver* s) { return s->solver->n_local_elems(); }
-int64_t warpii_box_solver_n_interface_elems(const warpii_box_solver* s) { return s->solver->tables().n_interface(); }
-int64_t warpii_box_solver_n_ghost_faces(const warpii_box_solver* s) { return s->solver->tables().n_ghost_faces(); }
+int64_t warpii_box_solver_n_interface_elems(const warpii_box_solver* s) {
+    return s->solver->general_geometry() ? s->solver->general_mesh()->n_interface : s->solver->tables().n_interface();
+}
+int64_t warpii_box_solver_n_ghost_faces(const warpii_box_solver* s) {
+    return s->solver->general_geometry() ? s->solver->general_mesh()->n_ghost_faces : s->solver->tables().n_ghost_faces();
+}
 int warpii_box_solver_n_components(const warpii_box_solver* s) { return s->solver->n_components(); }
 int warpii_box_solver_nodes_per_elem(const warpii_box_solver* s) { return s->solver->nodes_per_elem(); }
 
 int warpii_box_solver_local_to_global(const warpii_box_solver* s, int64_t* out) {
     GUARD({
-        if (s->solver->general_geometry()) {   // an extension's cells keep their order
-            for (int64_t i = 0; i < s->solver->n_local_elems(); i++) out[i] = i;
+        if (s->solver->general_geometry()) {   // an extension's cells keep their order; a mapped box has its slab's numbering
+            const auto& l2g = s->solver->general_mesh()->local_to_global;
+            for (int64_t i = 0; i < s->solver->n_local_elems(); i++) out[i] = l2g.empty() ? i : l2g[i];
             return 0;
         }
         const auto& v = s->solver->tables().local_to_global();
@@ -148,11 +192,7 @@ int warpii_box_solver_boundary_points(const warpii_box_solver* s, double* xyz, i
 }
 
 int warpii_box_solver_attach_comm(warpii_box_solver* s, const char id[WARPII_GPU_NCCL_ID_BYTES]) {
-    GUARD({
-        warpii_gpu_halo halo;
-        s->solver->tables().fill(halo);
-        check(warpii_gpu_attach_comm(s->solver->context()->get(), id, s->rank, s->n_ranks, &halo));
-    })
+    GUARD({ s->solver->attach_comm(id); })
 }
 
 int warpii_box_solver_solve(warpii_box_solver* s, double t_end, double fixed_dt, double callback_interval, warpii_callback_fn cb,
