@@ -178,6 +178,14 @@ int warpii_gpu_max_transport_speed(warpii_gpu_ctx* ctx, int vec, double* vmax_ou
 /* One SSPRK2 step (replaces SSPRK2Integrator::evolve_one_time_step, rk.h:97-106): two stages, the second with
  * the fused CFL reduction. */
 int warpii_gpu_ssprk2_step(warpii_gpu_ctx* ctx, int solution, int f1, double dt, double t);
+/* The same step for a state that lives in HOST memory (pinned, device layout): host_in -> HBM -> two stages -> host_out,
+ * with the transfers and the stages overlapped slab by slab on three streams (upload, compute, download; PCIe is full
+ * duplex and the stage kernels take element ranges), instead of upload, step, download one after the other.  dt comes from
+ * the caller: warpii_gpu_recommend_dt for the first step, then *next_dt_out of the previous call (the fused CFL reduction of
+ * the second stage, i.e. recommend_dt of the state just returned).  host_out may be host_in.  n_slabs = 0 picks 16.  Bit-identical
+ * to upload + warpii_gpu_ssprk2_step + download.  Contexts with boundary faces or a communicator run that plain sequence. */
+int warpii_gpu_host_ssprk2_step(warpii_gpu_ctx* ctx, int solution, int f1, const double* host_in, double* host_out, double dt,
+                                double t, double* next_dt_out, int n_slabs);
 /* Time loop resident on the device side of the ABI: repeats {dt = min(recommend_dt, t_stop - t); ssprk2} until
  * t >= t_stop - 1e-12 (the inner loop of advance(), timestepper.cc:34-42).  fixed_dt > 0 overrides recommend_dt.
  * max_steps > 0 bounds the number of steps.  *t_inout is advanced; *steps_out receives the step count. */

@@ -414,3 +414,42 @@ def test_rhs_with_active_subcell_fv_blend(dim, p, nx):
     err = cases.rel_l2_per_component(g.get_state_global(), u)
     assert (err < 1e-9).all(), err       # the logistic blend amplifies last-bit differences of the modal energies
     g.close()
+
+
+@pytest.mark.parametrize("dim,p,nx,slabs", [(2, 3, [32, 24], 0), (2, 3, [32, 24], 5), (3, 2, [6, 5, 7], 3), (1, 4, [40], 7), (2, 2, [4, 4], 16)])
+def test_streamed_host_step_is_the_plain_step_bit_for_bit(dim, p, nx, slabs):
+    """warpii_gpu_host_ssprk2_step (upload, stages and download overlapped slab by slab) == upload + ssprk2_step + download."""
+    left, right = [0.0, -5.0, -5.0][:dim], [10.0, 5.0, 5.0][:dim]
+    o, g = make_pair(dim, p, nx, left, right, gamma=1.4)
+    u = o.project(cases.isentropic_vortex(1.4) if dim > 1 else cases.sine_wave())[g.l2g].copy()
+    g.upload(0, u)
+    dt = g.recommend_dt(0)
+    want, dts = u.copy(), []
+    for k in range(3):
+        g.upload(0, want)
+        g.ssprk2_step(dt if k == 0 else dts[-1], 0.0)
+        want = g.download(0)
+        dts.append(g.recommend_dt(0))
+    host = u.copy()
+    got_dts, d = [], dt
+    for k in range(3):
+        d = g.host_step(host, host, d, 0.0, n_slabs=slabs)
+        got_dts.append(d)
+    assert np.array_equal(host, want)
+    assert got_dts == dts
+    g.close()
+
+
+def test_streamed_host_step_falls_back_with_boundaries():
+    bc = [[BC_WALL, BC_OUTFLOW, BC_WALL, BC_WALL]]
+    o, g = make_pair(2, 3, [10, 8], [0.0, -5.0], [10.0, 5.0], periodic=[0, 0], gamma=1.4, bc=bc)
+    u = o.project(cases.isentropic_vortex(1.4))[g.l2g].copy()
+    g.upload(0, u)
+    dt = g.recommend_dt(0)
+    g.ssprk2_step(dt, 0.0)
+    want, want_dt = g.download(0), g.recommend_dt(0)
+    host = u.copy()
+    out = np.zeros_like(host)
+    got_dt = g.host_step(host, out, dt, 0.0)
+    assert np.array_equal(out, want) and got_dt == want_dt and np.array_equal(host, u)
+    g.close()

@@ -429,6 +429,16 @@ class BoxSolver:
         L.warpii_gpu_lsrk_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
         _check(L.warpii_gpu_lsrk_stage(self.ctx, sol_out, r_out, sol_in, r_in, factor_solution, factor_ai, t))
 
+    def host_step(self, host_in, host_out, dt, t=0.0, solution=0, f1=1, n_slabs=0):
+        """warpii_gpu_host_ssprk2_step: one SSPRK2 step of a state in (pinned) host memory, transfers overlapped with the
+        stages; returns recommend_dt of the new state."""
+        L = lib()
+        L.warpii_gpu_host_ssprk2_step.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double, _dp, C.c_int]
+        assert host_in.dtype == np.float64 and host_out.dtype == np.float64 and host_in.size == self.n_dofs == host_out.size
+        nxt = C.c_double(0)
+        _check(L.warpii_gpu_host_ssprk2_step(self.ctx, solution, f1, _ptr(host_in), _ptr(host_out), dt, t, C.byref(nxt), n_slabs))
+        return nxt.value
+
     def recommend_dt(self, vec=0):
         dt = C.c_double(0)
         _check(lib().warpii_gpu_recommend_dt(self.ctx, vec, C.byref(dt)))

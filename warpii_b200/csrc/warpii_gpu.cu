@@ -90,6 +90,8 @@ int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
 
 }  // namespace
 
+void warpii_gpu_free_slab_plan(void* plan);
+
 struct warpii_gpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
@@ -133,6 +135,11 @@ struct warpii_gpu_ctx {
     double *d_gnode = nullptr, *d_gsub = nullptr, *d_gface = nullptr, *d_jdet = nullptr, *d_bgeo = nullptr, *d_bmass = nullptr;
     int2* d_nbr2 = nullptr;
     std::vector<int32_t> h_bf_elem, h_bf_side;
+    // streamed host step (warpii_gpu_host_ssprk2_step)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> slab_events;
+    void* slab_plan = nullptr;
+    int slab_plan_slabs = -1;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, n_ranks = 1;
@@ -527,6 +534,10 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     cudaFree(c->d_clock);
     cudaFree(c->d_probe);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->slab_events) cudaEventDestroy(e);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    warpii_gpu_free_slab_plan(c->slab_plan);
     if (c->ev_pack) cudaEventDestroy(c->ev_pack);
     if (c->ev_recv) cudaEventDestroy(c->ev_recv);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -876,6 +887,149 @@ int warpii_gpu_ssprk2_step(warpii_gpu_ctx* c, int solution, int f1, double dt, d
     if (warpii_gpu_forward_euler_step_ex(c, f1, solution, dt, t, 1.0, 0.0, 0)) return 1;
     return warpii_gpu_forward_euler_step_ex(c, solution, f1, dt, t + dt, 0.5, 0.5, WARPII_FUSE_CFL);
 }
+
+}  // extern "C" (the streamed host step needs helpers with C++ linkage)
+
+// ---- SSPRK2 step for a state that lives in HOST memory: copies and compute overlapped slab by slab ---------------------------
+// The adapter of INTEGRATION.md keeps FiveMSolutionVec on the device; a caller that cannot (post-processing on the host every
+// step, state larger than HBM) pays two PCIe transfers of the state per step, ten times the compute.  They are independent
+// directions of a full-duplex link and the stage kernels take element ranges, so the step is cut into slabs of consecutive
+// elements: slab k is uploaded on one stream; first-stage launches follow as soon as the slabs holding their face neighbours
+// have arrived, second-stage launches as soon as the first stage of their neighbours' slabs has been launched (one in-order
+// compute stream, so "launched" implies "ordered before"), and each finished slab returns on a third stream while later slabs
+// are still arriving.  Same kernels, same operands: the result is bit-identical to upload + warpii_gpu_ssprk2_step + download.
+namespace {
+struct SlabPlan {
+    int n = 0;
+    std::vector<int64_t> begin;              // [n+1] element ranges, multiples of the patch size
+    std::vector<std::vector<int>> deps;      // slabs holding face neighbours of slab k (k included)
+};
+
+int build_slab_plan(warpii_gpu_ctx* c, int n_slabs, SlabPlan& plan) {
+    const int nf = 2 * c->dim;
+    const int G = elems_per_block(c->dim, c->Np);
+    const int64_t n_patches = (c->n_elems + G - 1) / G;
+    int S = n_slabs > 0 ? n_slabs : 16;
+    if (S > n_patches) S = (int)(n_patches > 0 ? n_patches : 1);
+    plan.n = S;
+    plan.begin.assign(S + 1, 0);
+    for (int k = 0; k <= S; k++) plan.begin[k] = std::min<int64_t>(c->n_elems, ((n_patches * k) / S) * G);
+    plan.begin[S] = c->n_elems;
+    std::vector<int32_t> nbr((size_t)c->n_elems * nf);
+    CUDA_OK(cudaMemcpy(nbr.data(), c->d_nbr, nbr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    auto slab_of = [&](int64_t e) { return (int)(std::upper_bound(plan.begin.begin(), plan.begin.end(), e) - plan.begin.begin()) - 1; };
+    plan.deps.assign(S, {});
+    for (int k = 0; k < S; k++) {
+        std::vector<char> seen(S, 0);
+        seen[k] = 1;
+        for (int64_t e = plan.begin[k]; e < plan.begin[k + 1]; e++)
+            for (int f = 0; f < nf; f++) {
+                const int32_t v = nbr[(size_t)e * nf + f];
+                if (v >= 0 && v < c->n_elems) seen[slab_of(v)] = 1;
+            }
+        for (int j = 0; j < S; j++)
+            if (seen[j]) plan.deps[k].push_back(j);
+    }
+    return 0;
+}
+}  // namespace
+
+void warpii_gpu_free_slab_plan(void* plan) { delete (SlabPlan*)plan; }
+
+extern "C" int warpii_gpu_host_ssprk2_step(warpii_gpu_ctx* c, int solution, int f1, const double* host_in, double* host_out,
+                                           double dt, double t, double* next_dt_out, int n_slabs) {
+    if (check_vec(c, solution, "host_ssprk2_step") || check_vec(c, f1, "host_ssprk2_step")) return 1;
+    if (solution == f1) return fail("host_ssprk2_step: solution and f1 must be different vectors");
+    if (!host_in || !host_out) return fail("host_ssprk2_step: null host pointer");
+    if (!(dt > 0.0)) return fail("host_ssprk2_step: dt must be positive (take it from warpii_gpu_recommend_dt or from the previous call)");
+    CUDA_OK(cudaSetDevice(c->device));
+    const size_t per_elem = (size_t)c->nc * c->NN;
+    const bool streamed = c->n_bfaces == 0 && !c->comm && c->n_elems > 0;
+    if (!streamed) {
+        // boundary faces / sharded runs: plain sequence (the boundary kernel and the halo exchange work on the whole vector)
+        CUDA_OK(cudaMemcpyAsync(c->vec[solution], host_in, (size_t)c->n_dofs * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c->vmax_valid[solution] = 0;
+        if (warpii_gpu_ssprk2_step(c, solution, f1, dt, t)) return 1;
+        CUDA_OK(cudaMemcpyAsync(host_out, c->vec[solution], (size_t)c->n_dofs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        if (!c->h2d_stream) {
+            CUDA_OK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+            CUDA_OK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        }
+        if (c->slab_plan_slabs != n_slabs || !c->slab_plan) {
+            auto* plan = new SlabPlan();
+            if (build_slab_plan(c, n_slabs, *plan)) { delete plan; return 1; }
+            delete (SlabPlan*)c->slab_plan;
+            c->slab_plan = plan;
+            c->slab_plan_slabs = n_slabs;
+        }
+        const SlabPlan& plan = *(const SlabPlan*)c->slab_plan;
+        const int S = plan.n;
+        while ((int)c->slab_events.size() < 2 * S + 1) {
+            cudaEvent_t e;
+            CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->slab_events.push_back(e);
+        }
+        cudaEvent_t* up_done = c->slab_events.data();
+        cudaEvent_t* s2_done = c->slab_events.data() + S;
+        cudaEvent_t start = c->slab_events[2 * S];
+        // everything queued earlier on the main stream (previous steps, uploads) comes first
+        CUDA_OK(cudaMemsetAsync(c->d_vmax + solution, 0, sizeof(unsigned long long), c->stream));
+        CUDA_OK(cudaEventRecord(start, c->stream));
+        CUDA_OK(cudaStreamWaitEvent(c->h2d_stream, start, 0));
+        CUDA_OK(cudaStreamWaitEvent(c->d2h_stream, start, 0));
+        StageParams P1 = stage_params(c, f1, solution, dt, 1.0, 0.0, 0, false);        // rk.h:102-103
+        StageParams P2 = stage_params(c, solution, f1, dt, 0.5, 0.5, 0, true);         // rk.h:104-105, fused CFL
+        std::vector<char> uploaded(S, 0), s1(S, 0), s2(S, 0);
+        auto ready = [&](int k, const std::vector<char>& have) {
+            for (int j : plan.deps[k]) if (!have[j]) return false;
+            return true;
+        };
+        // Upload order: the last slab first, then 0, 1, 2, ...  On a periodic mesh slab 0 needs slab S-1; sent in plain order,
+        // the first and the last slabs could not start before the whole state had arrived.
+        for (int step = 0; step < S; step++) {
+            const int k = (S >= 3) ? (step == 0 ? S - 1 : step - 1) : step;
+            const size_t off = (size_t)plan.begin[k] * per_elem, cnt = (size_t)(plan.begin[k + 1] - plan.begin[k]) * per_elem;
+            CUDA_OK(cudaMemcpyAsync(c->vec[solution] + off, host_in + off, cnt * sizeof(double), cudaMemcpyHostToDevice, c->h2d_stream));
+            CUDA_OK(cudaEventRecord(up_done[k], c->h2d_stream));
+            uploaded[k] = 1;
+            bool waited = false;
+            for (int j = 0; j < S; j++) {
+                if (s1[j] || !ready(j, uploaded)) continue;
+                if (!waited) { CUDA_OK(cudaStreamWaitEvent(c->stream, up_done[k], 0)); waited = true; }
+                P1.elem_begin = plan.begin[j];
+                P1.elem_end = plan.begin[j + 1];
+                do_launch_stage(c, P1, c->stream);
+                c->launches++;
+                s1[j] = 1;
+            }
+            for (int j = 0; j < S; j++) {
+                if (s2[j] || !ready(j, s1)) continue;
+                P2.elem_begin = plan.begin[j];
+                P2.elem_end = plan.begin[j + 1];
+                do_launch_stage(c, P2, c->stream);
+                c->launches++;
+                s2[j] = 1;
+                CUDA_OK(cudaEventRecord(s2_done[j], c->stream));
+                CUDA_OK(cudaStreamWaitEvent(c->d2h_stream, s2_done[j], 0));
+                const size_t o2 = (size_t)plan.begin[j] * per_elem, n2 = (size_t)(plan.begin[j + 1] - plan.begin[j]) * per_elem;
+                CUDA_OK(cudaMemcpyAsync(host_out + o2, c->vec[solution] + o2, n2 * sizeof(double), cudaMemcpyDeviceToHost, c->d2h_stream));
+            }
+        }
+        for (int j = 0; j < S; j++)
+            if (!s1[j] || !s2[j]) return fail("host_ssprk2_step: internal scheduling error (slab %d never became ready)", j);
+        CUDA_OK(cudaGetLastError());
+        c->vmax_valid[solution] = 1;
+        c->vmax_valid[f1] = 0;
+        CUDA_OK(cudaStreamSynchronize(c->d2h_stream));
+    }
+    double vmax = 0.0;
+    if (max_speed(c, solution, &vmax)) return 1;   // synchronises the main stream; the slot was filled by the second stage
+    if (next_dt_out) *next_dt_out = 0.5 / (vmax * (c->p + 1) * (c->p + 1));
+    return 0;
+}
+
+extern "C" {
 
 int warpii_gpu_advance_to(warpii_gpu_ctx* c, int solution, int f1, double* t_inout, double t_stop, double fixed_dt,
                           int64_t max_steps, int64_t* steps_out) {
