@@ -86,7 +86,7 @@ int warpii_box_solver_solve(warpii_box_solver* s, double t_end, double fixed_dt,
 int warpii_box_solver_step(warpii_box_solver* s, double dt, double t);
 int warpii_box_solver_recommend_dt(warpii_box_solver* s, double* dt_out);
 /* LowStorageRungeKuttaIntegrator(scheme).perform_time_step on the solver's solution vector (rk.h:10-77);
- * scheme: 0 = stage_3_order_3, 1 = stage_5_order_4 (2, 3: ExcNotImplemented, see gpu_operator.hpp).
+ * scheme: 0 = stage_3_order_3, 1 = stage_5_order_4, 2 = stage_7_order_4, 3 = stage_9_order_5 (rk.h:10-15).
  * coefficients (may be NULL) receives b[n], a[n-1], c[n] back to back; n_stages_out the stage count. */
 int warpii_box_solver_lsrk_step(warpii_box_solver* s, int scheme, double dt, double t, double* coefficients, int* n_stages_out);
 

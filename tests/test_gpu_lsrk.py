@@ -50,7 +50,7 @@ def test_stage_matches_oracle(dim, p, nx):
     g.close()
 
 
-@pytest.mark.parametrize("scheme", [0, 1])
+@pytest.mark.parametrize("scheme", [0, 1, 2, 3])
 def test_host_integrator_steps(scheme):
     b, a, c = capi.lsrk_coefficients(scheme)
     bc = [[BC_WALL, BC_OUTFLOW, BC_WALL, BC_WALL]]
