@@ -437,6 +437,16 @@ def test_streamed_host_step_is_the_plain_step_bit_for_bit(dim, p, nx, slabs):
         got_dts.append(d)
     assert np.array_equal(host, want)
     assert got_dts == dts
+    # pinned buffers: the step is captured into a CUDA graph on the first call and replayed afterwards
+    import torch
+    pinned = torch.empty(u.size, dtype=torch.float64).pin_memory().numpy().reshape(u.shape)
+    pinned[...] = u
+    got_dts, d = [], dt
+    for k in range(3):
+        d = g.host_step(pinned, pinned, d, 0.0, n_slabs=slabs)
+        got_dts.append(d)
+    assert np.array_equal(pinned, want)
+    assert got_dts == dts
     g.close()
 
 

@@ -140,6 +140,12 @@ struct warpii_gpu_ctx {
     std::vector<cudaEvent_t> slab_events;
     void* slab_plan = nullptr;
     int slab_plan_slabs = -1;
+    // the whole streamed step as a CUDA graph, replayed while the caller keeps passing the same buffers and vectors
+    cudaGraphExec_t host_step_graph = nullptr;
+    const double* hsg_in = nullptr;
+    double* hsg_out = nullptr;
+    int hsg_solution = -1, hsg_f1 = -1, hsg_slabs = -1;
+    double* d_host_dt = nullptr;            // dt of the streamed step (a kernel argument by pointer, so the graph is reusable)
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, n_ranks = 1;
@@ -538,6 +544,8 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     warpii_gpu_free_slab_plan(c->slab_plan);
+    if (c->host_step_graph) cudaGraphExecDestroy(c->host_step_graph);
+    cudaFree(c->d_host_dt);
     if (c->ev_pack) cudaEventDestroy(c->ev_pack);
     if (c->ev_recv) cudaEventDestroy(c->ev_recv);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -619,6 +627,8 @@ int warpii_gpu_device_ptr(warpii_gpu_ctx* c, int vec, void** out) {
 namespace {
 // anything that changes kernel arguments (pointers, flags) makes the captured batch stale
 void drop_batch_graph(warpii_gpu_ctx* c) {
+    if (c->host_step_graph) cudaGraphExecDestroy(c->host_step_graph);
+    c->host_step_graph = nullptr;
     if (c->batch_graph) cudaGraphExecDestroy(c->batch_graph);
     c->batch_graph = nullptr;
     c->batch_graph_solution = c->batch_graph_f1 = -1;
@@ -965,6 +975,27 @@ extern "C" int warpii_gpu_host_ssprk2_step(warpii_gpu_ctx* c, int solution, int 
         }
         const SlabPlan& plan = *(const SlabPlan*)c->slab_plan;
         const int S = plan.n;
+        if (!c->d_host_dt) CUDA_OK(cudaMalloc((void**)&c->d_host_dt, sizeof(double)));
+        c->h_small[24] = dt;
+        CUDA_OK(cudaMemcpyAsync(c->d_host_dt, c->h_small + 24, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        const bool replay = c->use_graphs && c->host_step_graph && c->hsg_in == host_in && c->hsg_out == host_out &&
+                            c->hsg_solution == solution && c->hsg_f1 == f1 && c->hsg_slabs == n_slabs;
+        bool capturing = false;
+        if (replay) {
+            CUDA_OK(cudaGraphLaunch(c->host_step_graph, c->stream));
+            c->launches += 2 * S;
+        } else {
+        if (c->host_step_graph) { cudaGraphExecDestroy(c->host_step_graph); c->host_step_graph = nullptr; }
+        // ~10 API calls per slab cost as much host time as the slab's transfer: capture the step once, replay it afterwards
+        // (pageable host memory cannot be captured: such a call runs eagerly)
+        cudaPointerAttributes attr_in{}, attr_out{};
+        const bool pinned = cudaPointerGetAttributes(&attr_in, host_in) == cudaSuccess && attr_in.type == cudaMemoryTypeHost &&
+                            cudaPointerGetAttributes(&attr_out, host_out) == cudaSuccess && attr_out.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (c->use_graphs && pinned) {
+            CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            capturing = true;
+        }
         while ((int)c->slab_events.size() < 2 * S + 1) {
             cudaEvent_t e;
             CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -980,6 +1011,8 @@ extern "C" int warpii_gpu_host_ssprk2_step(warpii_gpu_ctx* c, int solution, int 
         CUDA_OK(cudaStreamWaitEvent(c->d2h_stream, start, 0));
         StageParams P1 = stage_params(c, f1, solution, dt, 1.0, 0.0, 0, false);        // rk.h:102-103
         StageParams P2 = stage_params(c, solution, f1, dt, 0.5, 0.5, 0, true);         // rk.h:104-105, fused CFL
+        P1.dt_dev = c->d_host_dt;
+        P2.dt_dev = c->d_host_dt;
         std::vector<char> uploaded(S, 0), s1(S, 0), s2(S, 0);
         auto ready = [&](int k, const std::vector<char>& have) {
             for (int j : plan.deps[k]) if (!have[j]) return false;
@@ -1016,12 +1049,37 @@ extern "C" int warpii_gpu_host_ssprk2_step(warpii_gpu_ctx* c, int solution, int 
                 CUDA_OK(cudaMemcpyAsync(host_out + o2, c->vec[solution] + o2, n2 * sizeof(double), cudaMemcpyDeviceToHost, c->d2h_stream));
             }
         }
-        for (int j = 0; j < S; j++)
-            if (!s1[j] || !s2[j]) return fail("host_ssprk2_step: internal scheduling error (slab %d never became ready)", j);
+        bool scheduled = true;
+        for (int j = 0; j < S; j++) scheduled = scheduled && s1[j] && s2[j];
+        if (capturing) {
+            // join the transfer streams back into the capturing stream
+            cudaEvent_t join_up = up_done[0], join_down = s2_done[0];   // (both already consumed by their waiters)
+            CUDA_OK(cudaEventRecord(join_up, c->h2d_stream));
+            CUDA_OK(cudaEventRecord(join_down, c->d2h_stream));
+            CUDA_OK(cudaStreamWaitEvent(c->stream, join_up, 0));
+            CUDA_OK(cudaStreamWaitEvent(c->stream, join_down, 0));
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            if (ce != cudaSuccess || !scheduled) {
+                if (graph) cudaGraphDestroy(graph);
+                return fail("host_ssprk2_step: %s", scheduled ? cudaGetErrorString(ce) : "internal scheduling error");
+            }
+            const cudaError_t ci = cudaGraphInstantiate(&c->host_step_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ci != cudaSuccess) {
+                c->host_step_graph = nullptr;
+                return fail("host_ssprk2_step: graph instantiation failed: %s", cudaGetErrorString(ci));
+            }
+            c->hsg_in = host_in; c->hsg_out = host_out; c->hsg_solution = solution; c->hsg_f1 = f1; c->hsg_slabs = n_slabs;
+            CUDA_OK(cudaGraphLaunch(c->host_step_graph, c->stream));   // the captured work has not run yet
+        } else if (!scheduled) {
+            return fail("host_ssprk2_step: internal scheduling error (a slab never became ready)");
+        }
+        }   // !replay
         CUDA_OK(cudaGetLastError());
         c->vmax_valid[solution] = 1;
         c->vmax_valid[f1] = 0;
-        CUDA_OK(cudaStreamSynchronize(c->d2h_stream));
+        if (!replay && !capturing) CUDA_OK(cudaStreamSynchronize(c->d2h_stream));   // (a graph ends on the main stream)
     }
     double vmax = 0.0;
     if (max_speed(c, solution, &vmax)) return 1;   // synchronises the main stream; the slot was filled by the second stage
