@@ -277,16 +277,12 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
             for (int r = 0; r < GEO::HROUNDS; r++) {
                 const int p = r * NN + j;
                 if (GEO::HTASKS % NN == 0 || p < GEO::HTASKS) {
-                    const int d = p / (NN / 2);
-                    int qq = p - d * (NN / 2);
-                    int n0 = 0, mul = 1;
-#pragma unroll
-                    for (int a = 0; a < DIM; a++) {
-                        const int ext = (a == d) ? NP / 2 : NP;
-                        n0 += (qq % ext) * mul;
-                        qq /= ext;
-                        mul *= NP;
-                    }
+                    const bool hi = j >= NN / 2;
+                    const int qq = hi ? j - NN / 2 : j;
+                    const int d = 2 * r + (hi ? 1 : 0);
+                    constexpr int DMAX = DIM - 1;
+                    const int n0 = hi ? half_class_node<DIM, NP>((2 * r + 1 < DIM) ? 2 * r + 1 : DMAX, qq)
+                                      : half_class_node<DIM, NP>((2 * r < DIM) ? 2 * r : DMAX, qq);
                     const int st = stride_of(NP, d);
                     const int na = le * NN + n0, nb = na + (NP / 2) * st;
                     const Prim a = load_prim_ec<NP>(sP, na);

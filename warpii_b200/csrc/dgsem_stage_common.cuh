@@ -132,6 +132,22 @@ __device__ __forceinline__ void group_sync(const int tid) {
     else asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / GROUP), "n"(GROUP) : "memory");
 }
 
+// Half-class pair tasks of an even NP: task q (0 <= q < NN/2) of direction d is the node whose coordinate along d is below
+// NP/2, numbered with d's extent halved.  Called with d known at compile time (the extents are then literals: no integer
+// division at run time, which is what the generic decode cost: ~50 instructions per node).
+template <int DIM, int NP>
+__device__ __forceinline__ int half_class_node(const int d, int q) {
+    int n = 0, mul = 1;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+        const int ext = (a == d) ? NP / 2 : NP;
+        n += (q % ext) * mul;
+        q /= ext;
+        mul *= NP;
+    }
+    return n;
+}
+
 // first node of pencil pe (= tangential index) in direction d
 template <int DIM, int NP>
 __device__ __forceinline__ int pencil_first_node(const int d, const int pe) {

@@ -188,16 +188,14 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
             for (int r = 0; r < GEO::HROUNDS; r++) {
                 const int p = r * NN + j;
                 if (GEO::HTASKS % NN == 0 || p < GEO::HTASKS) {
-                    const int d = p / (NN / 2);
-                    int q = p - d * (NN / 2);
-                    int n = 0, mul = 1;   // node whose coordinate along d is below NP/2
-#pragma unroll
-                    for (int a = 0; a < DIM; a++) {
-                        const int ext = (a == d) ? NP / 2 : NP;
-                        n += (q % ext) * mul;
-                        q /= ext;
-                        mul *= NP;
-                    }
+                    // NN/2 tasks per direction: round r covers direction 2r (threads j < NN/2) and 2r+1 (the others), so
+                    // both candidate decodes have compile-time extents
+                    const bool hi = j >= NN / 2;
+                    const int q = hi ? j - NN / 2 : j;
+                    const int d = 2 * r + (hi ? 1 : 0);
+                    constexpr int DMAX = DIM - 1;
+                    const int n = hi ? half_class_node<DIM, NP>((2 * r + 1 < DIM) ? 2 * r + 1 : DMAX, q)
+                                     : half_class_node<DIM, NP>((2 * r < DIM) ? 2 * r : DMAX, q);
                     const int st = stride_of(NP, d);
                     const Prim a = load_prim_ec<NP>(sP, le * NN + n);
                     const Prim b = load_prim_ec<NP>(sP, le * NN + n + (NP / 2) * st);
