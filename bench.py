@@ -69,6 +69,32 @@ def measured_traffic(workload):
         return None
 
 
+def measured_fp64_instr(workload):
+    """FP64 warp instructions of one stage-kernel launch from the committed SASS histogram of this workload, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return int(json.load(f)[workload]["fp64_warp_instr"])
+    except Exception:
+        return None
+
+
+def fp64_figure(workload, avg_stage_ms, device):
+    """The co-bound the HBM roofline does not show: FP64 warp instructions of the dominant kernel per second against the
+    FMA-chain rate of this GPU measured in the same run (measure the FP64 peak before quoting a %)."""
+    import ctypes as C
+    from warpii_b200 import lib
+    peak = C.c_double(0)
+    if lib().warpii_gpu_measure_fp64_peak(device, C.byref(peak)) != 0 or peak.value <= 0:
+        return None
+    out = {"peak_tflops": 2.0 * peak.value / 1e12, "peak_warp_instr_per_s": peak.value / 32.0,
+           "peak_source": "measured in this run: 8 independent FMA chains per thread, 8 x 256 threads per SM"}
+    n = measured_fp64_instr(workload)
+    if n is not None and avg_stage_ms > 0:
+        rate = n / (avg_stage_ms * 1e-3)
+        out.update({"fp64_warp_instr_per_launch": n, "achieved_warp_instr_per_s": rate, "frac": rate / (peak.value / 32.0)})
+    return out
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -412,6 +438,17 @@ def run_ours(args, w):
                          "algorithmic_bytes_per_launch": bytes_per_update * n_dofs_local,
                          "algorithmic_bytes_per_dof_update": bytes_per_update},
         }
+        if world == 1:
+            fp = fp64_figure(args.workload, avg_stage_ms, local_rank)
+            if fp is not None:
+                if "frac" in fp:   # the HBM-roofline fraction this kernel would reach with the FP64 pipe 100 % busy
+                    t_fp64_ms = 1e3 * fp["fp64_warp_instr_per_launch"] / fp["peak_warp_instr_per_s"]
+                    t_hbm_ms = 1e3 * bytes_per_update * n_dofs_local / (peak * 1e9)
+                    fp["note"] = ("DFMA+DMUL+DADD+DSETP of the captured launch (profiles/*_opcodes.txt) / measured kernel time; "
+                                  "with the FP64 pipe 100 %% busy the launch would take %.3f ms = %.2f of the HBM roofline"
+                                  % (t_fp64_ms, t_hbm_ms / t_fp64_ms))
+                    fp["hbm_frac_at_fp64_peak"] = t_hbm_ms / t_fp64_ms
+                line["fp64"] = fp
         if world == 1 and not args.no_cpu_baseline and not w.get("mapping"):
             nthreads = os.cpu_count() or 1
             cb = cpu_run(w, 1, 0, nthreads, budget_s=12.0)

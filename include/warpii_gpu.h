@@ -222,6 +222,9 @@ int warpii_gpu_stage_timing(warpii_gpu_ctx* ctx, int enable, double* ms_total, i
 int warpii_gpu_sm_clock_probes(warpii_gpu_ctx* ctx, double* mhz_out, int max_out, int* n_out);
 /* the CUDA stream (cudaStream_t) all work of this context is issued on */
 int warpii_gpu_stream(warpii_gpu_ctx* ctx, void** stream_out);
+/* Measured FP64 throughput of this GPU's CUDA cores, in fused multiply-adds per second (FMA-chain microbenchmark, all SMs
+ * full): the denominator of the FP64 figure bench.py reports beside the HBM roofline. */
+int warpii_gpu_measure_fp64_peak(int device, double* fma_per_second_out);
 
 /* -- point physics on the device, for known-answer tests ------------------------------------------------
  * For n state pairs (qa[i], qb[i]) of 5 conserved values: the direction-d entropy-conserving flux

@@ -308,6 +308,32 @@ __global__ void sm_clock_probe_kernel(double* out_mhz) {
 void launch_sm_clock_probe(double* out_mhz, cudaStream_t s) { sm_clock_probe_kernel<<<1, 1, 0, s>>>(out_mhz); }
 }  // namespace wgpu
 
+// ---- FP64 peak of the CUDA cores, measured: 8 independent fused-multiply-add chains per thread, all SMs full ----------
+// (the denominator of the FP64 figure bench.py reports next to the HBM roofline; SURVEY.md 8(d) asks for a measured value)
+namespace wgpu {
+constexpr int kFmaChains = 8, kFmaIters = 4096;
+__global__ void __launch_bounds__(256) fp64_fma_chain_kernel(double* sink, double seed) {
+    double a[kFmaChains];
+#pragma unroll
+    for (int k = 0; k < kFmaChains; k++) a[k] = seed + 1e-3 * (threadIdx.x + k);
+    const double m = 1.0 - 1e-9, c = 1e-9;
+#pragma unroll 4
+    for (int it = 0; it < kFmaIters; it++) {
+#pragma unroll
+        for (int k = 0; k < kFmaChains; k++) a[k] = fma(a[k], m, c);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < kFmaChains; k++) sum += a[k];
+    if (sum == 123.456) sink[0] = sum;   // never true: keeps the chains alive
+}
+// returns fused multiply-adds per launch (thread level)
+double launch_fp64_fma_chain(int blocks, double* sink, cudaStream_t s) {
+    fp64_fma_chain_kernel<<<blocks, 256, 0, s>>>(sink, 0.5);
+    return (double)blocks * 256.0 * kFmaChains * kFmaIters;
+}
+}  // namespace wgpu
+
 // ---- point physics on the device, for known-answer tests (the reference's euler_test.cc goldens) -----------------
 namespace wgpu {
 __global__ void point_flux_kernel(int n, const double* qa, const double* qb, int d, double gamma, double* ec,

@@ -1328,6 +1328,41 @@ extern "C" int warpii_gpu_point_fluxes(int device, int n, const double* qa, cons
 }
 
 namespace wgpu {
+double launch_fp64_fma_chain(int blocks, double* sink, cudaStream_t s);
+}
+
+// Measured FP64 throughput of the CUDA cores: fused multiply-adds per second over a launch that fills every SM (best of 5)
+extern "C" int warpii_gpu_measure_fp64_peak(int device, double* fma_per_second_out) {
+    if (!fma_per_second_out) return fail("null argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail("no CUDA device available");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    double* sink = nullptr;
+    if (upload<double>(&sink, nullptr, 1)) return 1;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8 * 4;   // 8 resident blocks of 256 threads per SM, four waves
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CUDA_OK(cudaEventRecord(e0, nullptr));
+        const double fmas = wgpu::launch_fp64_fma_chain(blocks, sink, nullptr);
+        CUDA_OK(cudaEventRecord(e1, nullptr));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms > 0) best = std::max(best, fmas / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *fma_per_second_out = best;
+    return 0;
+}
+
+namespace wgpu {
 void launch_division_check(long long n, unsigned long long seed, int mode, unsigned long long* mismatches, double* first_bad,
                            cudaStream_t s);
 }
