@@ -85,6 +85,10 @@ int warpii_box_solver_solve(warpii_box_solver* s, double t_end, double fixed_dt,
 /* SSPRK2Integrator::evolve_one_time_step / operator.recommend_dt on the solver's own solution vector */
 int warpii_box_solver_step(warpii_box_solver* s, double dt, double t);
 int warpii_box_solver_recommend_dt(warpii_box_solver* s, double* dt_out);
+/* FiveMomentDGSolutionHelper::compute_global_error (dg_solution_helper.cc:50-69): L2 norm of (solution - exact) in one fluid
+ * component of a species, QGauss(fe_degree) quadrature; exact(x, t = 0, q5, user) returns the five exact values at x. */
+int warpii_box_solver_global_error(warpii_box_solver* s, warpii_inflow_fn exact, void* user, int species, int component,
+                                   double* error_out);
 /* LowStorageRungeKuttaIntegrator(scheme).perform_time_step on the solver's solution vector (rk.h:10-77);
  * scheme: 0 = stage_3_order_3, 1 = stage_5_order_4, 2 = stage_7_order_4, 3 = stage_9_order_5 (rk.h:10-15).
  * coefficients (may be NULL) receives b[n], a[n-1], c[n] back to back; n_stages_out the stage count. */

@@ -263,10 +263,37 @@ def test_reference_freestream_1d_convergence():
         o, g = make_pair(1, 2, [nx], [0.0], [1.0], gamma=1.6666666666667)
         g.set_state_global(o.project(cases.sine_wave()))
         g.solve(0.04)
-        errs.append(_l2_error_density(o, g.get_state_global(), lambda x: 1 + 0.6 * np.sin(2 * np.pi * (x - 0.04)), 2))
+        exact = lambda x: 1 + 0.6 * np.sin(2 * np.pi * (x - 0.04))
+        errs.append(_l2_error_density(o, g.get_state_global(), exact, 2))
+        # the product's own compute_global_error (dg_solution_helper.cc:50-69) gives the same number
+        mine = g.global_error(lambda x: [exact(x[0]), 0, 0, 0, 0], component=0)
+        assert abs(mine - errs[-1]) <= 1e-12 * errs[-1]
         g.close()
     assert abs(errs[1]) < 1e-4
     assert abs(errs[0] / errs[1] - 1.5 ** 3) < 1.0
+
+
+def test_global_error_in_2d_against_numpy():
+    o, g = make_pair(2, 3, [6, 5], [0.0, -1.0], [2.0, 1.0], gamma=1.4)
+    u = o.project(cases.isentropic_vortex(1.4))
+    g.set_state_global(u)
+    exact = lambda x: np.array([1.0 + 0.1 * x[0], 0.2, 0.3 * x[1], 0.0, 2.5 + 0.05 * x[0] * x[1]])
+    xq, wq = oracle.gauss(3)
+    x, _ = oracle.gll(4)
+    I = np.array([[np.prod([(xq[q] - x[m]) / (x[i] - x[m]) for m in range(4) if m != i]) for i in range(4)] for q in range(3)])
+    h = [2.0 / 6, 2.0 / 5]
+    for comp in (0, 2, 4):
+        err2 = 0.0
+        for e in range(o.n_elems):
+            ex, ey = e % 6, e // 6
+            ue = u[e, comp].reshape(4, 4)           # [y][x]
+            uq = I @ ue @ I.T                       # [qy][qx]
+            for qy in range(3):
+                for qx in range(3):
+                    pt = np.array([0.0 + (ex + xq[qx]) * h[0], -1.0 + (ey + xq[qy]) * h[1]])
+                    err2 += (uq[qy, qx] - exact(pt)[comp]) ** 2 * wq[qx] * wq[qy] * h[0] * h[1]
+        assert abs(g.global_error(exact, component=comp) - np.sqrt(err2)) <= 1e-12 * np.sqrt(err2)
+    g.close()
 
 
 def test_solver_callbacks_and_step_count():

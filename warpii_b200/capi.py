@@ -390,6 +390,22 @@ class BoxSolver:
                                              None, C.byref(steps)), host=True)
         return steps.value
 
+    def global_error(self, exact, component=0, species=0):
+        """compute_global_error (dg_solution_helper.cc:50-69): exact(x: ndarray[dim]) -> 5 values."""
+        dim = self.dim
+
+        def thunk(x, _t, q5, _user):
+            v = exact(np.array([x[d] for d in range(dim)]))
+            for k in range(5):
+                q5[k] = float(v[k])
+
+        cb = INFLOW_FN(thunk)
+        L = lib()
+        L.warpii_box_solver_global_error.argtypes = [C.c_void_p, INFLOW_FN, C.c_void_p, C.c_int, C.c_int, _dp]
+        out = C.c_double(0)
+        _check(L.warpii_box_solver_global_error(self.h, cb, None, species, component, C.byref(out)), host=True)
+        return out.value
+
     def lsrk_step(self, scheme, dt, t=0.0):
         """LowStorageRungeKuttaIntegrator(scheme).perform_time_step on the solver's solution (host layer); the solution may
         live in another device vector afterwards: read it with get_state()."""

@@ -3,6 +3,7 @@
 // operator; reinit / project_initial_condition / solve keep the reference's meaning.
 #pragma once
 #include <array>
+#include <cmath>
 #include <functional>
 #include <memory>
 #include <vector>
@@ -173,6 +174,50 @@ class FiveMomentGpuSolver {
                 for (int k = 0; k < 5; k++) host_[((size_t)l * nc_ + 5 * species + k) * nn_ + j] = q[k];
             }
         solution_->upload(host_.data());
+    }
+
+    // FiveMomentDGSolutionHelper::compute_global_error (dg_solution_helper.cc:50-69): L2 norm of (solution - f) in one of
+    // the 5 components of a species, by VectorTools::integrate_difference with QGauss<dim>(fe_degree).  A diagnostic that
+    // runs once after a solve (test/input_test.cc:57-62): the state is downloaded and integrated on the host, element by
+    // element in a fixed order.  f(x, out5) returns the 5 exact values at a point.  Box grids (Cartesian JxW).
+    double compute_global_error(const std::function<void(const double* x, double* out5)>& f, unsigned int component, int species = 0) {
+        if (general_) throw std::runtime_error("compute_global_error: box grids only");
+        if (component >= 5) throw std::invalid_argument("compute_global_error: component must be one of the 5 fluid components");
+        const BoxDescription& box = tables_.box();
+        const int dim = box.dim, Np = fe_degree_ + 1, nq = fe_degree_;
+        std::vector<double> xq, wq, I;
+        element_.gauss_rule(nq, xq, wq, I);
+        int NQ = 1;
+        for (int d = 0; d < dim; d++) NQ *= nq;
+        std::vector<double> host((size_t)ctx_->n_dofs());
+        solution_->download(host.data());
+        double jdet = 1.0;
+        for (int d = 0; d < dim; d++) jdet *= tables_.h(d);
+        double err2 = 0.0;
+        for (int64_t l = 0; l < tables_.n_local(); l++) {
+            int idx[3];
+            tables_.elem_multi_index(tables_.local_to_global()[l], idx);
+            const double* ue = &host[((size_t)l * nc_ + 5 * species + component) * nn_];
+            double cell = 0.0;
+            for (int q = 0; q < NQ; q++) {
+                int qi[3] = {0, 0, 0}, t = q;
+                for (int d = 0; d < dim; d++) { qi[d] = t % nq; t /= nq; }
+                double uh = 0.0;
+                for (int j = 0; j < nn_; j++) {
+                    int tt = j;
+                    double phi = 1.0;
+                    for (int d = 0; d < dim; d++) { phi *= I[(size_t)qi[d] * Np + tt % Np]; tt /= Np; }
+                    uh += phi * ue[j];
+                }
+                double x[3] = {0, 0, 0}, w = jdet, exact[5];
+                for (int d = 0; d < dim; d++) { x[d] = box.left[d] + (idx[d] + xq[qi[d]]) * tables_.h(d); w *= wq[qi[d]]; }
+                f(x, exact);
+                const double diff = uh - exact[component];
+                cell += diff * diff * w;
+            }
+            err2 += cell;
+        }
+        return std::sqrt(err2);   // (a sharded run sums err2 over ranks before the root: the caller's reduction)
     }
 
     // dg_solver.cc:23-38.  Without time-dependent inflow the inner loop of advance() runs resident on the device side

@@ -137,6 +137,37 @@ struct ReferenceElement {
                 Ig[q * Np + i] = (double)v;
             }
     }
+
+   public:
+    // QGauss<1>(n) on [0,1] and the values of this element's Lagrange basis there: I[q*Np+i] = l_i(x_q)
+    // (for quadratures other than the two the operator uses, e.g. VectorTools::integrate_difference with QGauss(fe_degree))
+    void gauss_rule(int n, std::vector<double>& xq, std::vector<double>& wq, std::vector<double>& I) const {
+        const ld pi = std::acos((ld)-1);
+        std::vector<ld> g(n), gw(n);
+        for (int i = 0; i < n; i++) {
+            ld xi = -std::cos(pi * (i + 0.75L) / (n + 0.5L));
+            ld P, dP;
+            for (int it = 0; it < 60; it++) {
+                legendre(n, xi, P, dP);
+                const ld dx = P / dP;
+                xi -= dx;
+                if (std::fabs((double)dx) < 1e-20) break;
+            }
+            legendre(n, xi, P, dP);
+            g[i] = (xi + 1) / 2;
+            gw[i] = 1 / ((1 - xi * xi) * dP * dP);
+        }
+        xq.resize(n); wq.resize(n);
+        for (int i = 0; i < n; i++) { xq[i] = (double)g[i]; wq[i] = (double)gw[i]; }
+        I.assign((size_t)n * Np, 0.0);
+        for (int q = 0; q < n; q++)
+            for (int i = 0; i < Np; i++) {
+                ld v = 1;
+                for (int m = 0; m < Np; m++)
+                    if (m != i) v *= (g[q] - (ld)x[m]) / ((ld)x[i] - (ld)x[m]);
+                I[(size_t)q * Np + i] = (double)v;
+            }
+    }
 };
 
 }  // namespace warpii_b200

@@ -216,6 +216,17 @@ int warpii_box_solver_step(warpii_box_solver* s, double dt, double t) {
     })
 }
 
+int warpii_box_solver_global_error(warpii_box_solver* s, warpii_inflow_fn exact, void* user, int species, int component,
+                                   double* error_out) {
+    GUARD({
+        if (!exact || !error_out) throw std::invalid_argument("global_error: null argument");
+        if (species < 0 || species >= s->solver->n_species()) throw std::invalid_argument("global_error: species out of range");
+        if (component < 0) throw std::invalid_argument("global_error: component out of range");
+        *error_out = s->solver->compute_global_error([=](const double* x, double* q5) { exact(x, 0.0, q5, user); },
+                                                     (unsigned)component, species);
+    })
+}
+
 int warpii_box_solver_lsrk_step(warpii_box_solver* s, int scheme, double dt, double t, double* coefficients, int* n_stages_out) {
     GUARD({
         if (scheme < 0 || scheme > 3) throw std::invalid_argument("lsrk_step: scheme must be 0..3");
