@@ -8,7 +8,7 @@
 // (src/grid_generation.cc); this mesh is the uniform 15 x 5 (times RefinementFactor) channel with the step cells removed.
 //
 //   make -C warpii_b200 bin/forward_facing_step
-//   warpii_b200/bin/forward_facing_step examples/five-moment/forward_facing_step.inp
+//   warpii_b200/bin/forward_facing_step examples/five-moment/mach3_step.inp
 #include <cmath>
 #include <limits>
 

@@ -397,9 +397,13 @@ def test_forward_facing_step_example(tmp_path):
     import subprocess
     from warpii_b200 import App
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    text = open(os.path.join(root, "examples", "five-moment", "forward_facing_step.inp")).read()
-    text = text.replace("set t_end = 3.000", "set t_end = 0.01").replace("set n_writeout_frames = 100", "set n_writeout_frames = 1")
-    text = text.replace("set RefinementFactor = 2", "set RefinementFactor = 1")
+    text = open(os.path.join(root, "examples", "five-moment", "mach3_step.inp")).read()
+    import re
+    def setting(txt, key, value):
+        new, n = re.subn(r"set %s\s*=.*" % key, "set %s = %s" % (key, value), txt)
+        assert n == 1, key
+        return new
+    text = setting(setting(setting(text, "t_end", "0.01"), "n_writeout_frames", "1"), "RefinementFactor", "1")
     inp = tmp_path / "ffs.inp"
     inp.write_text(text)
     exe = os.path.join(root, "warpii_b200", "bin", "forward_facing_step")
@@ -412,7 +416,7 @@ def test_forward_facing_step_example(tmp_path):
     verts, cells, bid = ffs_triangulation(1)
     ids = np.array([[bid(0.5 * (verts[c[a]] + verts[c[b]])) for (a, b) in mc._FACE_VERTS] for c in cells], dtype=np.int32)
     # (the array-fed extension of the C API declares no entries of its own)
-    app = App.with_triangulation(text.replace("set RefinementFactor = 1", ""), verts, cells, ids)
+    app = App.with_triangulation(re.sub(r"set RefinementFactor\s*=.*", "", text), verts, cells, ids)
     app.set_device_loop(False)
     app.setup()
     mesh, xyz = mc.quad_mesh(verts, cells, p, bid)
