@@ -25,7 +25,20 @@ constexpr int prim_table_doubles(const int nodes) {
     return (NP % 2 == 0) ? nodes * kPS + 2 * (nodes / (NP * NP) + 1) : nodes * kPS;
 }
 
-template <int DIM, int NP>
+// SHUF: the pair fluxes of 2D p=3 elements are exchanged with warp shuffles instead of a shared-memory table (an element
+// is 16 consecutive lanes, so both endpoints of every pencil pair sit in one warp): 160 B of shared memory per thread less.
+// Measured on C2 (stage kernel): table 0.310 ms; shuffles at 5 blocks/SM (96 registers) 0.301 ms, 6 blocks (80 registers)
+// 0.308, 7 blocks (72) 0.301, 8 blocks (64) 0.329: the freed shared memory would allow 10 blocks, but the extra warps pay
+// for themselves in spills, so the gain is the table traffic alone.
+#ifndef WGPU_SHUFFLE_PAIRS
+#define WGPU_SHUFFLE_PAIRS 1
+#endif
+#ifndef WGPU_SHUFFLE_RESIDENT
+#define WGPU_SHUFFLE_RESIDENT 640
+#endif
+__host__ __device__ constexpr bool shuffle_pairs(int dim, int np) { return WGPU_SHUFFLE_PAIRS && dim == 2 && np == 4; }
+
+template <int DIM, int NP, bool SHUF = false>
 struct Geo {
     static constexpr int NN = ipow_c(NP, DIM);          // nodes per element
     static constexpr int NF = ipow_c(NP, DIM - 1);      // nodes per face = pencils per direction
@@ -46,7 +59,7 @@ struct Geo {
     // threads that synchronise among themselves after the node phase: whole warps holding whole elements
     static constexpr int GROUP = (32 % NN == 0 && NODES % 32 == 0) ? 32 : ((NN % 32 == 0 && NODES / NN <= 15) ? NN : NODES);
     // measured: 2D p=3 gains 6 % from the fifth block per SM despite 56 bytes of spills; 3D p=3 loses 9 %
-    static constexpr int RESIDENT = WGPU_RESIDENT_THREADS > 0 ? WGPU_RESIDENT_THREADS : (DIM <= 2 ? 640 : 512);
+    static constexpr int RESIDENT = SHUF ? WGPU_SHUFFLE_RESIDENT : (WGPU_RESIDENT_THREADS > 0 ? WGPU_RESIDENT_THREADS : (DIM <= 2 ? 640 : 512));
     static constexpr int MIN_BLOCKS = (RESIDENT / THREADS) > 0 ? (RESIDENT / THREADS) : 1;
     // dynamic shared memory, in doubles (every offset even => 16-byte aligned)
     static constexpr int even(int x) { return (x + 1) & ~1; }
@@ -56,7 +69,7 @@ struct Geo {
     static constexpr int OFF_P = OFF_W + 8;                                 // primitive records of the block's nodes
     static constexpr int OFF_A = even(OFF_P + prim_table_doubles<NP>(NODES));                      // [2][NODES] indicator scratch
     static constexpr int OFF_PAIR = OFF_A + 2 * NODES;                      // [5][PLANE] pair fluxes, component planes
-    static constexpr int OFF_FACE = even(OFF_PAIR + 5 * PLANE);             // [5][NSLOT] face-node records, component planes
+    static constexpr int OFF_FACE = even(OFF_PAIR + (SHUF ? 0 : 5 * PLANE)); // [5][NSLOT] face-node records, component planes
     static constexpr int OFF_ALPHA = even(OFF_FACE + 5 * NSLOT);            // [G]
     static constexpr int OFF_RED = even(OFF_ALPHA + G);                     // [32]
     static constexpr int SMEM_DOUBLES = OFF_RED + 32;

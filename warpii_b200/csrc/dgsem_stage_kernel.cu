@@ -27,8 +27,12 @@
 namespace wgpu {
 
 template <int DIM, int NP>
-__global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCKS) stage_kernel(const StageParams P) {
-    using GEO = Geo<DIM, NP>;
+using GeoC = Geo<DIM, NP, shuffle_pairs(DIM, NP)>;
+
+template <int DIM, int NP>
+__global__ void __launch_bounds__(GeoC<DIM, NP>::THREADS, GeoC<DIM, NP>::MIN_BLOCKS) stage_kernel(const StageParams P) {
+    using GEO = GeoC<DIM, NP>;
+    constexpr bool SHUF = shuffle_pairs(DIM, NP);
     constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G, NODES = GEO::NODES, NFACE = GEO::NFACE, NSLOT = GEO::NSLOT;
     constexpr int NFULL = GEO::NFULL, HALF = GEO::HALF, NCL = GEO::NCL, PLANE = GEO::PLANE, GROUP = GEO::GROUP;
 
@@ -119,7 +123,35 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
         // ---- task phase (a), full classes: unordered node pairs of the pencils, symmetric two-point flux, once ------
         // Full classes: this thread's own node is the first endpoint, so only the partner's record is loaded; the five
         // components go to this node's slot of the class (component planes: consecutive lanes, consecutive words).
-        {
+        // SHUF: accS[d][.] collects sum_l D[j_d][l] F#(u_j,u_l) in the order of the gather below (l = j+1, j+2, j+3 mod NP)
+        double accS[SHUF ? DIM : 1][5];
+        if (SHUF) {
+            const int lane = tid & 31;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                const int st = stride_of(NP, d);
+                const int jd = idx[d];
+                const int lp = (jd + 1) & (NP - 1), lm = (jd + NP - 1) & (NP - 1), lh = jd ^ (NP / 2);
+                // own pair (j, j+1): computed here, also needed by the node j+1, which fetches it from this lane
+                const Prim other = load_prim_ec<NP>(sP, tid + (lp - jd) * st);
+                double F[5], ibl;
+                ec_flux_d(d, mine, other, hig, F, ibl);
+                // half pair (j, j+2): both endpoints evaluate it (symmetric bit for bit; a warp instruction costs the same
+                // whether 16 or 32 lanes take part)
+                const Prim oh = load_prim_ec<NP>(sP, tid + (lh - jd) * st);
+                double Fh[5];
+                ec_flux_d(d, mine, oh, hig, Fh, ibl);
+                const double wp = sD[jd * NP + lp], wh = sD[jd * NP + lh], wm = sD[jd * NP + lm], djj = sD[jd * NP + jd];
+                const int src = lane + (lm - jd) * st;   // the lane of node j-1 (cyclic) of this pencil
+                double Fp[5];
+                phys_flux_d(d, mine, Fp);   // F#(u,u) = f(u), weight D[j][j]
+#pragma unroll
+                for (int q = 0; q < 5; q++) {
+                    const double Fm = __shfl_sync(0xffffffffu, F[q], src);
+                    accS[d][q] = fma(wm, Fm, fma(wh, Fh[q], fma(wp, F[q], djj * Fp[q])));   // same order as the table gather
+                }
+            }
+        } else {
             double* const slot = sPair + (le * DIM * NCL) * NN + j;
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
@@ -183,7 +215,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
         // (a) unordered node pairs of the pencils of this thread's element: symmetric two-point flux, once
         // Half class of an even NP (cyclic distance NP/2): one pair per node in the lower half of its pencil, DIM * NN/2
         // tasks per element spread over all threads; the direction is a run-time value (branch-free in ec_flux_d).
-        if (HALF) {
+        if (HALF && !SHUF) {
 #pragma unroll
             for (int r = 0; r < GEO::HROUNDS; r++) {
                 const int p = r * NN + j;
@@ -242,7 +274,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
         double dw[DIM][NP - 1];
         int poff[DIM][NP - 1];
 #pragma unroll
-        for (int d = 0; d < DIM; d++) {
+        for (int d = 0; d < (SHUF ? 0 : DIM); d++) {
             const int jd = idx[d];
             const int st = stride_of(NP, d);
 #pragma unroll
@@ -267,17 +299,22 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
         for (int d = 0; d < DIM; d++) {
             const int jd = idx[d];
             double acc[5];
-            {   // F#(u,u) = f(u); its weight D[j][j] vanishes except at the two end nodes
-                const double djj = sD[jd * NP + jd];
-                double Fp[5];
-                phys_flux_d(d, me, Fp);
+            if (SHUF) {
 #pragma unroll
-                for (int c = 0; c < 5; c++) acc[c] = djj * Fp[c];
-            }
+                for (int c = 0; c < 5; c++) acc[c] = accS[d][c];
+            } else {
+                {   // F#(u,u) = f(u); its weight D[j][j] vanishes except at the two end nodes
+                    const double djj = sD[jd * NP + jd];
+                    double Fp[5];
+                    phys_flux_d(d, me, Fp);
 #pragma unroll
-            for (int k = 0; k < NP - 1; k++) {
+                    for (int c = 0; c < 5; c++) acc[c] = djj * Fp[c];
+                }
 #pragma unroll
-                for (int c = 0; c < 5; c++) acc[c] = fma(dw[d][k], sPair[c * PLANE + poff[d][k]], acc[c]);
+                for (int k = 0; k < NP - 1; k++) {
+#pragma unroll
+                    for (int c = 0; c < 5; c++) acc[c] = fma(dw[d][k], sPair[c * PLANE + poff[d][k]], acc[c]);
+                }
             }
             const double s = -2.0 * P.inv_h[d];
 #pragma unroll
@@ -307,7 +344,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                     ec_flux_d(d, o, me, hig, Fd, ibl);   // only for 1/beta_ln; the flux itself comes from the table
                     es_dissipation(o, me, ibl, hig, Dv);
 #pragma unroll
-                    for (int c = 0; c < 5; c++) left[c] = cls0[c * PLANE - st] - Dv[c];
+                    for (int c = 0; c < 5; c++) left[c] = (SHUF ? Fd[c] : cls0[c * PLANE - st]) - Dv[c];
                 }
                 if (jd < NP - 1) {
                     const Prim o = load_prim<NP>(sP, tid + st);
@@ -315,7 +352,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
                     ec_flux_d(d, me, o, hig, Fd, ibl);
                     es_dissipation(me, o, ibl, hig, Dv);
 #pragma unroll
-                    for (int c = 0; c < 5; c++) right[c] = cls0[c * PLANE] - Dv[c];
+                    for (int c = 0; c < 5; c++) right[c] = (SHUF ? Fd[c] : cls0[c * PLANE]) - Dv[c];
                 }
                 const double cf = alpha * P.inv_h[d] / sW[jd];
 #pragma unroll
@@ -432,7 +469,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, Geo<DIM, NP>::MIN_BLOCK
 
 int stage_smem_bytes(int dim, int Np) {
     int bytes = 0;
-#define CALL(D_, N_) { bytes = Geo<D_, N_>::SMEM_DOUBLES * (int)sizeof(double); }
+#define CALL(D_, N_) { bytes = GeoC<D_, N_>::SMEM_DOUBLES * (int)sizeof(double); }
     WGPU_DISPATCH(dim, Np, CALL);
 #undef CALL
     return bytes;
@@ -443,7 +480,7 @@ int prepare_kernels(int dim, int Np) {
 #define CALL(D_, N_)                                                                                         \
     {                                                                                                        \
         err = cudaFuncSetAttribute(stage_kernel<D_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                   Geo<D_, N_>::SMEM_DOUBLES * (int)sizeof(double));                         \
+                                   GeoC<D_, N_>::SMEM_DOUBLES * (int)sizeof(double));                         \
         if (err == cudaSuccess)                                                                              \
             err = cudaFuncSetAttribute(stage_kernel<D_, N_>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                                        cudaSharedmemCarveoutMaxShared);                                      \
@@ -458,7 +495,7 @@ void launch_stage(int dim, int Np, const StageParams& P, cudaStream_t s) {
     if (n <= 0) return;
 #define CALL(D_, N_)                                                                                         \
     {                                                                                                        \
-        using GEO = Geo<D_, N_>;                                                                             \
+        using GEO = GeoC<D_, N_>;                                                                            \
         const int64_t blocks = (n + GEO::G - 1) / GEO::G;                                                    \
         stage_kernel<D_, N_><<<(unsigned)blocks, GEO::THREADS, GEO::SMEM_DOUBLES * sizeof(double), s>>>(P);  \
     }
