@@ -1,0 +1,113 @@
+// tests/emu/pencil_emu.cc -- TEST INFRASTRUCTURE ONLY.
+//
+// Executes the per-thread phase functions of the pencil stage kernel (warpii_b200/csrc/dgsem_pencil_stage.cuh) on the host,
+// thread by thread, one phase after the other: a block barrier separates the phases on the device, so running every thread
+// of a block through phase k before any thread enters phase k+1 is one legal schedule of the kernel.  The CPU-only test
+// tier uses it to check the kernel's indexing (pencil ownership, halo ends, partial patches, ghost traces, the
+// troubled-cell correction, the stage-update modes) against the oracle before a GPU is spent on it.  It is compiled by a
+// plain host compiler with wgpu_portable.cuh's shims (MUFU seeds replaced by single-precision ones), so its results agree
+// with the device's to round-off, not bit for bit.  Nothing under warpii_b200/ builds, links or loads this file; the
+// product has no CPU path.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../warpii_b200/csrc/dgsem_pencil_stage.cuh"
+#include "../../warpii_b200/host/reference_element.hpp"
+
+using namespace wgpu;
+
+namespace {
+
+template <int DIM, int NP>
+double run(const StageParams& P) {
+    using G = PGeo<DIM, NP>;
+    const int64_t n = P.elem_end - P.elem_begin;
+    const int64_t blocks = (n + G::E - 1) / G::E;
+    std::vector<double> smem(G::SMEM_DOUBLES + 2);
+    std::vector<PencilHalo> halo(G::THREADS);
+    double vmax = 0.0;
+    bool nan_seen = false;
+    double* sm = smem.data();
+    if ((reinterpret_cast<uintptr_t>(sm) & 15) != 0) sm++;   // 16-byte alignment of the double2 planes
+    for (int64_t b = 0; b < blocks; b++) {
+        const int64_t e0 = P.elem_begin + b * G::E;
+        std::fill(smem.begin(), smem.end(), std::nan(""));   // a read of something no phase wrote poisons the result
+        for (int sp = 0; sp < P.nsp; sp++) {
+            for (int t = 0; t < G::THREADS; t++) pencil_phase0<DIM, NP>(P, sm, t, e0, sp, halo[t]);
+            for (int t = 0; t < G::THREADS; t++) pencil_phase_mid<DIM, NP, 1>(P, sm, t, e0, sp, halo[t]);
+            if (DIM == 3)
+                for (int t = 0; t < G::THREADS; t++) pencil_phase_mid<DIM, NP, DIM - 1>(P, sm, t, e0, sp, halo[t]);
+            for (int t = 0; t < G::THREADS; t++) {
+                const double v = pencil_phase_final<DIM, NP>(P, sm, t, e0, sp, P.dt, halo[t]);
+                if (v != v) nan_seen = true;
+                vmax = std::max(vmax, v);
+            }
+        }
+        for (int t = 0; t < G::THREADS; t++) pencil_phase_fields<DIM, NP>(P, t, e0, P.dt);
+    }
+    return nan_seen ? std::nan("") : vmax;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emu_pencil_available(int dim, int np) { return (dim == 2 || dim == 3) && np >= 2 && np <= 6; }
+int emu_pencil_patch_elems(int dim, int np) { return pencil_elems(dim, np); }
+
+// One launch of the stage kernel over elements [elem_begin, elem_end).  Arguments mirror StageParams / stage_params()
+// of warpii_gpu.cu; h[d] are the element sizes.  Returns 0, or 1 for an unsupported (dim, np).
+int emu_pencil_stage(int dim, int np, int64_t n_elems, int64_t elem_begin, int64_t elem_end, int nc, int nsp, const double* u,
+                     double* dst, const int32_t* nbr, const double* ghost, const double* bres, double* alpha_out, double* vmax_out,
+                     int mode, double gamma, double dt, double a, double beta, const double* h, const double* sol_in, double* dst2,
+                     int src_on, double epsilon0, double chi, const double* qm) {
+    if (!emu_pencil_available(dim, np)) return 1;
+    StageParams P;
+    std::memset(&P, 0, sizeof P);
+    warpii_b200::ReferenceElement re(np - 1);
+    for (int i = 0; i < np * np; i++) { P.T.D[i] = re.D[i]; P.T.V[i] = re.V[i]; }
+    for (int i = 0; i < np; i++) P.T.w[i] = re.w[i];
+    double inv_h[3] = {1, 1, 1};
+    for (int d = 0; d < dim; d++) {
+        inv_h[d] = 1.0 / h[d];
+        P.inv_h[d] = inv_h[d];
+        P.inv_hw[d] = 1.0 / (h[d] * re.w[0]);
+    }
+    {   // fluid_flux_es_dgsem_operator.h:487-502 (as warpii_gpu_create does)
+        double ev[3] = {1, 1, 1};
+        for (int it = 0; it < 5; it++) {
+            double nrm = 0;
+            for (int d = 0; d < dim; d++) { ev[d] = inv_h[d] * (inv_h[d] * ev[d]); nrm = std::fmax(nrm, std::fabs(ev[d])); }
+            for (int d = 0; d < dim; d++) ev[d] /= nrm;
+        }
+        double num = 0, den = 0;
+        for (int d = 0; d < dim; d++) { const double jv = inv_h[d] * ev[d]; num += jv * jv; den += ev[d] * ev[d]; }
+        P.max_eig = std::sqrt(num / den);
+    }
+    P.ind_T = 0.5 * std::pow(10.0, -1.8 * std::pow((double)np, 0.25));
+    P.ind_sT = 9.21024 / P.ind_T;
+    P.u = u; P.dst = dst; P.nbr = nbr; P.ghost = ghost; P.bres = bres; P.alpha_out = alpha_out;
+    unsigned long long vslot = 0;
+    P.vmax = vmax_out ? &vslot : nullptr;
+    P.elem_begin = elem_begin; P.elem_end = elem_end; P.n_elems = n_elems;
+    P.nc = nc; P.nsp = nsp; P.mode = mode;
+    P.sol_in = sol_in; P.dst2 = dst2;
+    P.gamma = gamma; P.dt = dt; P.a = a; P.beta = beta;
+    P.hig = 0.5 / (gamma - 1.0);
+    P.src_on = src_on; P.inv_eps0 = src_on ? 1.0 / epsilon0 : 1.0; P.chi = chi; P.qm = qm;
+    double vmax = 0.0;
+#define CALL(D_, N_) vmax = run<D_, N_>(P)
+    if (dim == 2) {
+        switch (np) { case 2: CALL(2, 2); break; case 3: CALL(2, 3); break; case 4: CALL(2, 4); break; case 5: CALL(2, 5); break; case 6: CALL(2, 6); break; }
+    } else {
+        switch (np) { case 2: CALL(3, 2); break; case 3: CALL(3, 3); break; case 4: CALL(3, 4); break; case 5: CALL(3, 5); break; case 6: CALL(3, 6); break; }
+    }
+#undef CALL
+    if (vmax_out) *vmax_out = vmax;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,8 +1,9 @@
 // Kernel parameter blocks and launch prototypes of the ES-DGSEM stage (host <-> device contract inside the
 // library; nothing here is part of the C ABI).
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "wgpu_portable.cuh"
 
 namespace wgpu {
 
@@ -80,6 +81,7 @@ struct BoundaryParams {
     double Ig[(kMaxNp + 1) * kMaxNp];   // Ig[q*Np+i] = l_i(xg_q)
 };
 
+#if !WGPU_HOST_EMU
 // General geometry (curved / non-rectangular elements, arbitrary conforming connectivity): per-node and per-face metric
 // tables derived on the host from warpii_gpu_geometry (warpii_gpu_set_geometry), read by stage_kernel_general and the
 // *_general auxiliary kernels.  K = dim*dim below.
@@ -125,6 +127,12 @@ void launch_cfl(int dim, int Np, const double* u, int64_t n_elems, int nc, int n
 int integral_blocks(int64_t n_elems);
 void launch_integral(int dim, int Np, const double* u, int64_t n_elems, int nc, int species, double Jdet,
                      const double* w, double* partial, double* out, cudaStream_t s);
+// pencil-per-thread stage kernel (dgsem_pencil_kernel.cu, dgsem_pencil_stage.cuh): Cartesian boxes, 2-D / 3-D, Np = 3..5
+bool pencil_available(int dim, int Np);
+int pencil_patch_elems(int dim, int Np);   // elements per block (= patch of the element numbering); 0 if not available
+int pencil_smem_bytes(int dim, int Np);
+int prepare_pencil_kernels(int dim, int Np);
+void launch_pencil_stage(int dim, int Np, const StageParams& P, cudaStream_t s);
 // general-geometry counterparts (dgsem_general_kernel.cu)
 int stage_general_smem_bytes(int dim, int Np);
 int prepare_general_kernels(int dim, int Np);
@@ -137,5 +145,7 @@ void launch_integral_general(int dim, int Np, const double* u, int64_t n_elems, 
 // halo: sendbuf[i][5*nsp][nF] = trace of (send_elem[i], send_side[i])
 void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, const int32_t* send_side,
                  int64_t n_send, int nc, int nsp, double* sendbuf, cudaStream_t s);
+
+#endif  // !WGPU_HOST_EMU
 
 }  // namespace wgpu

@@ -1,0 +1,94 @@
+// The pencil-decomposed stage kernel for sm_100a: the __global__ wrapper around the per-thread phase functions of
+// dgsem_pencil_stage.cuh (design and reference citations there).  Used for Cartesian boxes in 2-D and 3-D with
+// 3 <= Np <= 5 nodes per direction; every other (dim, Np) keeps the node-per-thread kernel of dgsem_stage_kernel.cu.
+#include "dgsem_common.cuh"
+#include "dgsem_pencil_stage.cuh"
+
+namespace wgpu {
+
+// resident blocks per SM the register allocation is asked to allow (shared memory allows 3 blocks of the 512-node patches)
+#ifndef WGPU_PENCIL_MIN_BLOCKS
+#define WGPU_PENCIL_MIN_BLOCKS 3
+#endif
+
+template <int DIM, int NP>
+__global__ void __launch_bounds__(PGeo<DIM, NP>::THREADS, WGPU_PENCIL_MIN_BLOCKS) pencil_stage_kernel(const StageParams P) {
+    using G = PGeo<DIM, NP>;
+    extern __shared__ __align__(16) double smem[];
+    // device-resident time loop: "finished" flag and dt live in global memory
+    const int skip = P.skip_dev ? *P.skip_dev : 0;
+    const double dt = P.dt_dev ? *P.dt_dev : P.dt;
+    if (skip) return;   // uniform
+    const int tid = threadIdx.x;
+    const int64_t e0 = P.elem_begin + (int64_t)blockIdx.x * G::E;
+    double vmax_local = 0.0;
+    PencilHalo halo;
+    for (int sp = 0; sp < P.nsp; sp++) {
+        if (sp > 0) __syncthreads();   // shared-memory reuse across species
+        pencil_phase0<DIM, NP>(P, smem, tid, e0, sp, halo);
+        __syncthreads();
+        pencil_phase_mid<DIM, NP, 1>(P, smem, tid, e0, sp, halo);
+        __syncthreads();
+        if (DIM == 3) {
+            pencil_phase_mid<DIM, NP, DIM - 1>(P, smem, tid, e0, sp, halo);
+            __syncthreads();
+        }
+        vmax_local = nan_max(vmax_local, pencil_phase_final<DIM, NP>(P, smem, tid, e0, sp, dt, halo));
+    }
+    pencil_phase_fields<DIM, NP>(P, tid, e0, dt);
+    if (P.vmax && P.mode == 0) {
+        const double m = block_max(vmax_local, smem + G::OFF_RED);
+        if (tid == 0) atomicMax(P.vmax, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+#define WGPU_PENCIL_DISPATCH(dim, Np, CALL)                                                                      \
+    do {                                                                                                         \
+        if ((dim) == 2) {                                                                                        \
+            switch (Np) { case 3: { CALL(2, 3); } break; case 4: { CALL(2, 4); } break; case 5: { CALL(2, 5); } break; } \
+        } else if ((dim) == 3) {                                                                                 \
+            switch (Np) { case 3: { CALL(3, 3); } break; case 4: { CALL(3, 4); } break; case 5: { CALL(3, 5); } break; } \
+        }                                                                                                        \
+    } while (0)
+
+bool pencil_available(int dim, int Np) { return (dim == 2 || dim == 3) && Np >= 3 && Np <= 5; }
+
+int pencil_patch_elems(int dim, int Np) { return pencil_available(dim, Np) ? pencil_elems(dim, Np) : 0; }
+
+int pencil_smem_bytes(int dim, int Np) {
+    int bytes = 0;
+#define CALL(D_, N_) { bytes = PGeo<D_, N_>::SMEM_DOUBLES * (int)sizeof(double); }
+    WGPU_PENCIL_DISPATCH(dim, Np, CALL);
+#undef CALL
+    return bytes;
+}
+
+int prepare_pencil_kernels(int dim, int Np) {
+    cudaError_t err = cudaSuccess;
+#define CALL(D_, N_)                                                                                              \
+    {                                                                                                             \
+        err = cudaFuncSetAttribute(pencil_stage_kernel<D_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                   PGeo<D_, N_>::SMEM_DOUBLES * (int)sizeof(double));                              \
+        if (err == cudaSuccess)                                                                                   \
+            err = cudaFuncSetAttribute(pencil_stage_kernel<D_, N_>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                       cudaSharedmemCarveoutMaxShared);                                           \
+    }
+    WGPU_PENCIL_DISPATCH(dim, Np, CALL);
+#undef CALL
+    return err == cudaSuccess ? 0 : 1;
+}
+
+void launch_pencil_stage(int dim, int Np, const StageParams& P, cudaStream_t s) {
+    const int64_t n = P.elem_end - P.elem_begin;
+    if (n <= 0) return;
+#define CALL(D_, N_)                                                                                              \
+    {                                                                                                             \
+        using G = PGeo<D_, N_>;                                                                                   \
+        const int64_t blocks = (n + G::E - 1) / G::E;                                                             \
+        pencil_stage_kernel<D_, N_><<<(unsigned)blocks, G::THREADS, G::SMEM_DOUBLES * sizeof(double), s>>>(P);    \
+    }
+    WGPU_PENCIL_DISPATCH(dim, Np, CALL);
+#undef CALL
+}
+
+}  // namespace wgpu

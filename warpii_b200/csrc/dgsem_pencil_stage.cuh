@@ -1,0 +1,569 @@
+// The fused ES-DGSEM stage, "pencil" decomposition (round 2), per-thread phase functions.
+//
+// What is computed is the same forward-Euler stage as stage_kernel (dgsem_stage_kernel.cu; reference
+// fluid_flux_es_dgsem_operator.h:127-214 with split_form_volume_flux.h:61-99, subcell_finite_volume_flux.h:68-159,
+// persson_peraire_shock_indicator.h:44-123, :301-342 faces, :216-240 inverse mass, :450-514 transport speed).  How:
+//
+//   * one THREAD owns one PENCIL (the Np nodes of an element along one direction) instead of one node.  All Np(Np-1)/2
+//     unordered node pairs of the pencil are evaluated from registers (the Chandrashekar flux is symmetric, so each pair
+//     feeds both of its nodes), the two face nodes at the ends of the pencil are added by the same thread: no pair-flux
+//     table, no face records, no task lists, every direction is a compile-time constant (no selects), index arithmetic is
+//     paid once per Np nodes, and a thread has Np(Np-1)/2 + 2 independent flux evaluations to interleave;
+//   * a block works on a patch of E elements (2x2x2 for 3-D degree 3) in DIM+1 phases separated by block barriers:
+//       P0 (x-pencil owner)  load u, node primitives once -> shared records; first indicator transform
+//       Py (y-pencil owner)  pair + end fluxes along y -> shared accumulator (first writer); second indicator transform
+//       Pz (z-pencil owner)  pair + end fluxes along z -> accumulator += ; third transform, modal energies
+//       Px (x-pencil owner)  pair + end fluxes along x, + accumulator, blend, sources, stage update, store, CFL
+//     The last phase owns Np consecutive nodes per thread: 16-byte vector loads/stores of u and dst;
+//   * a pencil end whose neighbour element lies in the patch reads the neighbour's record from shared memory; otherwise
+//     the neighbour's 5 conserved values are fetched (other patch / NCCL ghost trace) and turned into a record by the
+//     thread itself (in a full 2x2x2 patch every thread has exactly one such end per direction: no divergence);
+//   * the diagonal term D_jj f(u_j) of the volume sum, the f(u_m).n part of the face term and the pencil-end terms
+//     alpha f(u_0)/(w_0 h) of the subcell scheme cancel analytically for every alpha ((1-alpha) + alpha - 1 = 0 with
+//     D_00 = -1/(2 w_0), the SBP property): none of them is evaluated.  The reference forms them separately and leaves
+//     their round-off (one ulp of f/(h w_0), the size of every other summand's rounding);
+//   * elements whose blending factor is positive (rare: the troubled cells) take a per-node correction
+//     -alpha vol + alpha fv recomputed from the shared records; everybody else never touches the subcell scheme.
+//
+// Shared memory: records as 5 planes of double2 [(rho,u0) (u1,u2) (beta,ln rho) (ln beta,|u|^2) (|u|+c, 1/beta)],
+// accumulator as 3 planes of double2 [(r0,r1) (r2,r3) (r4, indicator scratch)], node index XOR-swizzled for Np = 4 so
+// that the 16-byte accesses of x-, y- and z-pencil owners are all bank-conflict free.
+//
+// The functions are __device__ code; wgpu_portable.cuh lets tests/emu/ compile the same source for the host and run it
+// thread by thread, phase by phase (test infrastructure; the product has no CPU path).
+#pragma once
+#include "dgsem_kernels.cuh"
+#include "dgsem_physics.cuh"
+
+#ifndef WGPU_PENCIL_THREADS
+#define WGPU_PENCIL_THREADS 128
+#endif
+
+namespace wgpu {
+
+__host__ __device__ constexpr int pencil_elems(int dim, int np) {
+    int e = 1;
+    while (2 * e * ipow_c(np, dim - 1) <= WGPU_PENCIL_THREADS) e *= 2;
+    return e;
+}
+
+template <int DIM, int NP>
+struct PGeo {
+    static constexpr int NN = ipow_c(NP, DIM);
+    static constexpr int NPEN = ipow_c(NP, DIM - 1);      // pencils per element and direction = nodes per face
+    static constexpr int E = pencil_elems(DIM, NP);       // elements per block
+    static constexpr int USED = E * NPEN;                 // threads that own a pencil
+    static constexpr int THREADS = ((USED + 31) / 32) * 32;
+    static constexpr int NODES = E * NN;
+    static constexpr int NFACE = 2 * DIM;
+    // dynamic shared memory, in doubles
+    static constexpr int OFF_REC = 0;                     // double2 [5][NODES]
+    static constexpr int OFF_BUF = 10 * NODES;            // double2 [3][NODES]
+    static constexpr int OFF_EN = 16 * NODES;             // double2 [THREADS] modal-energy partials
+    static constexpr int OFF_NBR = OFF_EN + 2 * THREADS;  // int [E][NFACE]
+    static constexpr int OFF_RED = OFF_NBR + (E * NFACE + 1) / 2 + ((E * NFACE + 1) / 2) % 2;
+    static constexpr int SMEM_DOUBLES = OFF_RED + 32;
+};
+
+// node index -> slot in a shared plane.  Np = 4: slot = n ^ b1 ^ 6 c0 with n = i0 + 4 i1 + 16 (i2 or element) ..., which
+// makes the eight 16-byte accesses of a quarter-warp distinct modulo 8 for x-owners (n = 4 pe + m), y-owners
+// (n = i0 + 4 m + 16 i2) and z-owners (n = pe + 16 m) alike (tests/test_pencil_layout_cpu.py enumerates them).
+template <int NP>
+__device__ __forceinline__ constexpr int pslot(const int n) {
+    return (NP == 4) ? (n ^ ((n >> 3) & 1) ^ (((n >> 4) & 1) * 6)) : n;
+}
+
+// element-local node m of pencil pe along D
+template <int DIM, int NP, int D>
+__device__ __forceinline__ constexpr int pencil_node(const int pe, const int m) {
+    if (DIM == 2) return D == 0 ? pe * NP + m : pe + NP * m;
+    return D == 0 ? pe * NP + m : (D == 1 ? (pe % NP) + NP * m + NP * NP * (pe / NP) : pe + NP * NP * m);
+}
+
+__device__ __forceinline__ void put_rec(double2* sRec, const int nodes, const int slot, const Prim& r) {
+    sRec[slot] = make_double2(r.rho, r.u0);
+    sRec[nodes + slot] = make_double2(r.u1, r.u2);
+    sRec[2 * nodes + slot] = make_double2(r.beta, r.lrho);
+    sRec[3 * nodes + slot] = make_double2(r.lbeta, r.q2);
+    sRec[4 * nodes + slot] = make_double2(r.lam, r.ib);
+}
+// FULL: also the two fields only the dissipation needs
+template <bool FULL>
+__device__ __forceinline__ Prim get_rec(const double2* sRec, const int nodes, const int slot) {
+    const double2 a = sRec[slot], b = sRec[nodes + slot], c = sRec[2 * nodes + slot], d = sRec[3 * nodes + slot];
+    Prim o;
+    o.rho = a.x; o.u0 = a.y; o.u1 = b.x; o.u2 = b.y; o.beta = c.x; o.lrho = c.y; o.lbeta = d.x; o.q2 = d.y;
+    o.p = 0.0; o.H = 0.0; o.lam = 0.0; o.ib = 0.0;
+    if (FULL) {
+        const double2 e = sRec[4 * nodes + slot];
+        o.lam = e.x; o.ib = e.y;
+    }
+    return o;
+}
+
+// NP consecutive doubles owned by one thread: one 32-byte access for Np = 4 (LDG/STG.256, sm_100: the thread's data is
+// exactly one sector, so a warp instruction moves 1 KB of whole sectors), 16-byte accesses for other even Np
+template <int NP>
+__device__ __forceinline__ void load_run(const double* p, double (&v)[NP]) {
+#if !WGPU_HOST_EMU
+    if constexpr (NP == 4) {
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+        return;
+    } else if constexpr (NP % 2 == 0) {
+#pragma unroll
+        for (int m = 0; m + 1 < NP; m += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(p + m);
+            v[m] = t.x;
+            v[m + 1] = t.y;
+        }
+        return;
+    }
+#endif
+#pragma unroll
+    for (int m = 0; m < NP; m++) v[m] = p[m];
+}
+template <int NP>
+__device__ __forceinline__ void store_run(double* p, const double (&v)[NP]) {
+#if !WGPU_HOST_EMU
+    if constexpr (NP == 4) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+        return;
+    } else if constexpr (NP % 2 == 0) {
+#pragma unroll
+        for (int m = 0; m + 1 < NP; m += 2) *reinterpret_cast<double2*>(p + m) = make_double2(v[m], v[m + 1]);
+        return;
+    }
+#endif
+#pragma unroll
+    for (int m = 0; m < NP; m++) p[m] = v[m];
+}
+
+// What lies beyond the two ends of a pencil, fetched one phase ahead (the loads fly while the previous phase finishes and
+// the block barrier is crossed) and consumed first thing in the phase that owns the pencil
+struct PencilHalo {
+    double q[2][5];   // kind 1: conserved values of the neighbour's face node; kind 2: boundary_kernel's contribution
+    int kind[2];      // 0: record in shared memory, 1: conserved values (other patch / ghost trace), 2: domain boundary
+    int nslot[2];     // kind 0: slot of the neighbour's end node
+};
+
+template <int DIM, int NP, int D>
+__device__ __forceinline__ void pencil_halo_fetch(const StageParams& P, const int v0, const int v1, const int pe, const int64_t e0,
+                                                  const int64_t e_hi, const int sp, PencilHalo& h) {
+    using G = PGeo<DIM, NP>;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int v = side ? v1 : v0;
+        h.nslot[side] = 0;
+        if (v >= e0 && v < e_hi) {
+            h.kind[side] = 0;
+            h.nslot[side] = pslot<NP>((int)(v - e0) * G::NN + pencil_node<DIM, NP, D>(pe, side ? 0 : NP - 1));
+        } else {
+            const double* src;
+            size_t stride;
+            if (v < 0) {
+                h.kind[side] = 2;
+                src = P.bres + (((size_t)(-1 - v) * P.nsp + sp) * 5) * G::NPEN + pe;
+                stride = G::NPEN;
+            } else if (v < P.n_elems) {
+                h.kind[side] = 1;
+                src = P.u + ((size_t)v * P.nc + 5 * sp) * G::NN + pencil_node<DIM, NP, D>(pe, side ? 0 : NP - 1);
+                stride = G::NN;
+            } else {
+                h.kind[side] = 1;
+                src = P.ghost + ((size_t)(v - P.n_elems) * (5 * P.nsp) + 5 * sp) * G::NPEN + pe;
+                stride = G::NPEN;
+            }
+#pragma unroll
+            for (int c = 0; c < 5; c++) h.q[side][c] = src[(size_t)c * stride];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// P0: the thread that owns x-pencil (le, pe): node primitives, first indicator transform, neighbour table, and the
+// fetch of what lies beyond the ends of the y-pencil this thread owns in the next phase
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DIM, int NP>
+__device__ __forceinline__ void pencil_phase0(const StageParams& P, double* smem, const int tid, const int64_t e0, const int sp,
+                                              PencilHalo& next) {
+    using G = PGeo<DIM, NP>;
+    double2* const sRec = reinterpret_cast<double2*>(smem + G::OFF_REC);
+    double2* const sBuf = reinterpret_cast<double2*>(smem + G::OFF_BUF);
+    int* const sNbr = reinterpret_cast<int*>(smem + G::OFF_NBR);
+    if (tid >= G::USED) return;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    const int64_t e_hi = (e0 + G::E < P.elem_end) ? e0 + G::E : P.elem_end;
+    if (e >= P.elem_end) return;   // (its records are never read: the in-patch test uses e_hi)
+    double q[5][NP];
+    const double* src = P.u + ((size_t)e * P.nc + 5 * sp) * G::NN + pe * NP;
+#pragma unroll
+    for (int c = 0; c < 5; c++) load_run<NP>(src + (size_t)c * G::NN, q[c]);
+    {
+        const int v0 = P.nbr[(size_t)e * G::NFACE + 2], v1 = P.nbr[(size_t)e * G::NFACE + 3];
+        pencil_halo_fetch<DIM, NP, 1>(P, v0, v1, pe, e0, e_hi, sp, next);
+    }
+    if (sp == 0)
+        for (int f = pe; f < G::NFACE; f += G::NPEN) sNbr[le * G::NFACE + f] = P.nbr[(size_t)e * G::NFACE + f];
+    double v[NP];
+#pragma unroll
+    for (int m = 0; m < NP; m++) {
+        const Prim r = make_prim(q[0][m], q[1][m], q[2][m], q[3][m], q[4][m], P.gamma);
+        put_rec(sRec, G::NODES, pslot<NP>(le * G::NN + pe * NP + m), r);
+        v[m] = r.p * r.rho;   // indicator variable, fluid_flux_es_dgsem_operator.h:286-290
+    }
+    // Legendre analysis along x (persson_peraire_shock_indicator.h:56 via FESeries::Legendre, sum-factorised)
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        double ck = 0.0;
+#pragma unroll
+        for (int m = 0; m < NP; m++) ck = fma(P.T.V[k * NP + m], v[m], ck);
+        sBuf[2 * G::NODES + pslot<NP>(le * G::NN + pe * NP + k)].y = ck;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Flux sums of one pencil along D: acc[m][c] = sum_{l != m} (-2 D[m][l] / h_D) F#_D(u_m, u_l)  +  the face terms at the
+// two ends (split_form_volume_flux.h:68-98 without the cancelling diagonal; fluid_flux_es_dgsem_operator.h:318-333
+// without the cancelling f(u_m).n).  The ends come first (their data was fetched a phase ahead); the pairs are ordered
+// (0,1) (0,2) ... (0,Np-1) (1,2) ... so that node m is complete - done(m, acc[m]) - and its record dead as early as possible.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DIM, int NP, int D, class Done>
+__device__ __forceinline__ void pencil_sums(const StageParams& P, const double2* sRec, const PencilHalo& h, const int le, const int pe,
+                                            Done&& done) {
+    using G = PGeo<DIM, NP>;
+    const double hig = P.hig, gamma = P.gamma;
+    Prim r[NP];
+#pragma unroll
+    for (int m = 0; m < NP; m++) {
+        const int slot = pslot<NP>(le * G::NN + pencil_node<DIM, NP, D>(pe, m));
+        r[m] = (m == 0 || m == NP - 1) ? get_rec<true>(sRec, G::NODES, slot) : get_rec<false>(sRec, G::NODES, slot);
+    }
+    double acc[NP][5];
+#pragma unroll
+    for (int m = 0; m < NP; m++)
+#pragma unroll
+        for (int c = 0; c < 5; c++) acc[m][c] = 0.0;
+    // ---- the two ends: own side of the face, gather form (f*(a,b,n) = -f*(b,a,-n) bit for bit) -----------------------
+    const double cf = P.inv_hw[D];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int m = side ? NP - 1 : 0;
+        if (h.kind[side] == 2) {
+            // domain boundary: boundary_kernel's contribution (f(u_m).n - f*_LF, Gauss(p+2) quadrature) plus the diagonal
+            // volume term, which only cancels against a NODAL f(u_m).n
+            Prim a = r[m];
+            a.p = 0.5 * a.rho * a.ib;
+            a.H = a.p * (2.0 * hig) + 0.5 * a.rho * a.q2 + a.p;
+            double Fp[5];
+            phys_flux_d(D, a, Fp);
+            const double sg = side ? -cf : cf;
+#pragma unroll
+            for (int c = 0; c < 5; c++) acc[m][c] += h.q[side][c] + sg * Fp[c];
+        } else {
+            const Prim b = (h.kind[side] == 0) ? get_rec<true>(sRec, G::NODES, h.nslot[side])
+                                               : make_prim(h.q[side][0], h.q[side][1], h.q[side][2], h.q[side][3], h.q[side][4], gamma);
+            double Fe[5], Dv[5], ibl;
+            ec_flux_d(D, r[m], b, hig, Fe, ibl);
+            es_dissipation(r[m], b, ibl, hig, Dv);
+            // (f(u_m).n - f*) / (h w_0) with f* = sgn F# - D and the f(u_m).n part dropped (see the file header)
+#pragma unroll
+            for (int c = 0; c < 5; c++) acc[m][c] = fma(cf, side ? (Dv[c] - Fe[c]) : (Dv[c] + Fe[c]), acc[m][c]);
+        }
+    }
+    const double s = -2.0 * P.inv_h[D];
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+#pragma unroll
+        for (int l = j + 1; l < NP; l++) {
+            double F[5], ibl;
+            ec_flux_d(D, r[j], r[l], hig, F, ibl);
+            const double wj = s * P.T.D[j * NP + l], wl = s * P.T.D[l * NP + j];
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                acc[j][c] = fma(wj, F[c], acc[j][c]);
+                acc[l][c] = fma(wl, F[c], acc[l][c]);
+            }
+        }
+        done(j, acc[j]);
+    }
+}
+
+// Legendre analysis of the indicator scratch along one direction, in place in registers
+template <int NP>
+__device__ __forceinline__ void legendre_1d(const StageParams& P, double (&v)[NP]) {
+    double o[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        double ck = 0.0;
+#pragma unroll
+        for (int m = 0; m < NP; m++) ck = fma(P.T.V[k * NP + m], v[m], ck);
+        o[k] = ck;
+    }
+#pragma unroll
+    for (int k = 0; k < NP; k++) v[k] = o[k];
+}
+
+// modal energies of this pencil's coefficients (last transform direction LD): shell = some mode index equals NP-1
+template <int DIM, int NP, int LD>
+__device__ __forceinline__ double2 pencil_energies(const int pe, const double (&c)[NP]) {
+    bool shell_pencil;   // a tangential index of this pencil is already NP-1
+    if (DIM == 2) shell_pencil = (pe == NP - 1);
+    else shell_pencil = (pe % NP == NP - 1) || (pe / NP == NP - 1);
+    double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        const double sq = c[k] * c[k];
+        if (shell_pencil || k == NP - 1) g1 += sq; else g0 += sq;
+    }
+    return make_double2(g0, g1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Py / Pz: pencil owner along D (D >= 1).  FIRST: the accumulator is written, not added to.  LAST_IND: this is the last
+// indicator transform (the modal energies of the pencil go to sEn).  `h` holds this pencil's ends on entry and the ends of
+// the pencil the thread owns in the NEXT phase (direction D+1, or x for the final phase) on return.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DIM, int NP, int D>
+__device__ __forceinline__ void pencil_phase_mid(const StageParams& P, double* smem, const int tid, const int64_t e0, const int sp,
+                                                 PencilHalo& h) {
+    using G = PGeo<DIM, NP>;
+    constexpr bool FIRST = (D == 1), LAST_IND = (D == DIM - 1);
+    constexpr int NEXT = (D + 1 < DIM) ? D + 1 : 0;
+    const double2* const sRec = reinterpret_cast<const double2*>(smem + G::OFF_REC);
+    double2* const sBuf = reinterpret_cast<double2*>(smem + G::OFF_BUF);
+    double2* const sEn = reinterpret_cast<double2*>(smem + G::OFF_EN);
+    const int* const sNbr = reinterpret_cast<const int*>(smem + G::OFF_NBR);
+    if (tid >= G::USED) return;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    const int64_t e_hi = (e0 + G::E < P.elem_end) ? e0 + G::E : P.elem_end;
+    if (e >= P.elem_end) {
+        if (LAST_IND) sEn[tid] = make_double2(0.0, 0.0);
+        return;
+    }
+    // indicator scratch of the pencil's nodes: transform along D now (cheap), written back with the sums
+    double ind[NP];
+#pragma unroll
+    for (int m = 0; m < NP; m++) ind[m] = sBuf[2 * G::NODES + pslot<NP>(le * G::NN + pencil_node<DIM, NP, D>(pe, m))].y;
+    legendre_1d<NP>(P, ind);
+    if (LAST_IND) sEn[tid] = pencil_energies<DIM, NP, D>(pe, ind);
+
+    pencil_sums<DIM, NP, D>(P, sRec, h, le, pe, [&](const int m, const double (&a)[5]) {
+        const int slot = pslot<NP>(le * G::NN + pencil_node<DIM, NP, D>(pe, m));
+        if (FIRST) {
+            sBuf[slot] = make_double2(a[0], a[1]);
+            sBuf[G::NODES + slot] = make_double2(a[2], a[3]);
+            sBuf[2 * G::NODES + slot] = make_double2(a[4], ind[m]);
+        } else {
+            const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot];
+            sBuf[slot] = make_double2(a[0] + x.x, a[1] + x.y);
+            sBuf[G::NODES + slot] = make_double2(a[2] + y.x, a[3] + y.y);
+            sBuf[2 * G::NODES + slot] = make_double2(a[4] + z.x, ind[m]);
+        }
+    });
+    pencil_halo_fetch<DIM, NP, NEXT>(P, sNbr[le * G::NFACE + 2 * NEXT], sNbr[le * G::NFACE + 2 * NEXT + 1], pe, e0, e_hi, sp, h);
+}
+
+// Troubled elements only (alpha > 0): -alpha * (volume sums) + alpha * (interior subcell-interface fluxes) of node j,
+// recomputed from the shared records (subcell_finite_volume_flux.h:75-158; the pencil-end terms cancel, see header)
+template <int DIM, int NP>
+__device__ __forceinline__ void pencil_fv_correction(const StageParams& P, const double2* sRec, const int le, const int j, const double alpha,
+                                                     double (&corr)[5]) {
+    using G = PGeo<DIM, NP>;
+    const double hig = P.hig;
+    const Prim me = get_rec<true>(sRec, G::NODES, pslot<NP>(le * G::NN + j));
+#pragma unroll
+    for (int c = 0; c < 5; c++) corr[c] = 0.0;
+    int rem = j;
+#pragma unroll 1
+    for (int d = 0; d < DIM; d++) {
+        const int jd = rem % NP;
+        rem /= NP;
+        const int st = (d == 0) ? 1 : (d == 1 ? NP : NP * NP);
+        const double s = -2.0 * P.inv_h[d];
+        double vol[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int l = 0; l < NP; l++) {
+            if (l == jd) continue;
+            const Prim o = get_rec<true>(sRec, G::NODES, pslot<NP>(le * G::NN + j + (l - jd) * st));
+            double F[5], ibl;
+            ec_flux_d(d, me, o, hig, F, ibl);
+            const double w = s * P.T.D[jd * NP + l];
+#pragma unroll
+            for (int c = 0; c < 5; c++) vol[c] = fma(w, F[c], vol[c]);
+            if (l == jd - 1 || l == jd + 1) {
+                // interface between subcells l and jd: F# - D(left, right); it enters node jd with +/- alpha / (h w_jd)
+                double Dv[5];
+                if (l < jd) es_dissipation(o, me, ibl, hig, Dv); else es_dissipation(me, o, ibl, hig, Dv);
+                const double cfv = ((l < jd) ? alpha : -alpha) * P.inv_h[d] / P.T.w[jd];
+#pragma unroll
+                for (int c = 0; c < 5; c++) corr[c] = fma(cfv, F[c] - Dv[c], corr[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 5; c++) corr[c] = fma(-alpha, vol[c], corr[c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Px (final): x-pencil owner.  Returns this thread's maximum transport speed of the values it wrote (0 if none).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DIM, int NP>
+__device__ __forceinline__ double pencil_phase_final(const StageParams& P, double* smem, const int tid, const int64_t e0, const int sp,
+                                                     const double dt, const PencilHalo& h) {
+    using G = PGeo<DIM, NP>;
+    const double2* const sRec = reinterpret_cast<const double2*>(smem + G::OFF_REC);
+    double2* const sBuf = reinterpret_cast<double2*>(smem + G::OFF_BUF);
+    const double2* const sEn = reinterpret_cast<const double2*>(smem + G::OFF_EN);
+    if (tid >= G::USED) return 0.0;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    if (e >= P.elem_end) return 0.0;
+    const size_t off = ((size_t)e * P.nc + 5 * sp) * G::NN + pe * NP;   // of node 0 of the pencil, component 0
+
+    // blending factor of the element: fixed-order sum of the pencils' modal energies (persson_peraire...:96-122)
+    double g0 = 0.0, g1 = 0.0;
+    for (int k = 0; k < G::NPEN; k++) {
+        const double2 en = sEn[le * G::NPEN + k];
+        g0 += en.x;
+        g1 += en.y;
+    }
+    const double alpha = blending_from_energies(g0, g1, P.ind_T, P.ind_sT);
+    if (pe == 0 && P.alpha_out) P.alpha_out[(size_t)e * P.nsp + sp] = alpha;
+    if (alpha > 0.0) {
+        // troubled element (rare): the correction of this thread's nodes goes into their accumulator slots before the
+        // regular path reads them (a run-time loop over the nodes: nothing of the regular path is live yet)
+#pragma unroll 1
+        for (int m = 0; m < NP; m++) {
+            double corr[5];
+            pencil_fv_correction<DIM, NP>(P, sRec, le, pe * NP + m, alpha, corr);
+            const int slot = pslot<NP>(le * G::NN + pe * NP + m);
+            double2 a = sBuf[slot], b = sBuf[G::NODES + slot], c = sBuf[2 * G::NODES + slot];
+            a.x += corr[0]; a.y += corr[1]; b.x += corr[2]; b.y += corr[3]; c.x += corr[4];
+            sBuf[slot] = a; sBuf[G::NODES + slot] = b; sBuf[2 * G::NODES + slot] = c;
+        }
+    }
+
+    double rate[5][NP];   // [component][node of the pencil]: the layout of the vector loads / stores below
+    pencil_sums<DIM, NP, 0>(P, sRec, h, le, pe, [&](const int m, const double (&a)[5]) {
+        const int slot = pslot<NP>(le * G::NN + pe * NP + m);
+        const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot];
+        rate[0][m] = a[0] + x.x; rate[1][m] = a[1] + x.y; rate[2][m] = a[2] + y.x; rate[3][m] = a[3] + y.y; rate[4][m] = a[4] + z.x;
+    });
+
+    // two-fluid sources on this species: (q/m)(rho E + m x B) and (q/m) m.E.  (u is read again here and below: it was
+    // read by this very thread in P0, an L1/L2 hit, not HBM traffic.)
+    if (P.src_on) {
+        const double* const fp = P.u + ((size_t)e * P.nc + 5 * P.nsp) * G::NN + pe * NP;
+        const double qm = P.qm[sp];
+        double F[6][NP], m0[NP], m1[NP], m2[NP], m3[NP];
+#pragma unroll
+        for (int k = 0; k < 6; k++) load_run<NP>(fp + (size_t)k * G::NN, F[k]);
+        load_run<NP>(P.u + off, m0);
+        load_run<NP>(P.u + off + (size_t)G::NN, m1);
+        load_run<NP>(P.u + off + 2 * (size_t)G::NN, m2);
+        load_run<NP>(P.u + off + 3 * (size_t)G::NN, m3);
+#pragma unroll
+        for (int m = 0; m < NP; m++) {
+            rate[1][m] += qm * (m0[m] * F[0][m] + (m2[m] * F[5][m] - m3[m] * F[4][m]));
+            rate[2][m] += qm * (m0[m] * F[1][m] + (m3[m] * F[3][m] - m1[m] * F[5][m]));
+            rate[3][m] += qm * (m0[m] * F[2][m] + (m1[m] * F[4][m] - m2[m] * F[3][m]));
+            rate[4][m] += qm * (m1[m] * F[0][m] + m2[m] * F[1][m] + m3[m] * F[2][m]);
+        }
+    }
+
+    // stage update (inverse mass is folded into the factors above), :190-212 of the reference operator; component by
+    // component so that only one run of u / old values is live at a time.  rate[][] becomes the new state.
+    const bool need_old = (P.mode == 2) || (P.mode == 0 && P.beta != 0.0);
+    const double* const oldp = (P.mode == 2) ? P.sol_in : P.dst;
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        double q[NP], old[NP], out2[NP];
+        if (P.mode != 1) load_run<NP>(P.u + off + (size_t)c * G::NN, q);
+        if (need_old) load_run<NP>(oldp + off + (size_t)c * G::NN, old);
+#pragma unroll
+        for (int m = 0; m < NP; m++) {
+            const double r = rate[c][m];
+            double v;
+            if (P.mode == 1) v = r;
+            else if (P.mode == 2) { v = fma(P.a, r, old[m]); out2[m] = fma(P.beta, r, old[m]); }
+            else if (P.beta == 0.0) v = P.a * (q[m] + dt * r);
+            else v = P.beta * old[m] + P.a * (q[m] + dt * r);
+            rate[c][m] = v;
+        }
+        store_run<NP>(P.dst + off + (size_t)c * G::NN, rate[c]);
+        if (P.mode == 2 && P.beta != 0.0) store_run<NP>(P.dst2 + off + (size_t)c * G::NN, out2);
+    }
+
+    double vmax_local = 0.0;
+    if (P.vmax && P.mode == 0) {
+        // compute_cell_transport_speed (:450-514) of the updated state
+        const double gm1 = P.gamma - 1.0;
+#pragma unroll
+        for (int m = 0; m < NP; m++) {
+            const double inv = rcp_pos(rate[0][m]);
+            const double sm = rate[1][m] * rate[1][m] + rate[2][m] * rate[2][m] + rate[3][m] * rate[3][m];
+            const double pr = gm1 * (rate[4][m] - sm * (0.5 * inv));
+            double conv = fabs(rate[1][m] * inv) * P.inv_h[0];
+            if (DIM > 1) conv = fmax(conv, fabs(rate[2][m] * inv) * P.inv_h[1]);
+            if (DIM > 2) conv = fmax(conv, fabs(rate[3][m] * inv) * P.inv_h[2]);
+            const double c2 = P.gamma * pr * inv;
+            // a non-positive or NaN c^2 (unphysical state) must reach the host as a NaN speed, not be clamped
+            const double cs = (c2 > 0.0) ? sqrt_pos(c2) : sqrt(c2 - 1.0);
+            const double speed = P.max_eig * cs + conv;
+            vmax_local = (speed > vmax_local || speed != speed) ? speed : vmax_local;
+        }
+    }
+    return vmax_local;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Field components (after the species): carried through unchanged by the reference's operator; with the
+// two-fluid sources on, E gets -J/eps0 and phi gets chi rho_c/eps0.  x-pencil owner, Np consecutive nodes.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DIM, int NP>
+__device__ __forceinline__ void pencil_phase_fields(const StageParams& P, const int tid, const int64_t e0, const double dt) {
+    using G = PGeo<DIM, NP>;
+    if (tid >= G::USED) return;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    if (e >= P.elem_end || P.nc <= 5 * P.nsp) return;
+    for (int m = 0; m < NP; m++) {
+        const int j = pe * NP + m;
+        double S[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (P.src_on) {
+            double Jx = 0.0, Jy = 0.0, Jz = 0.0, rc = 0.0;
+            for (int sp = 0; sp < P.nsp; sp++) {
+                const size_t so = ((size_t)e * P.nc + 5 * sp) * G::NN + j;
+                const double qm = P.qm[sp];
+                rc += qm * P.u[so];
+                Jx += qm * P.u[so + G::NN];
+                Jy += qm * P.u[so + 2 * (size_t)G::NN];
+                Jz += qm * P.u[so + 3 * (size_t)G::NN];
+            }
+            S[0] = -Jx * P.inv_eps0;
+            S[1] = -Jy * P.inv_eps0;
+            S[2] = -Jz * P.inv_eps0;
+            S[6] = P.chi * rc * P.inv_eps0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {   // fields_enabled means exactly these 8 components (five_moment.h:123-138)
+            if (5 * P.nsp + k >= P.nc) break;
+            const size_t off = ((size_t)e * P.nc + 5 * P.nsp + k) * G::NN + j;
+            const double rate = S[k];
+            double v;
+            if (P.mode == 1) v = rate;
+            else if (P.mode == 2) {
+                const double s0 = P.sol_in[off];
+                v = fma(P.a, rate, s0);
+                if (P.beta != 0.0) P.dst2[off] = fma(P.beta, rate, s0);
+            }
+            else if (P.beta == 0.0) v = P.a * (P.u[off] + dt * rate);
+            else v = P.beta * P.dst[off] + P.a * (P.u[off] + dt * rate);
+            P.dst[off] = v;
+        }
+    }
+}
+
+}  // namespace wgpu

@@ -75,21 +75,6 @@ struct Geo {
     static constexpr int SMEM_DOUBLES = OFF_RED + 32;
 };
 
-// persson_peraire_shock_indicator.h:96-122 given the two modal energies g = (group norm)^2; T and s/T are host
-// constants.  A group whose norm is below 1e-10 is dropped (deal.II process_coefficients).  alpha < 1e-3 -> 0, which is
-// decided without the exponential for the (overwhelmingly common) smooth elements.
-__device__ __forceinline__ double blending_from_energies(const double g0, const double g1, const double T, const double sT) {
-    const double e0 = g0 > 1e-20 ? g0 : 0.0, e1 = g1 > 1e-20 ? g1 : 0.0;
-    const double total = e0 + e1;
-    if (!(total > 0.0)) return 0.0;
-    const double E = e1 * rcp_pos(total);
-    if (sT * (T - E) > 6.95) return 0.0;          // 1/(1+exp(x)) < 1e-3  <=>  x > ln 999 = 6.9068
-    double alpha = 1.0 / (1.0 + exp(-sT * (E - T)));
-    if (alpha < 1e-3) alpha = 0.0;
-    else if (alpha > 0.5) alpha = 0.5;
-    return alpha;
-}
-
 // node record: [rho u0 | u1 u2 | beta lrho | lbeta q2 | p H | lam ib | - -]
 template <int NP>
 __device__ __forceinline__ void store_prim(double* sP, const int n, const Prim& P) {

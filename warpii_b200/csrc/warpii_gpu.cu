@@ -88,6 +88,18 @@ int load_nccl() {
 
 int ipow(int b, int e) { int r = 1; while (e-- > 0) r *= b; return r; }
 
+// Which stage kernel a Cartesian context runs: the pencil-per-thread kernel where it exists (2-D / 3-D, Np = 3..5), the
+// node-per-thread kernel otherwise.  WARPII_GPU_STAGE=node forces the latter (A/B measurements, profiles/README.md); the
+// variable is read once per process because the element numbering (patch size) depends on the choice.
+bool use_pencil(int dim, int Np) {
+    static const bool forced_node = [] {
+        const char* env = std::getenv("WARPII_GPU_STAGE");
+        return env && std::strcmp(env, "node") == 0;
+    }();
+    return !forced_node && pencil_available(dim, Np);
+}
+int patch_elems(int dim, int Np) { return use_pencil(dim, Np) ? pencil_patch_elems(dim, Np) : elems_per_block(dim, Np); }
+
 }  // namespace
 
 void warpii_gpu_free_slab_plan(void* plan);
@@ -109,6 +121,7 @@ struct warpii_gpu_ctx {
     int batch_graph_solution = -1, batch_graph_f1 = -1;
     int64_t batch_graph_launches = 0;
     bool use_graphs = true;
+    bool pencil = false;                    // Cartesian stage launches go to pencil_stage_kernel (dgsem_pencil_kernel.cu)
     bool src_on = false;                    // two-fluid source terms (warpii_gpu_set_sources)
     double inv_eps0 = 1.0, chi = 0.0;
     double* d_qm = nullptr;                 // [nsp] charge / mass
@@ -198,6 +211,7 @@ int get_events(warpii_gpu_ctx* c, cudaEvent_t* a, cudaEvent_t* b) {
 // the Cartesian kernels or their general-geometry counterparts
 void do_launch_stage(warpii_gpu_ctx* c, const StageParams& P, cudaStream_t s) {
     if (c->general) launch_stage_general(c->dim, c->Np, P, c->GP, s);
+    else if (c->pencil) launch_pencil_stage(c->dim, c->Np, P, s);
     else launch_stage(c->dim, c->Np, P, s);
 }
 void do_launch_boundary(warpii_gpu_ctx* c, const BoundaryParams& B, cudaStream_t s) {
@@ -350,7 +364,7 @@ const char* warpii_gpu_last_error(void) { return g_last_error.c_str(); }
 int warpii_gpu_abi_version(void) { return 1; }
 int warpii_gpu_elems_per_block(int dim, int fe_degree) {
     if (dim < 1 || dim > 3 || fe_degree < 1 || fe_degree > 6) return 1;
-    return elems_per_block(dim, fe_degree + 1);
+    return patch_elems(dim, fe_degree + 1);
 }
 
 int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out) {
@@ -488,7 +502,8 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
     // persson_peraire_shock_indicator.h:110-112
     c->ind_T = 0.5 * std::pow(10.0, -1.8 * std::pow((double)c->Np, 0.25));
     c->ind_sT = 9.21024 / c->ind_T;
-    if (prepare_kernels(c->dim, c->Np)) {
+    c->pencil = use_pencil(c->dim, c->Np);
+    if (prepare_kernels(c->dim, c->Np) || (c->pencil && prepare_pencil_kernels(c->dim, c->Np))) {
         std::string keep = g_last_error.empty() ? std::string("kernel preparation failed") : g_last_error;
         warpii_gpu_destroy(c);
         g_last_error = keep;
@@ -917,7 +932,7 @@ struct SlabPlan {
 
 int build_slab_plan(warpii_gpu_ctx* c, int n_slabs, SlabPlan& plan) {
     const int nf = 2 * c->dim;
-    const int G = elems_per_block(c->dim, c->Np);
+    const int G = (c->pencil && !c->general) ? pencil_patch_elems(c->dim, c->Np) : elems_per_block(c->dim, c->Np);
     const int64_t n_patches = (c->n_elems + G - 1) / G;
     int S = n_slabs > 0 ? n_slabs : 16;
     if (S > n_patches) S = (int)(n_patches > 0 ? n_patches : 1);
