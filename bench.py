@@ -7,8 +7,12 @@
 
 One "step" is one SSPRK2 time step of the workload = 2 RHS evaluations (+ the CFL reduction the time loop asks
 for every step, fluid_flux_es_dgsem_operator.h:442-448), so DoF-updates per step = 2 * n_dofs.
-Workload at N=1: BASELINE config 2 (2D Euler isentropic vortex, p=3, 512x512, periodic).  For N>1 the mesh is
-extended by 512 element rows per GPU (weak scaling) and sharded in slabs with an NCCL halo exchange per RHS.
+Default workload: the shape BASELINE.json quotes its target on, "degree-3 3D five-moment RHS" (N3D: 3D, p=3, two species +
+8 field components, 64^3 elements per GPU, periodic).  For N>1 the mesh is extended by 64 element layers per GPU (weak
+scaling) and sharded in slabs with an NCCL halo exchange per RHS (a 64x64-face 3-D halo, 2.9 MB per direction and RHS).
+At N=1 the line also carries `other_workloads`: BASELINE configs 2-5 at their stated shapes (C2, C3, C4s = one GPU's share
+of config 4, C5s) measured in the same run.  For N>1 a sharded-vs-oracle RHS check runs outside the timed region and is
+reported as `parity_check`.  The timed region is repeated 5 times (K steps each); `ms_per_step` is the median repetition.
 """
 import argparse
 import json
@@ -58,6 +62,9 @@ WORKLOADS = {
     "C4s": dict(dim=3, p=4, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[10.0, 5.0, 5.0], gamma=1.4, ic="vortex",
                 label="3D Euler periodic vortex, degree 4, 64^3 elements per GPU (C4 shape)"),
 }
+
+
+OTHER_WORKLOADS = ["C2", "C3", "C4s", "C5s"]   # BASELINE configs 2-5 at their stated shapes, one GPU's share
 
 
 def measured_traffic(workload):
@@ -164,6 +171,17 @@ class ClockSampler:
                 "source": "device clock64/globaltimer probes inside the timed region; NVML before and after"}
 
 
+def base_config(w, world):
+    """The part of `config` both arms print identically (the driver compares it)."""
+    NN = (w["p"] + 1) ** w["dim"]
+    nc = 5 * w.get("n_species", 1) + (8 if w.get("fields") else 0)
+    n_local = int(np.prod(w["nx"])) * NN * nc
+    label = w["label"]
+    if world > 1:
+        label += f" per GPU ({w['nx'][-1] * world} layers in total, slab-sharded)"
+    return {"workload": label, "n_dofs": int(n_local * world), "state_bytes_per_gpu": int(8 * n_local)}
+
+
 def build_ic(w, xyz):
     if w["ic"] == "vortex":
         return cases.to_state(cases.isentropic_vortex(w["gamma"])(xyz), w["gamma"])
@@ -252,6 +270,7 @@ def cpu_run(w, steps, warmup, threads, budget_s, rows=None):
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
@@ -260,8 +279,10 @@ def run_reference(args, w):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["label"], "note": "CPU restatement (oracle/) of the reference algorithm; the reference itself "
-                   "needs deal.II 9.5.1 + MPI and cannot be built in this image"},
+        "config": base_config(w, world),
+        "details": {"note": "CPU restatement (oracle/) of the reference algorithm on all host cores of rank 0, on a bounded sample of the "
+                            "workload (same h, degree, initial condition); the reference itself needs deal.II 9.5.1 + MPI and cannot be "
+                            "built in this image"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -270,26 +291,12 @@ def run_reference(args, w):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args, w):
-    import torch
-    import torch.distributed as dist
-
-    from warpii_b200 import BoxSolver, nccl_unique_id
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
+def make_solver(w, world, rank, local_rank):
+    """Solver, per-GPU mesh and geometry-bytes figure of one workload (weak scaling: one workload-sized slab per GPU)."""
+    from warpii_b200 import BoxSolver
     dim, p, gamma = w["dim"], w["p"], w["gamma"]
     nx = list(w["nx"])
     left, right = list(w["left"]), list(w["right"])
-    # weak scaling: one workload-sized slab per GPU along the last dimension
     nx[-1] *= world
     right[-1] = left[-1] + (right[-1] - left[-1]) * world
     geo_bytes_per_dof = 0.0
@@ -321,6 +328,108 @@ def run_ours(args, w):
         g = BoxSolver(dim, p, nx, left, right, gamma=gamma, rank=rank, n_ranks=world, device=local_rank, **species_kwargs(w))
     if w.get("sources"):
         g.set_sources(True, **w["sources"])
+    return g, nx, geo_bytes_per_dof
+
+
+def stage_kernel_name(w, g):
+    from warpii_b200 import lib as _lib
+    dim, np1 = w["dim"], w["p"] + 1
+    if w.get("mapping"):
+        return f"wgpu::stage_kernel_general<{dim},{np1}>"
+    L = _lib()
+    pencil = hasattr(L, "warpii_gpu_stage_kernel_is_pencil") and L.warpii_gpu_stage_kernel_is_pencil(dim, w["p"]) == 1
+    return f"wgpu::{'pencil_stage_kernel' if pencil else 'stage_kernel'}<{dim},{np1}>"
+
+
+N_REPEAT = 5
+
+
+def device_resident(g, args, stream, barrier, max_over_ranks, steps, warmup, repeats):
+    """`repeats` timed regions of exactly `steps` SSPRK2 steps each (device-resident time loop, CUDA events on the library's
+    stream bracketed by barrier + synchronize, max over ranks); returns the median region and the per-launch stage time."""
+    import torch
+    t = 0.0
+    t, _ = g.advance_to(t, 1e30, max_steps=max(warmup, 1))
+    regions, stage_tot, stage_n, launches = [], 0.0, 0, 0
+    for _ in range(repeats):
+        barrier()
+        g.stage_timing(True)
+        l0 = g.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t, done = g.advance_to(t, 1e30, max_steps=steps)
+        e1.record(stream)
+        barrier()
+        assert done == steps
+        regions.append(max_over_ranks(e0.elapsed_time(e1)))
+        launches = g.launch_count() - l0
+        ms, n = g.stage_timing(False)
+        stage_tot += ms
+        stage_n += n
+    return t, float(np.median(regions)), regions, stage_tot / max(stage_n, 1), stage_n, launches
+
+
+def parity_check_sharded(world, rank, local_rank, dist, torch):
+    """N > 1: one RHS of a small 3-D mesh sharded over all ranks (NCCL halo exchange, interface / interior launches) against
+    the CPU oracle on the unsharded mesh.  Outside the timed region; the criterion is the parity tests' (dgsem_cases.py)."""
+    from warpii_b200 import BoxSolver, nccl_unique_id
+    import oracle
+    from oracle import Oracle
+    dim, p, gamma = 3, 3, 1.4
+    nx = [8, 8, 4 * world]
+    left, right = [0.0, -5.0, -5.0], [10.0, 5.0, 5.0]
+    g = BoxSolver(dim, p, nx, left, right, gamma=gamma, rank=rank, n_ranks=world, device=local_rank)
+    uid = torch.tensor(list(nccl_unique_id()) if rank == 0 else [0] * 128, dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    g.attach_comm(bytes(uid.cpu().tolist()))
+    o = Oracle(dim, p, nx, left, right, gamma=gamma, threads=max(1, (os.cpu_count() or 8) // world))
+    u = o.project(cases.isentropic_vortex(gamma))
+    want, _ = o.rhs(u)
+    g.upload(0, np.ascontiguousarray(u[g.l2g]))
+    g.rhs(1, 0)
+    got = g.download(1)
+    g.close()
+    h = [(r - l) / n for l, r, n in zip(left, right, nx)]
+    scale = cases.summand_scale(u, gamma, dim, h, oracle.diff_matrix(p + 1))
+    # per-rank sums of squares -> global norms
+    num = np.array([np.sum((got[:, c] - want[g.l2g][:, c]) ** 2) for c in range(5)])
+    t = torch.tensor(num, dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    err = np.sqrt(t.cpu().numpy())
+    den = np.array([np.linalg.norm(want[:, c]) for c in range(5)])
+    bound = np.maximum(1e-12 * den, cases.RHS_ULPS * 2.0 ** -52 * scale)
+    live = den > 1e-9 * scale
+    plain = np.where(live, err / np.where(den > 0, den, 1.0), 0.0)
+    return {"mesh": f"3D p=3 {nx[0]}x{nx[1]}x{nx[2]} vortex sharded over {world} ranks, one RHS vs CPU oracle",
+            "rel_l2_per_component": [float(v) for v in plain], "tolerance": 1e-12, "pass": bool((err <= bound).all()),
+            "note": "component 3 (z-momentum of a flow extruded in z) vanishes identically and is judged against the differenced terms"}
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from warpii_b200 import nccl_unique_id
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dim, p = w["dim"], w["p"]
+    g, nx, geo_bytes_per_dof = make_solver(w, world, rank, local_rank)
     if world > 1:
         if rank == 0:
             uid = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
@@ -344,36 +453,18 @@ def run_ours(args, w):
         g.synchronize()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---- device-resident throughput -----------------------------------------------------------------
-    t = 0.0
     sampler = ClockSampler(local_rank)
-    t, _ = g.advance_to(t, 1e30, max_steps=max(args.warmup - 1, 1))
     if rank == 0 and not args.no_clocks:
-        sampler.poll()      # under load (the warm-up steps), one more warm-up step and a barrier before the timed region
-    t, _ = g.advance_to(t, 1e30, max_steps=1)
-    barrier()
-    g.stage_timing(True)
-    launches0 = g.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    t, steps = g.advance_to(t, 1e30, max_steps=args.steps)
-    e1.record(stream)
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = g.launch_count() - launches0
-    stage_ms, stage_n = g.stage_timing(False)
+        g.advance_to(0.0, 1e30, max_steps=1)
+        sampler.poll()      # under load (a warm-up step); the remaining warm-up steps and a barrier follow before the timed region
+    g.upload(0, host_np)
+    t, ms, regions, avg_stage_ms, stage_n, launches = device_resident(g, args, stream, barrier, max_over_ranks, args.steps,
+                                                                      args.warmup, N_REPEAT)
     clocks = None
     if rank == 0 and not args.no_clocks:
         sampler.poll()
         clocks = sampler.result(g.sm_clock_probes())
-    assert steps == args.steps
     value = 2.0 * n_dofs_total * args.steps / (ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------------
@@ -385,8 +476,8 @@ def run_ours(args, w):
     e2e_steps = max(3, min(args.steps, 10))
 
     # warpii_gpu_host_ssprk2_step: the state goes host -> HBM -> host every step; dt is the fused CFL result of the previous
-    # step (= recommend_dt of the state being uploaded).  Single-GPU periodic workloads overlap the two transfers and the
-    # stages slab by slab; with boundary faces or a communicator the call runs upload, step, download in sequence.
+    # step (= recommend_dt of the state being uploaded).  Periodic workloads overlap the two transfers and the
+    # stages slab by slab; with boundary faces the call runs upload, step, download in sequence.
     def e2e_step(tt, dt_now):
         dt_next = g.host_step(host_np, host_np, dt_now, tt)
         return tt + dt_now, dt_next
@@ -396,6 +487,7 @@ def run_ours(args, w):
     for _ in range(2):
         t, dt_e2e = e2e_step(t, dt_e2e)
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
     for _ in range(e2e_steps):
@@ -408,36 +500,70 @@ def run_ours(args, w):
     e2e_value = 2.0 * n_dofs_total * e2e_steps / (e2e_ms * 1e-3)
     assert np.isfinite(host_np).all()
     fv_frac = float((g.shock_indicator(0) > 0.0).mean())   # elements (x species) whose subcell-FV blend is active now
+    kernel = stage_kernel_name(w, g)
+    g.close()
+    del host, host_np
+
+    parity = parity_check_sharded(world, rank, local_rank, dist, torch) if world > 1 else None
+
+    # ---- the other BASELINE shapes, same run, same build (N = 1 only) ------------------------------------------------
+    others = {}
+    if world == 1 and not args.no_other_workloads:
+        peak_o, _ = measured_peaks()
+        for name in OTHER_WORKLOADS:
+            if name == args.workload:
+                continue
+            wo = WORKLOADS[name]
+            go, _, _ = make_solver(wo, 1, 0, local_rank)
+            uo = build_ic(wo, go.node_coords())
+            go.upload(0, uo)
+            del uo
+            so = torch.cuda.ExternalStream(go.stream(), device=torch.device("cuda", local_rank))
+
+            def barrier_o():
+                go.synchronize()
+                torch.cuda.synchronize()
+
+            steps_o = max(3, args.steps // 2)
+            _, ms_o, _, stage_o, _, _ = device_resident(go, args, so, barrier_o, lambda x: x, steps_o, 3, 3)
+            others[name] = {"workload": wo["label"], "n_dofs": int(go.n_dofs), "value": 2.0 * go.n_dofs * steps_o / (ms_o * 1e-3),
+                            "unit": UNIT, "ms_per_step": ms_o / steps_o, "steps": steps_o, "stage_kernel": stage_kernel_name(wo, go),
+                            "stage_kernel_ms": stage_o, "roofline_frac": BYTES_PER_DOF_UPDATE * go.n_dofs / (stage_o * 1e-3) / 1e9 / peak_o}
+            go.close()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         # dominant kernel = the fused stage kernel; algorithmic bytes per launch = 20 B (SSPRK2 average) x local DoFs
-        avg_stage_ms = stage_ms / max(stage_n, 1)
         bytes_per_update = BYTES_PER_DOF_UPDATE + geo_bytes_per_dof
         achieved = bytes_per_update * n_dofs_local / (avg_stage_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": w["label"] + (f" per GPU ({nx[-1]} rows in total, slab-sharded)" if world > 1 else ""),
-                       "n_dofs": int(n_dofs_total), "state_bytes": int(8 * n_dofs_local),
-                       "l2_policy": "state (2 x %.0f MB per GPU) exceeds the 126 MB L2; no flush" % (8e-6 * n_dofs_local),
-                       "parallelism": f"elements sharded over {world} GPU(s), NCCL send/recv halo + allreduce(max) dt",
-                       "fv_blend_active_fraction_rank0": fv_frac},
+            "config": base_config(w, world),
+            "details": {"l2_policy": "state (2 x %.0f MB per GPU) exceeds the 126 MB L2; no flush" % (8e-6 * n_dofs_local),
+                        "parallelism": f"elements sharded over {world} GPU(s), NCCL send/recv halo + allreduce(max) dt",
+                        "timed_regions": f"{N_REPEAT} x {args.steps} steps, median reported",
+                        "fv_blend_active_fraction_rank0": fv_frac},
+            "timed_regions_ms": regions,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_dofs_local),
                     "d2h_bytes_per_step": int(8 * n_dofs_local), "steps": e2e_steps,
                     "note": "per step: warpii_gpu_host_ssprk2_step(pinned host state in, pinned host state out): whole state host -> "
                             "HBM, SSPRK2 step with fused CFL (next dt), whole state HBM -> host; transfers and stages overlapped "
-                            "slab by slab on three streams where the mesh is periodic and unsharded"},
+                            "slab by slab on three streams where the mesh is periodic"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(args.workload) if world == 1 else None,
-                         "kernel": f"wgpu::stage_kernel{'_general' if w.get('mapping') else ''}<{dim},{p + 1}>", "peak_source": peak_src,
+                         "kernel": kernel, "peak_source": peak_src,
                          "avg_launch_ms": avg_stage_ms, "launches_timed": int(stage_n),
                          "algorithmic_bytes_per_launch": bytes_per_update * n_dofs_local,
                          "algorithmic_bytes_per_dof_update": bytes_per_update},
         }
+        if parity is not None:
+            line["parity_check"] = parity
+        if others:
+            line["other_workloads"] = others
         if world == 1:
             fp = fp64_figure(args.workload, avg_stage_ms, local_rank)
             if fp is not None:
@@ -456,7 +582,6 @@ def run_ours(args, w):
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": nthreads, "kind": "port", "sample": cb["sample"],
                                     "single_core_value": cb1["value"], "single_core_sample": cb1["sample"]}
         print(json.dumps(line), flush=True)
-    g.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -467,7 +592,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="N3D", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the other BASELINE shapes (other_workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
     args = ap.parse_args()

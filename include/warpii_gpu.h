@@ -90,6 +90,9 @@ int warpii_gpu_abi_version(void);
  * from the block's shared memory instead of L2/HBM, so compact patches (e.g. 4x2 in 2D p=3) should be numbered
  * consecutively.  Any ordering is correct. */
 int warpii_gpu_elems_per_block(int dim, int fe_degree);
+/* 1 if Cartesian contexts of this (dim, fe_degree) run the pencil-per-thread stage kernel (dgsem_pencil_kernel.cu), 0 if the
+ * node-per-thread one (dgsem_stage_kernel.cu); diagnostic, used by bench.py to name the kernel in its roofline line. */
+int warpii_gpu_stage_kernel_is_pencil(int dim, int fe_degree);
 
 /* -- lifetime -------------------------------------------------------------- */
 int warpii_gpu_create(const warpii_gpu_mesh* mesh, int device, warpii_gpu_ctx** out);
@@ -225,6 +228,9 @@ int warpii_gpu_stream(warpii_gpu_ctx* ctx, void** stream_out);
 /* Measured FP64 throughput of this GPU's CUDA cores, in fused multiply-adds per second (FMA-chain microbenchmark, all SMs
  * full): the denominator of the FP64 figure bench.py reports beside the HBM roofline. */
 int warpii_gpu_measure_fp64_peak(int device, double* fma_per_second_out);
+/* Tuning diagnostic: the same FMA rate with ONE block of threads_per_sm threads per SM and `ilp` (1,2,3,4,6,8) independent
+ * chains per thread: what a kernel with that many resident warps and that much instruction-level parallelism can reach. */
+int warpii_gpu_fp64_rate_probe(int device, int threads_per_sm, int ilp, double* fma_per_second_out);
 
 /* -- point physics on the device, for known-answer tests ------------------------------------------------
  * For n state pairs (qa[i], qb[i]) of 5 conserved values: the direction-d entropy-conserving flux

@@ -40,76 +40,89 @@ def _f64(a):
 
 
 _lib = None
+_variants = {}
 
 
-def lib():
+def lib(variant=None):
+    """The oracle library; variant="fma" is the same source compiled with multiply-add contraction (liboracle_fma.so), used
+    only to measure how far two legitimate FP64 builds of the algorithm are apart."""
     global _lib
+    if variant is not None:
+        if variant not in _variants:
+            path = os.path.join(_HERE, "_build", f"liboracle_{variant}.so")
+            if not os.path.exists(path):
+                subprocess.check_call(["make", "-C", _HERE, f"_build/liboracle_{variant}.so"], stdout=subprocess.DEVNULL)
+            _variants[variant] = _bind(C.CDLL(path))
+        return _variants[variant]
     if _lib is None:
         if not os.path.exists(_LIB_PATH):
             build()
-        L = C.CDLL(_LIB_PATH)
-        L.orc_ln_avg.restype = C.c_double
-        L.orc_ln_avg.argtypes = [C.c_double, C.c_double]
-        L.orc_det_log.restype = C.c_double
-        L.orc_det_log.argtypes = [C.c_double]
-        L.orc_set_log_impl.argtypes = [C.c_int]
-        L.orc_pressure.restype = C.c_double
-        L.orc_pressure.argtypes = [_dp, C.c_double]
-        L.orc_euler_flux.argtypes = [C.c_int, _dp, C.c_double, _dp]
-        L.orc_lf_flux.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, _dp]
-        L.orc_ec_flux.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp]
-        L.orc_es_flux.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, _dp]
-        L.orc_entropy_variables.argtypes = [_dp, C.c_double, _dp]
-        L.orc_mathematical_entropy.restype = C.c_double
-        L.orc_mathematical_entropy.argtypes = [_dp, C.c_double]
-        L.orc_entropy_flux.argtypes = [C.c_int, _dp, C.c_double, _dp]
-        L.orc_primitive_to_conserved.argtypes = [_dp, C.c_double, _dp]
-        for name in ("orc_pencil_stride",):
-            getattr(L, name).restype = C.c_uint
-            getattr(L, name).argtypes = [C.c_uint, C.c_uint]
-        L.orc_pencil_base.restype = C.c_uint
-        L.orc_pencil_base.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint]
-        L.orc_quadrature_point_neighbor.restype = C.c_uint
-        L.orc_quadrature_point_neighbor.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
-        L.orc_quad_point_1d_index.restype = C.c_uint
-        L.orc_quad_point_1d_index.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint]
-        L.orc_pencil_starts.restype = C.c_int
-        L.orc_pencil_starts.argtypes = [C.c_int, C.c_uint, C.c_uint, _up]
-        L.orc_gll.argtypes = [C.c_int, _dp, _dp]
-        L.orc_gauss.argtypes = [C.c_int, _dp, _dp]
-        L.orc_diff_matrix.argtypes = [C.c_int, _dp]
-        L.orc_legendre_analysis_1d.argtypes = [C.c_int, _dp]
-        L.orc_create.restype = C.c_void_p
-        L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _ip, _dp, _dp, _ip, _ip]
-        L.orc_destroy.argtypes = [C.c_void_p]
-        L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
-        L.orc_n_elems.restype = C.c_int64
-        L.orc_n_elems.argtypes = [C.c_void_p]
-        L.orc_n_dofs.restype = C.c_int64
-        L.orc_n_dofs.argtypes = [C.c_void_p]
-        L.orc_n_components.argtypes = [C.c_void_p]
-        L.orc_nodes_per_elem.argtypes = [C.c_void_p]
-        L.orc_n_boundaries.argtypes = [C.c_void_p]
-        L.orc_node_coords.argtypes = [C.c_void_p, _dp]
-        L.orc_set_inflow.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
-        L.orc_set_inflow_function.argtypes = [C.c_void_p, C.c_int, C.c_int, INFLOW_FN, C.c_void_p]
-        L.orc_rhs.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp]
-        L.orc_alpha.argtypes = [C.c_void_p, _dp, _dp]
-        L.orc_cell_residual.argtypes = [C.c_void_p, _dp, C.c_double, _dp]
-        L.orc_shock_indicator.restype = C.c_double
-        L.orc_shock_indicator.argtypes = [C.c_void_p, _dp]
-        L.orc_forward_euler_step.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_double, C.c_double,
-                                             C.c_double, _dp, _dp]
-        L.orc_max_transport_speed.restype = C.c_double
-        L.orc_max_transport_speed.argtypes = [C.c_void_p, _dp]
-        L.orc_recommend_dt.restype = C.c_double
-        L.orc_recommend_dt.argtypes = [C.c_void_p, _dp]
-        L.orc_ssprk2_step.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_double, _dp, _dp]
-        L.orc_solve.restype = C.c_int64
-        L.orc_solve.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int64, C.c_double]
-        L.orc_global_integral.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
-        _lib = L
+        _lib = _bind(C.CDLL(_LIB_PATH))
     return _lib
+
+
+def _bind(L):
+    L.orc_ln_avg.restype = C.c_double
+    L.orc_ln_avg.argtypes = [C.c_double, C.c_double]
+    L.orc_det_log.restype = C.c_double
+    L.orc_det_log.argtypes = [C.c_double]
+    L.orc_set_log_impl.argtypes = [C.c_int]
+    L.orc_pressure.restype = C.c_double
+    L.orc_pressure.argtypes = [_dp, C.c_double]
+    L.orc_euler_flux.argtypes = [C.c_int, _dp, C.c_double, _dp]
+    L.orc_lf_flux.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, _dp]
+    L.orc_ec_flux.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp]
+    L.orc_es_flux.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, _dp]
+    L.orc_entropy_variables.argtypes = [_dp, C.c_double, _dp]
+    L.orc_mathematical_entropy.restype = C.c_double
+    L.orc_mathematical_entropy.argtypes = [_dp, C.c_double]
+    L.orc_entropy_flux.argtypes = [C.c_int, _dp, C.c_double, _dp]
+    L.orc_primitive_to_conserved.argtypes = [_dp, C.c_double, _dp]
+    for name in ("orc_pencil_stride",):
+        getattr(L, name).restype = C.c_uint
+        getattr(L, name).argtypes = [C.c_uint, C.c_uint]
+    L.orc_pencil_base.restype = C.c_uint
+    L.orc_pencil_base.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint]
+    L.orc_quadrature_point_neighbor.restype = C.c_uint
+    L.orc_quadrature_point_neighbor.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+    L.orc_quad_point_1d_index.restype = C.c_uint
+    L.orc_quad_point_1d_index.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint]
+    L.orc_pencil_starts.restype = C.c_int
+    L.orc_pencil_starts.argtypes = [C.c_int, C.c_uint, C.c_uint, _up]
+    L.orc_gll.argtypes = [C.c_int, _dp, _dp]
+    L.orc_gauss.argtypes = [C.c_int, _dp, _dp]
+    L.orc_diff_matrix.argtypes = [C.c_int, _dp]
+    L.orc_legendre_analysis_1d.argtypes = [C.c_int, _dp]
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _ip, _dp, _dp, _ip, _ip]
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
+    L.orc_n_elems.restype = C.c_int64
+    L.orc_n_elems.argtypes = [C.c_void_p]
+    L.orc_n_dofs.restype = C.c_int64
+    L.orc_n_dofs.argtypes = [C.c_void_p]
+    L.orc_n_components.argtypes = [C.c_void_p]
+    L.orc_nodes_per_elem.argtypes = [C.c_void_p]
+    L.orc_n_boundaries.argtypes = [C.c_void_p]
+    L.orc_node_coords.argtypes = [C.c_void_p, _dp]
+    L.orc_set_inflow.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+    L.orc_set_inflow_function.argtypes = [C.c_void_p, C.c_int, C.c_int, INFLOW_FN, C.c_void_p]
+    L.orc_rhs.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp]
+    L.orc_alpha.argtypes = [C.c_void_p, _dp, _dp]
+    L.orc_cell_residual.argtypes = [C.c_void_p, _dp, C.c_double, _dp]
+    L.orc_shock_indicator.restype = C.c_double
+    L.orc_shock_indicator.argtypes = [C.c_void_p, _dp]
+    L.orc_forward_euler_step.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_double, C.c_double,
+                                         C.c_double, _dp, _dp]
+    L.orc_max_transport_speed.restype = C.c_double
+    L.orc_max_transport_speed.argtypes = [C.c_void_p, _dp]
+    L.orc_recommend_dt.restype = C.c_double
+    L.orc_recommend_dt.argtypes = [C.c_void_p, _dp]
+    L.orc_ssprk2_step.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_double, _dp, _dp]
+    L.orc_solve.restype = C.c_int64
+    L.orc_solve.argtypes = [C.c_void_p, _dp, C.c_double, _dp, C.c_int64, C.c_double]
+    L.orc_global_integral.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
+    return L
 
 
 STEP_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_double, C.c_void_p)
@@ -241,8 +254,8 @@ class Oracle:
     """Discretised ES-DGSEM operator on a Cartesian box, CPU restatement of the reference."""
 
     def __init__(self, dim, fe_degree, nx, left, right, periodic=None, gamma=1.6666666666667,
-                 n_species=1, fields_enabled=False, bc_kinds=None, threads=1):
-        L = lib()
+                 n_species=1, fields_enabled=False, bc_kinds=None, threads=1, variant=None):
+        L = self._L = lib(variant)
         self.dim, self.p, self.gamma, self.nsp = dim, fe_degree, gamma, n_species
         self.nx, self.left, self.right = list(nx), list(left), list(right)
         periodic = [1] * dim if periodic is None else [int(bool(x)) for x in periodic]
@@ -269,26 +282,33 @@ class Oracle:
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().orc_destroy(self.h)
+            self._L.orc_destroy(self.h)
             self.h = None
 
     def set_threads(self, n):
-        lib().orc_set_threads(self.h, n)
+        self._L.orc_set_threads(self.h, n)
 
     def node_coords(self):
         xyz = np.zeros((self.n_elems, self.NN, self.dim))
-        lib().orc_node_coords(self.h, _ptr(xyz))
+        self._L.orc_node_coords(self.h, _ptr(xyz))
         return xyz
 
     def set_inflow(self, species, boundary_id, q):
-        lib().orc_set_inflow(self.h, species, boundary_id, _ptr(_f64(q)))
+        self._L.orc_set_inflow(self.h, species, boundary_id, _ptr(_f64(q)))
 
     def set_sources(self, enabled, epsilon0=1.0, chi=0.0, charge_over_mass=None):
         """Two-fluid source terms (new physics, not in the reference): see dgsem_oracle.cc::add_sources."""
         qm = _f64(charge_over_mass if charge_over_mass is not None else np.zeros(self.nsp))
-        L = lib()
+        L = self._L
         L.orc_set_sources.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, _dp]
         L.orc_set_sources(self.h, int(enabled), epsilon0, chi, _ptr(qm))
+
+    def set_maxwell(self, enabled, light_speed=1.0, chi=0.0, gamma=0.0):
+        """Perfectly hyperbolic Maxwell fluxes for the 8 field components (new physics): dgsem_oracle.cc::add_maxwell."""
+        L = self._L
+        L.orc_set_maxwell.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        if L.orc_set_maxwell(self.h, int(enabled), light_speed, chi, gamma) != 0:
+            raise ValueError("set_maxwell: needs the 8 field components, a Cartesian box and light_speed > 0")
 
     def set_inflow_function(self, species, boundary_id, fn):
         """fn(x: ndarray[dim], t: float) -> 5 conserved values, evaluated at every boundary quadrature point with the
@@ -304,7 +324,7 @@ class Oracle:
         if not hasattr(self, "_inflow_cbs"):
             self._inflow_cbs = {}
         self._inflow_cbs[(species, boundary_id)] = cb   # keep the thunk alive
-        lib().orc_set_inflow_function(self.h, species, boundary_id, cb, None)
+        self._L.orc_set_inflow_function(self.h, species, boundary_id, cb, None)
 
     def project(self, prim_fn, species=0, u=None, conserved=False):
         """Nodal interpolation of an IC given as fn(xyz[...,dim]) -> [...,5] (dg_solution_helper.cc:24-48)."""
@@ -320,35 +340,35 @@ class Oracle:
         u = _f64(u)
         dudt = np.zeros(self.shape)
         bif = np.zeros(5 * self.n_boundaries)
-        lib().orc_rhs(self.h, _ptr(u), t, _ptr(dudt), _ptr(bif))
+        self._L.orc_rhs(self.h, _ptr(u), t, _ptr(dudt), _ptr(bif))
         return dudt, bif
 
     def alpha(self, u):
         u = _f64(u)
         a = np.zeros((self.n_elems, self.nsp))
-        lib().orc_alpha(self.h, _ptr(u), _ptr(a))
+        self._L.orc_alpha(self.h, _ptr(u), _ptr(a))
         return a
 
     def cell_residual(self, ue, alpha):
         ue = _f64(ue)
         R = np.zeros((5, self.NN))
-        lib().orc_cell_residual(self.h, _ptr(ue), alpha, _ptr(R))
+        self._L.orc_cell_residual(self.h, _ptr(ue), alpha, _ptr(R))
         return R
 
     def shock_indicator(self, v):
-        return lib().orc_shock_indicator(self.h, _ptr(_f64(v)))
+        return self._L.orc_shock_indicator(self.h, _ptr(_f64(v)))
 
     def forward_euler_step(self, dst, u, dt, t, a=1.0, beta=0.0, bif_dst=None, bif_u=None):
         assert dst.flags.c_contiguous and dst.dtype == np.float64
         u = _f64(u)
-        lib().orc_forward_euler_step(self.h, _ptr(dst), _ptr(u), dt, t, a, beta,
+        self._L.orc_forward_euler_step(self.h, _ptr(dst), _ptr(u), dt, t, a, beta,
                                      _ptr(bif_dst) if bif_dst is not None else None,
                                      _ptr(bif_u) if bif_u is not None else None)
         return dst
 
     def lsrk_stage(self, sol, r_out, r_in, factor_solution, factor_ai, t=0.0):
         """k = M^-1 R(r_in); r_out = sol + factor_ai k; sol += factor_solution k (rk.h:53-71); r_out may be r_in."""
-        L = lib()
+        L = self._L
         L.orc_lsrk_stage.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double]
         assert sol.flags.c_contiguous and r_out.flags.c_contiguous and r_in.flags.c_contiguous
         L.orc_lsrk_stage(self.h, _ptr(sol), _ptr(r_out), _ptr(r_in), factor_solution, factor_ai, t)
@@ -362,27 +382,27 @@ class Oracle:
         return u
 
     def max_transport_speed(self, u):
-        return lib().orc_max_transport_speed(self.h, _ptr(_f64(u)))
+        return self._L.orc_max_transport_speed(self.h, _ptr(_f64(u)))
 
     def recommend_dt(self, u):
-        return lib().orc_recommend_dt(self.h, _ptr(_f64(u)))
+        return self._L.orc_recommend_dt(self.h, _ptr(_f64(u)))
 
     def ssprk2_step(self, u, dt, t, bif=None):
         assert u.flags.c_contiguous and u.dtype == np.float64
         f1 = np.zeros_like(u)
         bif_f1 = np.zeros(5 * self.n_boundaries) if bif is not None else None
-        lib().orc_ssprk2_step(self.h, _ptr(u), _ptr(f1), dt, t,
+        self._L.orc_ssprk2_step(self.h, _ptr(u), _ptr(f1), dt, t,
                               _ptr(bif) if bif is not None else None,
                               _ptr(bif_f1) if bif is not None else None)
         return u
 
     def solve(self, u, t_end, bif=None, max_steps=0, fixed_dt=0.0):
         assert u.flags.c_contiguous and u.dtype == np.float64
-        return lib().orc_solve(self.h, _ptr(u), t_end, _ptr(bif) if bif is not None else None, max_steps, fixed_dt)
+        return self._L.orc_solve(self.h, _ptr(u), t_end, _ptr(bif) if bif is not None else None, max_steps, fixed_dt)
 
     def global_integral(self, u, species=0):
         out = np.zeros(5)
-        lib().orc_global_integral(self.h, _ptr(_f64(u)), species, _ptr(out))
+        self._L.orc_global_integral(self.h, _ptr(_f64(u)), species, _ptr(out))
         return out
 
 

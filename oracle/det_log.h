@@ -21,7 +21,12 @@
 
 namespace detlog {
 
-inline double det_log(double x) {
+// (a build that contracts multiply-adds elsewhere keeps this function as written: oracle/Makefile, liboracle_fma.so)
+#ifndef DETLOG_ATTR
+#define DETLOG_ATTR
+#endif
+
+inline DETLOG_ATTR double det_log(double x) {
     uint64_t ix;
     std::memcpy(&ix, &x, sizeof ix);
     uint32_t hx = (uint32_t)(ix >> 32);

@@ -110,6 +110,11 @@ void orc_set_inflow(void* h, int species, int boundary_id, const double q[5]);
 // reference has no such terms (field components are carried through unchanged), so this is new physics defined in
 // dgsem_oracle.cc::add_sources; off unless enabled here.  charge_over_mass[n_species].
 void orc_set_sources(void* h, int enabled, double epsilon0, double chi, const double* charge_over_mass);
+// Perfectly hyperbolic Maxwell fluxes for the 8 field components (curl, divergence cleaning; new physics, see
+// dgsem_oracle.cc::add_maxwell): light speed c, cleaning speeds chi (electric) and gamma (magnetic) in units of c.  With
+// it the transport speed of recommend_dt also covers c max(1, chi, gamma) and (sources on) the plasma / cyclotron frequency.
+// Returns non-zero if the context has no field components, is not a Cartesian box or light_speed <= 0.
+int orc_set_maxwell(void* h, int enabled, double light_speed, double chi, double gamma);
 typedef void (*orc_inflow_fn)(const double* x, double t, double* q5, void* user);
 void orc_set_inflow_function(void* h, int species, int boundary_id, orc_inflow_fn fn, void* user);
 // dudt = M^-1 R(u) (fluid comps only; field comps 0); bif_rate[5*n_boundaries] per species summed as the reference does.

@@ -155,6 +155,24 @@ def rhs_error_and_bound(got, want, scale, tol=1e-12):
     return err, bound
 
 
+def mirror_x(u, dim, Np, nx):
+    """The same state on the mirror image of the box (x -> -x): element and node order reversed along x, x-momentum
+    negated.  The scheme is exactly symmetric under it, so rhs(mirror_x(u)) == mirror_x(rhs(u)) in exact arithmetic; in
+    floating point the sums run in the opposite order, which makes the difference a measurement of the formula's own
+    rounding floor (elements are numbered lexicographically, x fastest: the oracle's order)."""
+    n_elems, nc, NN = u.shape
+    shp_e = tuple(reversed(nx))               # [..., ey, ex]
+    shp_n = (Np,) * dim                       # [..., i1, i0]
+    v = u.reshape(shp_e + (nc,) + shp_n)
+    v = np.flip(v, axis=dim - 1)              # ex
+    v = np.flip(v, axis=v.ndim - 1)           # i0
+    v = np.ascontiguousarray(v).reshape(u.shape).copy()
+    nsp = nc // 5 if nc % 5 == 0 else (nc - 8) // 5
+    for s in range(nsp):
+        v[:, 5 * s + 1, :] *= -1.0
+    return v
+
+
 def rel_l2_guarded(got, want, scale, kappa=1e-2):
     """||got - want||_2 / max(||want||_2, kappa * scale) per component (see summand_scale)."""
     out = []

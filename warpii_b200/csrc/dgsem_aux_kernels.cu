@@ -334,6 +334,39 @@ double launch_fp64_fma_chain(int blocks, double* sink, cudaStream_t s) {
 }
 }  // namespace wgpu
 
+// ---- FP64 rate as a function of resident warps and independent chains per thread (tuning diagnostic) ------------------
+// One block of `threads` threads per SM and `ILP` independent FMA chains per thread: the rate this reaches relative to the peak
+// above tells how many warps x chains the stage kernel needs in flight to keep the FP64 pipe busy (profiles/README.md).
+namespace wgpu {
+template <int ILP>
+__global__ void fp64_ilp_kernel(double* sink, double seed) {
+    double a[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; k++) a[k] = seed + 1e-3 * (threadIdx.x + k);
+    const double m = 1.0 - 1e-9, c = 1e-9;
+#pragma unroll 4
+    for (int it = 0; it < kFmaIters; it++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) a[k] = fma(a[k], m, c);
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++) sum += a[k];
+    if (sum == 123.456) sink[0] = sum;
+}
+double launch_fp64_ilp(int blocks, int threads, int ilp, double* sink, cudaStream_t s) {
+    switch (ilp) {
+        case 1: fp64_ilp_kernel<1><<<blocks, threads, 0, s>>>(sink, 0.5); break;
+        case 2: fp64_ilp_kernel<2><<<blocks, threads, 0, s>>>(sink, 0.5); break;
+        case 3: fp64_ilp_kernel<3><<<blocks, threads, 0, s>>>(sink, 0.5); break;
+        case 4: fp64_ilp_kernel<4><<<blocks, threads, 0, s>>>(sink, 0.5); break;
+        case 6: fp64_ilp_kernel<6><<<blocks, threads, 0, s>>>(sink, 0.5); break;
+        default: fp64_ilp_kernel<8><<<blocks, threads, 0, s>>>(sink, 0.5); ilp = 8; break;
+    }
+    return (double)blocks * threads * ilp * kFmaIters;
+}
+}  // namespace wgpu
+
 // ---- point physics on the device, for known-answer tests (the reference's euler_test.cc goldens) -----------------
 namespace wgpu {
 __global__ void point_flux_kernel(int n, const double* qa, const double* qb, int d, double gamma, double* ec,

@@ -47,6 +47,18 @@ __host__ __device__ constexpr int pencil_elems(int dim, int np) {
     return e;
 }
 
+// compile-time loop: f(IC<B>{}), ..., f(IC<E-1>{}) (the pair loops must be unrolled whatever the unroller's budget says:
+// a rolled iteration would index the register arrays dynamically, i.e. put them in local memory)
+template <int I>
+struct IC { static constexpr int value = I; };
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(IC<B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
 template <int DIM, int NP>
 struct PGeo {
     static constexpr int NN = ipow_c(NP, DIM);
@@ -195,14 +207,13 @@ __device__ __forceinline__ void pencil_phase0(const StageParams& P, double* smem
     const int64_t e = e0 + le;
     const int64_t e_hi = (e0 + G::E < P.elem_end) ? e0 + G::E : P.elem_end;
     if (e >= P.elem_end) return;   // (its records are never read: the in-patch test uses e_hi)
+    // neighbour ids of the y-faces first: the loads they address (ends of next phase's pencil) then overlap with the state's
+    const int v0 = P.nbr[(size_t)e * G::NFACE + 2], v1 = P.nbr[(size_t)e * G::NFACE + 3];
     double q[5][NP];
     const double* src = P.u + ((size_t)e * P.nc + 5 * sp) * G::NN + pe * NP;
 #pragma unroll
     for (int c = 0; c < 5; c++) load_run<NP>(src + (size_t)c * G::NN, q[c]);
-    {
-        const int v0 = P.nbr[(size_t)e * G::NFACE + 2], v1 = P.nbr[(size_t)e * G::NFACE + 3];
-        pencil_halo_fetch<DIM, NP, 1>(P, v0, v1, pe, e0, e_hi, sp, next);
-    }
+    pencil_halo_fetch<DIM, NP, 1>(P, v0, v1, pe, e0, e_hi, sp, next);
     if (sp == 0)
         for (int f = pe; f < G::NFACE; f += G::NPEN) sNbr[le * G::NFACE + f] = P.nbr[(size_t)e * G::NFACE + f];
     double v[NP];
@@ -245,10 +256,37 @@ __device__ __forceinline__ void pencil_sums(const StageParams& P, const double2*
 #pragma unroll
         for (int c = 0; c < 5; c++) acc[m][c] = 0.0;
     // ---- the two ends: own side of the face, gather form (f*(a,b,n) = -f*(b,a,-n) bit for bit) -----------------------
+    // In a full patch every thread has exactly ONE end whose neighbour lies outside the patch, but WHICH one differs between
+    // the lanes of a warp (the left elements of the patch look left, the right ones right).  So the outside end's record is
+    // formed once, side-agnostic (no divergence: one make_prim per warp instead of two half-empty ones), and each side then
+    // picks its neighbour record with selects; the in-patch read always happens (slot 0 when unused) to stay branch-free.
     const double cf = P.inv_hw[D];
+    const int os = (h.kind[0] == 1) ? 0 : 1;
+    Prim bo;
+    {
+        double qo[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) qo[c] = os ? h.q[1][c] : h.q[0][c];
+        if (h.kind[0] == 1 || h.kind[1] == 1) bo = make_prim(qo[0], qo[1], qo[2], qo[3], qo[4], gamma);
+        else bo = r[0];
+    }
 #pragma unroll
     for (int side = 0; side < 2; side++) {
         const int m = side ? NP - 1 : 0;
+        Prim b = get_rec<true>(sRec, G::NODES, h.nslot[side]);
+        if (h.kind[side] == 1) {
+            if (side == os) b = bo;
+            else b = make_prim(h.q[side][0], h.q[side][1], h.q[side][2], h.q[side][3], h.q[side][4], gamma);   // both ends outside
+        }
+        // (a domain-boundary end evaluates the flux against a harmless record and discards it: the common path stays one
+        // basic block with the pair loop below, which is what lets the scheduler interleave the two ends and the pairs)
+        double Fe[5], Dv[5], ibl;
+        ec_flux_d(D, r[m], b, hig, Fe, ibl);
+        es_dissipation(r[m], b, ibl, hig, Dv);
+        // (f(u_m).n - f*) / (h w_0) with f* = sgn F# - D and the f(u_m).n part dropped (see the file header)
+        double ct[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) ct[c] = cf * (side ? (Dv[c] - Fe[c]) : (Dv[c] + Fe[c]));
         if (h.kind[side] == 2) {
             // domain boundary: boundary_kernel's contribution (f(u_m).n - f*_LF, Gauss(p+2) quadrature) plus the diagonal
             // volume term, which only cancels against a NODAL f(u_m).n
@@ -259,23 +297,16 @@ __device__ __forceinline__ void pencil_sums(const StageParams& P, const double2*
             phys_flux_d(D, a, Fp);
             const double sg = side ? -cf : cf;
 #pragma unroll
-            for (int c = 0; c < 5; c++) acc[m][c] += h.q[side][c] + sg * Fp[c];
-        } else {
-            const Prim b = (h.kind[side] == 0) ? get_rec<true>(sRec, G::NODES, h.nslot[side])
-                                               : make_prim(h.q[side][0], h.q[side][1], h.q[side][2], h.q[side][3], h.q[side][4], gamma);
-            double Fe[5], Dv[5], ibl;
-            ec_flux_d(D, r[m], b, hig, Fe, ibl);
-            es_dissipation(r[m], b, ibl, hig, Dv);
-            // (f(u_m).n - f*) / (h w_0) with f* = sgn F# - D and the f(u_m).n part dropped (see the file header)
-#pragma unroll
-            for (int c = 0; c < 5; c++) acc[m][c] = fma(cf, side ? (Dv[c] - Fe[c]) : (Dv[c] + Fe[c]), acc[m][c]);
+            for (int c = 0; c < 5; c++) ct[c] = h.q[side][c] + sg * Fp[c];
         }
+#pragma unroll
+        for (int c = 0; c < 5; c++) acc[m][c] += ct[c];
     }
     const double s = -2.0 * P.inv_h[D];
-#pragma unroll
-    for (int j = 0; j < NP; j++) {
-#pragma unroll
-        for (int l = j + 1; l < NP; l++) {
+    static_for<0, NP>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        static_for<j + 1, NP>([&](auto L) {
+            constexpr int l = decltype(L)::value;
             double F[5], ibl;
             ec_flux_d(D, r[j], r[l], hig, F, ibl);
             const double wj = s * P.T.D[j * NP + l], wl = s * P.T.D[l * NP + j];
@@ -284,9 +315,9 @@ __device__ __forceinline__ void pencil_sums(const StageParams& P, const double2*
                 acc[j][c] = fma(wj, F[c], acc[j][c]);
                 acc[l][c] = fma(wl, F[c], acc[l][c]);
             }
-        }
+        });
         done(j, acc[j]);
-    }
+    });
 }
 
 // Legendre analysis of the indicator scratch along one direction, in place in registers
@@ -474,14 +505,21 @@ __device__ __forceinline__ double pencil_phase_final(const StageParams& P, doubl
     }
 
     // stage update (inverse mass is folded into the factors above), :190-212 of the reference operator; component by
-    // component so that only one run of u / old values is live at a time.  rate[][] becomes the new state.
+    // component with the next component's runs of u / old values already in flight.  rate[][] becomes the new state.
     const bool need_old = (P.mode == 2) || (P.mode == 0 && P.beta != 0.0);
     const double* const oldp = (P.mode == 2) ? P.sol_in : P.dst;
+    double qn[NP] = {}, on[NP] = {};
+    if (P.mode != 1) load_run<NP>(P.u + off, qn);
+    if (need_old) load_run<NP>(oldp + off, on);
 #pragma unroll
     for (int c = 0; c < 5; c++) {
         double q[NP], old[NP], out2[NP];
-        if (P.mode != 1) load_run<NP>(P.u + off + (size_t)c * G::NN, q);
-        if (need_old) load_run<NP>(oldp + off + (size_t)c * G::NN, old);
+#pragma unroll
+        for (int m = 0; m < NP; m++) { q[m] = qn[m]; old[m] = on[m]; }
+        if (c < 4) {
+            if (P.mode != 1) load_run<NP>(P.u + off + (size_t)(c + 1) * G::NN, qn);
+            if (need_old) load_run<NP>(oldp + off + (size_t)(c + 1) * G::NN, on);
+        }
 #pragma unroll
         for (int m = 0; m < NP; m++) {
             const double r = rate[c][m];
@@ -510,7 +548,7 @@ __device__ __forceinline__ double pencil_phase_final(const StageParams& P, doubl
             if (DIM > 2) conv = fmax(conv, fabs(rate[3][m] * inv) * P.inv_h[2]);
             const double c2 = P.gamma * pr * inv;
             // a non-positive or NaN c^2 (unphysical state) must reach the host as a NaN speed, not be clamped
-            const double cs = (c2 > 0.0) ? sqrt_pos(c2) : sqrt(c2 - 1.0);
+            const double cs = (c2 > 0.0) ? sqrt_pos(c2) : __hiloint2double(0x7ff80000, 0);
             const double speed = P.max_eig * cs + conv;
             vmax_local = (speed > vmax_local || speed != speed) ? speed : vmax_local;
         }
@@ -529,40 +567,44 @@ __device__ __forceinline__ void pencil_phase_fields(const StageParams& P, const 
     const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
     const int64_t e = e0 + le;
     if (e >= P.elem_end || P.nc <= 5 * P.nsp) return;
-    for (int m = 0; m < NP; m++) {
-        const int j = pe * NP + m;
-        double S[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        if (P.src_on) {
-            double Jx = 0.0, Jy = 0.0, Jz = 0.0, rc = 0.0;
-            for (int sp = 0; sp < P.nsp; sp++) {
-                const size_t so = ((size_t)e * P.nc + 5 * sp) * G::NN + j;
-                const double qm = P.qm[sp];
-                rc += qm * P.u[so];
-                Jx += qm * P.u[so + G::NN];
-                Jy += qm * P.u[so + 2 * (size_t)G::NN];
-                Jz += qm * P.u[so + 3 * (size_t)G::NN];
-            }
-            S[0] = -Jx * P.inv_eps0;
-            S[1] = -Jy * P.inv_eps0;
-            S[2] = -Jz * P.inv_eps0;
-            S[6] = P.chi * rc * P.inv_eps0;
-        }
+    const size_t base = (size_t)e * P.nc * G::NN + pe * NP;   // node 0 of the pencil, component 0
+    double J[3][NP], rc[NP];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {   // fields_enabled means exactly these 8 components (five_moment.h:123-138)
-            if (5 * P.nsp + k >= P.nc) break;
-            const size_t off = ((size_t)e * P.nc + 5 * P.nsp + k) * G::NN + j;
-            const double rate = S[k];
+    for (int m = 0; m < NP; m++) { J[0][m] = 0.0; J[1][m] = 0.0; J[2][m] = 0.0; rc[m] = 0.0; }
+    if (P.src_on) {
+        for (int sp = 0; sp < P.nsp; sp++) {
+            const double qm = P.qm[sp];
+            double r[NP], mx[NP], my[NP], mz[NP];
+            load_run<NP>(P.u + base + (size_t)(5 * sp) * G::NN, r);
+            load_run<NP>(P.u + base + (size_t)(5 * sp + 1) * G::NN, mx);
+            load_run<NP>(P.u + base + (size_t)(5 * sp + 2) * G::NN, my);
+            load_run<NP>(P.u + base + (size_t)(5 * sp + 3) * G::NN, mz);
+#pragma unroll
+            for (int m = 0; m < NP; m++) { rc[m] += qm * r[m]; J[0][m] += qm * mx[m]; J[1][m] += qm * my[m]; J[2][m] += qm * mz[m]; }
+        }
+    }
+    const bool need_old = (P.mode == 2) || (P.mode == 0 && P.beta != 0.0);
+    const double* const oldp = (P.mode == 2) ? P.sol_in : P.dst;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {   // fields_enabled means exactly these 8 components (five_moment.h:123-138)
+        if (5 * P.nsp + k >= P.nc) break;
+        const size_t off = base + (size_t)(5 * P.nsp + k) * G::NN;
+        double f[NP], old[NP], out[NP], out2[NP];
+        if (P.mode != 1) load_run<NP>(P.u + off, f);
+        if (need_old) load_run<NP>(oldp + off, old);
+#pragma unroll
+        for (int m = 0; m < NP; m++) {
+            double rate = 0.0;
+            if (P.src_on) rate = (k < 3) ? -J[k < 3 ? k : 0][m] * P.inv_eps0 : (k == 6 ? P.chi * rc[m] * P.inv_eps0 : 0.0);
             double v;
             if (P.mode == 1) v = rate;
-            else if (P.mode == 2) {
-                const double s0 = P.sol_in[off];
-                v = fma(P.a, rate, s0);
-                if (P.beta != 0.0) P.dst2[off] = fma(P.beta, rate, s0);
-            }
-            else if (P.beta == 0.0) v = P.a * (P.u[off] + dt * rate);
-            else v = P.beta * P.dst[off] + P.a * (P.u[off] + dt * rate);
-            P.dst[off] = v;
+            else if (P.mode == 2) { v = fma(P.a, rate, old[m]); out2[m] = fma(P.beta, rate, old[m]); }
+            else if (P.beta == 0.0) v = P.a * (f[m] + dt * rate);
+            else v = P.beta * old[m] + P.a * (f[m] + dt * rate);
+            out[m] = v;
         }
+        store_run<NP>(P.dst + off, out);
+        if (P.mode == 2 && P.beta != 0.0) store_run<NP>(P.dst2 + off, out2);
     }
 }
 

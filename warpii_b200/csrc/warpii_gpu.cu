@@ -367,6 +367,11 @@ int warpii_gpu_elems_per_block(int dim, int fe_degree) {
     return patch_elems(dim, fe_degree + 1);
 }
 
+int warpii_gpu_stage_kernel_is_pencil(int dim, int fe_degree) {
+    if (dim < 1 || dim > 3 || fe_degree < 1 || fe_degree > 6) return 0;
+    return use_pencil(dim, fe_degree + 1) ? 1 : 0;
+}
+
 int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out) {
     if (!m || !out) return fail("warpii_gpu_create: null argument");
     *out = nullptr;
@@ -1364,6 +1369,42 @@ extern "C" int warpii_gpu_measure_fp64_peak(int device, double* fma_per_second_o
     for (int rep = 0; rep < 6; rep++) {
         CUDA_OK(cudaEventRecord(e0, nullptr));
         const double fmas = wgpu::launch_fp64_fma_chain(blocks, sink, nullptr);
+        CUDA_OK(cudaEventRecord(e1, nullptr));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms > 0) best = std::max(best, fmas / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *fma_per_second_out = best;
+    return 0;
+}
+
+namespace wgpu {
+double launch_fp64_ilp(int blocks, int threads, int ilp, double* sink, cudaStream_t s);
+}
+
+// Tuning diagnostic: FMA rate (per second, thread level) with ONE block of `threads_per_sm` threads per SM and `ilp`
+// independent chains per thread, i.e. the FP64 throughput a kernel with that many resident warps and that much
+// instruction-level parallelism can reach (compare with warpii_gpu_measure_fp64_peak).
+extern "C" int warpii_gpu_fp64_rate_probe(int device, int threads_per_sm, int ilp, double* fma_per_second_out) {
+    if (!fma_per_second_out || threads_per_sm < 32 || threads_per_sm > 1024) return fail("fp64_rate_probe: bad argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail("no CUDA device available");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    double* sink = nullptr;
+    if (upload<double>(&sink, nullptr, 1)) return 1;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CUDA_OK(cudaEventRecord(e0, nullptr));
+        const double fmas = wgpu::launch_fp64_ilp(prop.multiProcessorCount, threads_per_sm, ilp, sink, nullptr);
         CUDA_OK(cudaEventRecord(e1, nullptr));
         CUDA_OK(cudaEventSynchronize(e1));
         float ms = 0;
