@@ -51,11 +51,14 @@ WORKLOADS = {
                       "degree 3, 1024x1024 elements"),
     "C5s": dict(dim=2, p=3, nx=[1024, 512], left=[0.0, -5.0], right=[20.0, 5.0], gamma=5.0 / 3.0, ic="two_fluid", n_species=2,
                 fields=True, sources=dict(epsilon0=1.0, chi=1.0, charge_over_mass=[1.0 / 25.0, -1.0]),
-                label="C5 shape: 2D two-species five-moment + 8 field components with Lorentz/current sources "
-                      "(no Maxwell curl fluxes), degree 3, 1024x512 elements"),
+                maxwell=dict(light_speed=10.0, chi=1.0, gamma=1.0),
+                label="C5: 2D two-species five-moment + Maxwell (8 field components evolved by the PHM fluxes, Lorentz/current "
+                      "sources), degree 3, 1024x512 elements"),
     "N3D": dict(dim=3, p=3, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[20.0, 5.0, 5.0], gamma=5.0 / 3.0, ic="two_fluid", n_species=2,
                 fields=True, sources=dict(epsilon0=1.0, chi=1.0, charge_over_mass=[1.0 / 25.0, -1.0]),
-                label="north-star shape: 3D two-species five-moment + 8 field components with sources, degree 3, 64^3 elements"),
+                maxwell=dict(light_speed=10.0, chi=1.0, gamma=1.0),
+                label="north-star shape: 3D two-species five-moment + Maxwell (8 field components evolved, Lorentz/current sources), "
+                      "degree 3, 64^3 elements"),
     "C2c": dict(dim=2, p=3, nx=[512, 512], left=[0.0, -5.0], right=[10.0, 5.0], gamma=1.4, ic="vortex", mapping="wavy",
                 label="C2 on curved elements: the 512x512 degree-3 box pushed through a smooth periodic mapping "
                       "(general-geometry kernels, metric terms read from HBM)"),
@@ -238,6 +241,8 @@ def cpu_run(w, steps, warmup, threads, budget_s, rows=None):
         o = Oracle(dim, w["p"], nxp, w["left"], right, gamma=w["gamma"], threads=threads, **species_kwargs(w))
         if w.get("sources"):
             o.set_sources(True, **w["sources"])
+        if w.get("maxwell"):
+            o.set_maxwell(True, **w["maxwell"])
         u = build_ic(w, o.node_coords())
         dt = o.recommend_dt(u)
         t0 = time.perf_counter()
@@ -250,6 +255,8 @@ def cpu_run(w, steps, warmup, threads, budget_s, rows=None):
     o = Oracle(dim, w["p"], nxs, w["left"], right, gamma=w["gamma"], threads=threads, **species_kwargs(w))
     if w.get("sources"):
         o.set_sources(True, **w["sources"])
+    if w.get("maxwell"):
+        o.set_maxwell(True, **w["maxwell"])
     u = build_ic(w, o.node_coords())
     t = 0.0
     for _ in range(warmup):
@@ -328,6 +335,8 @@ def make_solver(w, world, rank, local_rank):
         g = BoxSolver(dim, p, nx, left, right, gamma=gamma, rank=rank, n_ranks=world, device=local_rank, **species_kwargs(w))
     if w.get("sources"):
         g.set_sources(True, **w["sources"])
+    if w.get("maxwell"):
+        g.set_maxwell(True, **w["maxwell"])
     return g, nx, geo_bytes_per_dof
 
 

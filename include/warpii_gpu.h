@@ -156,6 +156,15 @@ int warpii_gpu_set_inflow_table(warpii_gpu_ctx* ctx, int species, const double* 
  * rho_c = sum_s (q/m)_s rho_s (Species::charge / Species::mass, species.h:43-44).  The curl and divergence-cleaning
  * fluxes of Maxwell's equations are not evolved.  recommend_dt does not know about the plasma frequency. */
 int warpii_gpu_set_sources(warpii_gpu_ctx* ctx, int enabled, double epsilon0, double chi, const double* charge_over_mass);
+/* Perfectly hyperbolic Maxwell (PHM) fluxes for the 8 field components (north_star kernel 4, BASELINE config 5).  NOT in
+ * the reference, which only allocates [Ex,Ey,Ez,Bx,By,Bz,phi,psi] (five_moment.h:123-138); the system is the one
+ * SURVEY.md 8(c) names:  dE/dt - c^2 curl B + chi c^2 grad phi = -J/eps0,  dB/dt + curl E + gamma grad psi = 0,
+ * dphi/dt + chi div E = chi rho_c/eps0,  dpsi/dt + gamma c^2 div B = 0  (sources: warpii_gpu_set_sources), discretised as a
+ * linear DGSEM flux on the fluid's nodes with a Rusanov numerical flux.
+ * With it recommend_dt also covers the wave speed c max(1, chi, gamma) and, with the sources on, the plasma and cyclotron
+ * frequencies (omega dt <= 0.1); halo exchanges carry the field traces too.  Non-periodic boundaries are zero-gradient for
+ * the fields.  Cartesian boxes only (not after warpii_gpu_set_geometry).  Off by default. */
+int warpii_gpu_set_maxwell(warpii_gpu_ctx* ctx, int enabled, double light_speed, double chi, double gamma);
 
 /* -- the operator ----------------------------------------------------------------------------------
  * dst = beta*dst + alpha*(u + dt * M^-1 R(u)), and the same for the boundary-integrated fluxes

@@ -69,6 +69,8 @@ int warpii_box_solver_set_inflow_function(warpii_box_solver* s, int species, int
 /* two-fluid source terms on/off (warpii_gpu_set_sources); charge_over_mass[n_species] */
 int warpii_box_solver_set_sources(warpii_box_solver* s, int enabled, double epsilon0, double chi,
                                   const double* charge_over_mass);
+/* perfectly hyperbolic Maxwell fluxes for the field components on/off (warpii_gpu_set_maxwell) */
+int warpii_box_solver_set_maxwell(warpii_box_solver* s, int enabled, double light_speed, double chi, double gamma);
 /* this rank's boundary faces: xyz[face][point][dim] of the quadrature points (Gauss(fe_degree+2)^(dim-1) per face) and
  * the boundary id of every face, in the order of the inflow table; either output may be NULL */
 int64_t warpii_box_solver_n_boundary_faces(const warpii_box_solver* s);

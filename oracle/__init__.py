@@ -416,7 +416,7 @@ class GeneralOracle(Oracle):
 
     def __init__(self, dim, fe_degree, mesh, geometry, n_boundaries=0, bc_kinds=None, gamma=1.6666666666667, n_species=1,
                  fields_enabled=False, threads=1):
-        L = lib()
+        L = self._L = lib()
         i64p, i32p = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
         L.orc_create_general.restype = C.c_void_p
         L.orc_create_general.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_int, i64p, i32p,

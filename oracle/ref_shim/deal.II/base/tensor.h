@@ -6,7 +6,11 @@
 #include <initializer_list>
 #include <type_traits>
 #include "table_indices.h"
+#include "vectorization.h"
 namespace dealii {
+// what may multiply / divide a tensor: built-in arithmetic types and (one-lane) VectorizedArray
+template <typename S> struct is_tensor_scalar : std::is_arithmetic<S> {};
+template <typename N, std::size_t w> struct is_tensor_scalar<VectorizedArray<N, w>> : std::true_type {};
 template <int rank, int dim, typename Number = double>
 class Tensor;
 
@@ -19,12 +23,12 @@ class Tensor<1, dim, Number> {
     const Number& operator[](unsigned i) const { return v[i]; }
     Tensor& operator+=(const Tensor& o) { for (int i = 0; i < dim; i++) v[i] += o.v[i]; return *this; }
     Tensor& operator-=(const Tensor& o) { for (int i = 0; i < dim; i++) v[i] -= o.v[i]; return *this; }
-    template <typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+    template <typename S, typename = typename std::enable_if<is_tensor_scalar<S>::value>::type>
     Tensor& operator*=(const S s) { for (int i = 0; i < dim; i++) v[i] *= s; return *this; }
-    template <typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+    template <typename S, typename = typename std::enable_if<is_tensor_scalar<S>::value>::type>
     Tensor& operator/=(const S s) { for (int i = 0; i < dim; i++) v[i] /= s; return *this; }
-    Number norm_square() const { Number s = Number(); for (int i = 0; i < dim; i++) s += v[i] * v[i]; return s; }
-    Number norm() const { return std::sqrt(norm_square()); }
+    Number norm_square() const { Number s = v[0] * v[0]; for (int i = 1; i < dim; i++) s += v[i] * v[i]; return s; }
+    Number norm() const { using std::sqrt; return sqrt(norm_square()); }
    private:
     Number v[dim > 0 ? dim : 1];
 };
@@ -44,14 +48,14 @@ template <int dim, typename Number>
 inline Tensor<1, dim, Number> operator-(Tensor<1, dim, Number> a, const Tensor<1, dim, Number>& b) { a -= b; return a; }
 template <int dim, typename Number>
 inline Tensor<1, dim, Number> operator-(Tensor<1, dim, Number> a) { for (int i = 0; i < dim; i++) a[i] = -a[i]; return a; }
-template <int dim, typename Number, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+template <int dim, typename Number, typename S, typename = typename std::enable_if<is_tensor_scalar<S>::value>::type>
 inline Tensor<1, dim, Number> operator*(const S s, Tensor<1, dim, Number> a) { for (int i = 0; i < dim; i++) a[i] = s * a[i]; return a; }
-template <int dim, typename Number, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+template <int dim, typename Number, typename S, typename = typename std::enable_if<is_tensor_scalar<S>::value>::type>
 inline Tensor<1, dim, Number> operator*(Tensor<1, dim, Number> a, const S s) { for (int i = 0; i < dim; i++) a[i] = a[i] * s; return a; }
-template <int dim, typename Number, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+template <int dim, typename Number, typename S, typename = typename std::enable_if<is_tensor_scalar<S>::value>::type>
 inline Tensor<1, dim, Number> operator/(Tensor<1, dim, Number> a, const S s) { for (int i = 0; i < dim; i++) a[i] = a[i] / s; return a; }
 // scalar product of two rank-1 tensors of arithmetic type
-template <int dim, typename Number, typename = typename std::enable_if<std::is_arithmetic<Number>::value>::type>
+template <int dim, typename Number, typename = typename std::enable_if<is_tensor_scalar<Number>::value>::type>
 inline Number operator*(const Tensor<1, dim, Number>& a, const Tensor<1, dim, Number>& b) {
     Number s = a[0] * b[0];
     for (int i = 1; i < dim; i++) s += a[i] * b[i];

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/../warpii_b200"
 mkdir -p variants build/var_$name
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -ccbin /usr/bin/g++ -Xcompiler -fPIC $*"
-for f in dgsem_stage_kernel dgsem_pencil_kernel dgsem_general_kernel dgsem_aux_kernels warpii_gpu; do
+for f in dgsem_stage_kernel dgsem_pencil_kernel dgsem_maxwell_kernel dgsem_general_kernel dgsem_aux_kernels warpii_gpu; do
   $NVCC $FLAGS -Xptxas -v -c csrc/$f.cu -o build/var_$name/$f.o 2> build/var_$name/$f.log
 done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o variants/$name.so build/var_$name/*.o build/solver_capi.o -ldl

@@ -24,6 +24,8 @@ def main():
         g = BoxSolver(w["dim"], w["p"], w["nx"], w["left"], w["right"], gamma=w["gamma"], **bench.species_kwargs(w))
         if w.get("sources"):
             g.set_sources(True, **w["sources"])
+        if w.get("maxwell") and not os.environ.get("WARPII_NO_MAXWELL"):
+            g.set_maxwell(True, **w["maxwell"])
         u0 = bench.build_ic(w, g.node_coords())
         g.upload(0, u0)
         t, _ = g.advance_to(0.0, 1e30, max_steps=3)

@@ -173,6 +173,22 @@ def mirror_x(u, dim, Np, nx):
     return v
 
 
+def field_summand_scale(u, n_species, dim, h, D, light_speed, chi, gamma):
+    """summand_scale for the 8 field components of the PHM system (oracle add_maxwell): magnitude of the differenced flux terms."""
+    amp = 2.0 * dim * np.abs(D).max() / min(h)
+    F = u[:, 5 * n_species:5 * n_species + 8, :]
+    c2 = light_speed ** 2
+    E = np.sqrt(F[:, 0] ** 2 + F[:, 1] ** 2 + F[:, 2] ** 2)
+    B = np.sqrt(F[:, 3] ** 2 + F[:, 4] ** 2 + F[:, 5] ** 2)
+    lam = light_speed * max(1.0, chi, gamma)
+    out = np.zeros(u.shape[1])
+    mag = [c2 * B + chi * c2 * np.abs(F[:, 6]) + lam * E] * 3 + [E + gamma * np.abs(F[:, 7]) + lam * B] * 3 + \
+          [chi * E + lam * np.abs(F[:, 6]), gamma * c2 * B + lam * np.abs(F[:, 7])]
+    for k in range(8):
+        out[5 * n_species + k] = amp * np.linalg.norm(mag[k])
+    return out
+
+
 def rel_l2_guarded(got, want, scale, kappa=1e-2):
     """||got - want||_2 / max(||want||_2, kappa * scale) per component (see summand_scale)."""
     out = []

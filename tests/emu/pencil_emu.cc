@@ -93,7 +93,7 @@ int emu_pencil_stage(int dim, int np, int64_t n_elems, int64_t elem_begin, int64
     unsigned long long vslot = 0;
     P.vmax = vmax_out ? &vslot : nullptr;
     P.elem_begin = elem_begin; P.elem_end = elem_end; P.n_elems = n_elems;
-    P.nc = nc; P.nsp = nsp; P.mode = mode;
+    P.nc = nc; P.nsp = nsp; P.ncf = 5 * nsp; P.fields_skip = 0; P.mode = mode;
     P.sol_in = sol_in; P.dst2 = dst2;
     P.gamma = gamma; P.dt = dt; P.a = a; P.beta = beta;
     P.hig = 0.5 / (gamma - 1.0);

@@ -69,6 +69,40 @@ def main():
             g1.close()
         g.close()
         dist.barrier()
+    # ---- two fluids + the field system (PHM Maxwell fluxes + sources): the halo carries the field traces too ----------------
+    from test_gpu_maxwell import MX, SRC, two_fluid_state
+    for (dim, p, nx) in [(2, 3, [6, 8]), (3, 3, [4, 4, 6]), (1, 2, [12])]:
+        left, right = [0.0] * dim, [1.0] * dim
+        kw = dict(gamma=5.0 / 3.0, n_species=2, fields_enabled=True)
+        o = Oracle(dim, p, nx, left, right, threads=4, **kw)
+        o.set_sources(True, SRC["epsilon0"], SRC["chi"], SRC["charge_over_mass"])
+        o.set_maxwell(True, **MX)
+        u = two_fluid_state(o)
+        g = BoxSolver(dim, p, nx, left, right, rank=rank, n_ranks=world, device=local, **kw)
+        g.set_sources(True, SRC["epsilon0"], SRC["chi"], SRC["charge_over_mass"])
+        g.set_maxwell(True, **MX)
+        g.attach_comm(fresh_id())
+        g.upload_global(0, u)
+        g.rhs(1, 0)
+        want, _ = o.rhs(u)
+        err = cases.rel_l2_per_component(g.download(1), want[g.l2g])
+        assert (err <= 1e-12).all(), (rank, dim, err)
+        dt = g.recommend_dt(0)
+        assert abs(dt - o.recommend_dt(u)) <= 1e-13 * dt
+        t, steps = g.advance_to(0.0, 1e9, max_steps=20)
+        o.solve(u, t, max_steps=20)
+        got = g.download(0)
+        assert (cases.rel_l2_per_component(got, u[g.l2g]) <= 1e-11).all()
+        if rank == 0:
+            g1 = BoxSolver(dim, p, nx, left, right, device=local, **kw)
+            g1.set_sources(True, SRC["epsilon0"], SRC["chi"], SRC["charge_over_mass"])
+            g1.set_maxwell(True, **MX)
+            g1.upload_global(0, two_fluid_state(o))
+            g1.advance_to(0.0, 1e9, max_steps=20)
+            assert np.array_equal(g1.download_global(0)[g.l2g], got), "sharded and single-GPU runs differ (field system)"
+            g1.close()
+        g.close()
+        dist.barrier()
     # ---- curved elements (general-geometry kernels), slab-sharded: halo traces, ghost-face normals from the own element ----
     import mesh_cases as mc
     from oracle import GeneralOracle

@@ -286,7 +286,7 @@ def test_reference_freestream_1d_convergence():
         errs.append(_l2_error_density(o, g.get_state_global(), exact, 2))
         # the product's own compute_global_error (dg_solution_helper.cc:50-69) gives the same number
         mine = g.global_error(lambda x: [exact(x[0]), 0, 0, 0, 0], component=0)
-        assert abs(mine - errs[-1]) <= 1e-12 * errs[-1]
+        assert abs(mine - errs[-1]) <= 1e-11 * errs[-1]   # (two summation orders of the same quadrature)
         g.close()
     assert abs(errs[1]) < 1e-4
     assert abs(errs[0] / errs[1] - 1.5 ** 3) < 1.0

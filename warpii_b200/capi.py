@@ -88,6 +88,7 @@ def lib():
     L.warpii_box_solver_attach_comm.argtypes = [vp, C.c_char_p]
     L.warpii_box_solver_set_inflow_function.argtypes = [vp, C.c_int, C.c_int, INFLOW_FN, vp, C.c_int]
     L.warpii_box_solver_set_sources.argtypes = [vp, C.c_int, C.c_double, C.c_double, _dp]
+    L.warpii_box_solver_set_maxwell.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double]
     L.warpii_box_solver_n_boundary_faces.restype = C.c_int64
     L.warpii_box_solver_n_boundary_faces.argtypes = [vp]
     L.warpii_box_solver_boundary_points.argtypes = [vp, _dp, _i32p]
@@ -361,6 +362,10 @@ class BoxSolver:
             self._inflow_cbs = []
         self._inflow_cbs.append(cb)   # keep the thunk alive as long as the solver
         _check(lib().warpii_box_solver_set_inflow_function(self.h, species, boundary_id, cb, None, int(time_dependent)), host=True)
+
+    def set_maxwell(self, enabled, light_speed=1.0, chi=0.0, gamma=0.0):
+        """Perfectly hyperbolic Maxwell fluxes for the field components (not in the reference operator): warpii_gpu_set_maxwell."""
+        _check(lib().warpii_box_solver_set_maxwell(self.h, int(enabled), light_speed, chi, gamma), host=True)
 
     def set_sources(self, enabled, epsilon0=1.0, chi=0.0, charge_over_mass=None):
         """Two-fluid source terms (north_star kernel 4; not in the reference operator): warpii_gpu_set_sources."""

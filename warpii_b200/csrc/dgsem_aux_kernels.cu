@@ -191,10 +191,9 @@ __global__ void integral_final_kernel(const double* partial, int n_blocks, doubl
 
 template <int DIM, int NP>
 __global__ void pack_kernel(const double* __restrict__ u, const int32_t* __restrict__ send_elem,
-                            const int32_t* __restrict__ send_side, int64_t n_send, int nc, int nsp,
+                            const int32_t* __restrict__ send_side, int64_t n_send, int nc, int ncf,
                             double* __restrict__ sendbuf) {
     constexpr int NN = ipow_c(NP, DIM), NF = ipow_c(NP, DIM - 1);
-    const int ncf = 5 * nsp;
     const int64_t total = n_send * ncf * NF;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int t = (int)(i % NF);
@@ -249,9 +248,9 @@ void launch_integral(int dim, int Np, const double* u, int64_t n_elems, int nc, 
 }
 
 void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, const int32_t* send_side,
-                 int64_t n_send, int nc, int nsp, double* sendbuf, cudaStream_t s) {
+                 int64_t n_send, int nc, int ncf, double* sendbuf, cudaStream_t s) {
     if (n_send <= 0) return;
-#define CALL(D_, N_) { pack_kernel<D_, N_><<<148 * 4, 256, 0, s>>>(u, send_elem, send_side, n_send, nc, nsp, sendbuf); }
+#define CALL(D_, N_) { pack_kernel<D_, N_><<<148 * 4, 256, 0, s>>>(u, send_elem, send_side, n_send, nc, ncf, sendbuf); }
     WGPU_DISPATCH(dim, Np, CALL);
 #undef CALL
 }

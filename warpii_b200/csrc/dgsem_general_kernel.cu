@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(Geo<DIM, NP>::THREADS, GeoG<DIM, NP>::MIN_BLOC
                         src = P.u + ((size_t)v * nc + 5 * sp) * NN + node_of_face_node<DIM, NP>(nfa >> 1, nfa & 1, tp);
                         stride = NN;
                     } else {
-                        src = P.ghost + ((size_t)(v - P.n_elems) * (5 * P.nsp) + 5 * sp) * NF + tp;
+                        src = P.ghost + ((size_t)(v - P.n_elems) * P.ncf + 5 * sp) * NF + tp;
                         stride = NF;
                     }
                 }

@@ -41,6 +41,8 @@ struct StageParams {
     int64_t elem_begin, elem_end; // element range of this launch
     int64_t n_elems;
     int32_t nc, nsp;
+    int32_t ncf;                  // components per ghost face trace: 5*nsp, or nc when the field system is evolved (Maxwell)
+    int32_t fields_skip;          // != 0: the field components are updated by maxwell_kernel, not by the stage kernel
     int32_t mode;                 // 0: dst = beta*dst + a*(u + dt*rate); 1: dst = rate;
                                   // 2: dst = sol_in + a*rate, dst2 = sol_in + beta*rate (low-storage RK stage, rk.h:53-71)
     const double* sol_in;         // mode 2 only (may alias dst: every thread touches its own node only)
@@ -142,9 +144,14 @@ void launch_cfl_general(int dim, int Np, const double* u, int64_t n_elems, int n
                         const GeneralParams& GP, unsigned long long* vmax, cudaStream_t s);
 void launch_integral_general(int dim, int Np, const double* u, int64_t n_elems, int nc, int species, const GeneralParams& GP,
                              const double* w, double* partial, double* out, cudaStream_t s);
-// halo: sendbuf[i][5*nsp][nF] = trace of (send_elem[i], send_side[i])
+// halo: sendbuf[i][ncf][nF] = trace of the first ncf components on (send_elem[i], send_side[i])
 void launch_pack(int dim, int Np, const double* u, const int32_t* send_elem, const int32_t* send_side,
-                 int64_t n_send, int nc, int nsp, double* sendbuf, cudaStream_t s);
+                 int64_t n_send, int nc, int ncf, double* sendbuf, cudaStream_t s);
+// perfectly hyperbolic Maxwell fluxes for the field components (dgsem_maxwell_kernel.cu)
+void launch_maxwell(int dim, int Np, const StageParams& P, double light_speed, double chi, double gamma, cudaStream_t s);
+void launch_maxwell_cfl(int dim, int Np, const double* u, int64_t n_elems, int nc, int nsp, const double* qm, double light_speed,
+                        double chi, double gamma, double inv_eps0, double max_eig, bool sources_on, unsigned long long* vmax,
+                        cudaStream_t s);
 
 #endif  // !WGPU_HOST_EMU
 

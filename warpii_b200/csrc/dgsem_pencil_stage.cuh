@@ -182,7 +182,7 @@ __device__ __forceinline__ void pencil_halo_fetch(const StageParams& P, const in
                 stride = G::NN;
             } else {
                 h.kind[side] = 1;
-                src = P.ghost + ((size_t)(v - P.n_elems) * (5 * P.nsp) + 5 * sp) * G::NPEN + pe;
+                src = P.ghost + ((size_t)(v - P.n_elems) * P.ncf + 5 * sp) * G::NPEN + pe;
                 stride = G::NPEN;
             }
 #pragma unroll
@@ -566,7 +566,7 @@ __device__ __forceinline__ void pencil_phase_fields(const StageParams& P, const 
     if (tid >= G::USED) return;
     const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
     const int64_t e = e0 + le;
-    if (e >= P.elem_end || P.nc <= 5 * P.nsp) return;
+    if (e >= P.elem_end || P.nc <= 5 * P.nsp || P.fields_skip) return;
     const size_t base = (size_t)e * P.nc * G::NN + pe * NP;   // node 0 of the pencil, component 0
     double J[3][NP], rc[NP];
 #pragma unroll

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(GeoC<DIM, NP>::THREADS, GeoC<DIM, NP>::MIN_BLO
                     src = P.u + ((size_t)v * nc + 5 * sp) * NN + node_of_face_node<DIM, NP>(f >> 1, 1 - (f & 1), t);
                     stride = NN;
                 } else {
-                    src = P.ghost + ((size_t)(v - P.n_elems) * (5 * P.nsp) + 5 * sp) * NF + t;
+                    src = P.ghost + ((size_t)(v - P.n_elems) * P.ncf + 5 * sp) * NF + t;
                     stride = NF;
                 }
 #pragma unroll
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(GeoC<DIM, NP>::THREADS, GeoC<DIM, NP>::MIN_BLO
 
     // ---- field components: carried through unchanged by the reference's operator; with the two-fluid
     // sources switched on, E gets -J/eps0 and phi gets chi rho_c/eps0 (J, rho_c summed over the species of this node)
-    if (active && nc > 5 * P.nsp) {
+    if (active && nc > 5 * P.nsp && !P.fields_skip) {
         double S[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         if (P.src_on) {
             double Jx = 0.0, Jy = 0.0, Jz = 0.0, rc = 0.0;

@@ -124,6 +124,9 @@ struct warpii_gpu_ctx {
     bool pencil = false;                    // Cartesian stage launches go to pencil_stage_kernel (dgsem_pencil_kernel.cu)
     bool src_on = false;                    // two-fluid source terms (warpii_gpu_set_sources)
     double inv_eps0 = 1.0, chi = 0.0;
+    bool maxwell_on = false;                // PHM fluxes for the field components (warpii_gpu_set_maxwell)
+    double light_speed = 1.0, mx_chi = 0.0, mx_gamma = 0.0;
+    int ncf = 5;                            // components per halo face trace: 5*nsp, or nc with the field system evolved
     double* d_qm = nullptr;                 // [nsp] charge / mass
     std::vector<double> h_inflow;           // mirror of d_inflow
     std::vector<double> h_inflow_table;     // mirror of d_inflow_table (empty until warpii_gpu_set_inflow_table)
@@ -213,6 +216,10 @@ void do_launch_stage(warpii_gpu_ctx* c, const StageParams& P, cudaStream_t s) {
     if (c->general) launch_stage_general(c->dim, c->Np, P, c->GP, s);
     else if (c->pencil) launch_pencil_stage(c->dim, c->Np, P, s);
     else launch_stage(c->dim, c->Np, P, s);
+    if (c->maxwell_on && P.elem_end > P.elem_begin) {   // the field components of the same range, right behind the fluids
+        launch_maxwell(c->dim, c->Np, P, c->light_speed, c->mx_chi, c->mx_gamma, s);
+        c->launches++;
+    }
 }
 void do_launch_boundary(warpii_gpu_ctx* c, const BoundaryParams& B, cudaStream_t s) {
     if (c->general) launch_boundary_general(c->dim, c->Np, B, c->GP, s);
@@ -221,6 +228,11 @@ void do_launch_boundary(warpii_gpu_ctx* c, const BoundaryParams& B, cudaStream_t
 void do_launch_cfl(warpii_gpu_ctx* c, int vec) {
     if (c->general) launch_cfl_general(c->dim, c->Np, c->vec[vec], c->n_elems, c->nc, c->nsp, c->gamma, c->GP, c->d_vmax + vec, c->stream);
     else launch_cfl(c->dim, c->Np, c->vec[vec], c->n_elems, c->nc, c->nsp, c->gamma, c->inv_h, c->max_eig, c->d_vmax + vec, c->stream);
+    if (c->maxwell_on) {
+        launch_maxwell_cfl(c->dim, c->Np, c->vec[vec], c->n_elems, c->nc, c->nsp, c->d_qm, c->light_speed, c->mx_chi, c->mx_gamma,
+                           c->inv_eps0, c->max_eig, c->src_on, c->d_vmax + vec, c->stream);
+        c->launches++;
+    }
 }
 
 StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double beta, int mode, bool fuse_cfl) {
@@ -241,6 +253,8 @@ StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a,
     P.n_elems = c->n_elems;
     P.nc = c->nc;
     P.nsp = c->nsp;
+    P.ncf = c->ncf;
+    P.fields_skip = c->maxwell_on ? 1 : 0;
     P.mode = mode;
     P.dt_dev = nullptr;
     P.skip_dev = nullptr;
@@ -262,11 +276,11 @@ StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a,
 // halo exchange of the face traces of vector u: pack on the main stream, send/recv on the comm stream
 int start_exchange(warpii_gpu_ctx* c, int u) {
     if (!c->comm || c->peer_rank.empty()) return 0;
-    launch_pack(c->dim, c->Np, c->vec[u], c->d_send_elem, c->d_send_side, c->n_send, c->nc, c->nsp, c->d_sendbuf, c->stream);
+    launch_pack(c->dim, c->Np, c->vec[u], c->d_send_elem, c->d_send_side, c->n_send, c->nc, c->ncf, c->d_sendbuf, c->stream);
     c->launches++;
     CUDA_OK(cudaEventRecord(c->ev_pack, c->stream));
     CUDA_OK(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
-    const size_t per_face = (size_t)5 * c->nsp * c->NF;
+    const size_t per_face = (size_t)c->ncf * c->NF;
     NCCL_OK(g_nccl.GroupStart());
     for (size_t p = 0; p < c->peer_rank.size(); p++) {
         const int64_t ns = c->send_offset[p + 1] - c->send_offset[p];
@@ -402,6 +416,7 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
     c->n_boundaries = m->n_boundaries;
     c->n_vectors = m->n_vectors < 2 ? 2 : m->n_vectors;
     c->n_dofs = c->n_elems * c->nc * c->NN;
+    c->ncf = 5 * c->nsp;
 
     warpii_b200::ReferenceElement re(c->p);
     std::memset(&c->T, 0, sizeof c->T);
@@ -481,7 +496,7 @@ int warpii_gpu_create(const warpii_gpu_mesh* m, int device, warpii_gpu_ctx** out
     rc |= upload(&c->d_w, re.w.data(), (size_t)c->Np);
     rc |= upload<double>(&c->d_bres, nullptr, (size_t)c->n_bfaces * c->nsp * 5 * c->NF);
     rc |= upload<double>(&c->d_bflux, nullptr, (size_t)c->n_bfaces * c->nsp * 5);
-    rc |= upload<double>(&c->d_ghost, nullptr, (size_t)c->n_ghost * 5 * c->nsp * c->NF);
+    rc |= upload<double>(&c->d_ghost, nullptr, (size_t)c->n_ghost * c->nc * c->NF);   // (room for the field traces too)
     rc |= upload<double>(&c->d_partial, nullptr, (size_t)5 * integral_blocks(c->n_elems));
     rc |= upload<double>(&c->d_out5, nullptr, 8);
     rc |= upload<unsigned long long>(&c->d_vmax, nullptr, (size_t)c->n_vectors);
@@ -706,8 +721,34 @@ int warpii_gpu_set_sources(warpii_gpu_ctx* c, int enabled, double epsilon0, doub
     return 0;
 }
 
+int warpii_gpu_set_maxwell(warpii_gpu_ctx* c, int enabled, double light_speed, double chi, double gamma) {
+    if (!c) return fail("null context");
+    drop_batch_graph(c);
+    std::fill(c->vmax_valid.begin(), c->vmax_valid.end(), 0);
+    if (!enabled) {
+        c->maxwell_on = false;
+        c->ncf = 5 * c->nsp;
+        return 0;
+    }
+    if (c->nc < 5 * c->nsp + 8) return fail("set_maxwell: the field system needs the 8 field components (fields_enabled)");
+    if (c->general) return fail("set_maxwell: the field system is implemented on Cartesian boxes only");
+    if (!(light_speed > 0.0) || chi < 0.0 || gamma < 0.0) return fail("set_maxwell: light_speed must be positive, chi and gamma non-negative");
+    CUDA_OK(cudaSetDevice(c->device));
+    if (!c->d_qm) {   // the transport-speed kernels read charge / mass only with the sources on, but want a valid pointer
+        CUDA_OK(cudaMalloc((void**)&c->d_qm, (size_t)c->nsp * sizeof(double)));
+        CUDA_OK(cudaMemset(c->d_qm, 0, (size_t)c->nsp * sizeof(double)));
+    }
+    c->light_speed = light_speed;
+    c->mx_chi = chi;
+    c->mx_gamma = gamma;
+    c->maxwell_on = true;
+    c->ncf = c->nc;
+    return 0;
+}
+
 int warpii_gpu_set_geometry(warpii_gpu_ctx* c, const warpii_gpu_geometry* g) {
     if (!c) return fail("null context");
+    if (c->maxwell_on) return fail("set_geometry: the field system (set_maxwell) is implemented on Cartesian boxes only");
     if (!g || !g->inverse_jacobian || !g->face_normal || !g->face_jacobian) return fail("set_geometry: null table");
     if (c->n_bfaces > 0 && (!g->boundary_normal || !g->boundary_jacobian)) return fail("set_geometry: boundary tables missing");
     if (c->general) return fail("set_geometry: geometry already set");
@@ -1290,7 +1331,7 @@ int warpii_gpu_attach_comm(warpii_gpu_ctx* c, const char id[WARPII_GPU_NCCL_ID_B
         c->n_interface = halo->n_interface_elems;
         if (upload(&c->d_send_elem, halo->send_elem, (size_t)c->n_send)) return 1;
         if (upload(&c->d_send_side, halo->send_side, (size_t)c->n_send)) return 1;
-        if (upload<double>(&c->d_sendbuf, nullptr, (size_t)c->n_send * 5 * c->nsp * c->NF)) return 1;
+        if (upload<double>(&c->d_sendbuf, nullptr, (size_t)c->n_send * c->nc * c->NF)) return 1;
     }
     return 0;
 }

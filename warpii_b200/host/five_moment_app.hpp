@@ -159,6 +159,11 @@ class FiveMomentGpuApp {
         prm.declare_entry("five_moment_sources", "false", Pat::Bool());
         prm.declare_entry("epsilon0", "1.0", Pat::Double(1e-300));
         prm.declare_entry("phm_chi", "0.0", Pat::Double(0.0));
+        // ... and the perfectly hyperbolic Maxwell fluxes that evolve the field components (warpii_gpu_set_maxwell): light
+        // speed and the magnetic cleaning speed (phm_chi above is the electric one); the fields start from zero
+        prm.declare_entry("five_moment_maxwell", "false", Pat::Bool());
+        prm.declare_entry("light_speed", "1.0", Pat::Double(1e-300));
+        prm.declare_entry("phm_gamma", "0.0", Pat::Double(0.0));
         prm.parse_input_from_string(input, false);
 
         // FiveMomentApp<dim>::create_from_parameters (five_moment.h:149-198)
@@ -207,8 +212,13 @@ class FiveMomentGpuApp {
         app->sources_ = prm.get_bool("five_moment_sources");
         app->epsilon0_ = prm.get_double("epsilon0");
         app->chi_ = prm.get_double("phm_chi");
-        if (app->sources_ && !app->fields_enabled_)
-            throw std::invalid_argument("five_moment_sources = true needs the field components (fields_enabled)");
+        app->maxwell_ = prm.get_bool("five_moment_maxwell");
+        app->light_speed_ = prm.get_double("light_speed");
+        app->phm_gamma_ = prm.get_double("phm_gamma");
+        if ((app->sources_ || app->maxwell_) && !app->fields_enabled_)
+            throw std::invalid_argument("five_moment_sources / five_moment_maxwell = true needs the field components (fields_enabled)");
+        if (app->maxwell_ && grid_type == "Extension")
+            throw std::invalid_argument("five_moment_maxwell = true is implemented on HyperRectangle grids only");
         app->rank_ = rank;
         app->n_ranks_ = n_ranks;
 
@@ -244,6 +254,7 @@ class FiveMomentGpuApp {
             for (const SpeciesDescription& sp : species_) qm.push_back(sp.charge / sp.mass);
             solver_->get_fluid_flux_operator().set_sources(true, epsilon0_, chi_, qm);
         }
+        if (maxwell_) solver_->get_fluid_flux_operator().set_maxwell(true, light_speed_, chi_, phm_gamma_);
         for (int s = 0; s < n_species_; s++) {
             std::shared_ptr<SpeciesFunc> ic = species_[s].initial_condition;
             solver_->project_initial_condition(s, [ic](const double* x, double* q5) { ic->conserved(x, 0.0, q5); }, false);
@@ -390,8 +401,8 @@ class FiveMomentGpuApp {
     }
 
     int dim_ = 1, n_species_ = 1, n_boundaries_ = 0, fe_degree_ = 2, n_writeout_frames_ = 10, rank_ = 0, n_ranks_ = 1;
-    bool fields_enabled_ = false, write_output_ = true, setup_done_ = false, sources_ = false;
-    double gas_gamma_ = 5.0 / 3.0, t_end_ = 0.0, epsilon0_ = 1.0, chi_ = 0.0;
+    bool fields_enabled_ = false, write_output_ = true, setup_done_ = false, sources_ = false, maxwell_ = false;
+    double gas_gamma_ = 5.0 / 3.0, t_end_ = 0.0, epsilon0_ = 1.0, chi_ = 0.0, light_speed_ = 1.0, phm_gamma_ = 0.0;
     BoxDescription box_;
     std::vector<SpeciesDescription> species_;
     std::shared_ptr<FiveMomentGpuSolver> solver_;

@@ -149,6 +149,10 @@ class GpuFluidFluxESDGSEMOperator {
     }
 
     // Two-fluid source terms (north_star kernel 4; not in the reference operator, off by default): see warpii_gpu_set_sources.
+    // Perfectly hyperbolic Maxwell fluxes for the field components (not in the reference, off by default): warpii_gpu_set_maxwell.
+    void set_maxwell(bool enabled, double light_speed, double chi, double gamma) {
+        check(warpii_gpu_set_maxwell(ctx_->get(), enabled ? 1 : 0, light_speed, chi, gamma));
+    }
     void set_sources(bool enabled, double epsilon0, double chi, const std::vector<double>& charge_over_mass) {
         check(warpii_gpu_set_sources(ctx_->get(), enabled ? 1 : 0, epsilon0, chi, charge_over_mass.data()));
     }

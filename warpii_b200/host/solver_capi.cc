@@ -177,6 +177,9 @@ int warpii_box_solver_set_sources(warpii_box_solver* s, int enabled, double epsi
         s->solver->get_fluid_flux_operator().set_sources(enabled != 0, epsilon0, chi, qm);
     })
 }
+int warpii_box_solver_set_maxwell(warpii_box_solver* s, int enabled, double light_speed, double chi, double gamma) {
+    GUARD({ s->solver->get_fluid_flux_operator().set_maxwell(enabled != 0, light_speed, chi, gamma); })
+}
 int64_t warpii_box_solver_n_boundary_faces(const warpii_box_solver* s) {
     return s->solver->general_geometry() ? (int64_t)s->solver->general_mesh()->bf_elem.size()
                                          : (int64_t)s->solver->tables().boundary_face_elem().size();
