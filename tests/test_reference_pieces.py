@@ -175,3 +175,74 @@ def test_time_loops_are_the_reference(ref):
         assert _run_advance(oracle.lib(), "orc_advance", seq, t_end, cbs) == want
         got = _run_advance(warpii_b200.lib(), "warpii_host_advance", seq, t_end, [(c[0], c[1], c[2]) for c in cbs])
         assert got == want
+
+
+# ---- the reference's volume and subcell-FV DRIVERS ------------------------------------------------------
+# SplitFormVolumeFlux<dim>::calculate_flux (split_form_volume_flux.h:61-99) and SubcellFiniteVolumeFlux<dim>::calculate_flux
+# (subcell_finite_volume_flux.h:68-159), compiled from the reference sources against the one-cell FEEvaluation /
+# VectorizedArray / FullMatrix stand-in of oracle/ref_shim/deal.II/matrix_free/fe_evaluation.h, evaluate ONE cell; the
+# oracle's cell_residual must give the same integrated residual, on Cartesian and on curved cells.
+def _cell_state(rng, NN, gamma, amp=0.2):
+    prim = np.zeros((NN, 5))
+    prim[:, 0] = 1.0 + amp * rng.uniform(-1, 1, NN)
+    prim[:, 1:4] = 0.4 * rng.uniform(-1, 1, (NN, 3))
+    prim[:, 4] = 1.0 + amp * rng.uniform(-1, 1, NN)
+    cons = oracle.primitive_to_conserved(prim, gamma) if hasattr(oracle, "primitive_to_conserved") else None
+    return np.ascontiguousarray(np.asarray(cons).T)     # [5][NN]
+
+
+@pytest.mark.parametrize("dim,fe_degree,h", [(1, 2, [0.3]), (1, 4, [1.7]), (2, 1, [0.5, 0.25]), (2, 3, [0.02, 0.05]), (2, 4, [1.0, 1.0])])
+@pytest.mark.parametrize("alpha", [0.0, 0.37])
+def test_volume_and_fv_drivers_on_a_cartesian_cell(ref, dim, fe_degree, h, alpha):
+    ref.ref_cell_residual.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, C.c_double, C.c_int, _dp]
+    ref.ref_diff_matrix.argtypes = [C.c_int, _dp]
+    Np, gamma = fe_degree + 1, 1.4
+    NN = Np ** dim
+    D = np.zeros((Np, Np))
+    ref.ref_diff_matrix(Np, p(D))
+    assert np.abs(D - oracle.diff_matrix(Np)).max() <= 2e-14 * np.abs(D).max()       # D(j,l) = shape_grad(l, x_j)[0]
+    o = oracle.Oracle(dim, fe_degree, [2] * dim, [0.0] * dim, [2 * v for v in h], gamma=gamma)
+    rng = np.random.default_rng(11 * dim + fe_degree)
+    ue = _cell_state(rng, NN, gamma)
+    jinv = np.zeros((NN, dim, dim))
+    for d in range(dim):
+        jinv[:, d, d] = 1.0 / h[d]
+    want = np.zeros((5, NN))
+    assert ref.ref_cell_residual(dim, Np, gamma, p(ue), p(jinv), alpha, 3, p(want)) == 0
+    got = o.cell_residual(ue, alpha)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-14 * scale, np.abs(got - want).max() / scale
+    # the two drivers separately: the subcell scheme is evaluated (and multiplied by alpha) whatever alpha is
+    vol, fv = np.zeros((5, NN)), np.zeros((5, NN))
+    ref.ref_cell_residual(dim, Np, gamma, p(ue), p(jinv), alpha, 1, p(vol))
+    ref.ref_cell_residual(dim, Np, gamma, p(ue), p(jinv), alpha, 2, p(fv))
+    assert np.abs(vol + fv - want).max() <= 1e-15 * scale
+    if alpha == 0.0:
+        assert np.abs(fv).max() == 0.0
+
+
+@pytest.mark.parametrize("fe_degree", [2, 3])
+@pytest.mark.parametrize("alpha", [0.0, 0.5])
+def test_volume_and_fv_drivers_on_a_curved_cell(ref, fe_degree, alpha):
+    """Curved 2-D cells (MappingQ(p) geometry): metric terms averaged between the nodes of a pair
+    (split_form_volume_flux.h:82-84) and subcell normals accumulated with Q (subcell_finite_volume_flux.h:101-106)."""
+    import mesh_cases as mc
+    from oracle import GeneralOracle
+    from warpii_b200.capi import mapped_metrics
+    ref.ref_cell_residual.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, C.c_double, C.c_int, _dp]
+    dim, gamma = 2, 5.0 / 3.0
+    Np = fe_degree + 1
+    NN = Np ** dim
+    left, right = [0.0, 0.0], [1.0, 1.3]
+    mesh, xyz = mc.mapped_box(dim, fe_degree, [3, 2], left, right, [1, 1], mc.wavy(left, right, 0.06))
+    geo = mapped_metrics(dim, fe_degree, xyz, mesh["face_neighbor"])
+    o = GeneralOracle(dim, fe_degree, mesh, geo, gamma=gamma)
+    rng = np.random.default_rng(5 + fe_degree)
+    ue = _cell_state(rng, NN, gamma)
+    jinv = np.ascontiguousarray(np.asarray(geo["inverse_jacobian"]).reshape(-1, NN, dim, dim)[0])
+    assert np.abs(jinv[:, 0, 1]).max() > 1e-3          # the cell really is curved
+    want = np.zeros((5, NN))
+    assert ref.ref_cell_residual(dim, Np, gamma, p(ue), p(jinv), alpha, 3, p(want)) == 0
+    got = o.cell_residual(ue, alpha)                    # element 0 of the mesh
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-14 * scale, np.abs(got - want).max() / scale
