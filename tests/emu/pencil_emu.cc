@@ -46,7 +46,20 @@ double run(const StageParams& P) {
                 vmax = std::max(vmax, v);
             }
         }
-        for (int t = 0; t < G::THREADS; t++) pencil_phase_fields<DIM, NP>(P, t, e0, P.dt);
+        if (P.mx_on && P.nc >= 5 * P.nsp + 8) {
+            std::vector<FieldHalo> fh(G::THREADS);
+            for (int t = 0; t < G::THREADS; t++) field_phase0<DIM, NP>(P, sm, t, e0, fh[t]);
+            for (int t = 0; t < G::THREADS; t++) field_phase_mid<DIM, NP, 1>(P, sm, t, e0, fh[t]);
+            if (DIM == 3)
+                for (int t = 0; t < G::THREADS; t++) field_phase_mid<DIM, NP, DIM - 1>(P, sm, t, e0, fh[t]);
+            for (int t = 0; t < G::THREADS; t++) {
+                const double v = field_phase_final<DIM, NP>(P, sm, t, e0, P.dt, fh[t]);
+                if (v != v) nan_seen = true;
+                vmax = std::max(vmax, v);
+            }
+        } else {
+            for (int t = 0; t < G::THREADS; t++) pencil_phase_fields<DIM, NP>(P, t, e0, P.dt);
+        }
     }
     return nan_seen ? std::nan("") : vmax;
 }
@@ -63,7 +76,8 @@ int emu_pencil_patch_elems(int dim, int np) { return pencil_elems(dim, np); }
 int emu_pencil_stage(int dim, int np, int64_t n_elems, int64_t elem_begin, int64_t elem_end, int nc, int nsp, const double* u,
                      double* dst, const int32_t* nbr, const double* ghost, const double* bres, double* alpha_out, double* vmax_out,
                      int mode, double gamma, double dt, double a, double beta, const double* h, const double* sol_in, double* dst2,
-                     int src_on, double epsilon0, double chi, const double* qm) {
+                     int src_on, double epsilon0, double chi, const double* qm, int mx_on, double light_speed, double mx_chi,
+                     double mx_gamma) {
     if (!emu_pencil_available(dim, np)) return 1;
     StageParams P;
     std::memset(&P, 0, sizeof P);
@@ -98,6 +112,12 @@ int emu_pencil_stage(int dim, int np, int64_t n_elems, int64_t elem_begin, int64
     P.gamma = gamma; P.dt = dt; P.a = a; P.beta = beta;
     P.hig = 0.5 / (gamma - 1.0);
     P.src_on = src_on; P.inv_eps0 = src_on ? 1.0 / epsilon0 : 1.0; P.chi = chi; P.qm = qm;
+    if (mx_on) {   // as stage_params() of warpii_gpu.cu
+        const double big = std::max(1.0, std::max(mx_chi, mx_gamma));
+        P.mx_on = 1; P.fields_skip = 1; P.ncf = nc;
+        P.mx_c2 = light_speed * light_speed; P.mx_chi = mx_chi; P.mx_gam = mx_gamma; P.mx_lam = light_speed * big;
+        P.mx_floor = P.max_eig * P.mx_lam; P.mx_omega_factor = 5.0 / (double)(np * np);
+    }
     double vmax = 0.0;
 #define CALL(D_, N_) vmax = run<D_, N_>(P)
     if (dim == 2) {

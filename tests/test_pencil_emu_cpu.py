@@ -171,3 +171,76 @@ def test_sharded_with_ghost_traces_and_split_launches(dim, p, nx):
         emu.stage(dim, p, ul, tab["face_neighbor"], h, gamma, mode=1, dst=dst, ghost=ghost, elem_range=(0, ni))
         emu.stage(dim, p, ul, tab["face_neighbor"], h, gamma, mode=1, dst=dst, ghost=ghost, elem_range=(ni, len(l2g)))
         check(dst, want[l2g], ul, o, h)
+
+
+# ---- the field system fused into the kernel (perfectly hyperbolic Maxwell fluxes; definition pinned in test_maxwell_cpu.py) ----
+MX = dict(light_speed=2.5, chi=0.8, gamma=1.2)
+SRC = dict(epsilon0=1.3, chi=0.8, charge_over_mass=[0.04, -1.0])
+
+
+def _two_fluid(o):
+    xyz = o.node_coords()
+    x = [xyz[..., d] for d in range(o.dim)] + [0.0, 0.0]
+    s = np.sin(2 * np.pi * x[0]) * np.cos(2 * np.pi * x[1]) + 0.3 * np.sin(2 * np.pi * (x[2] + x[0]))
+    u = np.zeros(o.shape)
+    for sp, (rho0, vel) in enumerate([(25.0, (0.05, -0.02, 0.01)), (1.0, (-0.2, 0.1, 0.05))]):
+        prim = np.zeros(xyz.shape[:-1] + (5,))
+        prim[..., 0] = rho0 * (1 + 0.1 * s)
+        for d in range(3):
+            prim[..., 1 + d] = vel[d] * (1 + 0.2 * s)
+        prim[..., 4] = 1 + 0.05 * s
+        cases.to_state(prim, o.gamma, nc=o.nc, species=sp, u=u)
+    for c, amp in enumerate([0.3, -0.2, 0.15, 0.1, -0.05, 0.2, 0.02, -0.03]):
+        u[:, 10 + c, :] = 0.1 * amp * (1 + 0.5 * np.cos(2 * np.pi * (x[0] + 0.3 * c)) * np.cos(2 * np.pi * x[1] * (1 + c % 2)))
+    return u
+
+
+@pytest.mark.parametrize("dim,p,nx", [(2, 3, [6, 5]), (2, 2, [5, 4]), (3, 3, [4, 3, 2]), (3, 2, [3, 3, 3]), (2, 4, [3, 3])])
+def test_fused_field_system_rhs_step_and_transport_speed(dim, p, nx):
+    gamma = 5.0 / 3.0
+    o, tab, h = setup(dim, p, nx, [0.0] * dim, [1.0] * dim, gamma, n_species=2, fields=True)
+    o.set_sources(True, **SRC)
+    o.set_maxwell(True, **MX)
+    u = _two_fluid(o)
+    l2g = tab["local_to_global"]
+    ul = u[l2g].copy()
+    want, _ = o.rhs(u)
+    got = emu.stage(dim, p, ul, tab["face_neighbor"], h, gamma, mode=1, nsp=2, sources=SRC, maxwell=MX)
+    D = oracle.diff_matrix(p + 1)
+    scale = cases.summand_scale(ul, gamma, dim, h, D) + cases.field_summand_scale(ul, 2, dim, h, D, **MX)
+    err, bound = cases.rhs_error_and_bound(got, want[l2g], scale)
+    assert (err <= bound).all(), (err, bound)
+    assert (cases.rel_l2_per_component(got, want[l2g])[10:] <= 1e-12).all()
+    dt = 0.5 * o.recommend_dt(u)
+    f1 = emu.stage(dim, p, ul, tab["face_neighbor"], h, gamma, mode=0, dt=dt, nsp=2, sources=SRC, maxwell=MX)
+    new, vmax = emu.stage(dim, p, f1, tab["face_neighbor"], h, gamma, mode=0, dt=dt, a=0.5, beta=0.5, dst=ul.copy(), nsp=2, sources=SRC,
+                          maxwell=MX, want_vmax=True)
+    ref = u.copy()
+    o.ssprk2_step(ref, dt, 0.0)
+    assert (cases.rel_l2_per_component(new, ref[l2g]) < 1e-13).all()
+    assert abs(vmax - o.max_transport_speed(ref)) <= 1e-13 * vmax
+
+
+def test_fused_field_system_sharded():
+    """the ghost traces carry all nc components once the field system is evolved"""
+    dim, p, nx, gamma = 3, 3, [4, 4, 6], 5.0 / 3.0
+    Np, NF = p + 1, (p + 1) ** (dim - 1)
+    o = Oracle(dim, p, nx, [0.0] * 3, [1.0] * 3, gamma=gamma, n_species=2, fields_enabled=True, threads=4)
+    o.set_sources(True, **SRC)
+    o.set_maxwell(True, **MX)
+    h = [1.0 / n for n in nx]
+    u = _two_fluid(o)
+    want, _ = o.rhs(u)
+    for rank in range(2):
+        tab = box_tables(dim, nx, [1] * dim, rank=rank, n_ranks=2, group=emu.patch_elems(dim, Np))
+        l2g = tab["local_to_global"]
+        ghost = np.zeros((tab["n_ghost"], 18, NF))
+        for s in range(tab["n_ghost"]):
+            ge, side = int(tab["ghost_global_elem"][s]), int(tab["ghost_side"][s])
+            ghost[s] = u[ge][:, [face_node_to_node(dim, Np, side // 2, side % 2, t) for t in range(NF)]]
+        ul = u[l2g].copy()
+        got = emu.stage(dim, p, ul, tab["face_neighbor"], h, gamma, mode=1, nsp=2, ghost=ghost, sources=SRC, maxwell=MX)
+        D = oracle.diff_matrix(Np)
+        scale = cases.summand_scale(ul, gamma, dim, h, D) + cases.field_summand_scale(ul, 2, dim, h, D, **MX)
+        err, bound = cases.rhs_error_and_bound(got, want[l2g], scale)
+        assert (err <= bound).all(), (rank, err, bound)

@@ -60,6 +60,12 @@ struct StageParams {
     int32_t src_on;
     double inv_eps0, chi;
     const double* qm;             // [nsp] charge / mass
+    // perfectly hyperbolic Maxwell fluxes for the field components, fused into the pencil stage kernel (mx_on; the other
+    // stage kernels leave the fields to maxwell_kernel, see fields_skip): c^2, cleaning speeds chi / gamma (units of c),
+    // Rusanov speed c max(1, chi, gamma), the field system's constant share of the transport speed (max_eig * lam) and the
+    // factor 5 / Np^2 that turns the plasma / cyclotron frequency bound omega dt <= 0.1 into an equivalent speed
+    int32_t mx_on;
+    double mx_c2, mx_chi, mx_gam, mx_lam, mx_floor, mx_omega_factor;
     ElemTables T;
 };
 

@@ -35,7 +35,22 @@ __global__ void __launch_bounds__(PGeo<DIM, NP>::THREADS, WGPU_PENCIL_MIN_BLOCKS
         }
         vmax_local = nan_max(vmax_local, pencil_phase_final<DIM, NP>(P, smem, tid, e0, sp, dt, halo));
     }
-    pencil_phase_fields<DIM, NP>(P, tid, e0, dt);
+    if (P.mx_on && P.nc >= 5 * P.nsp + 8) {
+        // the field system, same phases (uniform branch: kernel parameter)
+        FieldHalo fh;
+        __syncthreads();   // the last species' final phase still reads the record planes
+        field_phase0<DIM, NP>(P, smem, tid, e0, fh);
+        __syncthreads();
+        field_phase_mid<DIM, NP, 1>(P, smem, tid, e0, fh);
+        __syncthreads();
+        if (DIM == 3) {
+            field_phase_mid<DIM, NP, DIM - 1>(P, smem, tid, e0, fh);
+            __syncthreads();
+        }
+        vmax_local = nan_max(vmax_local, field_phase_final<DIM, NP>(P, smem, tid, e0, dt, fh));
+    } else {
+        pencil_phase_fields<DIM, NP>(P, tid, e0, dt);
+    }
     if (P.vmax && P.mode == 0) {
         const double m = block_max(vmax_local, smem + G::OFF_RED);
         if (tid == 0) atomicMax(P.vmax, (unsigned long long)__double_as_longlong(m));

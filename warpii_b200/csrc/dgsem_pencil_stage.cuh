@@ -557,6 +557,267 @@ __device__ __forceinline__ double pencil_phase_final(const StageParams& P, doubl
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// The field system fused into the same kernel (mx_on): perfectly hyperbolic Maxwell fluxes for [Ex,Ey,Ez,Bx,By,Bz,phi,psi]
+// (north_star kernel 4; new physics, see include/warpii_gpu.h::warpii_gpu_set_maxwell), the same pencil phases as a species:
+//   F0 (x owner) fields -> shared planes   Fy, Fz  -(1/h) sum_l D[m][l] f_d(F_l) + Rusanov face terms at the two ends -> accumulator
+//   Fx (x owner) x sums + accumulator + sources, stage update, store, the field system's share of the transport speed.
+// Shared memory: the record planes 0-3 hold the fields [(Ex,Ey) (Ez,Bx) (By,Bz) (phi,psi)], the accumulator planes plus record
+// plane 4 hold the 8 partial rates.  The flux is linear and sparse: ~150 FMAs per node against ~750 FP64 instructions per
+// node and species of the fluid, and no extra pass over HBM.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FieldHalo {
+    double q[2][8];
+    int kind[2];      // 0: in the patch (nslot), 1: values in q, 2: domain boundary (zero gradient)
+    int nslot[2];
+};
+
+template <int D>
+__device__ __forceinline__ void phm_flux_d(const StageParams& P, const double (&F)[8], double (&f)[8]) {
+    constexpr int i1 = (D + 1) % 3, i2 = (D + 2) % 3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) f[i] = 0.0;
+    f[i1] = P.mx_c2 * F[3 + i2];            // -c^2 (e_d x B)
+    f[i2] = -P.mx_c2 * F[3 + i1];
+    f[3 + i1] = -F[i2];                     // e_d x E
+    f[3 + i2] = F[i1];
+    f[D] = P.mx_chi * P.mx_c2 * F[6];
+    f[3 + D] = P.mx_gam * F[7];
+    f[6] = P.mx_chi * F[D];
+    f[7] = P.mx_gam * P.mx_c2 * F[3 + D];
+}
+
+template <int DIM, int NP, int D>
+__device__ __forceinline__ void field_halo_fetch(const StageParams& P, const int v0, const int v1, const int pe, const int64_t e0,
+                                                 const int64_t e_hi, FieldHalo& h) {
+    using G = PGeo<DIM, NP>;
+    const int nf0 = 5 * P.nsp;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int v = side ? v1 : v0;
+        h.nslot[side] = 0;
+        if (v >= e0 && v < e_hi) {
+            h.kind[side] = 0;
+            h.nslot[side] = pslot<NP>((int)(v - e0) * G::NN + pencil_node<DIM, NP, D>(pe, side ? 0 : NP - 1));
+        } else if (v < 0) {
+            h.kind[side] = 2;
+        } else {
+            h.kind[side] = 1;
+            const double* src;
+            size_t stride;
+            if (v < P.n_elems) {
+                src = P.u + ((size_t)v * P.nc + nf0) * G::NN + pencil_node<DIM, NP, D>(pe, side ? 0 : NP - 1);
+                stride = G::NN;
+            } else {
+                src = P.ghost + ((size_t)(v - P.n_elems) * P.ncf + nf0) * G::NPEN + pe;
+                stride = G::NPEN;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) h.q[side][k] = src[(size_t)k * stride];
+        }
+    }
+}
+
+__device__ __forceinline__ void get_fields(const double2* sFld, const int nodes, const int slot, double (&F)[8]) {
+    const double2 a = sFld[slot], b = sFld[nodes + slot], c = sFld[2 * nodes + slot], d = sFld[3 * nodes + slot];
+    F[0] = a.x; F[1] = a.y; F[2] = b.x; F[3] = b.y; F[4] = c.x; F[5] = c.y; F[6] = d.x; F[7] = d.y;
+}
+
+template <int DIM, int NP, int D, class Done>
+__device__ __forceinline__ void field_sums(const StageParams& P, const double2* sFld, const FieldHalo& h, const int le, const int pe,
+                                           Done&& done) {
+    using G = PGeo<DIM, NP>;
+    double F[NP][8], acc[NP][8];
+#pragma unroll
+    for (int m = 0; m < NP; m++) {
+        get_fields(sFld, G::NODES, pslot<NP>(le * G::NN + pencil_node<DIM, NP, D>(pe, m)), F[m]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[m][k] = 0.0;
+    }
+    // the two ends: (f(F_m).n - f*) / (h w_0) = (lambda dF - sgn f_d(dF)) / (2 h w_0), dF = F_p - F_m
+    const double cf = 0.5 * P.inv_hw[D];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int m = side ? NP - 1 : 0;
+        double Fn[8], dF[8], fn[8];
+        get_fields(sFld, G::NODES, h.nslot[side], Fn);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double other = (h.kind[side] == 0) ? Fn[k] : ((h.kind[side] == 1) ? h.q[side][k] : F[m][k]);
+            dF[k] = other - F[m][k];
+        }
+        phm_flux_d<D>(P, dF, fn);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[m][k] = cf * (P.mx_lam * dF[k] - (side ? fn[k] : -fn[k]));
+    }
+    // volume: -(1/h) sum_l D[m][l] f_d(F_l)
+    double f[NP][8];
+#pragma unroll
+    for (int l = 0; l < NP; l++) phm_flux_d<D>(P, F[l], f[l]);
+    static_for<0, NP>([&](auto M_) {
+        constexpr int m = decltype(M_)::value;
+#pragma unroll
+        for (int l = 0; l < NP; l++) {
+            const double w = -P.inv_h[D] * P.T.D[m * NP + l];
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[m][k] = fma(w, f[l][k], acc[m][k]);
+        }
+        done(m, acc[m]);
+    });
+}
+
+template <int DIM, int NP>
+__device__ __forceinline__ void field_phase0(const StageParams& P, double* smem, const int tid, const int64_t e0, FieldHalo& next) {
+    using G = PGeo<DIM, NP>;
+    double2* const sFld = reinterpret_cast<double2*>(smem + G::OFF_REC);
+    const int* const sNbr = reinterpret_cast<const int*>(smem + G::OFF_NBR);
+    if (tid >= G::USED) return;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    const int64_t e_hi = (e0 + G::E < P.elem_end) ? e0 + G::E : P.elem_end;
+    if (e >= P.elem_end) return;
+    double F[8][NP];
+    const double* src = P.u + ((size_t)e * P.nc + 5 * P.nsp) * G::NN + pe * NP;
+#pragma unroll
+    for (int k = 0; k < 8; k++) load_run<NP>(src + (size_t)k * G::NN, F[k]);
+    field_halo_fetch<DIM, NP, 1>(P, sNbr[le * G::NFACE + 2], sNbr[le * G::NFACE + 3], pe, e0, e_hi, next);
+#pragma unroll
+    for (int m = 0; m < NP; m++) {
+        const int slot = pslot<NP>(le * G::NN + pe * NP + m);
+        sFld[slot] = make_double2(F[0][m], F[1][m]);
+        sFld[G::NODES + slot] = make_double2(F[2][m], F[3][m]);
+        sFld[2 * G::NODES + slot] = make_double2(F[4][m], F[5][m]);
+        sFld[3 * G::NODES + slot] = make_double2(F[6][m], F[7][m]);
+    }
+}
+
+template <int DIM, int NP, int D>
+__device__ __forceinline__ void field_phase_mid(const StageParams& P, double* smem, const int tid, const int64_t e0, FieldHalo& h) {
+    using G = PGeo<DIM, NP>;
+    constexpr bool FIRST = (D == 1);
+    constexpr int NEXT = (D + 1 < DIM) ? D + 1 : 0;
+    double2* const sFld = reinterpret_cast<double2*>(smem + G::OFF_REC);   // planes 0-3 fields (read), plane 4 rates 6,7
+    double2* const sBuf = reinterpret_cast<double2*>(smem + G::OFF_BUF);
+    const int* const sNbr = reinterpret_cast<const int*>(smem + G::OFF_NBR);
+    if (tid >= G::USED) return;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    const int64_t e_hi = (e0 + G::E < P.elem_end) ? e0 + G::E : P.elem_end;
+    if (e >= P.elem_end) return;
+    field_sums<DIM, NP, D>(P, sFld, h, le, pe, [&](const int m, const double (&a)[8]) {
+        const int slot = pslot<NP>(le * G::NN + pencil_node<DIM, NP, D>(pe, m));
+        if (FIRST) {
+            sBuf[slot] = make_double2(a[0], a[1]);
+            sBuf[G::NODES + slot] = make_double2(a[2], a[3]);
+            sBuf[2 * G::NODES + slot] = make_double2(a[4], a[5]);
+            sFld[4 * G::NODES + slot] = make_double2(a[6], a[7]);
+        } else {
+            const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot], w = sFld[4 * G::NODES + slot];
+            sBuf[slot] = make_double2(a[0] + x.x, a[1] + x.y);
+            sBuf[G::NODES + slot] = make_double2(a[2] + y.x, a[3] + y.y);
+            sBuf[2 * G::NODES + slot] = make_double2(a[4] + z.x, a[5] + z.y);
+            sFld[4 * G::NODES + slot] = make_double2(a[6] + w.x, a[7] + w.y);
+        }
+    });
+    field_halo_fetch<DIM, NP, NEXT>(P, sNbr[le * G::NFACE + 2 * NEXT], sNbr[le * G::NFACE + 2 * NEXT + 1], pe, e0, e_hi, h);
+}
+
+// Fx: returns the field system's share of the transport speed at this thread's nodes (0 unless the CFL reduction is fused)
+template <int DIM, int NP>
+__device__ __forceinline__ double field_phase_final(const StageParams& P, double* smem, const int tid, const int64_t e0, const double dt,
+                                                    const FieldHalo& h) {
+    using G = PGeo<DIM, NP>;
+    const double2* const sFld = reinterpret_cast<const double2*>(smem + G::OFF_REC);
+    const double2* const sBuf = reinterpret_cast<const double2*>(smem + G::OFF_BUF);
+    if (tid >= G::USED) return 0.0;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    if (e >= P.elem_end) return 0.0;
+    const size_t base = (size_t)e * P.nc * G::NN + pe * NP;   // node 0 of the pencil, component 0
+    double rate[8][NP];
+    field_sums<DIM, NP, 0>(P, sFld, h, le, pe, [&](const int m, const double (&a)[8]) {
+        const int slot = pslot<NP>(le * G::NN + pe * NP + m);
+        const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot], w = sFld[4 * G::NODES + slot];
+        rate[0][m] = a[0] + x.x; rate[1][m] = a[1] + x.y; rate[2][m] = a[2] + y.x; rate[3][m] = a[3] + y.y;
+        rate[4][m] = a[4] + z.x; rate[5][m] = a[5] + z.y; rate[6][m] = a[6] + w.x; rate[7][m] = a[7] + w.y;
+    });
+    // sources: -J/eps0 on E, chi rho_c/eps0 on phi (species in order, as everywhere)
+    if (P.src_on) {
+        double J[3][NP], rc[NP];
+#pragma unroll
+        for (int m = 0; m < NP; m++) { J[0][m] = 0.0; J[1][m] = 0.0; J[2][m] = 0.0; rc[m] = 0.0; }
+        for (int sp = 0; sp < P.nsp; sp++) {
+            const double qm = P.qm[sp];
+            double r[NP], mx[NP], my[NP], mz[NP];
+            load_run<NP>(P.u + base + (size_t)(5 * sp) * G::NN, r);
+            load_run<NP>(P.u + base + (size_t)(5 * sp + 1) * G::NN, mx);
+            load_run<NP>(P.u + base + (size_t)(5 * sp + 2) * G::NN, my);
+            load_run<NP>(P.u + base + (size_t)(5 * sp + 3) * G::NN, mz);
+#pragma unroll
+            for (int m = 0; m < NP; m++) { rc[m] += qm * r[m]; J[0][m] += qm * mx[m]; J[1][m] += qm * my[m]; J[2][m] += qm * mz[m]; }
+        }
+#pragma unroll
+        for (int m = 0; m < NP; m++) {
+            rate[0][m] += -J[0][m] * P.inv_eps0;
+            rate[1][m] += -J[1][m] * P.inv_eps0;
+            rate[2][m] += -J[2][m] * P.inv_eps0;
+            rate[6][m] += P.chi * rc[m] * P.inv_eps0;
+        }
+    }
+    const bool need_old = (P.mode == 2) || (P.mode == 0 && P.beta != 0.0);
+    const double* const oldp = (P.mode == 2) ? P.sol_in : P.dst;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const size_t off = base + (size_t)(5 * P.nsp + k) * G::NN;
+        double F[NP], old[NP] = {}, out2[NP];
+        const int slotbase = le * G::NN + pe * NP;
+#pragma unroll
+        for (int m = 0; m < NP; m++) {
+            const double2 v = sFld[(k / 2) * G::NODES + pslot<NP>(slotbase + m)];
+            F[m] = (k & 1) ? v.y : v.x;
+        }
+        if (need_old) load_run<NP>(oldp + off, old);
+#pragma unroll
+        for (int m = 0; m < NP; m++) {
+            const double r = rate[k][m];
+            double v;
+            if (P.mode == 1) v = r;
+            else if (P.mode == 2) { v = fma(P.a, r, old[m]); out2[m] = fma(P.beta, r, old[m]); }
+            else if (P.beta == 0.0) v = P.a * (F[m] + dt * r);
+            else v = P.beta * old[m] + P.a * (F[m] + dt * r);
+            rate[k][m] = v;
+        }
+        store_run<NP>(P.dst + off, rate[k]);
+        if (P.mode == 2 && P.beta != 0.0) store_run<NP>(P.dst2 + off, out2);
+    }
+    double vmax_local = 0.0;
+    if (P.vmax && P.mode == 0) {
+        vmax_local = P.mx_floor;
+        if (P.src_on) {
+            // plasma and cyclotron frequency of the UPDATED state (this thread wrote the species' part of dst itself)
+            double wp2[NP], qmax = 0.0;
+#pragma unroll
+            for (int m = 0; m < NP; m++) wp2[m] = 0.0;
+            for (int sp = 0; sp < P.nsp; sp++) {
+                const double qm = P.qm[sp];
+                double r[NP];
+                load_run<NP>(P.dst + base + (size_t)(5 * sp) * G::NN, r);
+#pragma unroll
+                for (int m = 0; m < NP; m++) wp2[m] += qm * qm * r[m] * P.inv_eps0;
+                qmax = fmax(qmax, fabs(qm));
+            }
+#pragma unroll
+            for (int m = 0; m < NP; m++) {
+                const double b2 = rate[3][m] * rate[3][m] + rate[4][m] * rate[4][m] + rate[5][m] * rate[5][m];
+                const double omega = fmax(sqrt(wp2[m]), qmax * sqrt(b2));
+                const double sp_ = P.mx_omega_factor * omega;
+                vmax_local = (sp_ > vmax_local || sp_ != sp_) ? sp_ : vmax_local;
+            }
+        }
+    }
+    return vmax_local;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Field components (after the species): carried through unchanged by the reference's operator; with the
 // two-fluid sources on, E gets -J/eps0 and phi gets chi rho_c/eps0.  x-pencil owner, Np consecutive nodes.
 // ---------------------------------------------------------------------------------------------------------------------

@@ -216,7 +216,8 @@ void do_launch_stage(warpii_gpu_ctx* c, const StageParams& P, cudaStream_t s) {
     if (c->general) launch_stage_general(c->dim, c->Np, P, c->GP, s);
     else if (c->pencil) launch_pencil_stage(c->dim, c->Np, P, s);
     else launch_stage(c->dim, c->Np, P, s);
-    if (c->maxwell_on && P.elem_end > P.elem_begin) {   // the field components of the same range, right behind the fluids
+    if (c->maxwell_on && !(c->pencil && !c->general) && P.elem_end > P.elem_begin) {
+        // the field components of the same range, right behind the fluids (the pencil kernel evolves them itself)
         launch_maxwell(c->dim, c->Np, P, c->light_speed, c->mx_chi, c->mx_gamma, s);
         c->launches++;
     }
@@ -255,6 +256,18 @@ StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a,
     P.nsp = c->nsp;
     P.ncf = c->ncf;
     P.fields_skip = c->maxwell_on ? 1 : 0;
+    P.mx_on = c->maxwell_on ? 1 : 0;
+    {
+        double big = 1.0;
+        if (c->mx_chi > big) big = c->mx_chi;
+        if (c->mx_gamma > big) big = c->mx_gamma;
+        P.mx_c2 = c->light_speed * c->light_speed;
+        P.mx_chi = c->mx_chi;
+        P.mx_gam = c->mx_gamma;
+        P.mx_lam = c->light_speed * big;
+        P.mx_floor = c->max_eig * P.mx_lam;
+        P.mx_omega_factor = 5.0 / (double)(c->Np * c->Np);
+    }
     P.mode = mode;
     P.dt_dev = nullptr;
     P.skip_dev = nullptr;
