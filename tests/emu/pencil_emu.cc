@@ -37,6 +37,14 @@ double run(const StageParams& P) {
         std::fill(smem.begin(), smem.end(), std::nan(""));   // a read of something no phase wrote poisons the result
         for (int sp = 0; sp < P.nsp; sp++) {
             for (int t = 0; t < G::THREADS; t++) pencil_phase0<DIM, NP>(P, sm, t, e0, sp, halo[t]);
+#if WGPU_PENCIL_RTDIR
+            for (int ph = 1; ph <= DIM; ph++)
+                for (int t = 0; t < G::THREADS; t++) {
+                    const double v = pencil_phase_flux_rt<DIM, NP>(P, sm, t, e0, sp, P.dt, ph < DIM ? ph : 0, halo[t]);
+                    if (v != v) nan_seen = true;
+                    vmax = std::max(vmax, v);
+                }
+#else
             for (int t = 0; t < G::THREADS; t++) pencil_phase_mid<DIM, NP, 1>(P, sm, t, e0, sp, halo[t]);
             if (DIM == 3)
                 for (int t = 0; t < G::THREADS; t++) pencil_phase_mid<DIM, NP, DIM - 1>(P, sm, t, e0, sp, halo[t]);
@@ -45,10 +53,19 @@ double run(const StageParams& P) {
                 if (v != v) nan_seen = true;
                 vmax = std::max(vmax, v);
             }
+#endif
         }
         if (P.mx_on && P.nc >= 5 * P.nsp + 8) {
             std::vector<FieldHalo> fh(G::THREADS);
             for (int t = 0; t < G::THREADS; t++) field_phase0<DIM, NP>(P, sm, t, e0, fh[t]);
+#if WGPU_PENCIL_RTDIR
+            for (int ph = 1; ph <= DIM; ph++)
+                for (int t = 0; t < G::THREADS; t++) {
+                    const double v = field_phase_flux_rt<DIM, NP>(P, sm, t, e0, P.dt, ph < DIM ? ph : 0, fh[t]);
+                    if (v != v) nan_seen = true;
+                    vmax = std::max(vmax, v);
+                }
+#else
             for (int t = 0; t < G::THREADS; t++) field_phase_mid<DIM, NP, 1>(P, sm, t, e0, fh[t]);
             if (DIM == 3)
                 for (int t = 0; t < G::THREADS; t++) field_phase_mid<DIM, NP, DIM - 1>(P, sm, t, e0, fh[t]);
@@ -57,6 +74,7 @@ double run(const StageParams& P) {
                 if (v != v) nan_seen = true;
                 vmax = std::max(vmax, v);
             }
+#endif
         } else {
             for (int t = 0; t < G::THREADS; t++) pencil_phase_fields<DIM, NP>(P, t, e0, P.dt);
         }

@@ -26,6 +26,23 @@ __global__ void __launch_bounds__(PGeo<DIM, NP>::THREADS, WGPU_PENCIL_MIN_BLOCKS
     for (int sp = 0; sp < P.nsp; sp++) {
         if (sp > 0) __syncthreads();   // shared-memory reuse across species
         pencil_phase0<DIM, NP>(P, smem, tid, e0, sp, halo);
+#if WGPU_PENCIL_RTDIR == 2
+        // the mid phases (y, z) through one copy of the flux code, the final x phase through its own
+#pragma unroll 1
+        for (int ph = 1; ph < DIM; ph++) {
+            __syncthreads();
+            pencil_phase_flux_rt<DIM, NP, false>(P, smem, tid, e0, sp, dt, ph, halo);
+        }
+        __syncthreads();
+        vmax_local = nan_max(vmax_local, pencil_phase_final<DIM, NP>(P, smem, tid, e0, sp, dt, halo));
+#elif WGPU_PENCIL_RTDIR
+        // directions 1, .., DIM-1, 0 through ONE copy of the flux code (a real loop: the body must not be replicated)
+#pragma unroll 1
+        for (int ph = 1; ph <= DIM; ph++) {
+            __syncthreads();
+            vmax_local = nan_max(vmax_local, pencil_phase_flux_rt<DIM, NP>(P, smem, tid, e0, sp, dt, ph < DIM ? ph : 0, halo));
+        }
+#else
         __syncthreads();
         pencil_phase_mid<DIM, NP, 1>(P, smem, tid, e0, sp, halo);
         __syncthreads();
@@ -34,12 +51,20 @@ __global__ void __launch_bounds__(PGeo<DIM, NP>::THREADS, WGPU_PENCIL_MIN_BLOCKS
             __syncthreads();
         }
         vmax_local = nan_max(vmax_local, pencil_phase_final<DIM, NP>(P, smem, tid, e0, sp, dt, halo));
+#endif
     }
     if (P.mx_on && P.nc >= 5 * P.nsp + 8) {
         // the field system, same phases (uniform branch: kernel parameter)
         FieldHalo fh;
         __syncthreads();   // the last species' final phase still reads the record planes
         field_phase0<DIM, NP>(P, smem, tid, e0, fh);
+#if WGPU_PENCIL_RTDIR
+#pragma unroll 1
+        for (int ph = 1; ph <= DIM; ph++) {
+            __syncthreads();
+            vmax_local = nan_max(vmax_local, field_phase_flux_rt<DIM, NP>(P, smem, tid, e0, dt, ph < DIM ? ph : 0, fh));
+        }
+#else
         __syncthreads();
         field_phase_mid<DIM, NP, 1>(P, smem, tid, e0, fh);
         __syncthreads();
@@ -48,6 +73,7 @@ __global__ void __launch_bounds__(PGeo<DIM, NP>::THREADS, WGPU_PENCIL_MIN_BLOCKS
             __syncthreads();
         }
         vmax_local = nan_max(vmax_local, field_phase_final<DIM, NP>(P, smem, tid, e0, dt, fh));
+#endif
     } else {
         pencil_phase_fields<DIM, NP>(P, tid, e0, dt);
     }

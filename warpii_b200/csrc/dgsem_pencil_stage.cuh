@@ -38,6 +38,12 @@
 #ifndef WGPU_PENCIL_THREADS
 #define WGPU_PENCIL_THREADS 128
 #endif
+#ifndef WGPU_PENCIL_P0_ROLL
+#define WGPU_PENCIL_P0_ROLL 0    // 1: P0 forms the node records two at a time in a rolled loop (half the code, ILP 2 instead of NP)
+#endif
+#ifndef WGPU_PENCIL_RTDIR
+#define WGPU_PENCIL_RTDIR 0      // 1: one flux-phase body for all directions (run-time direction, pencil_phase_flux_rt); measured slower
+#endif
 
 namespace wgpu {
 
@@ -191,6 +197,13 @@ __device__ __forceinline__ void pencil_halo_fetch(const StageParams& P, const in
     }
 }
 
+// make_prim for the rare second outside end of a pencil (partial patches, patches of one element): out of line, so that the
+// hot code of every flux phase carries one inlined copy of the ~200-instruction routine instead of two
+__device__ __noinline__ void make_prim_cold(const double q0, const double q1, const double q2, const double q3, const double q4,
+                                            const double gamma, Prim* out) {
+    *out = make_prim(q0, q1, q2, q3, q4, gamma);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // P0: the thread that owns x-pencil (le, pe): node primitives, first indicator transform, neighbour table, and the
 // fetch of what lies beyond the ends of the y-pencil this thread owns in the next phase
@@ -209,19 +222,51 @@ __device__ __forceinline__ void pencil_phase0(const StageParams& P, double* smem
     if (e >= P.elem_end) return;   // (its records are never read: the in-patch test uses e_hi)
     // neighbour ids of the y-faces first: the loads they address (ends of next phase's pencil) then overlap with the state's
     const int v0 = P.nbr[(size_t)e * G::NFACE + 2], v1 = P.nbr[(size_t)e * G::NFACE + 3];
-    double q[5][NP];
     const double* src = P.u + ((size_t)e * P.nc + 5 * sp) * G::NN + pe * NP;
-#pragma unroll
-    for (int c = 0; c < 5; c++) load_run<NP>(src + (size_t)c * G::NN, q[c]);
+    double v[NP];
+#if WGPU_PENCIL_P0_ROLL
     pencil_halo_fetch<DIM, NP, 1>(P, v0, v1, pe, e0, e_hi, sp, next);
     if (sp == 0)
         for (int f = pe; f < G::NFACE; f += G::NPEN) sNbr[le * G::NFACE + f] = P.nbr[(size_t)e * G::NFACE + f];
-    double v[NP];
+    if (NP % 2 == 0) {
+        // two nodes per iteration of a REAL loop: half the code of four inlined make_prim, two independent chains in flight
+        double va[NP / 2 > 0 ? NP / 2 : 1], vb[NP / 2 > 0 ? NP / 2 : 1];
+#pragma unroll 1
+        for (int it = 0; it < NP / 2; it++) {
+            double qa[5], qb[5];
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                const double2 t = *reinterpret_cast<const double2*>(src + (size_t)c * G::NN + 2 * it);
+                qa[c] = t.x;
+                qb[c] = t.y;
+            }
+            const Prim ra = make_prim(qa[0], qa[1], qa[2], qa[3], qa[4], P.gamma);
+            const Prim rb = make_prim(qb[0], qb[1], qb[2], qb[3], qb[4], P.gamma);
+            put_rec(sRec, G::NODES, pslot<NP>(le * G::NN + pe * NP + 2 * it), ra);
+            put_rec(sRec, G::NODES, pslot<NP>(le * G::NN + pe * NP + 2 * it + 1), rb);
+            // (the indicator variable goes through the scratch slot of its own node; transformed below)
+            sBuf[2 * G::NODES + pslot<NP>(le * G::NN + pe * NP + 2 * it)].y = ra.p * ra.rho;
+            sBuf[2 * G::NODES + pslot<NP>(le * G::NN + pe * NP + 2 * it + 1)].y = rb.p * rb.rho;
+        }
+#pragma unroll
+        for (int m = 0; m < NP; m++) v[m] = sBuf[2 * G::NODES + pslot<NP>(le * G::NN + pe * NP + m)].y;
+    } else
+#endif
+    {
+    double q[5][NP];
+#pragma unroll
+    for (int c = 0; c < 5; c++) load_run<NP>(src + (size_t)c * G::NN, q[c]);
+#if !WGPU_PENCIL_P0_ROLL
+    pencil_halo_fetch<DIM, NP, 1>(P, v0, v1, pe, e0, e_hi, sp, next);
+    if (sp == 0)
+        for (int f = pe; f < G::NFACE; f += G::NPEN) sNbr[le * G::NFACE + f] = P.nbr[(size_t)e * G::NFACE + f];
+#endif
 #pragma unroll
     for (int m = 0; m < NP; m++) {
         const Prim r = make_prim(q[0][m], q[1][m], q[2][m], q[3][m], q[4][m], P.gamma);
         put_rec(sRec, G::NODES, pslot<NP>(le * G::NN + pe * NP + m), r);
         v[m] = r.p * r.rho;   // indicator variable, fluid_flux_es_dgsem_operator.h:286-290
+    }
     }
     // Legendre analysis along x (persson_peraire_shock_indicator.h:56 via FESeries::Legendre, sum-factorised)
 #pragma unroll
@@ -276,7 +321,11 @@ __device__ __forceinline__ void pencil_sums(const StageParams& P, const double2*
         Prim b = get_rec<true>(sRec, G::NODES, h.nslot[side]);
         if (h.kind[side] == 1) {
             if (side == os) b = bo;
-            else b = make_prim(h.q[side][0], h.q[side][1], h.q[side][2], h.q[side][3], h.q[side][4], gamma);   // both ends outside
+            else {   // both ends outside
+                Prim cold;
+                make_prim_cold(h.q[side][0], h.q[side][1], h.q[side][2], h.q[side][3], h.q[side][4], gamma, &cold);
+                b = cold;
+            }
         }
         // (a domain-boundary end evaluates the flux against a harmless record and discards it: the common path stays one
         // basic block with the pair loop below, which is what lets the scheduler interleave the two ends and the pairs)
@@ -437,52 +486,13 @@ __device__ __forceinline__ void pencil_fv_correction(const StageParams& P, const
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Px (final): x-pencil owner.  Returns this thread's maximum transport speed of the values it wrote (0 if none).
-// ---------------------------------------------------------------------------------------------------------------------
+// Final-phase epilogue of a species: sources, stage update, store, transport speed of the values written.  rate[c][m] holds
+// the complete rate of node m of the x-pencil (e, pe) on entry and the new state on return.
 template <int DIM, int NP>
-__device__ __forceinline__ double pencil_phase_final(const StageParams& P, double* smem, const int tid, const int64_t e0, const int sp,
-                                                     const double dt, const PencilHalo& h) {
+__device__ __forceinline__ double pencil_finish(const StageParams& P, const int64_t e, const int pe, const int sp, const double dt,
+                                                double (&rate)[5][NP]) {
     using G = PGeo<DIM, NP>;
-    const double2* const sRec = reinterpret_cast<const double2*>(smem + G::OFF_REC);
-    double2* const sBuf = reinterpret_cast<double2*>(smem + G::OFF_BUF);
-    const double2* const sEn = reinterpret_cast<const double2*>(smem + G::OFF_EN);
-    if (tid >= G::USED) return 0.0;
-    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
-    const int64_t e = e0 + le;
-    if (e >= P.elem_end) return 0.0;
     const size_t off = ((size_t)e * P.nc + 5 * sp) * G::NN + pe * NP;   // of node 0 of the pencil, component 0
-
-    // blending factor of the element: fixed-order sum of the pencils' modal energies (persson_peraire...:96-122)
-    double g0 = 0.0, g1 = 0.0;
-    for (int k = 0; k < G::NPEN; k++) {
-        const double2 en = sEn[le * G::NPEN + k];
-        g0 += en.x;
-        g1 += en.y;
-    }
-    const double alpha = blending_from_energies(g0, g1, P.ind_T, P.ind_sT);
-    if (pe == 0 && P.alpha_out) P.alpha_out[(size_t)e * P.nsp + sp] = alpha;
-    if (alpha > 0.0) {
-        // troubled element (rare): the correction of this thread's nodes goes into their accumulator slots before the
-        // regular path reads them (a run-time loop over the nodes: nothing of the regular path is live yet)
-#pragma unroll 1
-        for (int m = 0; m < NP; m++) {
-            double corr[5];
-            pencil_fv_correction<DIM, NP>(P, sRec, le, pe * NP + m, alpha, corr);
-            const int slot = pslot<NP>(le * G::NN + pe * NP + m);
-            double2 a = sBuf[slot], b = sBuf[G::NODES + slot], c = sBuf[2 * G::NODES + slot];
-            a.x += corr[0]; a.y += corr[1]; b.x += corr[2]; b.y += corr[3]; c.x += corr[4];
-            sBuf[slot] = a; sBuf[G::NODES + slot] = b; sBuf[2 * G::NODES + slot] = c;
-        }
-    }
-
-    double rate[5][NP];   // [component][node of the pencil]: the layout of the vector loads / stores below
-    pencil_sums<DIM, NP, 0>(P, sRec, h, le, pe, [&](const int m, const double (&a)[5]) {
-        const int slot = pslot<NP>(le * G::NN + pe * NP + m);
-        const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot];
-        rate[0][m] = a[0] + x.x; rate[1][m] = a[1] + x.y; rate[2][m] = a[2] + y.x; rate[3][m] = a[3] + y.y; rate[4][m] = a[4] + z.x;
-    });
-
     // two-fluid sources on this species: (q/m)(rho E + m x B) and (q/m) m.E.  (u is read again here and below: it was
     // read by this very thread in P0, an L1/L2 hit, not HBM traffic.)
     if (P.src_on) {
@@ -557,6 +567,298 @@ __device__ __forceinline__ double pencil_phase_final(const StageParams& P, doubl
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Px (final): x-pencil owner.  Returns this thread's maximum transport speed of the values it wrote (0 if none).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DIM, int NP>
+__device__ __forceinline__ double pencil_phase_final(const StageParams& P, double* smem, const int tid, const int64_t e0, const int sp,
+                                                     const double dt, const PencilHalo& h) {
+    using G = PGeo<DIM, NP>;
+    const double2* const sRec = reinterpret_cast<const double2*>(smem + G::OFF_REC);
+    double2* const sBuf = reinterpret_cast<double2*>(smem + G::OFF_BUF);
+    const double2* const sEn = reinterpret_cast<const double2*>(smem + G::OFF_EN);
+    if (tid >= G::USED) return 0.0;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    if (e >= P.elem_end) return 0.0;
+
+    // blending factor of the element: fixed-order sum of the pencils' modal energies (persson_peraire...:96-122)
+    double g0 = 0.0, g1 = 0.0;
+    for (int k = 0; k < G::NPEN; k++) {
+        const double2 en = sEn[le * G::NPEN + k];
+        g0 += en.x;
+        g1 += en.y;
+    }
+    const double alpha = blending_from_energies(g0, g1, P.ind_T, P.ind_sT);
+    if (pe == 0 && P.alpha_out) P.alpha_out[(size_t)e * P.nsp + sp] = alpha;
+    if (alpha > 0.0) {
+        // troubled element (rare): the correction of this thread's nodes goes into their accumulator slots before the
+        // regular path reads them (a run-time loop over the nodes: nothing of the regular path is live yet)
+#pragma unroll 1
+        for (int m = 0; m < NP; m++) {
+            double corr[5];
+            pencil_fv_correction<DIM, NP>(P, sRec, le, pe * NP + m, alpha, corr);
+            const int slot = pslot<NP>(le * G::NN + pe * NP + m);
+            double2 a = sBuf[slot], b = sBuf[G::NODES + slot], c = sBuf[2 * G::NODES + slot];
+            a.x += corr[0]; a.y += corr[1]; b.x += corr[2]; b.y += corr[3]; c.x += corr[4];
+            sBuf[slot] = a; sBuf[G::NODES + slot] = b; sBuf[2 * G::NODES + slot] = c;
+        }
+    }
+
+    double rate[5][NP];   // [component][node of the pencil]: the layout of the vector loads / stores below
+    pencil_sums<DIM, NP, 0>(P, sRec, h, le, pe, [&](const int m, const double (&a)[5]) {
+        const int slot = pslot<NP>(le * G::NN + pe * NP + m);
+        const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot];
+        rate[0][m] = a[0] + x.x; rate[1][m] = a[1] + x.y; rate[2][m] = a[2] + y.x; rate[3][m] = a[3] + y.y; rate[4][m] = a[4] + z.x;
+    });
+
+    return pencil_finish<DIM, NP>(P, e, pe, sp, dt, rate);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ONE code body for the flux phases of all directions (WGPU_PENCIL_RTDIR, the default).  With a direction-templated body the
+// kernel is ~9000 instructions of straight-line code per species pass (146 KB), the 12 resident warps of an SM sit at
+// different places in it and 11-18 % of the stall samples were instruction-cache misses (profiles/README.md).  Here the
+// direction is a run-time value that only enters (a) the node addressing and (b) a ROTATION of the velocity / momentum
+// components when records are read and rates are written: the pencil's records are relabelled so that the pencil direction
+// is component 0, the fluxes are evaluated for "direction 0" (compile-time constant inside the flux code, no selects
+// there), and the five rates are relabelled back when they leave the registers.  Bit for bit the same arithmetic as the
+// templated body (the relabelling is exact), a third of the code.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int DIM, int NP>
+__device__ __forceinline__ int pencil_base_rt(const int d, const int pe) {
+    if (DIM == 2) return d == 0 ? pe * NP : pe;
+    return d == 0 ? pe * NP : (d == 1 ? (pe % NP) + NP * NP * (pe / NP) : pe);
+}
+template <int DIM, int NP>
+__device__ __forceinline__ int pencil_stride_rt(const int d) { return d == 0 ? 1 : (d == 1 ? NP : NP * NP); }
+
+// relabel (x, y, z) components so that direction d becomes component 0 (cyclic): (a0,a1,a2) -> (a_d, a_{d+1}, a_{d+2})
+__device__ __forceinline__ void rot3(const int d, double& a0, double& a1, double& a2) {
+    const double x = a0, y = a1, z = a2;
+    a0 = (d == 0) ? x : (d == 1 ? y : z);
+    a1 = (d == 0) ? y : (d == 1 ? z : x);
+    a2 = (d == 0) ? z : (d == 1 ? x : y);
+}
+// ... and back: (b0,b1,b2) in the rotated frame -> (x, y, z)
+__device__ __forceinline__ void unrot3(const int d, double& b0, double& b1, double& b2) {
+    const double p = b0, q = b1, r = b2;
+    b0 = (d == 0) ? p : (d == 1 ? r : q);
+    b1 = (d == 0) ? q : (d == 1 ? p : r);
+    b2 = (d == 0) ? r : (d == 1 ? q : p);
+}
+
+template <int DIM, int NP>
+__device__ __forceinline__ void pencil_halo_fetch_rt(const StageParams& P, const int d, const int v0, const int v1, const int pe,
+                                                     const int64_t e0, const int64_t e_hi, const int sp, PencilHalo& h) {
+    using G = PGeo<DIM, NP>;
+    const int base = pencil_base_rt<DIM, NP>(d, pe), st = pencil_stride_rt<DIM, NP>(d);
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int v = side ? v1 : v0;
+        const int nn = base + (side ? 0 : NP - 1) * st;   // the neighbour's end node: its opposite face, same tangential index
+        h.nslot[side] = 0;
+        if (v >= e0 && v < e_hi) {
+            h.kind[side] = 0;
+            h.nslot[side] = pslot<NP>((int)(v - e0) * G::NN + nn);
+        } else {
+            const double* src;
+            size_t stride;
+            if (v < 0) {
+                h.kind[side] = 2;
+                src = P.bres + (((size_t)(-1 - v) * P.nsp + sp) * 5) * G::NPEN + pe;
+                stride = G::NPEN;
+            } else if (v < P.n_elems) {
+                h.kind[side] = 1;
+                src = P.u + ((size_t)v * P.nc + 5 * sp) * G::NN + nn;
+                stride = G::NN;
+            } else {
+                h.kind[side] = 1;
+                src = P.ghost + ((size_t)(v - P.n_elems) * P.ncf + 5 * sp) * G::NPEN + pe;
+                stride = G::NPEN;
+            }
+#pragma unroll
+            for (int c = 0; c < 5; c++) h.q[side][c] = src[(size_t)c * stride];
+        }
+    }
+}
+
+// Flux phase of direction d (run-time): d = 1 .. DIM-1 deposit their sums in the shared accumulator (d = 1 writes, the
+// others add) and carry the indicator transform along; d = 0 is the final phase (x-pencil owner: blend, sources, stage
+// update, store, transport speed).  On return h holds the ends of the pencil this thread owns in the next phase.
+// Returns the thread's maximum transport speed (final phase with the fused CFL reduction, else 0).
+template <int DIM, int NP, bool WITH_FINAL = true>
+__device__ __forceinline__ double pencil_phase_flux_rt(const StageParams& P, double* smem, const int tid, const int64_t e0, const int sp,
+                                                       const double dt, const int d, PencilHalo& h) {
+    using G = PGeo<DIM, NP>;
+    const double2* const sRec = reinterpret_cast<const double2*>(smem + G::OFF_REC);
+    double2* const sBuf = reinterpret_cast<double2*>(smem + G::OFF_BUF);
+    double2* const sEn = reinterpret_cast<double2*>(smem + G::OFF_EN);
+    const int* const sNbr = reinterpret_cast<const int*>(smem + G::OFF_NBR);
+    if (tid >= G::USED) return 0.0;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    const int64_t e_hi = (e0 + G::E < P.elem_end) ? e0 + G::E : P.elem_end;
+    const bool final_phase = WITH_FINAL && (d == 0), first = (d == 1), last_ind = (d == DIM - 1);
+    if (e >= P.elem_end) {
+        if (last_ind) sEn[tid] = make_double2(0.0, 0.0);
+        return 0.0;
+    }
+    const int base = le * G::NN + pencil_base_rt<DIM, NP>(d, pe), st = pencil_stride_rt<DIM, NP>(d);
+    const double hig = P.hig, gamma = P.gamma;
+
+    double ind[NP];
+    if (!final_phase) {
+        // indicator scratch of the pencil's nodes: transform along d now (cheap), written back with the sums
+#pragma unroll
+        for (int m = 0; m < NP; m++) ind[m] = sBuf[2 * G::NODES + pslot<NP>(base + m * st)].y;
+        legendre_1d<NP>(P, ind);
+        if (last_ind) {
+            bool shell_pencil;   // a tangential mode index of this pencil is already NP-1 (pencil_energies)
+            if (DIM == 2) shell_pencil = (pe == NP - 1);
+            else shell_pencil = (pe % NP == NP - 1) || (pe / NP == NP - 1);
+            double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                const double sq = ind[k] * ind[k];
+                if (shell_pencil || k == NP - 1) g1 += sq; else g0 += sq;
+            }
+            sEn[tid] = make_double2(g0, g1);
+        }
+    } else {
+        // blending factor of the element: fixed-order sum of the pencils' modal energies (persson_peraire...:96-122)
+        double g0 = 0.0, g1 = 0.0;
+        for (int k = 0; k < G::NPEN; k++) {
+            const double2 en = sEn[le * G::NPEN + k];
+            g0 += en.x;
+            g1 += en.y;
+        }
+        const double alpha = blending_from_energies(g0, g1, P.ind_T, P.ind_sT);
+        if (pe == 0 && P.alpha_out) P.alpha_out[(size_t)e * P.nsp + sp] = alpha;
+        if (alpha > 0.0) {
+            // troubled element (rare): the correction of this thread's nodes goes into their accumulator slots before the
+            // regular path reads them
+#pragma unroll 1
+            for (int m = 0; m < NP; m++) {
+                double corr[5];
+                pencil_fv_correction<DIM, NP>(P, sRec, le, pe * NP + m, alpha, corr);
+                const int slot = pslot<NP>(le * G::NN + pe * NP + m);
+                double2 a = sBuf[slot], b = sBuf[G::NODES + slot], c = sBuf[2 * G::NODES + slot];
+                a.x += corr[0]; a.y += corr[1]; b.x += corr[2]; b.y += corr[3]; c.x += corr[4];
+                sBuf[slot] = a; sBuf[G::NODES + slot] = b; sBuf[2 * G::NODES + slot] = c;
+            }
+        }
+    }
+
+    // ---- the pencil's records, relabelled so that the pencil direction is component 0 ---------------------------------
+    Prim r[NP];
+#pragma unroll
+    for (int m = 0; m < NP; m++) {
+        const int slot = pslot<NP>(base + m * st);
+        r[m] = (m == 0 || m == NP - 1) ? get_rec<true>(sRec, G::NODES, slot) : get_rec<false>(sRec, G::NODES, slot);
+        rot3(d, r[m].u0, r[m].u1, r[m].u2);
+    }
+    double acc[NP][5];
+#pragma unroll
+    for (int m = 0; m < NP; m++)
+#pragma unroll
+        for (int c = 0; c < 5; c++) acc[m][c] = 0.0;
+    // ---- the two ends (see pencil_sums) --------------------------------------------------------------------------------
+    const double cf = P.inv_hw[d];
+    const int os = (h.kind[0] == 1) ? 0 : 1;
+    Prim bo;
+    {
+        double qo[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) qo[c] = os ? h.q[1][c] : h.q[0][c];
+        if (h.kind[0] == 1 || h.kind[1] == 1) bo = make_prim(qo[0], qo[1], qo[2], qo[3], qo[4], gamma);
+        else bo = r[0];
+        if (h.kind[0] == 1 || h.kind[1] == 1) rot3(d, bo.u0, bo.u1, bo.u2);
+    }
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int m = side ? NP - 1 : 0;
+        Prim b = get_rec<true>(sRec, G::NODES, h.nslot[side]);
+        rot3(d, b.u0, b.u1, b.u2);
+        if (h.kind[side] == 1) {
+            if (side == os) b = bo;
+            else {
+                Prim cold;   // both ends outside
+                make_prim_cold(h.q[side][0], h.q[side][1], h.q[side][2], h.q[side][3], h.q[side][4], gamma, &cold);
+                b = cold;
+                rot3(d, b.u0, b.u1, b.u2);
+            }
+        }
+        double Fe[5], Dv[5], ibl;
+        ec_flux_d(0, r[m], b, hig, Fe, ibl);
+        es_dissipation(r[m], b, ibl, hig, Dv);
+        double ct[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) ct[c] = cf * (side ? (Dv[c] - Fe[c]) : (Dv[c] + Fe[c]));
+        if (h.kind[side] == 2) {
+            // domain boundary: boundary_kernel's contribution (in x, y, z labels: relabel) plus the diagonal volume term
+            Prim a = r[m];
+            a.p = 0.5 * a.rho * a.ib;
+            a.H = a.p * (2.0 * hig) + 0.5 * a.rho * a.q2 + a.p;
+            double Fp[5], bq[5];
+            phys_flux_d(0, a, Fp);
+#pragma unroll
+            for (int c = 0; c < 5; c++) bq[c] = h.q[side][c];
+            rot3(d, bq[1], bq[2], bq[3]);
+            const double sg = side ? -cf : cf;
+#pragma unroll
+            for (int c = 0; c < 5; c++) ct[c] = bq[c] + sg * Fp[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 5; c++) acc[m][c] += ct[c];
+    }
+
+    // ---- what the final phase needs besides the sums --------------------------------------------------------------------
+    double rate[5][NP];   // final phase: [component][node], the layout of the vector loads / stores
+
+    // ---- the pairs; node m is complete after its row --------------------------------------------------------------------
+    const double s = -2.0 * P.inv_h[d];
+    static_for<0, NP>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        static_for<j + 1, NP>([&](auto L) {
+            constexpr int l = decltype(L)::value;
+            double F[5], ibl;
+            ec_flux_d(0, r[j], r[l], hig, F, ibl);
+            const double wj = s * P.T.D[j * NP + l], wl = s * P.T.D[l * NP + j];
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                acc[j][c] = fma(wj, F[c], acc[j][c]);
+                acc[l][c] = fma(wl, F[c], acc[l][c]);
+            }
+        });
+        // node j is complete: back to x, y, z labels, then into the accumulator (or out of it, in the final phase)
+        double a1 = acc[j][1], a2 = acc[j][2], a3 = acc[j][3];
+        unrot3(d, a1, a2, a3);
+        const int slot = pslot<NP>(base + j * st);
+        if (final_phase) {
+            const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot];
+            rate[0][j] = acc[j][0] + x.x; rate[1][j] = a1 + x.y; rate[2][j] = a2 + y.x; rate[3][j] = a3 + y.y; rate[4][j] = acc[j][4] + z.x;
+        } else if (first) {
+            sBuf[slot] = make_double2(acc[j][0], a1);
+            sBuf[G::NODES + slot] = make_double2(a2, a3);
+            sBuf[2 * G::NODES + slot] = make_double2(acc[j][4], ind[j]);
+        } else {
+            const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot];
+            sBuf[slot] = make_double2(acc[j][0] + x.x, a1 + x.y);
+            sBuf[G::NODES + slot] = make_double2(a2 + y.x, a3 + y.y);
+            sBuf[2 * G::NODES + slot] = make_double2(acc[j][4] + z.x, ind[j]);
+        }
+    });
+
+    if (!final_phase) {
+        const int nd = (d + 1 < DIM) ? d + 1 : 0;
+        pencil_halo_fetch_rt<DIM, NP>(P, nd, sNbr[le * G::NFACE + 2 * nd], sNbr[le * G::NFACE + 2 * nd + 1], pe, e0, e_hi, sp, h);
+        return 0.0;
+    }
+    if (WITH_FINAL) return pencil_finish<DIM, NP>(P, e, pe, sp, dt, rate);
+    return 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // The field system fused into the same kernel (mx_on): perfectly hyperbolic Maxwell fluxes for [Ex,Ey,Ez,Bx,By,Bz,phi,psi]
 // (north_star kernel 4; new physics, see include/warpii_gpu.h::warpii_gpu_set_maxwell), the same pencil phases as a species:
 //   F0 (x owner) fields -> shared planes   Fy, Fz  -(1/h) sum_l D[m][l] f_d(F_l) + Rusanov face terms at the two ends -> accumulator
@@ -626,43 +928,43 @@ template <int DIM, int NP, int D, class Done>
 __device__ __forceinline__ void field_sums(const StageParams& P, const double2* sFld, const FieldHalo& h, const int le, const int pe,
                                            Done&& done) {
     using G = PGeo<DIM, NP>;
-    double F[NP][8], acc[NP][8];
+    // Only the NP x 8 partial rates stay in registers: the nodes' fields are read from shared memory one node at a time,
+    // turned into the flux and scattered to all nodes of the pencil with the column of D.
+    double acc[NP][8];
 #pragma unroll
-    for (int m = 0; m < NP; m++) {
-        get_fields(sFld, G::NODES, pslot<NP>(le * G::NN + pencil_node<DIM, NP, D>(pe, m)), F[m]);
+    for (int m = 0; m < NP; m++)
 #pragma unroll
         for (int k = 0; k < 8; k++) acc[m][k] = 0.0;
-    }
-    // the two ends: (f(F_m).n - f*) / (h w_0) = (lambda dF - sgn f_d(dF)) / (2 h w_0), dF = F_p - F_m
     const double cf = 0.5 * P.inv_hw[D];
+    static_for<0, NP>([&](auto L_) {
+        constexpr int l = decltype(L_)::value;
+        double F[8], f[8];
+        get_fields(sFld, G::NODES, pslot<NP>(le * G::NN + pencil_node<DIM, NP, D>(pe, l)), F);
+        if (l == 0 || l == NP - 1) {
+            // an end: (f(F_m).n - f*) / (h w_0) = (lambda dF - sgn f_d(dF)) / (2 h w_0), dF = F_p - F_m
+            constexpr int side = (l == 0) ? 0 : 1;
+            double Fn[8], dF[8], fn[8];
+            get_fields(sFld, G::NODES, h.nslot[side], Fn);
 #pragma unroll
-    for (int side = 0; side < 2; side++) {
-        const int m = side ? NP - 1 : 0;
-        double Fn[8], dF[8], fn[8];
-        get_fields(sFld, G::NODES, h.nslot[side], Fn);
+            for (int k = 0; k < 8; k++) {
+                const double other = (h.kind[side] == 0) ? Fn[k] : ((h.kind[side] == 1) ? h.q[side][k] : F[k]);
+                dF[k] = other - F[k];
+            }
+            phm_flux_d<D>(P, dF, fn);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const double other = (h.kind[side] == 0) ? Fn[k] : ((h.kind[side] == 1) ? h.q[side][k] : F[m][k]);
-            dF[k] = other - F[m][k];
+            for (int k = 0; k < 8; k++) acc[l][k] += cf * (P.mx_lam * dF[k] - (side ? fn[k] : -fn[k]));
         }
-        phm_flux_d<D>(P, dF, fn);
+        // volume: -(1/h) D[m][l] f_d(F_l) to every node m of the pencil
+        phm_flux_d<D>(P, F, f);
 #pragma unroll
-        for (int k = 0; k < 8; k++) acc[m][k] = cf * (P.mx_lam * dF[k] - (side ? fn[k] : -fn[k]));
-    }
-    // volume: -(1/h) sum_l D[m][l] f_d(F_l)
-    double f[NP][8];
-#pragma unroll
-    for (int l = 0; l < NP; l++) phm_flux_d<D>(P, F[l], f[l]);
-    static_for<0, NP>([&](auto M_) {
-        constexpr int m = decltype(M_)::value;
-#pragma unroll
-        for (int l = 0; l < NP; l++) {
+        for (int m = 0; m < NP; m++) {
             const double w = -P.inv_h[D] * P.T.D[m * NP + l];
 #pragma unroll
-            for (int k = 0; k < 8; k++) acc[m][k] = fma(w, f[l][k], acc[m][k]);
+            for (int k = 0; k < 8; k++) acc[m][k] = fma(w, f[k], acc[m][k]);
         }
-        done(m, acc[m]);
     });
+#pragma unroll
+    for (int m = 0; m < NP; m++) done(m, acc[m]);
 }
 
 template <int DIM, int NP>
@@ -721,25 +1023,13 @@ __device__ __forceinline__ void field_phase_mid(const StageParams& P, double* sm
     field_halo_fetch<DIM, NP, NEXT>(P, sNbr[le * G::NFACE + 2 * NEXT], sNbr[le * G::NFACE + 2 * NEXT + 1], pe, e0, e_hi, h);
 }
 
-// Fx: returns the field system's share of the transport speed at this thread's nodes (0 unless the CFL reduction is fused)
+// Final-phase epilogue of the field system: sources, stage update, store, the field system's share of the transport speed.
 template <int DIM, int NP>
-__device__ __forceinline__ double field_phase_final(const StageParams& P, double* smem, const int tid, const int64_t e0, const double dt,
-                                                    const FieldHalo& h) {
+__device__ __forceinline__ double field_finish(const StageParams& P, double* smem, const int64_t e, const int le, const int pe,
+                                               const double dt, double (&rate)[8][NP]) {
     using G = PGeo<DIM, NP>;
     const double2* const sFld = reinterpret_cast<const double2*>(smem + G::OFF_REC);
-    const double2* const sBuf = reinterpret_cast<const double2*>(smem + G::OFF_BUF);
-    if (tid >= G::USED) return 0.0;
-    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
-    const int64_t e = e0 + le;
-    if (e >= P.elem_end) return 0.0;
     const size_t base = (size_t)e * P.nc * G::NN + pe * NP;   // node 0 of the pencil, component 0
-    double rate[8][NP];
-    field_sums<DIM, NP, 0>(P, sFld, h, le, pe, [&](const int m, const double (&a)[8]) {
-        const int slot = pslot<NP>(le * G::NN + pe * NP + m);
-        const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot], w = sFld[4 * G::NODES + slot];
-        rate[0][m] = a[0] + x.x; rate[1][m] = a[1] + x.y; rate[2][m] = a[2] + y.x; rate[3][m] = a[3] + y.y;
-        rate[4][m] = a[4] + z.x; rate[5][m] = a[5] + z.y; rate[6][m] = a[6] + w.x; rate[7][m] = a[7] + w.y;
-    });
     // sources: -J/eps0 on E, chi rho_c/eps0 on phi (species in order, as everywhere)
     if (P.src_on) {
         double J[3][NP], rc[NP];
@@ -815,6 +1105,147 @@ __device__ __forceinline__ double field_phase_final(const StageParams& P, double
         }
     }
     return vmax_local;
+}
+
+// Fx: returns the field system's share of the transport speed at this thread's nodes (0 unless the CFL reduction is fused)
+template <int DIM, int NP>
+__device__ __forceinline__ double field_phase_final(const StageParams& P, double* smem, const int tid, const int64_t e0, const double dt,
+                                                    const FieldHalo& h) {
+    using G = PGeo<DIM, NP>;
+    const double2* const sFld = reinterpret_cast<const double2*>(smem + G::OFF_REC);
+    const double2* const sBuf = reinterpret_cast<const double2*>(smem + G::OFF_BUF);
+    if (tid >= G::USED) return 0.0;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    if (e >= P.elem_end) return 0.0;
+    double rate[8][NP];
+    field_sums<DIM, NP, 0>(P, sFld, h, le, pe, [&](const int m, const double (&a)[8]) {
+        const int slot = pslot<NP>(le * G::NN + pe * NP + m);
+        const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot], w = sFld[4 * G::NODES + slot];
+        rate[0][m] = a[0] + x.x; rate[1][m] = a[1] + x.y; rate[2][m] = a[2] + y.x; rate[3][m] = a[3] + y.y;
+        rate[4][m] = a[4] + z.x; rate[5][m] = a[5] + z.y; rate[6][m] = a[6] + w.x; rate[7][m] = a[7] + w.y;
+    });
+    return field_finish<DIM, NP>(P, smem, e, le, pe, dt, rate);
+}
+
+// The field phases with a run-time direction (one code body, see pencil_phase_flux_rt): E and B are relabelled so that the
+// pencil direction is component 0, the flux is evaluated for direction 0, the rates are relabelled back.
+template <int DIM, int NP>
+__device__ __forceinline__ void field_halo_fetch_rt(const StageParams& P, const int d, const int v0, const int v1, const int pe,
+                                                    const int64_t e0, const int64_t e_hi, FieldHalo& h) {
+    using G = PGeo<DIM, NP>;
+    const int nf0 = 5 * P.nsp;
+    const int base = pencil_base_rt<DIM, NP>(d, pe), st = pencil_stride_rt<DIM, NP>(d);
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int v = side ? v1 : v0;
+        const int nn = base + (side ? 0 : NP - 1) * st;
+        h.nslot[side] = 0;
+        if (v >= e0 && v < e_hi) {
+            h.kind[side] = 0;
+            h.nslot[side] = pslot<NP>((int)(v - e0) * G::NN + nn);
+        } else if (v < 0) {
+            h.kind[side] = 2;
+        } else {
+            h.kind[side] = 1;
+            const double* src;
+            size_t stride;
+            if (v < P.n_elems) {
+                src = P.u + ((size_t)v * P.nc + nf0) * G::NN + nn;
+                stride = G::NN;
+            } else {
+                src = P.ghost + ((size_t)(v - P.n_elems) * P.ncf + nf0) * G::NPEN + pe;
+                stride = G::NPEN;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) h.q[side][k] = src[(size_t)k * stride];
+        }
+    }
+}
+
+__device__ __forceinline__ void rot_fields(const int d, double (&F)[8]) {
+    rot3(d, F[0], F[1], F[2]);
+    rot3(d, F[3], F[4], F[5]);
+}
+
+// direction d = 1 .. DIM-1: sums into the accumulator; d = 0: final phase.  Returns the transport-speed share (final phase).
+template <int DIM, int NP>
+__device__ __forceinline__ double field_phase_flux_rt(const StageParams& P, double* smem, const int tid, const int64_t e0, const double dt,
+                                                      const int d, FieldHalo& h) {
+    using G = PGeo<DIM, NP>;
+    double2* const sFld = reinterpret_cast<double2*>(smem + G::OFF_REC);   // planes 0-3 fields (read), plane 4 rates 6,7
+    double2* const sBuf = reinterpret_cast<double2*>(smem + G::OFF_BUF);
+    const int* const sNbr = reinterpret_cast<const int*>(smem + G::OFF_NBR);
+    if (tid >= G::USED) return 0.0;
+    const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
+    const int64_t e = e0 + le;
+    const int64_t e_hi = (e0 + G::E < P.elem_end) ? e0 + G::E : P.elem_end;
+    if (e >= P.elem_end) return 0.0;
+    const bool final_phase = (d == 0), first = (d == 1);
+    const int base = le * G::NN + pencil_base_rt<DIM, NP>(d, pe), st = pencil_stride_rt<DIM, NP>(d);
+    double acc[NP][8];
+#pragma unroll
+    for (int m = 0; m < NP; m++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[m][k] = 0.0;
+    const double cf = 0.5 * P.inv_hw[d], ihd = -P.inv_h[d];
+    // the two ends first (their outside data was fetched a phase ahead and now leaves the registers)
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int l = side ? NP - 1 : 0;
+        double F[8], Fn[8], dF[8], fn[8];
+        get_fields(sFld, G::NODES, pslot<NP>(base + l * st), F);
+        get_fields(sFld, G::NODES, h.nslot[side], Fn);
+#pragma unroll
+        for (int k = 0; k < 8; k++) dF[k] = (h.kind[side] == 2) ? 0.0 : ((h.kind[side] == 0) ? Fn[k] : h.q[side][k]) - F[k];
+        rot_fields(d, dF);
+        phm_flux_d<0>(P, dF, fn);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[l][k] = cf * (P.mx_lam * dF[k] - (side ? fn[k] : -fn[k]));
+    }
+    static_for<0, NP>([&](auto L_) {
+        constexpr int l = decltype(L_)::value;
+        double F[8], f[8];
+        get_fields(sFld, G::NODES, pslot<NP>(base + l * st), F);
+        rot_fields(d, F);
+        phm_flux_d<0>(P, F, f);
+#pragma unroll
+        for (int m = 0; m < NP; m++) {
+            const double w = ihd * P.T.D[m * NP + l];
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[m][k] = fma(w, f[k], acc[m][k]);
+        }
+    });
+    double rate[8][NP];
+#pragma unroll
+    for (int m = 0; m < NP; m++) {
+        unrot3(d, acc[m][0], acc[m][1], acc[m][2]);
+        unrot3(d, acc[m][3], acc[m][4], acc[m][5]);
+        const int slot = pslot<NP>(base + m * st);
+        if (first) {
+            sBuf[slot] = make_double2(acc[m][0], acc[m][1]);
+            sBuf[G::NODES + slot] = make_double2(acc[m][2], acc[m][3]);
+            sBuf[2 * G::NODES + slot] = make_double2(acc[m][4], acc[m][5]);
+            sFld[4 * G::NODES + slot] = make_double2(acc[m][6], acc[m][7]);
+        } else {
+            const double2 x = sBuf[slot], y = sBuf[G::NODES + slot], z = sBuf[2 * G::NODES + slot], w = sFld[4 * G::NODES + slot];
+            if (final_phase) {
+                rate[0][m] = acc[m][0] + x.x; rate[1][m] = acc[m][1] + x.y; rate[2][m] = acc[m][2] + y.x; rate[3][m] = acc[m][3] + y.y;
+                rate[4][m] = acc[m][4] + z.x; rate[5][m] = acc[m][5] + z.y; rate[6][m] = acc[m][6] + w.x; rate[7][m] = acc[m][7] + w.y;
+            } else {
+                sBuf[slot] = make_double2(acc[m][0] + x.x, acc[m][1] + x.y);
+                sBuf[G::NODES + slot] = make_double2(acc[m][2] + y.x, acc[m][3] + y.y);
+                sBuf[2 * G::NODES + slot] = make_double2(acc[m][4] + z.x, acc[m][5] + z.y);
+                sFld[4 * G::NODES + slot] = make_double2(acc[m][6] + w.x, acc[m][7] + w.y);
+            }
+        }
+    }
+    if (!final_phase) {
+        const int nd = (d + 1 < DIM) ? d + 1 : 0;
+        field_halo_fetch_rt<DIM, NP>(P, nd, sNbr[le * G::NFACE + 2 * nd], sNbr[le * G::NFACE + 2 * nd + 1], pe, e0, e_hi, h);
+        return 0.0;
+    }
+    return field_finish<DIM, NP>(P, smem, e, le, pe, dt, rate);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -125,6 +125,7 @@ struct warpii_gpu_ctx {
     bool src_on = false;                    // two-fluid source terms (warpii_gpu_set_sources)
     double inv_eps0 = 1.0, chi = 0.0;
     bool maxwell_on = false;                // PHM fluxes for the field components (warpii_gpu_set_maxwell)
+    bool mx_fused = false;                  // ... evolved inside the pencil stage kernel (else by maxwell_kernel right behind it)
     double light_speed = 1.0, mx_chi = 0.0, mx_gamma = 0.0;
     int ncf = 5;                            // components per halo face trace: 5*nsp, or nc with the field system evolved
     double* d_qm = nullptr;                 // [nsp] charge / mass
@@ -216,7 +217,7 @@ void do_launch_stage(warpii_gpu_ctx* c, const StageParams& P, cudaStream_t s) {
     if (c->general) launch_stage_general(c->dim, c->Np, P, c->GP, s);
     else if (c->pencil) launch_pencil_stage(c->dim, c->Np, P, s);
     else launch_stage(c->dim, c->Np, P, s);
-    if (c->maxwell_on && !(c->pencil && !c->general) && P.elem_end > P.elem_begin) {
+    if (c->maxwell_on && !c->mx_fused && P.elem_end > P.elem_begin) {
         // the field components of the same range, right behind the fluids (the pencil kernel evolves them itself)
         launch_maxwell(c->dim, c->Np, P, c->light_speed, c->mx_chi, c->mx_gamma, s);
         c->launches++;
@@ -256,7 +257,7 @@ StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a,
     P.nsp = c->nsp;
     P.ncf = c->ncf;
     P.fields_skip = c->maxwell_on ? 1 : 0;
-    P.mx_on = c->maxwell_on ? 1 : 0;
+    P.mx_on = (c->maxwell_on && c->mx_fused) ? 1 : 0;
     {
         double big = 1.0;
         if (c->mx_chi > big) big = c->mx_chi;
@@ -756,6 +757,16 @@ int warpii_gpu_set_maxwell(warpii_gpu_ctx* c, int enabled, double light_speed, d
     c->mx_gamma = gamma;
     c->maxwell_on = true;
     c->ncf = c->nc;
+    {
+        // Fused into the pencil stage kernel in 2-D; in 3-D the fused kernel's instruction footprint passes the SM's
+        // instruction cache (no_instruction stalls 18 % -> 32 % of the samples in the second stage, profiles/README.md) and the
+        // stand-alone kernel right behind the fluid stage is faster.  WARPII_GPU_MAXWELL=fused|separate overrides.
+        const char* env = std::getenv("WARPII_GPU_MAXWELL");
+        bool fused = c->pencil && c->dim == 2;
+        if (env && std::strcmp(env, "fused") == 0) fused = c->pencil;
+        if (env && std::strcmp(env, "separate") == 0) fused = false;
+        c->mx_fused = fused;
+    }
     return 0;
 }
 
