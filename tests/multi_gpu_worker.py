@@ -69,6 +69,33 @@ def main():
             g1.close()
         g.close()
         dist.barrier()
+    # ---- streamed host step on a sharded context (interface elements + exchanges on the communication stream, interior
+    # slabs on the main stream) == upload + SSPRK2 step + download, bit for bit ---------------------------------------------------
+    for (dim, p, nx, slabs) in [(2, 3, [16, 24], 4), (3, 3, [6, 6, 12], 0), (3, 2, [4, 4, 8], 3)]:
+        left, right = [0.0, -5.0, -5.0][:dim], [10.0, 5.0, 5.0][:dim]
+        o = Oracle(dim, p, nx, left, right, gamma=1.4, threads=4)
+        u = o.project(cases.isentropic_vortex(1.4))
+        g = BoxSolver(dim, p, nx, left, right, gamma=1.4, rank=rank, n_ranks=world, device=local)
+        g.attach_comm(fresh_id())
+        ul = np.ascontiguousarray(u[g.l2g])
+        g.upload(0, ul)
+        dt = g.recommend_dt(0)
+        want, dts = ul.copy(), []
+        for k in range(3):
+            g.upload(0, want)
+            g.ssprk2_step(dt if k == 0 else dts[-1], 0.0)
+            want = g.download(0)
+            dts.append(g.recommend_dt(0))
+        host = torch.empty(ul.size, dtype=torch.float64).pin_memory().numpy().reshape(ul.shape)
+        host[...] = ul
+        got, d = [], dt
+        for k in range(3):
+            d = g.host_step(host, host, d, 0.0, n_slabs=slabs)
+            got.append(d)
+        assert np.array_equal(host, want), (rank, dim, "streamed sharded host step differs from the plain sequence")
+        assert got == dts, (got, dts)
+        g.close()
+        dist.barrier()
     # ---- two fluids + the field system (PHM Maxwell fluxes + sources): the halo carries the field traces too ----------------
     from test_gpu_maxwell import MX, SRC, two_fluid_state
     for (dim, p, nx) in [(2, 3, [6, 8]), (3, 3, [4, 4, 6]), (1, 2, [12])]:

@@ -157,6 +157,7 @@ struct warpii_gpu_ctx {
     std::vector<cudaEvent_t> slab_events;
     void* slab_plan = nullptr;
     int slab_plan_slabs = -1;
+    std::vector<std::vector<int>> shard_deps;   // neighbour slabs of the sharded streamed step (host_step_sharded)
     // the whole streamed step as a CUDA graph, replayed while the caller keeps passing the same buffers and vectors
     cudaGraphExec_t host_step_graph = nullptr;
     const double* hsg_in = nullptr;
@@ -306,6 +307,26 @@ int start_exchange(warpii_gpu_ctx* c, int u) {
     }
     NCCL_OK(g_nccl.GroupEnd());
     CUDA_OK(cudaEventRecord(c->ev_recv, c->comm_stream));
+    return 0;
+}
+
+// the same exchange issued entirely on the communication stream (pack kernel included): the caller has ordered that stream
+// behind whatever produced the interface elements of u
+int exchange_on_comm_stream(warpii_gpu_ctx* c, int u) {
+    if (!c->comm || c->peer_rank.empty()) return 0;
+    launch_pack(c->dim, c->Np, c->vec[u], c->d_send_elem, c->d_send_side, c->n_send, c->nc, c->ncf, c->d_sendbuf, c->comm_stream);
+    c->launches++;
+    const size_t per_face = (size_t)c->ncf * c->NF;
+    NCCL_OK(g_nccl.GroupStart());
+    for (size_t p = 0; p < c->peer_rank.size(); p++) {
+        const int64_t ns = c->send_offset[p + 1] - c->send_offset[p];
+        const int64_t nr = c->recv_offset[p + 1] - c->recv_offset[p];
+        if (ns > 0)
+            NCCL_OK(g_nccl.Send(c->d_sendbuf + c->send_offset[p] * per_face, ns * per_face, ncclDouble, c->peer_rank[p], c->comm, c->comm_stream));
+        if (nr > 0)
+            NCCL_OK(g_nccl.Recv(c->d_ghost + c->recv_offset[p] * per_face, nr * per_face, ncclDouble, c->peer_rank[p], c->comm, c->comm_stream));
+    }
+    NCCL_OK(g_nccl.GroupEnd());
     return 0;
 }
 
@@ -1031,6 +1052,166 @@ int build_slab_plan(warpii_gpu_ctx* c, int n_slabs, SlabPlan& plan) {
 
 void warpii_gpu_free_slab_plan(void* plan) { delete (SlabPlan*)plan; }
 
+namespace {
+// The streamed step on a SHARDED context (periodic mesh, NCCL halo).  Slab 0 = the interface elements (they are numbered
+// first), slabs 1.. = the interior cut into pieces of whole patches.  Slab 0 is uploaded first; its two exchanges and its two
+// stages run on the communication stream (as in run_stage), everything else on the main stream, ordered by events:
+//   upload(0) -> pack + send/recv u -> stage 1 of slab 0 (needs the uploads of its neighbours' slabs) -> pack + send/recv f1
+//   -> stage 2 of slab 0 (needs stage 1 of its neighbours' slabs) -> download(0)
+//   interior slab j: stage 1 once its neighbours' slabs are uploaded, stage 2 once their stage 1 is launched (main stream
+//   is in order; for slab 0 an event), download on the third stream.
+// Same kernels, same operands: bit-identical to upload + warpii_gpu_ssprk2_step + download.
+int host_step_sharded(warpii_gpu_ctx* c, int solution, int f1, const double* host_in, double* host_out, double dt, int n_slabs) {
+    const size_t per_elem = (size_t)c->nc * c->NN;
+    const int G = c->pencil && !c->general ? pencil_patch_elems(c->dim, c->Np) : elems_per_block(c->dim, c->Np);
+    const int64_t n_if = c->n_interface, n_in = c->n_elems - n_if;
+    int S = (n_slabs > 0 ? n_slabs : 16);
+    const int64_t in_patches = (n_in + G - 1) / G;
+    if (S - 1 > in_patches) S = (int)in_patches + 1;
+    if (S < 2) S = 2;
+    std::vector<int64_t> begin(S + 1, 0);
+    begin[0] = 0;
+    begin[1] = n_if;
+    for (int k = 1; k < S; k++) begin[k + 1] = std::min<int64_t>(c->n_elems, n_if + ((in_patches * k) / (S - 1)) * G);
+    begin[S] = c->n_elems;
+    // neighbour slabs from the face table (ghost faces are slab 0's business)
+    if ((int)c->shard_deps.size() != S) {
+        const int nf = 2 * c->dim;
+        std::vector<int32_t> nbr((size_t)c->n_elems * nf);
+        CUDA_OK(cudaMemcpy(nbr.data(), c->d_nbr, nbr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        auto slab_of = [&](int64_t e) { return (int)(std::upper_bound(begin.begin(), begin.end(), e) - begin.begin()) - 1; };
+        c->shard_deps.assign(S, {});
+        for (int k = 0; k < S; k++) {
+            std::vector<char> seen(S, 0);
+            seen[k] = 1;
+            for (int64_t e = begin[k]; e < begin[k + 1]; e++)
+                for (int f = 0; f < nf; f++) {
+                    const int32_t v = nbr[(size_t)e * nf + f];
+                    if (v >= 0 && v < c->n_elems) seen[slab_of(v)] = 1;
+                    else if (v >= c->n_elems && k != 0) return fail("host_ssprk2_step: a ghost face outside the interface elements");
+                }
+            for (int j = 0; j < S; j++)
+                if (seen[j]) c->shard_deps[k].push_back(j);
+        }
+    }
+    const std::vector<std::vector<int>>& deps = c->shard_deps;
+    if (!c->h2d_stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    }
+    while ((int)c->slab_events.size() < 3 * S + 4) {
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->slab_events.push_back(e);
+    }
+    cudaEvent_t* up_done = c->slab_events.data();
+    cudaEvent_t* s1_done = c->slab_events.data() + S;
+    cudaEvent_t* s2_done = c->slab_events.data() + 2 * S;
+    cudaEvent_t start = c->slab_events[3 * S], if_s1 = c->slab_events[3 * S + 1], main_s1 = c->slab_events[3 * S + 2],
+                joined = c->slab_events[3 * S + 3];
+    if (!c->d_host_dt) CUDA_OK(cudaMalloc((void**)&c->d_host_dt, sizeof(double)));
+    c->h_small[24] = dt;
+    CUDA_OK(cudaMemcpyAsync(c->d_host_dt, c->h_small + 24, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_vmax + solution, 0, sizeof(unsigned long long), c->stream));
+    CUDA_OK(cudaEventRecord(start, c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->h2d_stream, start, 0));
+    CUDA_OK(cudaStreamWaitEvent(c->d2h_stream, start, 0));
+    CUDA_OK(cudaStreamWaitEvent(c->comm_stream, start, 0));
+    StageParams P1 = stage_params(c, f1, solution, dt, 1.0, 0.0, 0, false);        // rk.h:102-103
+    StageParams P2 = stage_params(c, solution, f1, dt, 0.5, 0.5, 0, true);         // rk.h:104-105, fused CFL
+    P1.dt_dev = c->d_host_dt;
+    P2.dt_dev = c->d_host_dt;
+    auto upload = [&](int k) -> int {
+        const size_t off = (size_t)begin[k] * per_elem, cnt = (size_t)(begin[k + 1] - begin[k]) * per_elem;
+        if (cnt) CUDA_OK(cudaMemcpyAsync(c->vec[solution] + off, host_in + off, cnt * sizeof(double), cudaMemcpyHostToDevice, c->h2d_stream));
+        CUDA_OK(cudaEventRecord(up_done[k], c->h2d_stream));
+        return 0;
+    };
+    auto download = [&](int k, cudaEvent_t after) -> int {
+        CUDA_OK(cudaStreamWaitEvent(c->d2h_stream, after, 0));
+        const size_t off = (size_t)begin[k] * per_elem, cnt = (size_t)(begin[k + 1] - begin[k]) * per_elem;
+        if (cnt) CUDA_OK(cudaMemcpyAsync(host_out + off, c->vec[solution] + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->d2h_stream));
+        return 0;
+    };
+    // ---- uploads: the interface elements first (their exchange starts as soon as they have arrived), then the interior
+    // slabs next to them; stages and downloads are issued as soon as what they read has been issued ---------------------------
+    std::vector<char> uploaded(S, 0), s1(S, 0), s2(S, 0);
+    auto ready = [&](int k, const std::vector<char>& have) {
+        for (int j : deps[k]) if (!have[j]) return false;
+        return true;
+    };
+    std::vector<int> order;
+    order.push_back(0);
+    if (S > 2) order.push_back(S - 1);
+    for (int k = 1; k < (S > 2 ? S - 1 : S); k++) order.push_back(k);
+    for (int k : order) {
+        if (upload(k)) return 1;
+        uploaded[k] = 1;
+        if (k == 0) {
+            CUDA_OK(cudaStreamWaitEvent(c->comm_stream, up_done[0], 0));
+            if (exchange_on_comm_stream(c, solution)) return 1;
+        }
+        bool waited = false;
+        for (int j = 1; j < S; j++) {      // stage 1 of interior slabs, main stream
+            if (s1[j] || !ready(j, uploaded)) continue;
+            if (!waited) { CUDA_OK(cudaStreamWaitEvent(c->stream, up_done[k], 0)); waited = true; }
+            P1.elem_begin = begin[j];
+            P1.elem_end = begin[j + 1];
+            do_launch_stage(c, P1, c->stream);
+            c->launches++;
+            s1[j] = 1;
+        }
+        if (!s1[0] && ready(0, uploaded)) {
+            // stage 1 of the interface elements on the communication stream (behind the receive), then the exchange of f1
+            CUDA_OK(cudaStreamWaitEvent(c->comm_stream, up_done[k], 0));
+            P1.elem_begin = begin[0];
+            P1.elem_end = begin[1];
+            do_launch_stage(c, P1, c->comm_stream);
+            c->launches++;
+            s1[0] = 1;
+            CUDA_OK(cudaEventRecord(if_s1, c->comm_stream));
+            if (exchange_on_comm_stream(c, f1)) return 1;
+        }
+        for (int j = 1; j < S; j++) {      // stage 2 of interior slabs (those next to the interface wait for its stage 1)
+            if (s2[j] || !ready(j, s1)) continue;
+            bool needs_if = false;
+            for (int d : deps[j]) needs_if = needs_if || d == 0;
+            if (needs_if) CUDA_OK(cudaStreamWaitEvent(c->stream, if_s1, 0));
+            P2.elem_begin = begin[j];
+            P2.elem_end = begin[j + 1];
+            do_launch_stage(c, P2, c->stream);
+            c->launches++;
+            s2[j] = 1;
+            CUDA_OK(cudaEventRecord(s2_done[j], c->stream));
+            if (download(j, s2_done[j])) return 1;
+        }
+        if (!s2[0] && s1[0] && ready(0, s1)) {
+            // stage 2 of the interface elements: behind the second receive and the stage 1 of the interior slabs next to them
+            CUDA_OK(cudaEventRecord(main_s1, c->stream));   // (their stage 1 was launched before this point of the main stream)
+            CUDA_OK(cudaStreamWaitEvent(c->comm_stream, main_s1, 0));
+            P2.elem_begin = begin[0];
+            P2.elem_end = begin[1];
+            do_launch_stage(c, P2, c->comm_stream);
+            c->launches++;
+            s2[0] = 1;
+            CUDA_OK(cudaEventRecord(s2_done[0], c->comm_stream));
+            if (download(0, s2_done[0])) return 1;
+        }
+    }
+    for (int j = 0; j < S; j++)
+        if (!s1[j] || !s2[j]) return fail("host_ssprk2_step: internal scheduling error (a slab never became ready)");
+    (void)s1_done;
+    // join everything back into the main stream
+    CUDA_OK(cudaEventRecord(joined, c->d2h_stream));
+    CUDA_OK(cudaStreamWaitEvent(c->stream, joined, 0));
+    CUDA_OK(cudaStreamWaitEvent(c->stream, s2_done[0], 0));
+    CUDA_OK(cudaGetLastError());
+    c->vmax_valid[solution] = 1;
+    c->vmax_valid[f1] = 0;
+    return 0;
+}
+}  // namespace
+
 extern "C" int warpii_gpu_host_ssprk2_step(warpii_gpu_ctx* c, int solution, int f1, const double* host_in, double* host_out,
                                            double dt, double t, double* next_dt_out, int n_slabs) {
     if (check_vec(c, solution, "host_ssprk2_step") || check_vec(c, f1, "host_ssprk2_step")) return 1;
@@ -1040,7 +1221,11 @@ extern "C" int warpii_gpu_host_ssprk2_step(warpii_gpu_ctx* c, int solution, int 
     CUDA_OK(cudaSetDevice(c->device));
     const size_t per_elem = (size_t)c->nc * c->NN;
     const bool streamed = c->n_bfaces == 0 && !c->comm && c->n_elems > 0;
-    if (!streamed) {
+    const bool streamed_sharded = c->n_bfaces == 0 && c->comm && !c->peer_rank.empty() && c->n_interface > 0 &&
+                                  c->n_interface < c->n_elems;
+    if (streamed_sharded) {
+        if (host_step_sharded(c, solution, f1, host_in, host_out, dt, n_slabs)) return 1;
+    } else if (!streamed) {
         // boundary faces / sharded runs: plain sequence (the boundary kernel and the halo exchange work on the whole vector)
         CUDA_OK(cudaMemcpyAsync(c->vec[solution], host_in, (size_t)c->n_dofs * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         c->vmax_valid[solution] = 0;
