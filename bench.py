@@ -464,8 +464,8 @@ def run_ours(args, w):
 
     # ---- device-resident throughput -----------------------------------------------------------------
     sampler = ClockSampler(local_rank)
+    g.advance_to(0.0, 1e30, max_steps=1)   # (every rank: the step contains the halo exchange and the all-reduce)
     if rank == 0 and not args.no_clocks:
-        g.advance_to(0.0, 1e30, max_steps=1)
         sampler.poll()      # under load (a warm-up step); the remaining warm-up steps and a barrier follow before the timed region
     g.upload(0, host_np)
     t, ms, regions, avg_stage_ms, stage_n, launches = device_resident(g, args, stream, barrier, max_over_ranks, args.steps,
