@@ -114,6 +114,7 @@ class GpuESDGSEMOperator {
                 int32_t kind = WARPII_BC_OUTFLOW;   // supersonic outflow: ghost = inside state (species.cc:48-49)
                 if (sp->bc_map.is_wall(b)) kind = WARPII_BC_WALL;
                 else if (sp->bc_map.is_inflow(b)) kind = WARPII_BC_INFLOW;
+                else if (sp->bc_map.is_subsonic_outflow(b)) kind = WARPII_BC_SUBSONIC_OUTFLOW;   // (:385-390)
                 else AssertThrow(sp->bc_map.is_supersonic_outflow(b) || bf_id.empty(),
                                  ExcMessage("Unknown boundary id, did you set a boundary condition for this part of the domain boundary?"));
                 bc_kind.push_back(kind);
@@ -171,7 +172,7 @@ class GpuESDGSEMOperator {
                                     const ZeroOutPolicy /*zero_out_register*/ = DO_NOT_ZERO_DST_VECTOR) {
         // set_time(t) on the inflow functions + their values at the boundary quadrature points (:139-144, :381-384)
         for (unsigned s = 0; s < species.size(); ++s)
-            if (!species[s]->bc_map.inflow_boundaries().empty()) tabulate_inflow(s, t);
+            if (!species[s]->bc_map.inflow_boundaries().empty() || !species[s]->bc_map.subsonic_outflow_boundaries().empty()) tabulate_inflow(s, t);
         ok(warpii_gpu_forward_euler_step_ex(ctx, slot(dst), slot(u), dt, t, alpha, beta, beta != 0.0 ? WARPII_FUSE_CFL : 0));
     }
 
@@ -208,14 +209,19 @@ class GpuESDGSEMOperator {
     }
     void tabulate_inflow(unsigned s, double t) {
         const auto& bc = species[s]->bc_map;
-        if (bc.inflow_boundaries().empty() || bf_elem.empty()) return;
+        if ((bc.inflow_boundaries().empty() && bc.subsonic_outflow_boundaries().empty()) || bf_elem.empty()) return;
         for (const auto& entry : bc.inflow_boundaries()) entry.second->set_time(t);
         std::fill(inflow_table.begin(), inflow_table.end(), 0.0);
         for (size_t f = 0; f < bf_elem.size(); ++f) {
-            if (!bc.is_inflow((dealii::types::boundary_id)bf_id[f])) continue;
-            const auto fn = bc.get_inflow((dealii::types::boundary_id)bf_id[f]);
-            for (unsigned q = 0; q < nq; ++q)
-                for (unsigned c = 0; c < 5; ++c) inflow_table[(f * nq + q) * 5 + c] = fn->value(bpts[f * nq + q], c);
+            const auto id = (dealii::types::boundary_id)bf_id[f];
+            if (bc.is_inflow(id)) {
+                const auto fn = bc.get_inflow(id);
+                for (unsigned q = 0; q < nq; ++q)
+                    for (unsigned c = 0; c < 5; ++c) inflow_table[(f * nq + q) * 5 + c] = fn->value(bpts[f * nq + q], c);
+            } else if (bc.is_subsonic_outflow(id)) {   // only the energy component is read (:387-389)
+                const auto fn = bc.get_subsonic_outflow_energy(id);
+                for (unsigned q = 0; q < nq; ++q) inflow_table[(f * nq + q) * 5 + 4] = fn->value(bpts[f * nq + q], 4);
+            }
         }
         ok(warpii_gpu_set_inflow_table(ctx, (int)s, inflow_table.data()));
     }

@@ -35,8 +35,11 @@ extern "C" {
 typedef struct warpii_gpu_ctx warpii_gpu_ctx;
 
 /* Boundary-condition kinds, as Species::create_from_parameters maps them
- * (reference src/five_moment/species.cc:44-58): "Wall", "Outflow" (supersonic), "Inflow". */
-enum { WARPII_BC_WALL = 0, WARPII_BC_OUTFLOW = 1, WARPII_BC_INFLOW = 2 };
+ * (reference src/five_moment/species.cc:44-58): "Wall", "Outflow" (supersonic), "Inflow"; and the fourth kind the reference
+ * operator knows but no input file can select, EulerBCMap::set_subsonic_outflow_boundary (bc_helper.h:12-35,
+ * fluid_flux_es_dgsem_operator.h:385-390): ghost state = inside state with the total energy replaced by component 4 of the
+ * state given through warpii_gpu_set_inflow / warpii_gpu_set_inflow_table for that boundary. */
+enum { WARPII_BC_WALL = 0, WARPII_BC_OUTFLOW = 1, WARPII_BC_INFLOW = 2, WARPII_BC_SUBSONIC_OUTFLOW = 3 };
 
 /* Flags for warpii_gpu_forward_euler_step_ex. */
 enum {

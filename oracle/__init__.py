@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libwarpii_ref.so")
 
-BC_WALL, BC_OUTFLOW, BC_INFLOW = 0, 1, 2
+BC_WALL, BC_OUTFLOW, BC_INFLOW, BC_SUBSONIC_OUTFLOW = 0, 1, 2, 3
 INFLOW_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_void_p)
 
 _dp = C.POINTER(C.c_double)

@@ -730,12 +730,16 @@ void face_residual(const Ctx& c, const double* u, int64_t e, int sp, double* R, 
                 double rho_u_dot_n = wm[1] * n[0];
                 for (int a = 1; a < dim; a++) rho_u_dot_n += wm[1 + a] * n[a];
                 double wp[5];
-                if (kind == ORC_BC_INFLOW) {
+                if (kind == ORC_BC_INFLOW || kind == ORC_BC_SUBSONIC_OUTFLOW) {
                     if (!c.general && c.inflow_fn[(size_t)sp * c.nbnd + bid].fn) {
                         const int64_t bfn = bface;
                         for (int k = 0; k < 5; k++) wp[k] = c.inflow_vals[(((size_t)sp * c.n_bfaces + bfn) * nG + g) * 5 + k];
                     } else {
                         for (int k = 0; k < 5; k++) wp[k] = c.inflow[((size_t)sp * c.nbnd + bid) * 5 + k];
+                    }
+                    if (kind == ORC_BC_SUBSONIC_OUTFLOW) {
+                        // fluid_flux_es_dgsem_operator.h:385-390: w_p = w_m; w_p[4] = get_subsonic_outflow_energy(id) component 4
+                        for (int k = 0; k < 4; k++) wp[k] = wm[k];
                     }
                 } else if (kind == ORC_BC_OUTFLOW) {
                     for (int k = 0; k < 5; k++) wp[k] = wm[k];
@@ -891,7 +895,7 @@ void refresh_inflow(const Ctx& c, double t) {
             const int d = f / 2, side = f % 2;
             for (int sp = 0; sp < c.nsp; sp++) {
                 const auto& fn = c.inflow_fn[(size_t)sp * 2 * dim + f];
-                if (!fn.fn || c.bc_kind[(size_t)sp * 2 * dim + f] != ORC_BC_INFLOW) continue;
+                if (!fn.fn || (c.bc_kind[(size_t)sp * 2 * dim + f] != ORC_BC_INFLOW && c.bc_kind[(size_t)sp * 2 * dim + f] != ORC_BC_SUBSONIC_OUTFLOW)) continue;
                 for (int g = 0; g < nG; g++) {
                     int gi[2] = {g % Ng, (g / Ng) % Ng};
                     double x[3] = {0, 0, 0};

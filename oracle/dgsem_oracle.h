@@ -73,7 +73,7 @@ void orc_legendre_analysis_1d(int Np, double* V);  // V[k*Np+q] = (k+1/2) w_q sq
 
 // ---- discretised operator on a Cartesian box ---------------------------------
 // bc_kinds[species][2*dim]: 0 = Wall, 1 = Outflow (supersonic), 2 = Inflow; ignored on periodic dims.
-enum { ORC_BC_WALL = 0, ORC_BC_OUTFLOW = 1, ORC_BC_INFLOW = 2 };
+enum { ORC_BC_WALL = 0, ORC_BC_OUTFLOW = 1, ORC_BC_INFLOW = 2, ORC_BC_SUBSONIC_OUTFLOW = 3 };   // 3: fluid_flux_es_dgsem_operator.h:385-390
 void* orc_create(int dim, int fe_degree, int n_species, int fields_enabled, double gamma,
                  const int* nx, const double* left, const double* right, const int* periodic,
                  const int* bc_kinds);

@@ -173,6 +173,32 @@ def test_walls_2d_kelvin_helmholtz_rhs():
     g.close()
 
 
+@pytest.mark.parametrize("dim,p,nx", [(1, 3, [12]), (2, 2, [6, 5])])
+def test_subsonic_outflow_ghost_state(dim, p, nx):
+    """EulerBCMap::set_subsonic_outflow_boundary (bc_helper.h:12-35): ghost = inside state with the total energy replaced by
+    the prescribed one (fluid_flux_es_dgsem_operator.h:385-390).  No input file of the reference can select it
+    (species.cc:48-49 maps "Outflow" to the supersonic kind), the operator and the ABI know it."""
+    from warpii_b200 import BC_SUBSONIC_OUTFLOW
+    gamma = 1.4
+    kinds = [BC_INFLOW, BC_SUBSONIC_OUTFLOW] + [BC_WALL] * (2 * dim - 2)
+    o, g = make_pair(dim, p, nx, [0.0] * dim, [1.0] * dim, periodic=[0] * dim, gamma=gamma, bc=[kinds])
+    q_in = oracle.primitive_to_conserved([1.0, 0.3, 0.0, 0.0, 1.0], gamma)
+    q_out = np.array([0.0, 0.0, 0.0, 0.0, 2.4])     # only the energy is read
+    for s in (o, g):
+        s.set_inflow(0, 0, q_in)
+        s.set_inflow(0, 1, q_out)
+    u = o.project(cases.sine_wave(amp=0.1, vel=(0.3, 0.0, 0.0)))
+    check_rhs(o, g, u)
+    want, bif_o = o.rhs(u)
+    # the outflow face really used the prescribed energy: with the supersonic kind the answer differs
+    o2, g2 = make_pair(dim, p, nx, [0.0] * dim, [1.0] * dim, periodic=[0] * dim, gamma=gamma, bc=[[BC_INFLOW, BC_OUTFLOW] + [BC_WALL] * (2 * dim - 2)])
+    o2.set_inflow(0, 0, q_in)
+    other, _ = o2.rhs(u)
+    assert np.abs(other - want).max() > 1e-3
+    g.close()
+    g2.close()
+
+
 def test_mixed_bcs_3d_rhs():
     gamma = 1.4
     bc = [[BC_INFLOW, BC_OUTFLOW, BC_WALL, BC_WALL, BC_OUTFLOW, BC_WALL]]

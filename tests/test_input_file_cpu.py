@@ -131,12 +131,21 @@ def test_expression_language():
         ("1e-3*x + 2.5E2*y + .5", 1e-3 * x + 250.0 * y + 0.5),
         ("floor(3*x) + ceil(3*y) + sign(x - y) + log10(x) + log2(y)",
          np.floor(3 * x) + np.ceil(3 * y) + np.sign(x - y) + np.log10(x) + np.log2(y)),
+        # the rest of muparser's built-ins that deal.II's FunctionParser exposes
+        ("erf(x) + erfc(y) + asinh(x) + acosh(1 + y) + atanh(x / 2)",
+         np.array([math.erf(v) for v in x]) + np.array([math.erfc(v) for v in y]) + np.arcsinh(x) + np.arccosh(1 + y) + np.arctanh(x / 2)),
+        ("min(x, y, 0.5) + max(x, y, 0.9, 1.0) + sum(x, y, 1) + avg(x, y, 3) + min(x) + avg(x, y)",
+         np.minimum(np.minimum(x, y), 0.5) + np.maximum(np.maximum(x, y), 1.0) + (x + y + 1) + (x + y + 3) / 3 + x + (x + y) / 2),
+        ("if(x < 0.5 & y >= 0.4, 2, if(x > 0.8 | y == 7, 3, 4))",
+         np.where((x < 0.5) & (y >= 0.4), 2.0, np.where(x > 0.8, 3.0, 4.0))),
     ]
     for expr, want in cases:
         got, td = eval_expr(expr, pts)
         assert not td, expr
         np.testing.assert_allclose(got, want, rtol=4e-16, atol=1e-300, err_msg=expr)
 
+    with pytest.raises(Exception, match="hexadecimal"):
+        eval_expr("0x10 + x", pts)
     got, _ = eval_expr("k * sin(2*pi*x) + Pi + big_name_2", pts, constants="pi=3.1415926535, k = 0.6, big_name_2=-1")
     np.testing.assert_allclose(got, 0.6 * np.sin(2 * math.pi * x) + math.pi - 1, rtol=4e-16)
     got, td = eval_expr("x*t + y", pts, t=0.25)
@@ -260,3 +269,20 @@ def test_vtu_frames(tmp_path, dim, p):
         assert (((b - a)[:, 0] * (c - a)[:, 1] - (c - a)[:, 0] * (b - a)[:, 1]) > 0).all()
     if dim == 3:
         assert (pts[cells[:, 4], 2] > pts[cells[:, 0], 2]).all()
+
+
+def test_gpus_launcher_does_not_hang_when_rank_0_dies_early(tmp_path):
+    """`warpii_gpu --gpus N`: rank 0 hands the NCCL id to the launcher over a pipe, the launcher relays it.  If rank 0 dies
+    before it has an id (here: no CUDA device in the CPU container, so its context cannot be created) every reader must see
+    end-of-file and the launcher must come back with a non-zero exit code.  Each forked rank therefore closes every pipe
+    end it inherited and does not use (warpii_cli.hpp); a rank that kept the write end of the upward pipe open made the
+    launcher and all other ranks wait for ever."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU (rank 0 must fail before the id exists)")
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "warpii_b200", "bin", "warpii_gpu")
+    (tmp_path / "run.inp").write_text(read_input("inflow_channel_2d.inp"))
+    r = subprocess.run([exe, "--gpus", "3", "run.inp"], capture_output=True, text=True, cwd=tmp_path, timeout=60)
+    assert r.returncode != 0
+    assert "CUDA" in r.stderr or "cuda" in r.stderr, r.stderr[-500:]

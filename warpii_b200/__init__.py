@@ -6,8 +6,8 @@ and bench.py; there is no Python or CPU implementation of the operator behind it
 the shared library has not been built (`python -c "import __graft_entry__ as g; g.build()"` or
 `make -C warpii_b200`).
 """
-from .capi import (BC_INFLOW, BC_OUTFLOW, BC_WALL, FUSE_CFL, App, BoxSolver, WarpiiGpuError, box_tables, elems_per_block,
+from .capi import (BC_INFLOW, BC_OUTFLOW, BC_SUBSONIC_OUTFLOW, BC_WALL, FUSE_CFL, App, BoxSolver, WarpiiGpuError, box_tables, elems_per_block,
                    host_advance, lib, lib_path, nccl_unique_id)
 
 __all__ = ["App", "BoxSolver", "WarpiiGpuError", "lib", "lib_path", "box_tables", "host_advance", "nccl_unique_id", "elems_per_block",
-           "BC_WALL", "BC_OUTFLOW", "BC_INFLOW", "FUSE_CFL"]
+           "BC_WALL", "BC_OUTFLOW", "BC_INFLOW", "BC_SUBSONIC_OUTFLOW", "FUSE_CFL"]

@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-BC_WALL, BC_OUTFLOW, BC_INFLOW = 0, 1, 2
+BC_WALL, BC_OUTFLOW, BC_INFLOW, BC_SUBSONIC_OUTFLOW = 0, 1, 2, 3
 INFLOW_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.c_void_p)
 FRAME_FN = C.CFUNCTYPE(None, C.c_uint, C.c_double, C.c_void_p)
 FUSE_CFL = 1

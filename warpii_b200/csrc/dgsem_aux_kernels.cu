@@ -52,12 +52,15 @@ __global__ void __launch_bounds__(32 * kBoundaryWarps) boundary_kernel(const Bou
             for (int c = 0; c < 5; c++) wm[c] += phi * P.u[off + (size_t)c * NN];
         }
         double wp[5];
-        if (kind == 2) {   // inflow: prescribed conserved state
+        if (kind == 2 || kind == 3) {   // inflow: prescribed conserved state; subsonic outflow: only its energy is used
             if (P.inflow_table) {
                 const double* tab = P.inflow_table + (((size_t)sp * P.n_bfaces + bf) * NG + g) * 5;
                 for (int c = 0; c < 5; c++) wp[c] = tab[c];
             } else {
                 for (int c = 0; c < 5; c++) wp[c] = P.inflow[((size_t)sp * P.n_boundaries + bid) * 5 + c];
+            }
+            if (kind == 3) {   // fluid_flux_es_dgsem_operator.h:385-390: w_p = w_m with the total energy replaced
+                for (int c = 0; c < 4; c++) wp[c] = wm[c];
             }
         } else if (kind == 1) {   // (supersonic) outflow
             for (int c = 0; c < 5; c++) wp[c] = wm[c];

@@ -584,12 +584,15 @@ __global__ void __launch_bounds__(32 * kBoundaryWarpsG) boundary_kernel_general(
         for (int a = 0; a < DIM; a++) n[a] = bg[a];
         const double sJ = bg[DIM];
         double wp[5];
-        if (kind == 2) {
+        if (kind == 2 || kind == 3) {
             if (P.inflow_table) {
                 const double* tab = P.inflow_table + (((size_t)sp * P.n_bfaces + bf) * NG + g) * 5;
                 for (int c = 0; c < 5; c++) wp[c] = tab[c];
             } else {
                 for (int c = 0; c < 5; c++) wp[c] = P.inflow[((size_t)sp * P.n_boundaries + bid) * 5 + c];
+            }
+            if (kind == 3) {   // subsonic outflow (:385-390): w_p = w_m with the total energy replaced
+                for (int c = 0; c < 4; c++) wp[c] = wm[c];
             }
         } else if (kind == 1) {
             for (int c = 0; c < 5; c++) wp[c] = wm[c];

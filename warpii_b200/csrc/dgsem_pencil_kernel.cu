@@ -25,6 +25,20 @@ __global__ void __launch_bounds__(PGeo<DIM, NP>::THREADS, WGPU_PENCIL_MIN_BLOCKS
     PencilHalo halo;
     for (int sp = 0; sp < P.nsp; sp++) {
         if (sp > 0) __syncthreads();   // shared-memory reuse across species
+#if WGPU_PENCIL_TMA
+        if (tid == 0) {
+            // arm the barrier and let the bulk-copy engine fetch the patch's state block of this species (A/B variant)
+            void* const bar = smem + G::OFF_RED + 30;
+            if (sp == 0) mbar_init(bar, 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of the area come first
+            const int64_t e_hi = (e0 + G::E < P.elem_end) ? e0 + G::E : P.elem_end;
+            const unsigned per_elem = 5u * G::NN * (unsigned)sizeof(double);
+            mbar_expect_tx(bar, per_elem * (unsigned)(e_hi - e0));
+            for (int64_t e = e0; e < e_hi; e++)
+                bulk_g2s(smem + G::OFF_REC + (size_t)(e - e0) * 5 * G::NN, P.u + ((size_t)e * P.nc + 5 * sp) * G::NN, per_elem, bar);
+        }
+        if (sp == 0) __syncthreads();   // the barrier object is initialised before anybody waits on it
+#endif
         pencil_phase0<DIM, NP>(P, smem, tid, e0, sp, halo);
 #if WGPU_PENCIL_RTDIR == 2
         // the mid phases (y, z) through one copy of the flux code, the final x phase through its own

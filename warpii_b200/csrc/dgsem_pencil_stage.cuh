@@ -38,6 +38,9 @@
 #ifndef WGPU_PENCIL_THREADS
 #define WGPU_PENCIL_THREADS 128
 #endif
+#ifndef WGPU_PENCIL_TMA
+#define WGPU_PENCIL_TMA 0        // 1: P0 stages the patch's state block in shared memory with cp.async.bulk + mbarrier (A/B only)
+#endif
 #ifndef WGPU_PENCIL_P0_ROLL
 #define WGPU_PENCIL_P0_ROLL 0    // 1: P0 forms the node records two at a time in a rolled loop (half the code, ILP 2 instead of NP)
 #endif
@@ -197,6 +200,38 @@ __device__ __forceinline__ void pencil_halo_fetch(const StageParams& P, const in
     }
 }
 
+#if WGPU_PENCIL_TMA && !WGPU_HOST_EMU
+// The north_star sketch ("stages each element's block in shared memory via TMA"), as an A/B variant: one thread arms an
+// mbarrier with the byte count and issues one 1-D bulk copy (cp.async.bulk, the TMA engine) per element of the patch -- the
+// species' 5 x Np^dim doubles of an element are contiguous -- into the (still unused) record area; every thread waits on the
+// barrier's phase, reads its Np x 5 values back from shared memory, and a block barrier frees the area for the records.
+// Measured against the default (each thread loads its own 32 bytes per component straight into registers): profiles/README.md.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
 // make_prim for the rare second outside end of a pencil (partial patches, patches of one element): out of line, so that the
 // hot code of every flux phase carries one inlined copy of the ~200-instruction routine instead of two
 __device__ __noinline__ void make_prim_cold(const double q0, const double q1, const double q2, const double q3, const double q4,
@@ -215,6 +250,23 @@ __device__ __forceinline__ void pencil_phase0(const StageParams& P, double* smem
     double2* const sRec = reinterpret_cast<double2*>(smem + G::OFF_REC);
     double2* const sBuf = reinterpret_cast<double2*>(smem + G::OFF_BUF);
     int* const sNbr = reinterpret_cast<int*>(smem + G::OFF_NBR);
+#if WGPU_PENCIL_TMA && !WGPU_HOST_EMU
+    // staged through shared memory by the bulk-copy engine (see above); the staging area is the record area, so every
+    // thread of the block passes the barrier below before the first record is written
+    double tma_q[5][NP];
+    {
+        const int le_ = tid / G::NPEN, pe_ = tid - le_ * G::NPEN;
+        mbar_wait(smem + G::OFF_RED + 30, (unsigned)(sp & 1));
+        if (tid < G::USED && e0 + le_ < P.elem_end) {
+            const double* mine = smem + G::OFF_REC + (size_t)le_ * 5 * G::NN + pe_ * NP;
+#pragma unroll
+            for (int c = 0; c < 5; c++)
+#pragma unroll
+                for (int m = 0; m < NP; m++) tma_q[c][m] = mine[c * G::NN + m];
+        }
+        __syncthreads();
+    }
+#endif
     if (tid >= G::USED) return;
     const int le = tid / G::NPEN, pe = tid - le * G::NPEN;
     const int64_t e = e0 + le;
@@ -254,8 +306,15 @@ __device__ __forceinline__ void pencil_phase0(const StageParams& P, double* smem
 #endif
     {
     double q[5][NP];
+#if WGPU_PENCIL_TMA && !WGPU_HOST_EMU
+#pragma unroll
+    for (int c = 0; c < 5; c++)
+#pragma unroll
+        for (int m = 0; m < NP; m++) q[c][m] = tma_q[c][m];
+#else
 #pragma unroll
     for (int c = 0; c < 5; c++) load_run<NP>(src + (size_t)c * G::NN, q[c]);
+#endif
 #if !WGPU_PENCIL_P0_ROLL
     pencil_halo_fetch<DIM, NP, 1>(P, v0, v1, pe, e0, e_hi, sp, next);
     if (sp == 0)

@@ -129,6 +129,7 @@ struct warpii_gpu_ctx {
     double light_speed = 1.0, mx_chi = 0.0, mx_gamma = 0.0;
     int ncf = 5;                            // components per halo face trace: 5*nsp, or nc with the field system evolved
     double* d_qm = nullptr;                 // [nsp] charge / mass
+    double* d_scratch = nullptr;            // state-sized throw-away destination of warpii_gpu_shock_indicator (lazy)
     std::vector<double> h_inflow;           // mirror of d_inflow
     std::vector<double> h_inflow_table;     // mirror of d_inflow_table (empty until warpii_gpu_set_inflow_table)
     double* d_inflow_table = nullptr;
@@ -396,8 +397,10 @@ int max_speed(warpii_gpu_ctx* c, int vec, double* out) {
         c->vmax_valid[vec] = 1;
     }
     if (c->comm && c->n_ranks > 1) {
-        // the slot holds the bits of a non-negative double: reduce it as a double (replaces Utilities::MPI::max, :511)
-        NCCL_OK(g_nccl.AllReduce(c->d_vmax + vec, c->d_vmax + vec, 1, ncclDouble, ncclMax, c->comm, c->stream));
+        // The slot holds the bits of a non-negative double (or of a NaN: an unphysical state must surface as a NaN time step
+        // on EVERY rank).  Reduced as an unsigned integer: the order of the bit patterns is the order of the doubles, and a
+        // NaN (0x7ff8...) beats every finite maximum, which ncclMax on doubles does not promise.  (Utilities::MPI::max, :511)
+        NCCL_OK(g_nccl.AllReduce(c->d_vmax + vec, c->d_vmax + vec, 1, ncclUint64, ncclMax, c->comm, c->stream));
     }
     CUDA_OK(cudaMemcpyAsync(c->h_small, c->d_vmax + vec, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -599,7 +602,7 @@ int warpii_gpu_destroy(warpii_gpu_ctx* c) {
     for (double* v : c->bif) cudaFree(v);
     cudaFree(c->d_nbr); cudaFree(c->d_bf_elem); cudaFree(c->d_bf_side); cudaFree(c->d_bf_id); cudaFree(c->d_bc_kind);
     if (c->batch_graph) cudaGraphExecDestroy(c->batch_graph);
-    cudaFree(c->d_inflow); cudaFree(c->d_inflow_table); cudaFree(c->d_qm); cudaFree(c->d_w); cudaFree(c->d_bres); cudaFree(c->d_bflux); cudaFree(c->d_ghost);
+    cudaFree(c->d_inflow); cudaFree(c->d_inflow_table); cudaFree(c->d_qm); cudaFree(c->d_scratch); cudaFree(c->d_w); cudaFree(c->d_bres); cudaFree(c->d_bflux); cudaFree(c->d_ghost);
     cudaFree(c->d_sendbuf); cudaFree(c->d_partial); cudaFree(c->d_out5); cudaFree(c->d_alpha); cudaFree(c->d_vmax);
     cudaFree(c->d_send_elem); cudaFree(c->d_send_side);
     cudaFree(c->d_gnode); cudaFree(c->d_gsub); cudaFree(c->d_gface); cudaFree(c->d_jdet); cudaFree(c->d_bgeo); cudaFree(c->d_bmass);
@@ -1374,7 +1377,7 @@ int warpii_gpu_advance_to(warpii_gpu_ctx* c, int solution, int f1, double* t_ino
         c->vmax_valid[solution] = 1;
     }
     if (c->comm && c->n_ranks > 1)   // max over ranks; idempotent if the slot already holds the global maximum
-        NCCL_OK(g_nccl.AllReduce(c->d_vmax + solution, c->d_vmax + solution, 1, ncclDouble, ncclMax, c->comm, c->stream));
+        NCCL_OK(g_nccl.AllReduce(c->d_vmax + solution, c->d_vmax + solution, 1, ncclUint64, ncclMax, c->comm, c->stream));
     DevClock* hc = c->h_clock;
     *hc = DevClock{*t_inout, 0.0, t_stop, fixed_dt > 0.0 ? fixed_dt : 0.0, 0, max_steps > 0 ? max_steps : 0, 0, 0, 0, c->p + 1};
     CUDA_OK(cudaMemcpyAsync(c->d_clock, hc, sizeof(DevClock), cudaMemcpyHostToDevice, c->stream));
@@ -1402,7 +1405,7 @@ int warpii_gpu_advance_to(warpii_gpu_ctx* c, int solution, int f1, double* t_ino
                 rc = run_stage(c, f1, solution, 0.0, 1.0, 0.0, 0, false, true);                 // rk.h:102-103
                 if (!rc) rc = run_stage(c, solution, f1, 0.0, 0.5, 0.5, 0, true, true);         // rk.h:104-105
                 if (!rc && c->comm && c->n_ranks > 1)
-                    NCCL_OK(g_nccl.AllReduce(c->d_vmax + solution, c->d_vmax + solution, 1, ncclDouble, ncclMax, c->comm, c->stream));
+                    NCCL_OK(g_nccl.AllReduce(c->d_vmax + solution, c->d_vmax + solution, 1, ncclUint64, ncclMax, c->comm, c->stream));
             }
             if (!rc) launch_clock(c->d_clock, c->d_vmax + solution, 1, c->stream);   // book the last step of the batch, test for the end
             c->launches += n + 1;
@@ -1479,8 +1482,9 @@ int warpii_gpu_shock_indicator(warpii_gpu_ctx* c, int vec, double* alpha_out) {
     // run the stage kernel in rhs mode into a scratch vector-sized buffer? cheaper: use the last vector slot's
     // storage is not safe, so allocate the small alpha table and a throw-away destination lazily.
     if (!c->d_alpha) CUDA_OK(cudaMalloc((void**)&c->d_alpha, (size_t)(c->n_elems > 0 ? c->n_elems : 1) * c->nsp * sizeof(double)));
-    double* scratch = nullptr;
-    CUDA_OK(cudaMalloc((void**)&scratch, (size_t)(c->n_dofs > 0 ? c->n_dofs : 1) * sizeof(double)));
+    // throw-away destination of the launch, kept for the next call and freed with the context
+    if (!c->d_scratch) CUDA_OK(cudaMalloc((void**)&c->d_scratch, (size_t)(c->n_dofs > 0 ? c->n_dofs : 1) * sizeof(double)));
+    double* const scratch = c->d_scratch;
     StageParams P = stage_params(c, vec, vec, 0.0, 1.0, 0.0, 1, false);
     P.dst = scratch;
     P.alpha_out = c->d_alpha;
@@ -1490,7 +1494,7 @@ int warpii_gpu_shock_indicator(warpii_gpu_ctx* c, int vec, double* alpha_out) {
         do_launch_boundary(c, B, c->stream);
     }
     if (c->comm && !c->peer_rank.empty()) {
-        if (start_exchange(c, vec)) { cudaFree(scratch); return 1; }
+        if (start_exchange(c, vec)) return 1;
         CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_recv, 0));
     }
     if (c->n_interface > 0) {
@@ -1502,7 +1506,6 @@ int warpii_gpu_shock_indicator(warpii_gpu_ctx* c, int vec, double* alpha_out) {
     c->launches++;
     CUDA_OK(cudaMemcpyAsync(alpha_out, c->d_alpha, (size_t)c->n_elems * c->nsp * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    cudaFree(scratch);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

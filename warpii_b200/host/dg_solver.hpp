@@ -94,7 +94,7 @@ class FiveMomentGpuSolver {
         else op_->set_boundary_points(boundary_quadrature_points(), tables_.boundary_face_id(), tables_.box().dim, n_species_);
         for (int s = 0; s < n_species_ && s < (int)bcs_.size(); s++)
             for (int b = 0; b < n_boundaries_ && b < (int)bcs_[s].kind.size(); b++) {
-                if (bcs_[s].kind[b] != WARPII_BC_INFLOW) continue;
+                if (bcs_[s].kind[b] != WARPII_BC_INFLOW && bcs_[s].kind[b] != WARPII_BC_SUBSONIC_OUTFLOW) continue;
                 if (b < (int)bcs_[s].inflow_function.size() && bcs_[s].inflow_function[b])
                     op_->set_inflow_function(s, b, bcs_[s].inflow_function[b],
                                              b < (int)bcs_[s].time_dependent.size() ? (bool)bcs_[s].time_dependent[b] : true);

@@ -111,12 +111,12 @@ class Expression {
     }
     P parse_or() {
         P l = parse_and();
-        while (eat("||")) l = make(OR, std::move(l), parse_and());
+        while (eat("||") || eat("|")) l = make(OR, std::move(l), parse_and());
         return l;
     }
     P parse_and() {
         P l = parse_cmp();
-        while (eat("&&")) l = make(AND, std::move(l), parse_cmp());
+        while (eat("&&") || eat("&")) l = make(AND, std::move(l), parse_cmp());
         return l;
     }
     P parse_cmp() {
@@ -169,6 +169,7 @@ class Expression {
             return e;
         }
         if (std::isdigit((unsigned char)ch) || ch == '.') {
+            if (ch == '0' && pos_ + 1 < src_.size() && (src_[pos_ + 1] == 'x' || src_[pos_ + 1] == 'X')) fail("hexadecimal literals are not supported");
             size_t used = 0;
             double v = 0;
             try { v = std::stod(src_.substr(pos_), &used); } catch (...) { fail("bad number"); }
@@ -205,7 +206,7 @@ class Expression {
             {"sin", std::sin}, {"cos", std::cos}, {"tan", std::tan}, {"asin", std::asin}, {"acos", std::acos}, {"atan", std::atan},
             {"sinh", std::sinh}, {"cosh", std::cosh}, {"tanh", std::tanh}, {"exp", std::exp}, {"log", std::log}, {"ln", std::log},
             {"log2", std::log2}, {"log10", std::log10}, {"sqrt", std::sqrt}, {"abs", std::fabs}, {"ceil", std::ceil}, {"floor", std::floor},
-            {"erfc", std::erfc}, {"rint", std::rint}, {"sign", [](double v) { return v < 0 ? -1.0 : (v > 0 ? 1.0 : 0.0); }},
+            {"erfc", std::erfc}, {"erf", std::erf}, {"asinh", std::asinh}, {"acosh", std::acosh}, {"atanh", std::atanh}, {"rint", std::rint}, {"sign", [](double v) { return v < 0 ? -1.0 : (v > 0 ? 1.0 : 0.0); }},
             {"cot", [](double v) { return 1.0 / std::tan(v); }}, {"sec", [](double v) { return 1.0 / std::cos(v); }},
             {"csc", [](double v) { return 1.0 / std::sin(v); }}, {"int", [](double v) { return std::round(v); }}};
         static const std::map<std::string, double (*)(double, double)> f2 = {
@@ -214,6 +215,35 @@ class Expression {
         if (name == "if") {
             if (args.size() != 3) fail("if() takes 3 arguments");
             return make(SEL, std::move(args[0]), std::move(args[1]), std::move(args[2]));
+        }
+        if ((name == "min" || name == "max" || name == "sum" || name == "avg") && args.size() != 2) {
+            // muparser's variadic forms: fold the arguments pairwise (avg = sum / n)
+            if (args.empty()) fail(name + "() needs at least 1 argument");
+            const size_t n_args = args.size();
+            P acc = std::move(args[0]);
+            for (size_t i = 1; i < n_args; i++) {
+                if (name == "sum" || name == "avg") acc = make(ADD, std::move(acc), std::move(args[i]));
+                else {
+                    P c = make(CALL2, std::move(acc), std::move(args[i]));
+                    c->f2 = f2.find(name)->second;
+                    acc = std::move(c);
+                }
+            }
+            if (name == "avg") {
+                P cnt = make(NUM);
+                cnt->value = (double)n_args;
+                acc = make(DIV, std::move(acc), std::move(cnt));
+            }
+            return acc;
+        }
+        if (name == "sum" || name == "avg") {   // exactly two arguments
+            P acc = make(ADD, std::move(args[0]), std::move(args[1]));
+            if (name == "avg") {
+                P cnt = make(NUM);
+                cnt->value = 2.0;
+                acc = make(DIV, std::move(acc), std::move(cnt));
+            }
+            return acc;
         }
         auto i1 = f1.find(name);
         if (i1 != f1.end()) {

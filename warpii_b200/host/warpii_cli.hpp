@@ -150,7 +150,12 @@ inline int warpii_cli_main(int argc, char** argv, std::shared_ptr<warpii_b200::G
         pids[r] = fork();
         if (pids[r] < 0) { std::perror("fork"); return 1; }
         if (pids[r] == 0) {
+            // Keep only the ends this rank uses.  Every other inherited end must go: a child that kept the write end of `up`
+            // (or of an earlier rank's `down` pipe) would keep those pipes open after rank 0 has died without sending the id,
+            // and the launcher's read -- and with it every other rank's read -- would never see end-of-file.
             close(up[0]);
+            if (r != 0) close(up[1]);
+            for (int k = 1; k < r; k++) close(down[k][1]);     // (their read ends were closed by the launcher before this fork)
             if (r > 0) close(down[r][1]);
             const int rc = run_rank(text.str(), workdir, r, gpus, device + r, setup_only, r == 0 ? up[1] : -1, r > 0 ? down[r][0] : -1, ext);
             std::cout.flush();
