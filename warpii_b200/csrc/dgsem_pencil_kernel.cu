@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(PGeo<DIM, NP>::THREADS, WGPU_PENCIL_MIN_BLOCKS
     for (int sp = 0; sp < P.nsp; sp++) {
         if (sp > 0) __syncthreads();   // shared-memory reuse across species
 #if WGPU_PENCIL_TMA
-        if (tid == 0) {
+        if (pencil_tma_ok<DIM, NP>() && tid == 0) {
             // arm the barrier and let the bulk-copy engine fetch the patch's state block of this species (A/B variant)
             void* const bar = smem + G::OFF_RED + 30;
             if (sp == 0) mbar_init(bar, 1);
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(PGeo<DIM, NP>::THREADS, WGPU_PENCIL_MIN_BLOCKS
             for (int64_t e = e0; e < e_hi; e++)
                 bulk_g2s(smem + G::OFF_REC + (size_t)(e - e0) * 5 * G::NN, P.u + ((size_t)e * P.nc + 5 * sp) * G::NN, per_elem, bar);
         }
-        if (sp == 0) __syncthreads();   // the barrier object is initialised before anybody waits on it
+        if (pencil_tma_ok<DIM, NP>() && sp == 0) __syncthreads();   // the barrier object is initialised before anybody waits on it
 #endif
         pencil_phase0<DIM, NP>(P, smem, tid, e0, sp, halo);
 #if WGPU_PENCIL_RTDIR == 2

@@ -206,6 +206,9 @@ __device__ __forceinline__ void pencil_halo_fetch(const StageParams& P, const in
 // species' 5 x Np^dim doubles of an element are contiguous -- into the (still unused) record area; every thread waits on the
 // barrier's phase, reads its Np x 5 values back from shared memory, and a block barrier frees the area for the records.
 // Measured against the default (each thread loads its own 32 bytes per component straight into registers): profiles/README.md.
+// bulk copies move multiples of 16 bytes between 16-byte-aligned addresses: the element block of a species qualifies for Np = 4
+template <int DIM, int NP>
+__device__ __forceinline__ constexpr bool pencil_tma_ok() { return (PGeo<DIM, NP>::NN * sizeof(double)) % 16 == 0; }
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -254,7 +257,7 @@ __device__ __forceinline__ void pencil_phase0(const StageParams& P, double* smem
     // staged through shared memory by the bulk-copy engine (see above); the staging area is the record area, so every
     // thread of the block passes the barrier below before the first record is written
     double tma_q[5][NP];
-    {
+    if (pencil_tma_ok<DIM, NP>()) {
         const int le_ = tid / G::NPEN, pe_ = tid - le_ * G::NPEN;
         mbar_wait(smem + G::OFF_RED + 30, (unsigned)(sp & 1));
         if (tid < G::USED && e0 + le_ < P.elem_end) {
@@ -307,14 +310,17 @@ __device__ __forceinline__ void pencil_phase0(const StageParams& P, double* smem
     {
     double q[5][NP];
 #if WGPU_PENCIL_TMA && !WGPU_HOST_EMU
+    if (pencil_tma_ok<DIM, NP>()) {
 #pragma unroll
-    for (int c = 0; c < 5; c++)
+        for (int c = 0; c < 5; c++)
 #pragma unroll
-        for (int m = 0; m < NP; m++) q[c][m] = tma_q[c][m];
-#else
-#pragma unroll
-    for (int c = 0; c < 5; c++) load_run<NP>(src + (size_t)c * G::NN, q[c]);
+            for (int m = 0; m < NP; m++) q[c][m] = tma_q[c][m];
+    } else
 #endif
+    {
+#pragma unroll
+        for (int c = 0; c < 5; c++) load_run<NP>(src + (size_t)c * G::NN, q[c]);
+    }
 #if !WGPU_PENCIL_P0_ROLL
     pencil_halo_fetch<DIM, NP, 1>(P, v0, v1, pe, e0, e_hi, sp, next);
     if (sp == 0)
