@@ -244,3 +244,38 @@ def test_fused_field_system_sharded():
         scale = cases.summand_scale(ul, gamma, dim, h, D) + cases.field_summand_scale(ul, 2, dim, h, D, **MX)
         err, bound = cases.rhs_error_and_bound(got, want[l2g], scale)
         assert (err <= bound).all(), (rank, err, bound)
+
+
+def _pslot(n):
+    # dgsem_pencil_stage.cuh::pslot for Np = 4
+    return n ^ ((n >> 3) & 1) ^ (((n >> 4) & 1) * 6)
+
+
+def _pencil_node(dim, d, pe, m, np_=4):
+    # dgsem_pencil_stage.cuh::pencil_node
+    if dim == 2:
+        return pe * np_ + m if d == 0 else pe + np_ * m
+    if d == 0:
+        return pe * np_ + m
+    if d == 1:
+        return (pe % np_) + np_ * m + np_ * np_ * (pe // np_)
+    return pe + np_ * np_ * m
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_swizzled_planes_are_bijective_and_bank_conflict_free(dim):
+    """The Np = 4 layout claim of DESIGN.md section 3: a 16-byte access of a quarter-warp (8 consecutive pencil owners, the
+    unit the shared-memory pipe serves per wavefront) touches 8 distinct 16-byte bank groups, whatever direction the
+    threads own and whichever node m of their pencil they address; and the swizzle is a permutation of the patch's nodes."""
+    np_, nn, npen = 4, 4 ** dim, 4 ** (dim - 1)
+    elems = emu.patch_elems(dim, np_)
+    nodes = elems * nn
+    assert sorted(_pslot(n) for n in range(nodes)) == list(range(nodes))
+    for d in range(dim):
+        for m in range(np_):
+            for q0 in range(0, elems * npen, 8):
+                groups = set()
+                for tid in range(q0, q0 + 8):
+                    le, pe = divmod(tid, npen)
+                    groups.add(_pslot(le * nn + _pencil_node(dim, d, pe, m)) % 8)
+                assert len(groups) == 8, (dim, d, m, q0)

@@ -40,18 +40,32 @@ __device__ __forceinline__ void phm_flux(const int d, const MaxwellParams& M, co
     f[7] = M.gam * M.c2 * F[3 + d];
 }
 
+#ifndef WGPU_MAXWELL_BLOCKS
+#define WGPU_MAXWELL_BLOCKS 5
+#endif
+#ifndef WGPU_MAXWELL_PREFETCH_FACES
+#define WGPU_MAXWELL_PREFETCH_FACES 0   // 1: the neighbours' traces are loaded before the barrier too (48 more registers)
+#endif
+
 template <int DIM, int NP>
 struct MGeo {
     static constexpr int NN = ipow_c(NP, DIM), NF = ipow_c(NP, DIM - 1);
-    static constexpr int G = (256 / NN) > 0 ? (256 / NN) : 1;   // elements per block
+    static constexpr int G = (128 / NN) > 0 ? (128 / NN) : 1;   // elements per block
     static constexpr int THREADS = G * NN;
 };
 
+// Every global load of the thread is issued before the block barrier and before any arithmetic: its 8 field values, the
+// old destination (second stage), the species' densities and momenta for the current, the updated densities for the plasma
+// frequency, and the neighbours' traces for the (at most DIM) faces the node lies on -- through one unconditional load per
+// component and direction whose address falls back to the node itself where there is no face or no neighbour.  One
+// DRAM round trip per thread instead of four to six dependent ones (ncu, round 2: the serial version spent 5-10 stall
+// samples per issued instruction on long_scoreboard and reached 2.6-3.1 TB/s).
 template <int DIM, int NP>
-__global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS) maxwell_kernel(const StageParams P, const MaxwellParams M) {
+__global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS, (MGeo<DIM, NP>::THREADS <= 128) ? WGPU_MAXWELL_BLOCKS : 2)
+    maxwell_kernel(const StageParams P, const MaxwellParams M) {
     using GEO = MGeo<DIM, NP>;
     constexpr int NN = GEO::NN, NF = GEO::NF, G = GEO::G;
-    __shared__ double sF[G][8][NN];
+    __shared__ double2 sF[G][4][NN];   // component pairs (Ex,Ey) (Ez,Bx) (By,Bz) (phi,psi): 16-byte accesses
     __shared__ double sRed[32];
     const int skip = P.skip_dev ? *P.skip_dev : 0;
     const double dt = P.dt_dev ? *P.dt_dev : P.dt;
@@ -60,69 +74,56 @@ __global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS) maxwell_kernel(const S
     const int64_t e = P.elem_begin + (int64_t)blockIdx.x * G + le;
     const bool active = e < P.elem_end;
     const int nf0 = 5 * P.nsp;   // first field component
-    double F[8];
-    if (active) {
+    const bool want_speed = P.vmax && P.mode == 0;
+    const int i0 = j % NP, i1 = (DIM > 1) ? (j / NP) % NP : 0, i2 = (DIM > 2) ? j / (NP * NP) : 0;
+    const int idx[3] = {i0, i1, i2};
+    double old[8];
+#if WGPU_MAXWELL_PREFETCH_FACES
+    double Fo[DIM][8];
+#endif
+    const double* src[DIM];   // where the outside trace of direction d lives (the node itself: no jump)
+    int stride[DIM];
+    double Jx = 0.0, Jy = 0.0, Jz = 0.0, rc = 0.0, wp2 = 0.0, qmax = 0.0;
+    bool jump[DIM];   // the node lies on a face of direction d that has a neighbour
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            F[k] = P.u[((size_t)e * P.nc + nf0 + k) * NN + j];
-            sF[le][k][j] = F[k];
-        }
-    }
-    __syncthreads();
-    double vmax_local = 0.0;
+    for (int k = 0; k < 8; k++) old[k] = 0.0;
     if (active) {
-        const int i0 = j % NP, i1 = (DIM > 1) ? (j / NP) % NP : 0, i2 = (DIM > 2) ? j / (NP * NP) : 0;
-        const int idx[3] = {i0, i1, i2};
-        double rate[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        const size_t own = ((size_t)e * P.nc + nf0) * NN + j;
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
-            const int st = stride_of(NP, d), jd = idx[d];
-            // volume: -(1/h_d) sum_l D[j_d][l] f_d(F_l)
-            double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int l = 0; l < NP; l++) {
-                const int q = j + (l - jd) * st;
-                double Fq[8], fq[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) Fq[k] = sF[le][k][q];
-                phm_flux(d, M, Fq, fq);
-                const double w = P.T.D[jd * NP + l];
-#pragma unroll
-                for (int k = 0; k < 8; k++) acc[k] = fma(w, fq[k], acc[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) rate[k] -= acc[k] * P.inv_h[d];
-            // faces: (f(F_m).n - f*) / (h_d w_0) = (lambda dF - sgn f_d(dF)) / (2 h_d w_0), dF = F_p - F_m
-            if (jd == 0 || jd == NP - 1) {
-#pragma unroll
-                for (int side = 0; side < 2; side++) {
-                    if (jd != (side ? NP - 1 : 0)) continue;
-                    const int f = 2 * d + side;
-                    const int t = face_node_index<DIM, NP>(d, i0, i1, i2);
-                    const int v = P.nbr[(size_t)e * (2 * DIM) + f];
-                    double dF[8];
-                    if (v < 0) {
-#pragma unroll
-                        for (int k = 0; k < 8; k++) dF[k] = 0.0;   // domain boundary: outside state = inside state
-                    } else if (v < P.n_elems) {
-                        const int qn = node_of_face_node<DIM, NP>(d, 1 - side, t);
-#pragma unroll
-                        for (int k = 0; k < 8; k++) dF[k] = P.u[((size_t)v * P.nc + nf0 + k) * NN + qn] - F[k];
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 8; k++) dF[k] = P.ghost[((size_t)(v - P.n_elems) * P.ncf + nf0 + k) * NF + t] - F[k];
-                    }
-                    double fn[8];
-                    phm_flux(d, M, dF, fn);
-                    const double cf = 0.5 * P.inv_hw[d], sgn = side ? 1.0 : -1.0;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) rate[k] += cf * (M.lam * dF[k] - sgn * fn[k]);
-                }
+            const int jd = idx[d];
+            const bool on_face = (jd == 0 || jd == NP - 1);
+            const int side = (jd == 0) ? 0 : 1;   // (Np >= 2: a node is on at most one face per direction)
+            const int v = on_face ? P.nbr[(size_t)e * (2 * DIM) + 2 * d + side] : -1;
+            const int t = face_node_index<DIM, NP>(d, i0, i1, i2);
+            jump[d] = v >= 0;
+            src[d] = P.u + own;
+            stride[d] = NN;
+            if (v >= P.n_elems) {
+                src[d] = P.ghost + ((size_t)(v - P.n_elems) * P.ncf + nf0) * NF + t;
+                stride[d] = NF;
+            } else if (v >= 0) {
+                src[d] = P.u + ((size_t)v * P.nc + nf0) * NN + node_of_face_node<DIM, NP>(d, 1 - side, t);
             }
         }
-        // sources: -J/eps0 on E, chi rho_c/eps0 on phi (the same sums, in the same order, as the fluid kernels' field phase)
+        double F[8];   // parked in shared memory; re-read from there where needed (16 registers less across the kernel)
+#pragma unroll
+        for (int k = 0; k < 8; k++) F[k] = P.u[own + (size_t)k * NN];
+#if WGPU_MAXWELL_PREFETCH_FACES
+#pragma unroll
+        for (int d = 0; d < DIM; d++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) Fo[d][k] = src[d][(size_t)k * stride[d]];
+#endif
+        if (P.mode == 2) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) old[k] = P.sol_in[own + (size_t)k * NN];
+        } else if (P.mode == 0 && P.beta != 0.0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) old[k] = P.dst[own + (size_t)k * NN];
+        }
         if (P.src_on) {
-            double Jx = 0.0, Jy = 0.0, Jz = 0.0, rc = 0.0;
+            // the same sums, in the same order, as the fluid kernels' field phase
             for (int sp = 0; sp < P.nsp; sp++) {
                 const size_t so = ((size_t)e * P.nc + 5 * sp) * NN + j;
                 const double qm = P.qm[sp];
@@ -130,45 +131,104 @@ __global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS) maxwell_kernel(const S
                 Jx += qm * P.u[so + NN];
                 Jy += qm * P.u[so + 2 * (size_t)NN];
                 Jz += qm * P.u[so + 3 * (size_t)NN];
+                if (want_speed) {
+                    // plasma frequency of the UPDATED state (the fluid kernel of this range has already written dst)
+                    wp2 += qm * qm * P.dst[so] * P.inv_eps0;
+                    qmax = fmax(qmax, fabs(qm));
+                }
             }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) sF[le][k][j] = make_double2(F[2 * k], F[2 * k + 1]);
+    }
+    __syncthreads();
+    double vmax_local = 0.0;
+    if (active) {
+        double rate[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            const int st = stride_of(NP, d), jd = idx[d];
+#if !WGPU_MAXWELL_PREFETCH_FACES
+            // the outside trace (L2 hits: the neighbour's block has just been streamed), in flight during the volume term
+            double Fod[8];
+            if (jump[d]) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) Fod[k] = src[d][(size_t)k * stride[d]];
+            }
+#else
+            const double* const Fod = Fo[d];
+#endif
+            // volume: -(1/h_d) sum_l D[j_d][l] f_d(F_l) = -(1/h_d) f_d(sum_l D[j_d][l] F_l): the flux is linear
+            double dF_[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int l = 0; l < NP; l++) {
+                const int q = j + (l - jd) * st;
+                const double w = P.T.D[jd * NP + l];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const double2 v = sF[le][k][q];
+                    dF_[2 * k] = fma(w, v.x, dF_[2 * k]);
+                    dF_[2 * k + 1] = fma(w, v.y, dF_[2 * k + 1]);
+                }
+            }
+            double acc[8];
+            phm_flux(d, M, dF_, acc);
+#pragma unroll
+            for (int k = 0; k < 8; k++) rate[k] = fma(-P.inv_h[d], acc[k], rate[k]);
+            // faces: (f(F_m).n - f*) / (h_d w_0) = (lambda dF - sgn f_d(dF)) / (2 h_d w_0), dF = F_p - F_m; a domain boundary
+            // has outside state = inside state, i.e. no jump
+            if (jump[d]) {
+                double dF[8], fn[8];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const double2 own = sF[le][k][j];
+                    dF[2 * k] = Fod[2 * k] - own.x;
+                    dF[2 * k + 1] = Fod[2 * k + 1] - own.y;
+                }
+                phm_flux(d, M, dF, fn);
+                const double cf = 0.5 * P.inv_hw[d], cl = cf * M.lam, cs = (jd == 0) ? cf : -cf;
+#pragma unroll
+                for (int k = 0; k < 8; k++) rate[k] = fma(cs, fn[k], fma(cl, dF[k], rate[k]));
+            }
+        }
+        // sources: -J/eps0 on E, chi rho_c/eps0 on phi
+        if (P.src_on) {
             rate[0] += -Jx * P.inv_eps0;
             rate[1] += -Jy * P.inv_eps0;
             rate[2] += -Jz * P.inv_eps0;
             rate[6] += P.chi * rc * P.inv_eps0;
         }
-        double Fn[8];
+        double Fn[8], F[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double2 own = sF[le][k][j];
+            F[2 * k] = own.x;
+            F[2 * k + 1] = own.y;
+        }
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const size_t off = ((size_t)e * P.nc + nf0 + k) * NN + j;
             double v;
             if (P.mode == 1) v = rate[k];
             else if (P.mode == 2) {
-                const double s0 = P.sol_in[off];
-                v = fma(P.a, rate[k], s0);
-                if (P.beta != 0.0) P.dst2[off] = fma(P.beta, rate[k], s0);
+                v = fma(P.a, rate[k], old[k]);
+                if (P.beta != 0.0) P.dst2[off] = fma(P.beta, rate[k], old[k]);
             }
             else if (P.beta == 0.0) v = P.a * (F[k] + dt * rate[k]);
-            else v = P.beta * P.dst[off] + P.a * (F[k] + dt * rate[k]);
+            else v = P.beta * old[k] + P.a * (F[k] + dt * rate[k]);
             P.dst[off] = v;
             Fn[k] = v;
         }
-        if (P.vmax && P.mode == 0) {
+        if (want_speed) {
             vmax_local = M.speed_floor;
             if (P.src_on) {
-                // plasma and cyclotron frequency of the UPDATED state (the fluid kernel of this range has already written dst)
-                double wp2 = 0.0, qmax = 0.0;
-                for (int sp = 0; sp < P.nsp; sp++) {
-                    const double qm = P.qm[sp];
-                    wp2 += qm * qm * P.dst[((size_t)e * P.nc + 5 * sp) * NN + j] * P.inv_eps0;
-                    qmax = fmax(qmax, fabs(qm));
-                }
                 const double b2 = Fn[3] * Fn[3] + Fn[4] * Fn[4] + Fn[5] * Fn[5];
                 const double omega = fmax(sqrt(wp2), qmax * sqrt(b2));
                 vmax_local = nan_max(vmax_local, M.omega_factor * omega);
             }
         }
     }
-    if (P.vmax && P.mode == 0) {
+    if (want_speed) {
         const double m = block_max(vmax_local, sRed);
         if (tid == 0) atomicMax(P.vmax, (unsigned long long)__double_as_longlong(m));
     }

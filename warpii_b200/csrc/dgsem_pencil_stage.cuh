@@ -88,7 +88,7 @@ struct PGeo {
 
 // node index -> slot in a shared plane.  Np = 4: slot = n ^ b1 ^ 6 c0 with n = i0 + 4 i1 + 16 (i2 or element) ..., which
 // makes the eight 16-byte accesses of a quarter-warp distinct modulo 8 for x-owners (n = 4 pe + m), y-owners
-// (n = i0 + 4 m + 16 i2) and z-owners (n = pe + 16 m) alike (tests/test_pencil_layout_cpu.py enumerates them).
+// (n = i0 + 4 m + 16 i2) and z-owners (n = pe + 16 m) alike (tests/test_pencil_emu_cpu.py::test_swizzled_planes_are_bijective_and_bank_conflict_free enumerates them).
 template <int NP>
 __device__ __forceinline__ constexpr int pslot(const int n) {
     return (NP == 4) ? (n ^ ((n >> 3) & 1) ^ (((n >> 4) & 1) * 6)) : n;
