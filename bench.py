@@ -569,6 +569,10 @@ def run_ours(args, w):
                          "algorithmic_bytes_per_launch": bytes_per_update * n_dofs_local,
                          "algorithmic_bytes_per_dof_update": bytes_per_update},
         }
+        if w.get("maxwell") and w["dim"] == 3:
+            # in 3-D the field system is a second launch over the same element range
+            line["roofline"]["launch"] = ("one stage = %s + wgpu::maxwell_kernel<3,%d>, timed together; achieved, avg_launch_ms and "
+                                          "traffic are per stage" % (kernel, w["p"] + 1))
         if parity is not None:
             line["parity_check"] = parity
         if others:

@@ -41,6 +41,9 @@
 #ifndef WGPU_PENCIL_TMA
 #define WGPU_PENCIL_TMA 0        // 1: P0 stages the patch's state block in shared memory with cp.async.bulk + mbarrier (A/B only)
 #endif
+#ifndef WGPU_PENCIL_PREFETCH
+#define WGPU_PENCIL_PREFETCH 0   // 1: the final phase asks for its epilogue operands (u again: L1, old dst: L2) before the x pair fluxes
+#endif
 #ifndef WGPU_PENCIL_P0_ROLL
 #define WGPU_PENCIL_P0_ROLL 0    // 1: P0 forms the node records two at a time in a rolled loop (half the code, ILP 2 instead of NP)
 #endif
@@ -669,6 +672,22 @@ __device__ __forceinline__ double pencil_phase_final(const StageParams& P, doubl
         }
     }
 
+#if WGPU_PENCIL_PREFETCH && !WGPU_HOST_EMU
+    {
+        // the epilogue (pencil_finish) reads u again and, in a second stage, the old destination: ask for the lines now, the
+        // x pair fluxes below hide the latency (no registers held: prefetch instructions)
+        const size_t off = ((size_t)e * P.nc + 5 * sp) * G::NN + pe * NP;
+        const bool need_old = (P.mode == 2) || (P.mode == 0 && P.beta != 0.0);
+        const double* const oldp = (P.mode == 2) ? P.sol_in : P.dst;
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+#if WGPU_PENCIL_PREFETCH == 1
+            if (P.mode != 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.u + off + (size_t)c * G::NN));
+#endif
+            if (need_old) asm volatile("prefetch.global.L2 [%0];" ::"l"(oldp + off + (size_t)c * G::NN));
+        }
+    }
+#endif
     double rate[5][NP];   // [component][node of the pencil]: the layout of the vector loads / stores below
     pencil_sums<DIM, NP, 0>(P, sRec, h, le, pe, [&](const int m, const double (&a)[5]) {
         const int slot = pslot<NP>(le * G::NN + pe * NP + m);
