@@ -146,6 +146,15 @@ def test_expression_language():
 
     with pytest.raises(Exception, match="hexadecimal"):
         eval_expr("0x10 + x", pts)
+    # deal.II's random built-ins: rand_seed(s) is a reproducible uniform [0,1) stream per seed, rand() a clock-seeded one
+    a, _ = eval_expr("rand_seed(7) + 0*x", pts)
+    b, _ = eval_expr("rand_seed(8) + 0*x", pts)
+    r, _ = eval_expr("rand() + 0*x", pts)
+    for v in (a, b, r):
+        assert v.min() >= 0.0 and v.max() < 1.0 and len(np.unique(v)) == len(v)
+    assert not np.array_equal(a, b)
+    with pytest.raises(Exception, match="no argument"):
+        eval_expr("rand(1)", pts)
     got, _ = eval_expr("k * sin(2*pi*x) + Pi + big_name_2", pts, constants="pi=3.1415926535, k = 0.6, big_name_2=-1")
     np.testing.assert_allclose(got, 0.6 * np.sin(2 * math.pi * x) + math.pi - 1, rtol=4e-16)
     got, td = eval_expr("x*t + y", pts, t=0.25)

@@ -11,6 +11,8 @@
 #pragma once
 #include <cmath>
 #include <map>
+#include <random>
+#include <ctime>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -208,7 +210,25 @@ class Expression {
             {"log2", std::log2}, {"log10", std::log10}, {"sqrt", std::sqrt}, {"abs", std::fabs}, {"ceil", std::ceil}, {"floor", std::floor},
             {"erfc", std::erfc}, {"erf", std::erf}, {"asinh", std::asinh}, {"acosh", std::acosh}, {"atanh", std::atanh}, {"rint", std::rint}, {"sign", [](double v) { return v < 0 ? -1.0 : (v > 0 ? 1.0 : 0.0); }},
             {"cot", [](double v) { return 1.0 / std::tan(v); }}, {"sec", [](double v) { return 1.0 / std::cos(v); }},
-            {"csc", [](double v) { return 1.0 / std::sin(v); }}, {"int", [](double v) { return std::round(v); }}};
+            {"csc", [](double v) { return 1.0 / std::sin(v); }}, {"int", [](double v) { return std::round(v); }},
+            // deal.II's additions to muparser (function_parser / mu_rand_seed): a uniform [0,1) stream per seed value
+            {"rand_seed", [](double seed) {
+                 static std::map<double, std::mt19937> streams;
+                 auto it = streams.find(seed);
+                 if (it == streams.end()) it = streams.emplace(seed, std::mt19937((unsigned int)seed)).first;
+                 return (double)it->second() / 4294967296.0;
+             }}};
+        if (name == "rand") {   // mu_rand: no argument, a stream seeded from the clock
+            if (!args.empty()) fail("rand() takes no argument");
+            P zero = make(NUM);
+            zero->value = 0.0;
+            P n = make(CALL1, std::move(zero));
+            n->f1 = [](double) {
+                static std::mt19937 stream((unsigned int)std::time(nullptr));
+                return (double)stream() / 4294967296.0;
+            };
+            return n;
+        }
         static const std::map<std::string, double (*)(double, double)> f2 = {
             {"pow", std::pow}, {"min", [](double a, double b) { return a < b ? a : b; }}, {"max", [](double a, double b) { return a > b ? a : b; }},
             {"atan2", std::atan2}, {"fmod", std::fmod}};
