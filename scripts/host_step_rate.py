@@ -1,27 +1,36 @@
 """End-to-end rate of warpii_gpu_host_ssprk2_step (state in pinned host memory, whole state over PCIe both ways every step)
-against the plain upload / step / download sequence, for several slab counts.  C2 workload.
-Usage: python scripts/host_step_rate.py [n] [steps]"""
-import os, sys, time
+against the plain upload / step / download sequence, for several slab counts.
+Usage: python scripts/host_step_rate.py [workload=N3D] [steps=6] [slab counts ...]"""
+import ctypes as C
+import os
+import sys
+import time
+
 import numpy as np
 import torch
+
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import dgsem_cases as cases
-from warpii_b200 import BoxSolver
+import bench  # noqa: E402
+from warpii_b200 import BoxSolver, lib  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-g = BoxSolver(2, 3, [n, n], [0.0, -5.0], [10.0, 5.0], gamma=1.4)
+name = sys.argv[1] if len(sys.argv) > 1 else "N3D"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+slabs = [int(v) for v in sys.argv[3:]] or [8, 16, 32, 64, 128]
+w = bench.WORKLOADS[name]
+g = BoxSolver(w["dim"], w["p"], w["nx"], w["left"], w["right"], gamma=w["gamma"], **bench.species_kwargs(w))
+if w.get("sources"):
+    g.set_sources(True, **w["sources"])
+if w.get("maxwell"):
+    g.set_maxwell(True, **w["maxwell"])
 host = torch.empty(g.n_dofs, dtype=torch.float64).pin_memory().numpy()
-host[:] = cases.to_state(cases.isentropic_vortex(1.4)(g.node_coords()), 1.4).reshape(-1)
+host[:] = bench.build_ic(w, g.node_coords()).reshape(-1)
 g.upload(0, host)
 dt = g.recommend_dt(0)
-
-import ctypes as C
-from warpii_b200 import lib
 L = lib()
 hp = host.ctypes.data_as(C.POINTER(C.c_double))
+
 
 def plain(dt):
     assert L.warpii_gpu_upload_state(g.ctx, 0, hp, None) == 0
@@ -29,7 +38,8 @@ def plain(dt):
     assert L.warpii_gpu_download_state(g.ctx, 0, hp, None) == 0
     return g.recommend_dt(0)
 
-for label, fn in [("plain upload/step/download", None)] + [(f"streamed, {s} slabs", s) for s in (4, 8, 16, 32, 64, 128)]:
+
+for label, fn in [("plain upload/step/download", None)] + [(f"streamed, {s} slabs", s) for s in slabs]:
     d = dt
     for _ in range(2):
         d = plain(d) if fn is None else g.host_step(host, host, d, 0.0, n_slabs=fn)
@@ -39,5 +49,6 @@ for label, fn in [("plain upload/step/download", None)] + [(f"streamed, {s} slab
         d = plain(d) if fn is None else g.host_step(host, host, d, 0.0, n_slabs=fn)
     g.synchronize()
     ms = (time.perf_counter() - t0) * 1e3 / steps
-    print(f"{label:32s} {ms:7.3f} ms/step  {2 * g.n_dofs / (ms * 1e-3):.3e} DoF-updates/s  ({2 * 8 * g.n_dofs / (ms * 1e-3) / 1e9:.1f} GB/s over PCIe, both directions)", flush=True)
+    print(f"{name} {label:32s} {ms:8.3f} ms/step  {2 * g.n_dofs / (ms * 1e-3):.3e} DoF-updates/s  "
+          f"({2 * 8 * g.n_dofs / (ms * 1e-3) / 1e9:.1f} GB/s over PCIe, both directions)", flush=True)
 g.close()
