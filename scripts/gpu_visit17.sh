@@ -13,4 +13,4 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 1 --no-other-workloads --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 (time timeout 1200 python bench.py --impl reference) > gpurun_out/bench_r02_reference.log 2>&1; grep '^{' gpurun_out/bench_r02_reference.log | cut -c1-300
 (time timeout 1200 python bench.py) > gpurun_out/bench_r02_default.log 2>&1; grep '^{' gpurun_out/bench_r02_default.log | cut -c1-400
-timeout 900 python scripts/parity_table.py r02 > gpurun_out/parity_r02.log 2>&1; tail -2 gpurun_out/parity_r02.log
+timeout 900 python tests/tools/parity_table.py r02 > gpurun_out/parity_r02.log 2>&1; tail -2 gpurun_out/parity_r02.log

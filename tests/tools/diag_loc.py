@@ -1,7 +1,7 @@
 """Diagnostic: where is the GPU-vs-oracle energy RHS error, and who is closer to an extended-precision evaluation?"""
 import sys, os
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import dgsem_cases as cases
 import oracle

@@ -1,7 +1,7 @@
 """Diagnostic: print GPU-vs-oracle RHS errors per component for the parity cases."""
 import sys, os
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import dgsem_cases as cases
 from oracle import Oracle

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Plain per-component relative L2 error of one RHS evaluation, CUDA path (through the C ABI) against the CPU oracle,
 on the parity-test meshes AND at BASELINE.json's sizes.  Written to gpurun_out/parity_<round>.json (copied to
-profiles/ once looked at).  usage (GPU box): python scripts/parity_table.py [round] [--quick]
+profiles/ once looked at).  usage (GPU box): python tests/tools/parity_table.py [round] [--quick]
 
 "plain" = ||got - want||_2 / ||want||_2 per component, no guard; a component is only excused when the oracle's own
 RHS norm is below 1e-9 x the magnitude of the terms that are differenced to form it (pure cancellation noise in
@@ -13,7 +13,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
