@@ -414,7 +414,33 @@ def parity_check_sharded(world, rank, local_rank, dist, torch):
             "note": "component 3 (z-momentum of a flow extruded in z) vanishes identically and is judged against the differenced terms"}
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this rank's threads to the CPUs NVML lists as local to its GPU, BEFORE the pinned host buffer is allocated, so that
+    the buffer's pages land on that NUMA node (first touch).  What `mpirun --bind-to` / `numactl` do for an MPI rank of the
+    reference; matters for the e2e leg at N > 1, where every rank streams its whole state over its own PCIe link each step.
+    Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus:
+            return "GPU-local CPUs not in this process's cpuset: unbound"
+        if cpus == allowed:
+            return "all %d allowed CPUs are GPU-local" % len(allowed)
+        os.sched_setaffinity(0, cpus)
+        return "bound to %d of %d allowed CPUs (NVML CPU affinity of GPU %d)" % (len(cpus), len(allowed), index)
+    except Exception as exc:   # no NVML, no affinity support: run unbound
+        return "unbound (%s)" % type(exc).__name__
+
+
 def run_ours(args, w):
+    numa = bind_to_gpu_numa_node(int(os.environ.get("LOCAL_RANK", "0"))) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "single rank: unbound"
     import torch
     import torch.distributed as dist
 
@@ -553,6 +579,7 @@ def run_ours(args, w):
             "details": {"l2_policy": "state (2 x %.0f MB per GPU) exceeds the 126 MB L2; no flush" % (8e-6 * n_dofs_local),
                         "parallelism": f"elements sharded over {world} GPU(s), NCCL send/recv halo + allreduce(max) dt",
                         "timed_regions": f"{N_REPEAT} x {args.steps} steps, median reported",
+                        "host_numa_binding_rank0": numa,
                         "fv_blend_active_fraction_rank0": fv_frac},
             "timed_regions_ms": regions,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_dofs_local),
