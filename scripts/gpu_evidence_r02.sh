@@ -1,4 +1,6 @@
 #!/bin/bash
+# Round-2 evidence visit (one B200): GPU tests, smoke, stage times of every workload, ncu capture of the four N3D launches,
+# launch list of the bench command, both bench arms, parity table.  Run through gpurun; outputs land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
 rm -f gpurun_out/stage_rate.jsonl
