@@ -131,3 +131,33 @@ def test_vacuum_light_wave_on_the_gpu():
     exact = np.cos(2 * np.pi * (xyz[..., 0] - c * 0.25))
     assert np.sqrt(np.mean((got[:, 6, :] - exact) ** 2)) < 1e-3
     g.close()
+
+
+def test_two_fluid_langmuir_example_from_the_input_file():
+    """examples/five-moment/two_fluid_langmuir.inp through the application (sources + Maxwell fluxes from the input keys)
+    against the oracle driven the same way; the plasma oscillation is there: E_x builds up and the electron momentum comes back."""
+    import os
+    from warpii_b200 import App
+    from test_gpu_input_file import oracle_for, oracle_initial_state, oracle_run
+    here = os.path.dirname(os.path.abspath(__file__))
+    text = open(os.path.join(here, "..", "examples", "five-moment", "two_fluid_langmuir.inp")).read()
+    app = App(text)
+    app.setup()
+    steps = app.run()
+    s = app.solver.get_state_global()
+    assert steps > 100 and np.isfinite(s).all()            # c = 5 on h = 1/8, degree 3: dt ~ 1e-3
+    assert len(app.frames) == 4 and abs(app.frames[-1][1] - 1.0) < 1e-12   # frame 0 fired in setup(), before run()
+    o = oracle_for(app)
+    o.set_sources(True, 0.01, 1.0, [1.0 / 25.0, -1.0])
+    o.set_maxwell(True, light_speed=5.0, chi=1.0, gamma=1.0)
+    u = oracle_initial_state(app, o)
+    assert oracle_run(app, o, u) == steps
+    rel = cases.rel_l2_per_component(s, u)
+    assert (rel[[0, 4, 5, 6, 9, 10]] <= 1e-8).all(), rel   # densities, energies, electron momentum, E_x; 1280 steps (1e-10 per 100 steps)
+    # the physics: E_x(t) = -(J0 / (eps0 omega_p)) sin(omega_p t) with omega_p^2 = sum_s (q/m)^2 rho / eps0 (cold plasma; the
+    # thermal correction of the frequency is 3 % here)
+    wp = np.sqrt((25.0 / 25.0 ** 2 + 1.0) / 0.01)
+    want = 0.01 / (0.01 * wp) * abs(np.sin(wp * 1.0))
+    assert abs(np.abs(s[:, 10, :]).max() - want) < 0.05 * want
+    assert np.abs(s[:, 6, :]).max() < 0.01                 # the electrons are held in the oscillation
+    app.close()

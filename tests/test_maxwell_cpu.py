@@ -158,3 +158,21 @@ def test_two_fluid_total_energy_with_fields():
         drift = max(drift, abs(now - e0))
     assert moved > 1e-6                        # energy did move between fluids and field (it sloshes back and forth) ...
     assert drift < 2e-3 * moved                # ... while the total stayed put
+
+
+def test_input_keys_for_the_field_system():
+    """five_moment_maxwell / light_speed / phm_gamma of the application (warpii_b200/host/five_moment_app.hpp): parsing needs
+    no GPU; the example input parses with them."""
+    import os
+    from warpii_b200 import App, WarpiiGpuError
+    here = os.path.dirname(os.path.abspath(__file__))
+    text = open(os.path.join(here, "..", "examples", "five-moment", "two_fluid_langmuir.inp")).read()
+    app = App(text)
+    assert app.fields_enabled and app.n_species == 2 and app.nx == [8, 4] and app.t_end == 1.0
+    assert app.species(0)["mass"] == 25.0 and app.species(1)["charge"] == -1.0
+    with pytest.raises(WarpiiGpuError, match="needs the field components"):
+        App("set five_moment_maxwell = true\nset fields_enabled = false")
+    with pytest.raises(WarpiiGpuError, match="outside the allowed range"):
+        App("set n_species = 2\nset five_moment_maxwell = true\nset light_speed = 0")
+    with pytest.raises(WarpiiGpuError, match="outside the allowed range"):
+        App("set n_species = 2\nset five_moment_maxwell = true\nset phm_gamma = -1")
