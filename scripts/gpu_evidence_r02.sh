@@ -3,6 +3,7 @@
 # launch list of the bench command, both bench arms, parity table.  Run through gpurun; outputs land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
+(free -g; nproc; nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv) > gpurun_out/box.txt 2>&1
 rm -f gpurun_out/stage_rate.jsonl
 (time timeout 1500 python -m pytest tests -m gpu -q) > gpurun_out/gpu_tests_r02.log 2>&1
 tail -4 gpurun_out/gpu_tests_r02.log
