@@ -59,6 +59,11 @@ WORKLOADS = {
                 maxwell=dict(light_speed=10.0, chi=1.0, gamma=1.0),
                 label="north-star shape: 3D two-species five-moment + Maxwell (8 field components evolved, Lorentz/current sources), "
                       "degree 3, 64^3 elements"),
+    "N3D128": dict(dim=3, p=3, nx=[128, 128, 128], left=[0.0, -5.0, -5.0], right=[40.0, 15.0, 15.0], gamma=5.0 / 3.0, ic="two_fluid",
+                   n_species=2, fields=True, sources=dict(epsilon0=1.0, chi=1.0, charge_over_mass=[1.0 / 25.0, -1.0]),
+                   maxwell=dict(light_speed=10.0, chi=1.0, gamma=1.0),
+                   label="north-star shape at the size SURVEY 8(d) names for one GPU: 128^3 elements, 2.4e9 DoFs, 19.3 GB per state "
+                         "vector (capacity run: scripts/stage_rate.py; not a default bench line)"),
     "C2c": dict(dim=2, p=3, nx=[512, 512], left=[0.0, -5.0], right=[10.0, 5.0], gamma=1.4, ic="vortex", mapping="wavy",
                 label="C2 on curved elements: the 512x512 degree-3 box pushed through a smooth periodic mapping "
                       "(general-geometry kernels, metric terms read from HBM)"),
