@@ -197,8 +197,10 @@ int warpii_gpu_ssprk2_step(warpii_gpu_ctx* ctx, int solution, int f1, double dt,
  * with the transfers and the stages overlapped slab by slab on three streams (upload, compute, download; PCIe is full
  * duplex and the stage kernels take element ranges), instead of upload, step, download one after the other.  dt comes from
  * the caller: warpii_gpu_recommend_dt for the first step, then *next_dt_out of the previous call (the fused CFL reduction of
- * the second stage, i.e. recommend_dt of the state just returned).  host_out may be host_in.  n_slabs = 0 picks 16.  Bit-identical
- * to upload + warpii_gpu_ssprk2_step + download.  Contexts with boundary faces or a communicator run that plain sequence. */
+ * the second stage, i.e. recommend_dt of the state just returned).  host_out may be host_in.  n_slabs = 0 picks 32 (measured: 16 and 32 tie on a 168 MB state, 32 wins on a 2.4 GB one).  Bit-identical
+ * to upload + warpii_gpu_ssprk2_step + download.  Contexts with a communicator stream the interior slabs the same way and
+ * keep the interface elements and the halo exchanges on the communication stream; contexts with boundary faces run the
+ * plain sequence. */
 int warpii_gpu_host_ssprk2_step(warpii_gpu_ctx* ctx, int solution, int f1, const double* host_in, double* host_out, double dt,
                                 double t, double* next_dt_out, int n_slabs);
 /* Time loop resident on the device side of the ABI: repeats {dt = min(recommend_dt, t_stop - t); ssprk2} until

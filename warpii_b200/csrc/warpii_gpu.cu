@@ -1028,7 +1028,7 @@ int build_slab_plan(warpii_gpu_ctx* c, int n_slabs, SlabPlan& plan) {
     const int nf = 2 * c->dim;
     const int G = (c->pencil && !c->general) ? pencil_patch_elems(c->dim, c->Np) : elems_per_block(c->dim, c->Np);
     const int64_t n_patches = (c->n_elems + G - 1) / G;
-    int S = n_slabs > 0 ? n_slabs : 16;
+    int S = n_slabs > 0 ? n_slabs : 32;
     if (S > n_patches) S = (int)(n_patches > 0 ? n_patches : 1);
     plan.n = S;
     plan.begin.assign(S + 1, 0);
@@ -1068,7 +1068,7 @@ int host_step_sharded(warpii_gpu_ctx* c, int solution, int f1, const double* hos
     const size_t per_elem = (size_t)c->nc * c->NN;
     const int G = c->pencil && !c->general ? pencil_patch_elems(c->dim, c->Np) : elems_per_block(c->dim, c->Np);
     const int64_t n_if = c->n_interface, n_in = c->n_elems - n_if;
-    int S = (n_slabs > 0 ? n_slabs : 16);
+    int S = (n_slabs > 0 ? n_slabs : 32);
     const int64_t in_patches = (n_in + G - 1) / G;
     if (S - 1 > in_patches) S = (int)in_patches + 1;
     if (S < 2) S = 2;
