@@ -66,7 +66,9 @@ def check(o, g, u):
 
 
 @pytest.mark.parametrize("dim,p,nx,nsp", [(1, 2, [12], 2), (1, 4, [5], 1), (2, 3, [6, 5], 2), (2, 2, [5, 4], 2), (2, 5, [3, 3], 1),
-                                          (3, 3, [4, 3, 2], 2), (3, 2, [3, 3, 3], 2), (3, 4, [2, 2, 3], 1)])
+                                          (3, 3, [4, 3, 2], 2), (3, 2, [3, 3, 3], 2), (3, 4, [2, 2, 3], 1),
+                                          # the degrees the node-per-thread stage kernel serves (Np = 2, 6, 7), stand-alone field kernel
+                                          (2, 1, [7, 6], 2), (3, 1, [4, 3, 3], 2), (2, 6, [3, 2], 1), (3, 5, [2, 2, 2], 2), (3, 6, [2, 1, 2], 1)])
 def test_rhs_with_fields_evolving(dim, p, nx, nsp):
     o, g = make(dim, p, nx, nsp)
     u = two_fluid_state(o)
