@@ -782,9 +782,9 @@ int warpii_gpu_set_maxwell(warpii_gpu_ctx* c, int enabled, double light_speed, d
     c->maxwell_on = true;
     c->ncf = c->nc;
     {
-        // Fused into the pencil stage kernel in 2-D; in 3-D the fused kernel's instruction footprint passes the SM's
-        // instruction cache (no_instruction stalls 18 % -> 32 % of the samples in the second stage, profiles/README.md) and the
-        // stand-alone kernel right behind the fluid stage is faster.  WARPII_GPU_MAXWELL=fused|separate overrides.
+        // Fused into the pencil stage kernel in 2-D; in 3-D the stand-alone kernel right behind the fluid stage is faster
+        // (north-star shape, per stage: fused 4.78 ms, separate 3.81 ms; captures in profiles/README.md), although it
+        // re-reads the species' densities and momenta.  WARPII_GPU_MAXWELL=fused|separate overrides.
         const char* env = std::getenv("WARPII_GPU_MAXWELL");
         bool fused = c->pencil && c->dim == 2;
         if (env && std::strcmp(env, "fused") == 0) fused = c->pencil;
