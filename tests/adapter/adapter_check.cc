@@ -95,6 +95,8 @@ int run(int fe_degree, const int* nx, const double* left, const double* right, c
             if (k == WARPII_BC_WALL) bc.set_wall_boundary((types::boundary_id)b);
             else if (k == WARPII_BC_INFLOW)
                 bc.set_inflow_boundary((types::boundary_id)b, std::make_unique<ConstantState<dim>>(inflow + (s * 2 * dim + b) * 5));
+            else if (k == WARPII_BC_SUBSONIC_OUTFLOW)   // (the prescribed total energy is component 4 of the function)
+                bc.set_subsonic_outflow_boundary((types::boundary_id)b, std::make_unique<ConstantState<dim>>(inflow + (s * 2 * dim + b) * 5));
             else bc.set_supersonic_outflow_boundary((types::boundary_id)b);
         }
         species.push_back(std::make_shared<Species<dim>>("species" + std::to_string(s), 1.0, 1.0, bc));

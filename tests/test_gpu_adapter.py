@@ -71,3 +71,26 @@ def test_reference_integrator_over_the_adapter_with_boundaries():
     assert o.solve(u, t, bif=bif_o, max_steps=steps) == steps
     assert (cases.rel_l2_per_component(from_stub(st), u) <= 1e-11).all()
     assert np.allclose(bif, bif_o, rtol=1e-10, atol=1e-13)
+
+
+def test_reference_integrator_over_the_adapter_with_subsonic_outflow():
+    """EulerBCMap::set_subsonic_outflow_boundary (bc_helper.h:12-35) through the adapter: the ghost state keeps the interior
+    density and momentum and takes the prescribed total energy (fluid_flux_es_dgsem_operator.h:385-390)."""
+    from warpii_b200 import BC_SUBSONIC_OUTFLOW
+    dim, p, nx, left, right, gamma, steps = 2, 2, [5, 4], [0.0, 0.0], [1.0, 1.0], 1.4, 5
+    bc = [[BC_INFLOW, BC_SUBSONIC_OUTFLOW, BC_WALL, BC_WALL]]
+    q_in = oracle.primitive_to_conserved([1.0, 0.3, 0.0, 0.0, 1.0], gamma)
+    q_out = np.array([0.0, 0.0, 0.0, 0.0, 0.95 / (gamma - 1.0) + 0.5 * 0.09])     # only the energy is read
+    inflow = np.zeros((1, 4, 5))
+    inflow[0, 0], inflow[0, 1] = q_in, q_out
+    o = Oracle(dim, p, nx, left, right, periodic=[0, 0], gamma=gamma, bc_kinds=bc, threads=4)
+    o.set_inflow(0, 0, q_in)
+    o.set_inflow(0, 1, q_out)
+    u0 = o.project(cases.smooth_blob_3d(0.05))
+    rc, err, st, t, bif = adapter_check.run(dim, p, nx, left, right, [0, 0], to_stub(u0), steps, gamma, bc_kind=bc, inflow=inflow)
+    assert rc == 0, err
+    u = u0.copy()
+    bif_o = np.zeros(20)
+    assert o.solve(u, t, bif=bif_o, max_steps=steps) == steps
+    assert (cases.rel_l2_per_component(from_stub(st), u) <= 1e-11).all()
+    assert np.allclose(bif, bif_o, rtol=1e-10, atol=1e-13)
