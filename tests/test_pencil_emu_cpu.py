@@ -42,6 +42,9 @@ def check(got, want, u, o, h, tol=1e-12):
 RHS_CASES = [
     (2, 3, [8, 8], [0.0, -5.0], [10.0, 5.0], cases.isentropic_vortex(), 1.4),
     (2, 3, [7, 9], [0.0, -5.0], [10.0, 5.0], cases.isentropic_vortex(), 1.4),          # partial patches
+    (2, 3, [16, 12], [0.0, -5.0], [10.0, 5.0], cases.isentropic_vortex(), 1.4),        # 2 x 3 full 8x4 patches
+    (2, 3, [9, 5], [0.0, -5.0], [10.0, 5.0], cases.isentropic_vortex(), 1.4),          # one full patch + three partial ones
+    (2, 3, [3, 2], [0.0, -5.0], [10.0, 5.0], cases.isentropic_vortex(), 1.4),          # a single partial patch
     (2, 2, [9, 5], [0.0, 0.0], [1.0, 0.5], cases.sine_wave(vel=(1.0, 1.0, 0.0), wave=(1, 2, 0)), 5.0 / 3.0),
     (2, 4, [5, 6], [0.0, 0.0], [1.0, 1.0], cases.smooth_blob_3d(), 5.0 / 3.0),
     (2, 1, [6, 4], [0.0, 0.0], [1.0, 1.0], cases.smooth_blob_3d(), 1.4),
