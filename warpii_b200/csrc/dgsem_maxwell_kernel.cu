@@ -41,7 +41,10 @@ __device__ __forceinline__ void phm_flux(const int d, const MaxwellParams& M, co
 }
 
 #ifndef WGPU_MAXWELL_BLOCKS
-#define WGPU_MAXWELL_BLOCKS 5
+#define WGPU_MAXWELL_BLOCKS 6
+#endif
+#ifndef WGPU_MAXWELL_LATE_OLD
+#define WGPU_MAXWELL_LATE_OLD 1   // the old destination is only PREFETCHED (to L2) before the barrier and loaded at the update: 16 registers less (N3D stage 3.82 -> 3.75 ms)
 #endif
 #ifndef WGPU_MAXWELL_PREFETCH_FACES
 #define WGPU_MAXWELL_PREFETCH_FACES 0   // 1: the neighbours' traces are loaded before the barrier too (48 more registers)
@@ -54,8 +57,8 @@ struct MGeo {
     static constexpr int THREADS = G * NN;
 };
 
-// Every global load of the thread is issued before the block barrier and before any arithmetic: its 8 field values, the
-// old destination (second stage), the species' densities and momenta for the current, the updated densities for the plasma
+// Every DRAM access of the thread is issued before the block barrier and before any arithmetic: its 8 field values, the
+// old destination (second stage; as L2 prefetches, the values are loaded where the update needs them), the species' densities and momenta for the current, the updated densities for the plasma
 // frequency, and the neighbours' traces for the (at most DIM) faces the node lies on -- through one unconditional load per
 // component and direction whose address falls back to the node itself where there is no face or no neighbour.  One
 // DRAM round trip per thread instead of four to six dependent ones (ncu, round 2: the serial version spent 5-10 stall
@@ -115,6 +118,13 @@ __global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS, (MGeo<DIM, NP>::THREAD
 #pragma unroll
             for (int k = 0; k < 8; k++) Fo[d][k] = src[d][(size_t)k * stride[d]];
 #endif
+#if WGPU_MAXWELL_LATE_OLD
+        if (P.mode == 2 || (P.mode == 0 && P.beta != 0.0)) {
+            const double* const op = (P.mode == 2 ? P.sol_in : P.dst) + own;
+#pragma unroll
+            for (int k = 0; k < 8; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(op + (size_t)k * NN));
+        }
+#else
         if (P.mode == 2) {
 #pragma unroll
             for (int k = 0; k < 8; k++) old[k] = P.sol_in[own + (size_t)k * NN];
@@ -122,6 +132,7 @@ __global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS, (MGeo<DIM, NP>::THREAD
 #pragma unroll
             for (int k = 0; k < 8; k++) old[k] = P.dst[own + (size_t)k * NN];
         }
+#endif
         if (P.src_on) {
             // the same sums, in the same order, as the fluid kernels' field phase
             for (int sp = 0; sp < P.nsp; sp++) {
@@ -205,6 +216,13 @@ __global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS, (MGeo<DIM, NP>::THREAD
             F[2 * k] = own.x;
             F[2 * k + 1] = own.y;
         }
+#if WGPU_MAXWELL_LATE_OLD
+        if (P.mode == 2 || (P.mode == 0 && P.beta != 0.0)) {
+            const double* const op = (P.mode == 2 ? P.sol_in : P.dst) + ((size_t)e * P.nc + nf0) * NN + j;
+#pragma unroll
+            for (int k = 0; k < 8; k++) old[k] = op[(size_t)k * NN];
+        }
+#endif
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const size_t off = ((size_t)e * P.nc + nf0 + k) * NN + j;
