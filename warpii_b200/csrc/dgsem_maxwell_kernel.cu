@@ -46,6 +46,9 @@ __device__ __forceinline__ void phm_flux(const int d, const MaxwellParams& M, co
 #ifndef WGPU_MAXWELL_LATE_OLD
 #define WGPU_MAXWELL_LATE_OLD 1   // the old destination is only PREFETCHED (to L2) before the barrier and loaded at the update: 16 registers less (N3D stage 3.82 -> 3.75 ms)
 #endif
+#ifndef WGPU_MAXWELL_LATE_J
+#define WGPU_MAXWELL_LATE_J 1   // the species' values for the current are only prefetched (L2) before the barrier and loaded after the fluxes (N3D stage 3.74 -> 3.64 ms)
+#endif
 #ifndef WGPU_MAXWELL_PREFETCH_FACES
 #define WGPU_MAXWELL_PREFETCH_FACES 0   // 1: the neighbours' traces are loaded before the barrier too (48 more registers)
 #endif
@@ -58,7 +61,8 @@ struct MGeo {
 };
 
 // Every DRAM access of the thread is issued before the block barrier and before any arithmetic: its 8 field values, the
-// old destination (second stage; as L2 prefetches, the values are loaded where the update needs them), the species' densities and momenta for the current, the updated densities for the plasma
+// old destination (second stage) and the species' densities and momenta for the current (both as L2 prefetches: the values
+// are loaded where they are needed, from L2, and hold no registers across the barrier and the flux sums), the updated densities for the plasma
 // frequency, and the neighbours' traces for the (at most DIM) faces the node lies on -- through one unconditional load per
 // component and direction whose address falls back to the node itself where there is no face or no neighbour.  One
 // DRAM round trip per thread instead of four to six dependent ones (ncu, round 2: the serial version spent 5-10 stall
@@ -133,6 +137,16 @@ __global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS, (MGeo<DIM, NP>::THREAD
             for (int k = 0; k < 8; k++) old[k] = P.dst[own + (size_t)k * NN];
         }
 #endif
+#if WGPU_MAXWELL_LATE_J
+        if (P.src_on) {
+            for (int sp = 0; sp < P.nsp; sp++) {
+                const size_t so = ((size_t)e * P.nc + 5 * sp) * NN + j;
+#pragma unroll
+                for (int k = 0; k < 4; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.u + so + (size_t)k * NN));
+                if (want_speed) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.dst + so));
+            }
+        }
+#else
         if (P.src_on) {
             // the same sums, in the same order, as the fluid kernels' field phase
             for (int sp = 0; sp < P.nsp; sp++) {
@@ -149,6 +163,7 @@ __global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS, (MGeo<DIM, NP>::THREAD
                 }
             }
         }
+#endif
 #pragma unroll
         for (int k = 0; k < 4; k++) sF[le][k][j] = make_double2(F[2 * k], F[2 * k + 1]);
     }
@@ -202,6 +217,24 @@ __global__ void __launch_bounds__(MGeo<DIM, NP>::THREADS, (MGeo<DIM, NP>::THREAD
                 for (int k = 0; k < 8; k++) rate[k] = fma(cs, fn[k], fma(cl, dF[k], rate[k]));
             }
         }
+#if WGPU_MAXWELL_LATE_J
+        if (P.src_on) {
+            // the same sums, in the same order, as the fluid kernels' field phase
+            for (int sp = 0; sp < P.nsp; sp++) {
+                const size_t so = ((size_t)e * P.nc + 5 * sp) * NN + j;
+                const double qm = P.qm[sp];
+                rc += qm * P.u[so];
+                Jx += qm * P.u[so + NN];
+                Jy += qm * P.u[so + 2 * (size_t)NN];
+                Jz += qm * P.u[so + 3 * (size_t)NN];
+                if (want_speed) {
+                    // plasma frequency of the UPDATED state (the fluid kernel of this range has already written dst)
+                    wp2 += qm * qm * P.dst[so] * P.inv_eps0;
+                    qmax = fmax(qmax, fabs(qm));
+                }
+            }
+        }
+#endif
         // sources: -J/eps0 on E, chi rho_c/eps0 on phi
         if (P.src_on) {
             rate[0] += -Jx * P.inv_eps0;
