@@ -42,7 +42,7 @@
 #define WGPU_PENCIL_TMA 0        // 1: P0 stages the patch's state block in shared memory with cp.async.bulk + mbarrier (A/B only)
 #endif
 #ifndef WGPU_PENCIL_PREFETCH
-#define WGPU_PENCIL_PREFETCH 0   // 1: the final phase asks for its epilogue operands (u again: L1, old dst: L2) before the x pair fluxes
+#define WGPU_PENCIL_PREFETCH 3   // the final phase asks for its epilogue operands before the x pair fluxes (1: u again to L1 + old dst to L2, 2: old dst, 3: old dst + E, B of the Lorentz force; 0: off)
 #endif
 #ifndef WGPU_PENCIL_P0_ROLL
 #define WGPU_PENCIL_P0_ROLL 0    // 1: P0 forms the node records two at a time in a rolled loop (half the code, ILP 2 instead of NP)
@@ -686,6 +686,14 @@ __device__ __forceinline__ double pencil_phase_final(const StageParams& P, doubl
 #endif
             if (need_old) asm volatile("prefetch.global.L2 [%0];" ::"l"(oldp + off + (size_t)c * G::NN));
         }
+#if WGPU_PENCIL_PREFETCH == 3
+        // (3: also E and B for the Lorentz force: with the field system in its own kernel nobody has touched them yet)
+        if (P.src_on && sp == 0) {
+            const double* const fp = P.u + ((size_t)e * P.nc + 5 * P.nsp) * G::NN + pe * NP;
+#pragma unroll
+            for (int k = 0; k < 6; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + (size_t)k * G::NN));
+        }
+#endif
     }
 #endif
     double rate[5][NP];   // [component][node of the pencil]: the layout of the vector loads / stores below
