@@ -66,6 +66,9 @@ struct StageParams {
     // factor 5 / Np^2 that turns the plasma / cyclotron frequency bound omega dt <= 0.1 into an equivalent speed
     int32_t mx_on;
     double mx_c2, mx_chi, mx_gam, mx_lam, mx_floor, mx_omega_factor;
+    // pencil kernel: the patch this many elements ahead is the one the block that FOLLOWS this block on its SM will work on
+    // (resident blocks x elements per patch, set by launch_pencil_stage; 0: off); its state is prefetched to L2
+    int64_t lookahead;
     ElemTables T;
 };
 

@@ -180,8 +180,20 @@ void launch_pencil_stage(int dim, int Np, const StageParams& P, cudaStream_t s) 
         using G = PGeo<D_, N_>;                                                                                   \
         const int64_t per_cta = (int64_t)G::E * WGPU_PENCIL_SUB;                                                  \
         const int64_t blocks = (n + per_cta - 1) / per_cta;                                                       \
+        static int resident = -1;   /* blocks of this instantiation the device holds at once */                  \
+        if (resident < 0) {                                                                                       \
+            int per_sm = 0, dev = 0, sms = 0;                                                                     \
+            cudaGetDevice(&dev);                                                                                  \
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);                                    \
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pencil_stage_kernel<D_, N_>,                   \
+                                                          G::THREADS * WGPU_PENCIL_SUB,                            \
+                                                          G::SMEM_DOUBLES * WGPU_PENCIL_SUB * sizeof(double));     \
+            resident = per_sm * sms;                                                                              \
+        }                                                                                                         \
+        StageParams Q = P;                                                                                        \
+        Q.lookahead = (blocks > resident) ? (int64_t)resident * per_cta : 0;                                      \
         pencil_stage_kernel<D_, N_><<<(unsigned)blocks, G::THREADS * WGPU_PENCIL_SUB,                             \
-                                      G::SMEM_DOUBLES * WGPU_PENCIL_SUB * sizeof(double), s>>>(P);                \
+                                      G::SMEM_DOUBLES * WGPU_PENCIL_SUB * sizeof(double), s>>>(Q);                \
     }
     WGPU_PENCIL_DISPATCH(dim, Np, CALL);
 #undef CALL

@@ -42,7 +42,7 @@
 #define WGPU_PENCIL_TMA 0        // 1: P0 stages the patch's state block in shared memory with cp.async.bulk + mbarrier (A/B only)
 #endif
 #ifndef WGPU_PENCIL_PREFETCH
-#define WGPU_PENCIL_PREFETCH 3   // the final phase asks for its epilogue operands before the x pair fluxes (1: u again to L1 + old dst to L2, 2: old dst, 3: old dst + E, B of the Lorentz force; 0: off)
+#define WGPU_PENCIL_PREFETCH 5   // L2 prefetches ahead of use (0: off; 1: u again to L1 + old dst before the x pair fluxes; 2: old dst; 3: + E, B of the Lorentz force; 4: + the next species' state; 5: + the state of the patch the next block of this SM will work on)
 #endif
 #ifndef WGPU_PENCIL_P0_ROLL
 #define WGPU_PENCIL_P0_ROLL 0    // 1: P0 forms the node records two at a time in a rolled loop (half the code, ILP 2 instead of NP)
@@ -278,6 +278,15 @@ __device__ __forceinline__ void pencil_phase0(const StageParams& P, double* smem
     const int64_t e = e0 + le;
     const int64_t e_hi = (e0 + G::E < P.elem_end) ? e0 + G::E : P.elem_end;
     if (e >= P.elem_end) return;   // (its records are never read: the in-patch test uses e_hi)
+#if WGPU_PENCIL_PREFETCH >= 5 && !WGPU_HOST_EMU
+    // the block that follows this one on its SM starts by loading the state of the patch P.lookahead elements ahead: ask for
+    // those lines now (L2), a whole block lifetime early
+    if (sp == 0 && P.lookahead > 0 && e + P.lookahead < P.elem_end) {
+        const double* const nx = P.u + ((size_t)(e + P.lookahead) * P.nc) * G::NN + pe * NP;
+#pragma unroll
+        for (int c = 0; c < 5; c++) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)c * G::NN));
+    }
+#endif
     // neighbour ids of the y-faces first: the loads they address (ends of next phase's pencil) then overlap with the state's
     const int v0 = P.nbr[(size_t)e * G::NFACE + 2], v1 = P.nbr[(size_t)e * G::NFACE + 3];
     const double* src = P.u + ((size_t)e * P.nc + 5 * sp) * G::NN + pe * NP;
@@ -686,7 +695,14 @@ __device__ __forceinline__ double pencil_phase_final(const StageParams& P, doubl
 #endif
             if (need_old) asm volatile("prefetch.global.L2 [%0];" ::"l"(oldp + off + (size_t)c * G::NN));
         }
-#if WGPU_PENCIL_PREFETCH == 3
+#if WGPU_PENCIL_PREFETCH >= 4
+        // (4: also the next species' state, which its P0 loads right after the barrier that ends this phase)
+        if (sp + 1 < P.nsp) {
+#pragma unroll
+            for (int c = 0; c < 5; c++) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.u + off + (size_t)(5 + c) * G::NN));
+        }
+#endif
+#if WGPU_PENCIL_PREFETCH >= 3
         // (3: also E and B for the Lorentz force: with the field system in its own kernel nobody has touched them yet)
         if (P.src_on && sp == 0) {
             const double* const fp = P.u + ((size_t)e * P.nc + 5 * P.nsp) * G::NN + pe * NP;

@@ -241,6 +241,7 @@ void do_launch_cfl(warpii_gpu_ctx* c, int vec) {
 
 StageParams stage_params(warpii_gpu_ctx* c, int dst, int u, double dt, double a, double beta, int mode, bool fuse_cfl) {
     StageParams P;
+    P.lookahead = 0;   // (the pencil launcher sets it)
     P.u = c->vec[u];
     P.dst = c->vec[dst];
     P.nbr = c->d_nbr;
