@@ -42,7 +42,7 @@
 #define WGPU_PENCIL_TMA 0        // 1: P0 stages the patch's state block in shared memory with cp.async.bulk + mbarrier (A/B only)
 #endif
 #ifndef WGPU_PENCIL_PREFETCH
-#define WGPU_PENCIL_PREFETCH 5   // L2 prefetches ahead of use (0: off; 1: u again to L1 + old dst before the x pair fluxes; 2: old dst; 3: + E, B of the Lorentz force; 4: + the next species' state; 5: + the state of the patch the next block of this SM will work on)
+#define WGPU_PENCIL_PREFETCH 6   // L2 prefetches ahead of use (0: off; 1: u again to L1 + old dst before the x pair fluxes; 2: old dst; 3: + E, B of the Lorentz force; 4: + the next species' state; 5: + the state of the patch the next block of this SM will work on; 6: + phi, psi and the old field values for the fused field phases)
 #endif
 #ifndef WGPU_PENCIL_P0_ROLL
 #define WGPU_PENCIL_P0_ROLL 0    // 1: P0 forms the node records two at a time in a rolled loop (half the code, ILP 2 instead of NP)
@@ -709,6 +709,18 @@ __device__ __forceinline__ double pencil_phase_final(const StageParams& P, doubl
 #pragma unroll
             for (int k = 0; k < 6; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + (size_t)k * G::NN));
         }
+#if WGPU_PENCIL_PREFETCH >= 6
+        // (6: the fused field phases that follow the last species: phi, psi and, in a second stage, the old field values)
+        if (P.mx_on && sp == P.nsp - 1 && P.nc >= 5 * P.nsp + 8) {
+            const size_t fo = ((size_t)e * P.nc + 5 * P.nsp) * G::NN + pe * NP;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.u + fo + (size_t)6 * G::NN));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.u + fo + (size_t)7 * G::NN));
+            if (need_old) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(oldp + fo + (size_t)k * G::NN));
+            }
+        }
+#endif
 #endif
     }
 #endif
