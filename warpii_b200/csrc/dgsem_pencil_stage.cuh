@@ -22,6 +22,10 @@
 //     alpha f(u_0)/(w_0 h) of the subcell scheme cancel analytically for every alpha ((1-alpha) + alpha - 1 = 0 with
 //     D_00 = -1/(2 w_0), the SBP property): none of them is evaluated.  The reference forms them separately and leaves
 //     their round-off (one ulp of f/(h w_0), the size of every other summand's rounding);
+//   * DRAM latency is taken off the threads' paths with L2 prefetch instructions (no registers held): what lies beyond the
+//     pencil ends is LOADED one phase ahead; E and B of the Lorentz force, the old destination, the next species' state and
+//     the state of the patch that the next block of this SM will start with are PREFETCHED a phase or a block ahead
+//     (WGPU_PENCIL_PREFETCH, StageParams::lookahead);
 //   * elements whose blending factor is positive (rare: the troubled cells) take a per-node correction
 //     -alpha vol + alpha fv recomputed from the shared records; everybody else never touches the subcell scheme.
 //
