@@ -15,6 +15,9 @@ namespace wgpu {
 // its own shared-memory image), so that the 4 SUB warps of a CTA walk the same stretch of the (80 KB, straight-line) code at
 // about the same time and share its instruction-cache lines.  WGPU_PENCIL_SUB_HARD = 1 separates the phases with the CTA
 // barrier (lock step), 0 with one named barrier per sub-block (they start together and drift).
+#ifndef WGPU_PENCIL_LOOKAHEAD_MULT
+#define WGPU_PENCIL_LOOKAHEAD_MULT 1   // how many block generations ahead the state prefetch looks (measured: 1 and 2 tie)
+#endif
 #ifndef WGPU_PENCIL_SUB
 #define WGPU_PENCIL_SUB 1
 #endif
@@ -191,7 +194,7 @@ void launch_pencil_stage(int dim, int Np, const StageParams& P, cudaStream_t s) 
             resident = per_sm * sms;                                                                              \
         }                                                                                                         \
         StageParams Q = P;                                                                                        \
-        Q.lookahead = (blocks > resident) ? (int64_t)resident * per_cta : 0;                                      \
+        Q.lookahead = (blocks > resident) ? (int64_t)resident * per_cta * WGPU_PENCIL_LOOKAHEAD_MULT : 0;         \
         pencil_stage_kernel<D_, N_><<<(unsigned)blocks, G::THREADS * WGPU_PENCIL_SUB,                             \
                                       G::SMEM_DOUBLES * WGPU_PENCIL_SUB * sizeof(double), s>>>(Q);                \
     }
