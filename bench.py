@@ -67,6 +67,9 @@ WORKLOADS = {
     "C2c": dict(dim=2, p=3, nx=[512, 512], left=[0.0, -5.0], right=[10.0, 5.0], gamma=1.4, ic="vortex", mapping="wavy",
                 label="C2 on curved elements: the 512x512 degree-3 box pushed through a smooth periodic mapping "
                       "(general-geometry kernels, metric terms read from HBM)"),
+    "C4": dict(dim=3, p=4, nx=[128, 128, 16], left=[0.0, -5.0, -5.0], right=[10.0, 5.0, -3.75], gamma=1.4, ic="vortex",
+               label="C4 at its stated size when run on 8 GPUs (--gpus 8 --workload C4): 3D Euler periodic vortex, degree 4, 128^3 "
+                     "elements as eight 128x128x16 slabs, 16.4 MB of face traces per direction and RHS"),
     "C4s": dict(dim=3, p=4, nx=[64, 64, 64], left=[0.0, -5.0, -5.0], right=[10.0, 5.0, 5.0], gamma=1.4, ic="vortex",
                 label="3D Euler periodic vortex, degree 4, 64^3 elements per GPU (C4 shape)"),
 }
