@@ -14,6 +14,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../warpii_b200/csrc/dgsem_maxwell_thread.cuh"
 #include "../../warpii_b200/csrc/dgsem_pencil_stage.cuh"
 #include "../../warpii_b200/host/reference_element.hpp"
 
@@ -84,7 +85,36 @@ double run(const StageParams& P) {
 
 }  // namespace
 
+// The stand-alone field kernel (warpii_b200/csrc/dgsem_maxwell_thread.cuh, launched by dgsem_maxwell_kernel.cu): every
+// thread of a block through maxwell_pre, then - the block barrier - every thread through maxwell_post.
+template <int DIM, int NP>
+double run_maxwell(const StageParams& P, const MaxwellParams& M) {
+    using GEO = MGeo<DIM, NP>;
+    const int64_t n = P.elem_end - P.elem_begin;
+    const int64_t blocks = (n + GEO::G - 1) / GEO::G;
+    std::vector<double2> smem(GEO::SMEM_DOUBLE2);
+    std::vector<MaxwellCarry<DIM>> carry(GEO::THREADS);
+    double vmax = 0.0;
+    bool nan_seen = false;
+    for (int64_t b = 0; b < blocks; b++) {
+        for (auto& v : smem) v = make_double2(std::nan(""), std::nan(""));
+        for (int t = 0; t < GEO::THREADS; t++) maxwell_pre<DIM, NP>(P, smem.data(), t, b, carry[t]);
+        for (int t = 0; t < GEO::THREADS; t++) {
+            const double v = maxwell_post<DIM, NP>(P, M, smem.data(), P.dt, carry[t]);
+            if (v != v) nan_seen = true;
+            vmax = std::max(vmax, v);
+        }
+    }
+    return nan_seen ? std::nan("") : vmax;
+}
+
+int g_field_kernel = 0;
+
 extern "C" {
+
+// 1: the next emu_pencil_stage calls run the stand-alone field kernel (which updates the 8 field components only) instead
+// of the pencil stage kernel; 0: back to the pencil kernel
+void emu_select_field_kernel(int on) { g_field_kernel = on; }
 
 int emu_pencil_available(int dim, int np) { return (dim == 2 || dim == 3) && np >= 2 && np <= 6; }
 int emu_pencil_patch_elems(int dim, int np) { return pencil_elems(dim, np); }
@@ -130,13 +160,32 @@ int emu_pencil_stage(int dim, int np, int64_t n_elems, int64_t elem_begin, int64
     P.gamma = gamma; P.dt = dt; P.a = a; P.beta = beta;
     P.hig = 0.5 / (gamma - 1.0);
     P.src_on = src_on; P.inv_eps0 = src_on ? 1.0 / epsilon0 : 1.0; P.chi = chi; P.qm = qm;
-    if (mx_on) {   // as stage_params() of warpii_gpu.cu
+    if (mx_on == 2) {   // the field system is evolved by the stand-alone field kernel: the fluid kernel skips the field components
+        P.fields_skip = 1; P.ncf = nc;
+    } else if (mx_on) {   // as stage_params() of warpii_gpu.cu
         const double big = std::max(1.0, std::max(mx_chi, mx_gamma));
         P.mx_on = 1; P.fields_skip = 1; P.ncf = nc;
         P.mx_c2 = light_speed * light_speed; P.mx_chi = mx_chi; P.mx_gam = mx_gamma; P.mx_lam = light_speed * big;
         P.mx_floor = P.max_eig * P.mx_lam; P.mx_omega_factor = 5.0 / (double)(np * np);
     }
     double vmax = 0.0;
+    if (g_field_kernel) {
+        if (!mx_on) return 1;
+        // as make_params() of dgsem_maxwell_kernel.cu; the fluid kernels leave the field components alone
+        MaxwellParams M;
+        M.c2 = P.mx_c2; M.chi = P.mx_chi; M.gam = P.mx_gam; M.lam = P.mx_lam; M.inv_eps0 = P.inv_eps0;
+        M.speed_floor = P.mx_floor; M.omega_factor = P.mx_omega_factor; M.sources_on = src_on ? 1 : 0;
+        P.mx_on = 0;
+#define CALLM(D_, N_) vmax = run_maxwell<D_, N_>(P, M)
+        if (dim == 2) {
+            switch (np) { case 2: CALLM(2, 2); break; case 3: CALLM(2, 3); break; case 4: CALLM(2, 4); break; case 5: CALLM(2, 5); break; case 6: CALLM(2, 6); break; }
+        } else {
+            switch (np) { case 2: CALLM(3, 2); break; case 3: CALLM(3, 3); break; case 4: CALLM(3, 4); break; case 5: CALLM(3, 5); break; case 6: CALLM(3, 6); break; }
+        }
+#undef CALLM
+        if (vmax_out) *vmax_out = vmax;
+        return 0;
+    }
 #define CALL(D_, N_) vmax = run<D_, N_>(P)
     if (dim == 2) {
         switch (np) { case 2: CALL(2, 2); break; case 3: CALL(2, 3); break; case 4: CALL(2, 4); break; case 5: CALL(2, 5); break; case 6: CALL(2, 6); break; }

@@ -35,8 +35,10 @@ def _p(a):
 
 
 def stage(dim, p, u, nbr, h, gamma, mode=1, dt=0.0, a=1.0, beta=0.0, dst=None, ghost=None, bres=None, elem_range=None, nsp=1,
-          sol_in=None, dst2=None, sources=None, want_alpha=False, want_vmax=False, maxwell=None):
-    """One launch.  u, dst: [n_elems][nc][NN] (dst is updated in place and returned); nbr: int32 [n_elems][2 dim]."""
+          sol_in=None, dst2=None, sources=None, want_alpha=False, want_vmax=False, maxwell=None, field_kernel=False, fields_skip=False):
+    """One launch.  u, dst: [n_elems][nc][NN] (dst is updated in place and returned); nbr: int32 [n_elems][2 dim].
+    field_kernel=True runs the stand-alone field kernel (dgsem_maxwell_thread.cuh: the 8 field components only) instead of the
+    pencil stage kernel."""
     L = lib()
     n_elems, nc, NN = u.shape
     assert NN == (p + 1) ** dim
@@ -51,10 +53,12 @@ def stage(dim, p, u, nbr, h, gamma, mode=1, dt=0.0, a=1.0, beta=0.0, dst=None, g
     if sources:
         src_on, eps0, chi = 1, sources["epsilon0"], sources["chi"]
         qm = np.ascontiguousarray(sources["charge_over_mass"], dtype=np.float64)
+    L.emu_select_field_kernel(1 if field_kernel else 0)
     rc = L.emu_pencil_stage(dim, p + 1, n_elems, b, e, nc, nsp, _p(u), _p(dst), nbr.ctypes.data_as(_ip), _p(ghost), _p(bres), _p(alpha),
                             _p(vmax), mode, gamma, dt, a, beta, _p(hh), _p(sol_in), _p(dst2), src_on, eps0, chi, _p(qm),
-                            1 if maxwell else 0, (maxwell or {}).get("light_speed", 1.0), (maxwell or {}).get("chi", 0.0),
+                            2 if fields_skip else (1 if maxwell else 0), (maxwell or {}).get("light_speed", 1.0), (maxwell or {}).get("chi", 0.0),
                             (maxwell or {}).get("gamma", 0.0))
+    L.emu_select_field_kernel(0)
     assert rc == 0
     out = [dst]
     if want_alpha:

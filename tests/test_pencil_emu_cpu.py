@@ -249,6 +249,43 @@ def test_fused_field_system_sharded():
         assert (err <= bound).all(), (rank, err, bound)
 
 
+@pytest.mark.parametrize("dim,p,nx", [(3, 3, [4, 3, 2]), (3, 2, [3, 3, 3]), (3, 4, [2, 2, 3]), (2, 3, [6, 5]), (2, 1, [7, 6]), (3, 1, [4, 3, 3]),
+                                      (3, 5, [2, 2, 2])])
+def test_stand_alone_field_kernel_rhs_step_and_transport_speed(dim, p, nx):
+    """The 3-D field system's kernel (dgsem_maxwell_thread.cuh) on the host: field components of the RHS, a full SSPRK2 step
+    next to the pencil kernel that skips the fields, and the field system's share of the transport speed."""
+    gamma, nsp, nf = 5.0 / 3.0, 2, 10
+    o, tab, h = setup(dim, p, nx, [0.0] * dim, [1.0] * dim, gamma, n_species=nsp, fields=True)
+    o.set_sources(True, **SRC)
+    o.set_maxwell(True, **MX)
+    u = _two_fluid(o)
+    l2g = tab["local_to_global"]
+    ul = u[l2g].copy()
+    want, _ = o.rhs(u)
+    kw = dict(nsp=nsp, sources=SRC)
+    got = emu.stage(dim, p, ul, tab["face_neighbor"], h, gamma, mode=1, maxwell=MX, field_kernel=True, **kw)
+    assert (cases.rel_l2_per_component(got, want[l2g])[nf:] <= 1e-12).all()
+    assert np.abs(got[:, :nf, :]).max() == 0.0                      # the fluid components are not this kernel's business
+    if not 3 <= p + 1 <= 5:
+        return                                                      # (the pencil kernel serves Np = 3..5: RHS check only)
+    # SSPRK2 with both kernels, stage by stage: fluids by the pencil kernel (which then leaves the fields alone), fields by the
+    # field kernel
+    dt = 0.5 * o.recommend_dt(u)
+
+    def stage(src_vec, dst, a, beta):
+        dst, v_fluid = emu.stage(dim, p, src_vec, tab["face_neighbor"], h, gamma, mode=0, dt=dt, a=a, beta=beta, dst=dst, want_vmax=True,
+                                 fields_skip=True, **kw)
+        dst, v_field = emu.stage(dim, p, src_vec, tab["face_neighbor"], h, gamma, mode=0, dt=dt, a=a, beta=beta, dst=dst, want_vmax=True,
+                                 maxwell=MX, field_kernel=True, **kw)
+        return dst, max(v_fluid, v_field)
+    f1, _ = stage(ul, np.zeros_like(ul), 1.0, 0.0)
+    new, vmax = stage(f1, ul.copy(), 0.5, 0.5)
+    ref = u.copy()
+    o.ssprk2_step(ref, dt, 0.0)
+    assert (cases.rel_l2_per_component(new, ref[l2g]) < 1e-13).all()
+    assert abs(vmax - o.max_transport_speed(ref)) <= 1e-13 * vmax
+
+
 def _pslot(n):
     # dgsem_pencil_stage.cuh::pslot for Np = 4
     return n ^ ((n >> 3) & 1) ^ (((n >> 4) & 1) * 6)

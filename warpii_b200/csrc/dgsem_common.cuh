@@ -7,27 +7,7 @@
 
 namespace wgpu {
 
-__device__ __forceinline__ int stride_of(const int NP, const int d) { return d == 0 ? 1 : (d == 1 ? NP : NP * NP); }
-
-// tangential (face-node) index of node (i0,i1,i2) on a face normal to d: remaining dims in increasing order
-template <int DIM, int NP>
-__device__ __forceinline__ int face_node_index(const int d, const int i0, const int i1, const int i2) {
-    if (DIM == 1) return 0;
-    if (DIM == 2) return d == 0 ? i1 : i0;
-    return d == 0 ? (i1 + NP * i2) : (d == 1 ? (i0 + NP * i2) : (i0 + NP * i1));
-}
-// inverse: element-local node index of face node t on face (d, side)
-template <int DIM, int NP>
-__device__ __forceinline__ int node_of_face_node(const int d, const int side, const int t) {
-    const int e = side ? NP - 1 : 0;
-    if (DIM == 1) return e;
-    if (DIM == 2) return d == 0 ? (e + NP * t) : (t + NP * e);
-    const int t0 = t % NP, t1 = t / NP;
-    return d == 0 ? (e + NP * (t0 + NP * t1)) : (d == 1 ? (t0 + NP * (e + NP * t1)) : (t0 + NP * (t1 + NP * e)));
-}
-
-// max that keeps a NaN once it has seen one (an unphysical state must surface as a NaN time step)
-__device__ __forceinline__ double nan_max(const double a, const double b) { return (b > a || b != b) ? b : a; }
+// (stride_of, face_node_index, node_of_face_node and nan_max live in dgsem_kernels.cuh: host-portable)
 
 __device__ __forceinline__ double block_max(double v, double* s_red) {
     for (int o = 16; o > 0; o >>= 1) v = nan_max(v, __shfl_xor_sync(0xffffffffu, v, o));
