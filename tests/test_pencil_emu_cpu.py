@@ -286,6 +286,33 @@ def test_stand_alone_field_kernel_rhs_step_and_transport_speed(dim, p, nx):
     assert abs(vmax - o.max_transport_speed(ref)) <= 1e-13 * vmax
 
 
+def test_stand_alone_field_kernel_sharded():
+    """the field kernel reads the other rank's field traces from the ghost buffer (all nc components per face node)"""
+    dim, p, nx, gamma = 3, 3, [4, 4, 6], 5.0 / 3.0
+    Np, NF = p + 1, (p + 1) ** (dim - 1)
+    o = Oracle(dim, p, nx, [0.0] * 3, [1.0] * 3, gamma=gamma, n_species=2, fields_enabled=True, threads=4)
+    o.set_sources(True, **SRC)
+    o.set_maxwell(True, **MX)
+    h = [1.0 / n for n in nx]
+    u = _two_fluid(o)
+    want, _ = o.rhs(u)
+    for rank in range(2):
+        tab = box_tables(dim, nx, [1] * dim, rank=rank, n_ranks=2, group=emu.patch_elems(dim, Np))
+        l2g = tab["local_to_global"]
+        ghost = np.zeros((tab["n_ghost"], 18, NF))
+        for s in range(tab["n_ghost"]):
+            ge, side = int(tab["ghost_global_elem"][s]), int(tab["ghost_side"][s])
+            ghost[s] = u[ge][:, [face_node_to_node(dim, Np, side // 2, side % 2, t) for t in range(NF)]]
+        ul = u[l2g].copy()
+        # split launches like the product's: interface elements, then the interior ones
+        n_if = int(tab["n_interface"]) if "n_interface" in tab else 0
+        got = np.zeros_like(ul)
+        for rng in ([(0, n_if), (n_if, ul.shape[0])] if 0 < n_if < ul.shape[0] else [(0, ul.shape[0])]):
+            emu.stage(dim, p, ul, tab["face_neighbor"], h, gamma, mode=1, nsp=2, ghost=ghost, sources=SRC, maxwell=MX, field_kernel=True,
+                      dst=got, elem_range=rng)
+        assert (cases.rel_l2_per_component(got, want[l2g])[10:] <= 1e-12).all(), rank
+
+
 def _pslot(n):
     # dgsem_pencil_stage.cuh::pslot for Np = 4
     return n ^ ((n >> 3) & 1) ^ (((n >> 4) & 1) * 6)
